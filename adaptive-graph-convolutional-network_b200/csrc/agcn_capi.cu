@@ -1,0 +1,325 @@
+// C ABI of the SGC-LL layer (include/agcn_sgcll.h): orchestration of the node-level GEMMs and the
+// per-graph kernels for one whole batch.  Reference: models/layers/graphconv.py:85-252,
+// models/layers/graphconv_reslap.py:45-230.
+#include <algorithm>
+
+#include "agcn_internal.cuh"
+
+using namespace agcn;
+
+namespace {
+
+inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+struct Carver {
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* p) : base(reinterpret_cast<char*>(p)) {}
+  float* take(size_t floats) {
+    float* r = base ? reinterpret_cast<float*>(base + off) : nullptr;
+    off += align256(floats * sizeof(float));
+    return r;
+  }
+};
+
+struct Modes {
+  bool shortcut, paper, reslap, full, need_dL;
+};
+
+Modes modes_of(const agcn_sgcll_desc* d) {
+  Modes m;
+  m.shortcut = literal_shortcut(d->variant, d->laplacian_mode);
+  m.paper = d->laplacian_mode == AGCN_LAP_PAPER;
+  m.reslap = d->variant == AGCN_VARIANT_SGC_LL_RESLAP;
+  m.full = m.paper && d->metric_grad == AGCN_METRIC_GRAD_FULL;
+  m.need_dL = !m.shortcut;
+  return m;
+}
+
+// saved area layout (forward -> backward)
+struct Saved {
+  float *T, *Lall, *dist, *dis, *stats, *XW;
+  size_t bytes;
+};
+
+Saved carve_saved(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
+  const Modes m = modes_of(d);
+  Carver c(base);
+  Saved s{};
+  s.T = c.take((size_t)(d->K > 1 ? d->K - 1 : 0) * p->R * d->F);
+  s.Lall = m.shortcut ? nullptr : c.take((size_t)p->LL);
+  s.dist = m.paper ? c.take((size_t)p->LL) : nullptr;
+  s.dis = m.paper ? c.take((size_t)p->R) : nullptr;
+  s.stats = m.shortcut ? nullptr : c.take((size_t)4 * p->B);
+  s.XW = m.full ? c.take((size_t)p->R * d->F) : nullptr;
+  s.bytes = c.off;
+  return s;
+}
+
+struct Work {
+  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part;
+  size_t bytes;
+};
+
+Work carve_work(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
+  const Modes m = modes_of(d);
+  Carver c(base);
+  Work w{};
+  w.XW = c.take((size_t)p->R * d->F);  // forward: X M_L (when the similarity is needed and not saved)
+  w.dYp = c.take((size_t)p->R * d->Fo);
+  w.G = c.take((size_t)d->K * p->R * d->F);
+  size_t tn = gemm_tn_partial_floats((int)p->R, d->F, d->Fo, d->K);
+  if (m.full) tn = std::max(tn, gemm_tn_partial_floats((int)p->R, d->F, d->F, 1));
+  w.tn_part = c.take(tn);
+  w.act_part = c.take(act_bwd_partial_floats(p->R, d->Fo));
+  w.dL = m.need_dL ? c.take((size_t)p->LL) : nullptr;
+  w.dXW = m.full ? c.take((size_t)p->R * d->F) : nullptr;
+  w.dalpha_part = c.take((size_t)p->B);
+  w.dbeta_part = c.take((size_t)p->B);
+  w.bytes = c.off;
+  return w;
+}
+
+int check_desc(const agcn_sgcll_desc* d, const agcn_plan* p) {
+  AGCN_REQUIRE(d && p, "null desc or plan");
+  AGCN_REQUIRE(d->F >= 1 && d->Fo >= 1 && d->K >= 1, "F, Fo, K must be >= 1");
+  AGCN_REQUIRE(d->variant == AGCN_VARIANT_SGC_LL || d->variant == AGCN_VARIANT_SGC_LL_RESLAP, "unknown variant");
+  AGCN_REQUIRE(d->laplacian_mode == AGCN_LAP_REFERENCE_LITERAL || d->laplacian_mode == AGCN_LAP_PAPER,
+               "unknown laplacian_mode");
+  AGCN_REQUIRE(d->metric_grad == AGCN_METRIC_GRAD_REFERENCE || d->metric_grad == AGCN_METRIC_GRAD_FULL,
+               "unknown metric_grad");
+  AGCN_REQUIRE(d->activation == AGCN_ACT_LINEAR || d->activation == AGCN_ACT_RELU, "unknown activation");
+  AGCN_REQUIRE(p->R < (1ll << 31) / std::max(d->F, d->Fo), "batch too large for 32-bit row indexing");
+  if (p->large_count > 0) {
+    set_error("graphs with more than AGCN_SMALL_MAX nodes need the row-tiled path, which this build lacks");
+    return AGCN_ERR_INVALID;
+  }
+  return AGCN_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int agcn_sgcll_workspace_bytes(const agcn_sgcll_desc* desc, const agcn_plan* plan, size_t* saved_bytes,
+                               size_t* work_bytes) {
+  AGCN_REQUIRE(desc && plan, "null desc or plan");
+  if (saved_bytes) *saved_bytes = carve_saved(desc, plan, nullptr).bytes + 256;
+  if (work_bytes) *work_bytes = carve_work(desc, plan, nullptr).bytes + 256;
+  return AGCN_OK;
+}
+
+int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* d_X, const float* d_Lint,
+                       const float* d_Lprev, const float* d_M_L, const float* d_weight, const float* d_bias,
+                       const float* d_alpha, const float* d_beta, float* d_Y, float* d_resL, float* d_resW,
+                       float* d_Lall, void* d_saved, void* d_work, size_t work_bytes, void* stream) {
+  int rc = check_desc(desc, plan);
+  if (rc) return rc;
+  AGCN_REQUIRE(d_X && d_Lint && d_M_L && d_weight && d_bias && d_alpha && d_Y && d_saved && d_work,
+               "forward: null pointer");
+  const Modes m = modes_of(desc);
+  AGCN_REQUIRE(!m.reslap || d_beta, "forward: beta required for SGC_LL_Reslap");
+  AGCN_REQUIRE(!(desc->flags & AGCN_OUT_RES_L) || d_resL, "forward: d_resL missing");
+  AGCN_REQUIRE(!(desc->flags & AGCN_OUT_RES_W) || d_resW, "forward: d_resW missing");
+  AGCN_REQUIRE(!(desc->flags & AGCN_OUT_L_ALL) || d_Lall, "forward: d_Lall missing");
+  cudaStream_t st = (cudaStream_t)stream;
+  Saved sv = carve_saved(desc, plan, d_saved);
+  Work wk = carve_work(desc, plan, d_work);
+  if (wk.bytes > work_bytes) {
+    set_error("forward: workspace too small");
+    return AGCN_ERR_WORKSPACE;
+  }
+  const int F = desc->F, Fo = desc->Fo, K = desc->K;
+  const int R = (int)plan->R;
+  const bool want_resL = desc->flags & AGCN_OUT_RES_L, want_resW = desc->flags & AGCN_OUT_RES_W;
+  const bool want_Lall = desc->flags & AGCN_OUT_L_ALL;
+  const bool need_W = m.paper || want_resW;
+  const bool need_build = !m.shortcut || want_resL || want_resW || want_Lall;
+  float* XW = m.full ? sv.XW : wk.XW;
+
+  if (need_W) {  // x_w = np.dot(x, M)   graphconv.py:164
+    GemmArgs g;
+    g.M = R; g.N = F; g.Kd = F;
+    g.A0 = d_X; g.lda0 = F;
+    g.B = d_M_L; g.ldb = F;
+    g.C = XW; g.ldc = F;
+    if ((rc = gemm_rows(g, st))) return rc;
+  }
+  GraphArgs ga;
+  ga.plan = plan; ga.F = F; ga.K = K;
+  ga.variant = desc->variant; ga.lap_mode = desc->laplacian_mode; ga.metric_full = m.full;
+  ga.X = d_X; ga.XW = XW; ga.Lint = d_Lint; ga.Lprev = m.reslap ? d_Lprev : nullptr;
+  ga.alpha = d_alpha; ga.beta = d_beta;
+  ga.T = sv.T;
+  if (need_build) {
+    ga.Lall = m.shortcut ? nullptr : sv.Lall;
+    ga.Lall_out = want_Lall ? d_Lall : nullptr;
+    ga.resL = want_resL ? d_resL : nullptr;
+    ga.resW = want_resW ? d_resW : nullptr;
+    ga.dist = sv.dist; ga.dis = sv.dis; ga.stats = sv.stats;
+    if ((rc = graph_build_laplacian(ga, need_W, st))) return rc;
+  }
+  ga.Lall = m.shortcut ? nullptr : sv.Lall;
+  if ((rc = graph_chebyshev_fwd(ga, st))) return rc;  // graphconv.py:221-236
+  {  // x = reshape(transpose(stack T)) . weight + bias, activation   graphconv.py:238-247, :118-123
+    GemmArgs g;
+    g.M = R; g.N = Fo; g.Kd = F; g.S = K;
+    g.A0 = d_X; g.lda0 = F;
+    g.A1 = sv.T; g.lda1 = F; g.sliceA1 = (int64_t)R * F;
+    g.B = d_weight; g.ldb = K * Fo; g.sliceB = Fo;
+    g.C = d_Y; g.ldc = Fo;
+    g.bias = d_bias; g.act = desc->activation;
+    if ((rc = gemm_rows(g, st))) return rc;
+  }
+  return AGCN_OK;
+}
+
+int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* d_X, const float* d_Lint,
+                        const float* d_Lprev, const float* d_M_L, const float* d_weight, const float* d_alpha,
+                        const float* d_beta, const float* d_Y, const float* d_dY, const float* d_dLall_in,
+                        const void* d_saved, float* d_dX, float* d_dM_L, float* d_dweight, float* d_dbias,
+                        float* d_dalpha, float* d_dbeta, float* d_dLprev, void* d_work, size_t work_bytes,
+                        void* stream) {
+  int rc = check_desc(desc, plan);
+  if (rc) return rc;
+  AGCN_REQUIRE(d_X && d_Lint && d_M_L && d_weight && d_alpha && d_Y && d_dY && d_saved && d_work,
+               "backward: null input pointer");
+  AGCN_REQUIRE(d_dX && d_dM_L && d_dweight && d_dbias && d_dalpha, "backward: null output pointer");
+  const Modes m = modes_of(desc);
+  AGCN_REQUIRE(!m.reslap || (d_beta && d_dbeta), "backward: beta / dbeta required for SGC_LL_Reslap");
+  cudaStream_t st = (cudaStream_t)stream;
+  Saved sv = carve_saved(desc, plan, const_cast<void*>(d_saved));
+  Work wk = carve_work(desc, plan, d_work);
+  if (wk.bytes > work_bytes) {
+    set_error("backward: workspace too small");
+    return AGCN_ERR_WORKSPACE;
+  }
+  const int F = desc->F, Fo = desc->Fo, K = desc->K;
+  const int R = (int)plan->R;
+  const bool has_prev = m.reslap && d_Lprev;
+
+  // dYpre = dY * act'(Y);  dbias = colsum(dYpre)
+  const float* dYp = (desc->activation == AGCN_ACT_RELU) ? wk.dYp : d_dY;
+  if ((rc = act_bwd_colsum(d_dY, d_Y, wk.dYp, d_dbias, wk.act_part, R, Fo, desc->activation, st))) return rc;
+  {  // G_k = dYpre W_k^T   (K == 1: this is dX)
+    GemmArgs g;
+    g.M = R; g.N = F; g.Kd = Fo; g.Z = K;
+    g.A0 = dYp; g.lda0 = Fo;
+    g.B = d_weight; g.ldb = K * Fo; g.sliceB = Fo; g.transB = 1;
+    g.C = (K == 1) ? d_dX : wk.G; g.ldc = F; g.sliceC = (int64_t)R * F;
+    if ((rc = gemm_rows(g, st))) return rc;
+  }
+  GraphArgs ga;
+  ga.plan = plan; ga.F = F; ga.K = K;
+  ga.variant = desc->variant; ga.lap_mode = desc->laplacian_mode; ga.metric_full = m.full;
+  ga.X = d_X; ga.XW = sv.XW; ga.Lint = d_Lint; ga.Lprev = has_prev ? d_Lprev : nullptr;
+  ga.alpha = d_alpha; ga.beta = d_beta;
+  ga.T = sv.T; ga.Lall = m.shortcut ? nullptr : sv.Lall;
+  ga.dist = sv.dist; ga.dis = sv.dis; ga.stats = sv.stats;
+  ga.G = wk.G; ga.dLall_in = d_dLall_in; ga.dX = d_dX; ga.dL = wk.dL;
+  ga.dLprev = has_prev ? d_dLprev : nullptr;
+  ga.dXW = wk.dXW; ga.dalpha_part = wk.dalpha_part; ga.dbeta_part = m.reslap ? wk.dbeta_part : nullptr;
+  if (K >= 2) {
+    if ((rc = graph_recurrence_bwd(ga, m.need_dL, st))) return rc;
+  } else if (m.need_dL) {
+    if (d_dLall_in)
+      AGCN_CUDA(cudaMemcpyAsync(wk.dL, d_dLall_in, (size_t)plan->LL * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    else
+      AGCN_CUDA(cudaMemsetAsync(wk.dL, 0, (size_t)plan->LL * sizeof(float), st));
+  }
+  {  // dweight[f*K + k, :] = T_k^T dYpre
+    GemmTNArgs t;
+    t.M = R; t.Kd = F; t.N = Fo; t.S = K;
+    t.A0 = d_X; t.lda0 = F;
+    t.A1 = sv.T; t.lda1 = F; t.sliceA1 = (int64_t)R * F;
+    t.D = dYp; t.ldd = Fo;
+    t.out = d_dweight; t.partial = wk.tn_part;
+    if ((rc = gemm_tn(t, st))) return rc;
+  }
+  if (m.need_dL) {
+    if ((rc = graph_laplacian_bwd(ga, st))) return rc;
+    if ((rc = reduce_scalar_parts(wk.dalpha_part, plan->B, d_dalpha, st))) return rc;
+    if (m.reslap) {
+      if ((rc = reduce_scalar_parts(wk.dbeta_part, plan->B, d_dbeta, st))) return rc;
+    }
+  } else {
+    AGCN_CUDA(cudaMemsetAsync(d_dalpha, 0, sizeof(float), st));  // res_L == I >= 0: leaky never sees alpha
+  }
+  if (m.full) {
+    GemmTNArgs t;  // dM_L = X^T dXW
+    t.M = R; t.Kd = F; t.N = F; t.S = 1;
+    t.A0 = d_X; t.lda0 = F;
+    t.D = wk.dXW; t.ldd = F;
+    t.out = d_dM_L; t.partial = wk.tn_part;
+    if ((rc = gemm_tn(t, st))) return rc;
+    GemmArgs g;  // dX += dXW M_L^T
+    g.M = R; g.N = F; g.Kd = F;
+    g.A0 = wk.dXW; g.lda0 = F;
+    g.B = d_M_L; g.ldb = F; g.transB = 1;
+    g.C = d_dX; g.ldc = F; g.accumulate = 1;
+    if ((rc = gemm_rows(g, st))) return rc;
+  } else {
+    // tf.py_func has no gradient: M_L receives none (graphconv.py:211)
+    AGCN_CUDA(cudaMemsetAsync(d_dM_L, 0, (size_t)F * F * sizeof(float), st));
+  }
+  return AGCN_OK;
+}
+
+int agcn_sgcll_host_scratch_bytes(const agcn_sgcll_desc* desc, const agcn_plan* plan, size_t* bytes) {
+  AGCN_REQUIRE(desc && plan && bytes, "null pointer");
+  size_t saved = 0, work = 0;
+  agcn_sgcll_workspace_bytes(desc, plan, &saved, &work);
+  const size_t B = plan->B, N = plan->Nmax;
+  size_t total = 0;
+  total += align256(B * N * desc->F * 4) + align256(B * N * N * 4) + align256(B * N * desc->Fo * 4);  // padded X, L, Y
+  total += align256((size_t)plan->R * desc->F * 4) + align256((size_t)plan->LL * 4) +
+           align256((size_t)plan->R * desc->Fo * 4);  // packed X, L, Y
+  total += align256(saved) + align256(work);
+  *bytes = total;
+  return AGCN_OK;
+}
+
+int agcn_sgcll_forward_host(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* h_X_padded,
+                            const float* h_L_padded, const float* d_M_L, const float* d_weight, const float* d_bias,
+                            const float* d_alpha, float* h_Y_padded, void* d_scratch, size_t scratch_bytes,
+                            void* stream) {
+  int rc = check_desc(desc, plan);
+  if (rc) return rc;
+  AGCN_REQUIRE(h_X_padded && h_L_padded && h_Y_padded && d_scratch, "forward_host: null pointer");
+  AGCN_REQUIRE(desc->variant == AGCN_VARIANT_SGC_LL, "forward_host: SGC_LL only");
+  AGCN_REQUIRE((desc->flags & (AGCN_OUT_RES_L | AGCN_OUT_RES_W | AGCN_OUT_L_ALL)) == 0,
+               "forward_host: optional outputs are not supported");
+  size_t need = 0, saved = 0, work = 0;
+  agcn_sgcll_host_scratch_bytes(desc, plan, &need);
+  if (need > scratch_bytes) {
+    set_error("forward_host: scratch too small");
+    return AGCN_ERR_WORKSPACE;
+  }
+  agcn_sgcll_workspace_bytes(desc, plan, &saved, &work);
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t B = plan->B, N = plan->Nmax;
+  char* base = reinterpret_cast<char*>(d_scratch);
+  size_t off = 0;
+  auto take = [&](size_t bytes) { char* r = base + off; off += align256(bytes); return r; };
+  float* dXpad = (float*)take(B * N * desc->F * 4);
+  float* dLpad = (float*)take(B * N * N * 4);
+  float* dYpad = (float*)take(B * N * desc->Fo * 4);
+  float* dX = (float*)take((size_t)plan->R * desc->F * 4);
+  float* dL = (float*)take((size_t)plan->LL * 4);
+  float* dY = (float*)take((size_t)plan->R * desc->Fo * 4);
+  void* dsaved = take(saved);
+  void* dwork = take(work);
+  AGCN_CUDA(cudaMemcpyAsync(dXpad, h_X_padded, B * N * desc->F * 4, cudaMemcpyHostToDevice, st));
+  AGCN_CUDA(cudaMemcpyAsync(dLpad, h_L_padded, B * N * N * 4, cudaMemcpyHostToDevice, st));
+  if ((rc = agcn_pack_nodes(plan, dXpad, dX, desc->F, st))) return rc;
+  if ((rc = agcn_pack_lap(plan, dLpad, dL, st))) return rc;
+  if ((rc = agcn_sgcll_forward(desc, plan, dX, dL, nullptr, d_M_L, d_weight, d_bias, d_alpha, nullptr, dY, nullptr,
+                               nullptr, nullptr, dsaved, dwork, work, st)))
+    return rc;
+  if ((rc = agcn_unpack_nodes(plan, dY, dYpad, desc->Fo, st))) return rc;
+  AGCN_CUDA(cudaMemcpyAsync(h_Y_padded, dYpad, B * N * desc->Fo * 4, cudaMemcpyDeviceToHost, st));
+  AGCN_CUDA(cudaStreamSynchronize(st));
+  return AGCN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,169 @@
+// Internal declarations shared by the translation units of libagcn_sm100.so.
+// Public ABI: include/agcn_sgcll.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "agcn_sgcll.h"
+
+// Largest graph handled by the one-CTA-per-(graph, feature chunk) shared-memory kernels; bigger
+// graphs go through the row-tiled kernels (agcn_graph_large.cu).
+#define AGCN_SMALL_MAX 144
+
+namespace agcn {
+
+struct Bucket {
+  int start;  // first index into plan->order
+  int count;  // graphs in the bucket
+  int max_n;  // largest n in the bucket
+};
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+extern std::atomic<uint64_t> g_launches;
+
+#define AGCN_CUDA(call)                                                        \
+  do {                                                                         \
+    cudaError_t e__ = (call);                                                  \
+    if (e__ != cudaSuccess) return agcn::cuda_fail(e__, #call, __FILE__, __LINE__); \
+  } while (0)
+
+#define AGCN_LAUNCH_CHECK()                                                    \
+  do {                                                                         \
+    agcn::g_launches.fetch_add(1, std::memory_order_relaxed);                  \
+    cudaError_t e__ = cudaGetLastError();                                      \
+    if (e__ != cudaSuccess) return agcn::cuda_fail(e__, "kernel launch", __FILE__, __LINE__); \
+  } while (0)
+
+#define AGCN_REQUIRE(cond, msg)                                                \
+  do {                                                                         \
+    if (!(cond)) {                                                             \
+      agcn::set_error(std::string("invalid argument: ") + msg);               \
+      return AGCN_ERR_INVALID;                                                 \
+    }                                                                          \
+  } while (0)
+
+}  // namespace agcn
+
+struct agcn_plan {
+  int32_t B = 0, Nmax = 0, max_n = 0;
+  int64_t R = 0;   // total nodes
+  int64_t LL = 0;  // total n^2
+  std::vector<int32_t> n, node_off, order;
+  std::vector<int64_t> lap_off;
+  std::vector<agcn::Bucket> buckets;  // graphs with n <= AGCN_SMALL_MAX, biggest bucket first
+  int large_count = 0;                // graphs with n > AGCN_SMALL_MAX are order[0 .. large_count)
+  // row tiles of the large graphs: tile t covers rows [tile_row[t], tile_row[t]+64) of graph tile_graph[t]
+  std::vector<int32_t> tile_graph, tile_row;
+  int large_tiles = 0;
+  // device copies (one allocation)
+  void* d_block = nullptr;
+  int32_t* d_n = nullptr;
+  int32_t* d_node_off = nullptr;
+  int32_t* d_order = nullptr;
+  int64_t* d_lap_off = nullptr;
+  int32_t* d_tile_graph = nullptr;
+  int32_t* d_tile_row = nullptr;
+  // side streams so the per-bucket launches of one phase overlap on the device
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr;
+  cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
+};
+
+namespace agcn {
+
+// ---------------------------------------------------------------- node-level GEMMs (agcn_node_gemm.cu)
+// C_z[M,N] (+)= act( sum_{s<S} A_s[M,Kd] * op(B_{z*? + s}) + bias ),   op(B) = B or B^T
+struct GemmArgs {
+  int M = 0, N = 0, Kd = 0;
+  int S = 1;  // inner slices summed into one output
+  int Z = 1;  // independent output slices (grid.z)
+  const float* A0 = nullptr;  // inner slice 0
+  int lda0 = 0;
+  const float* A1 = nullptr;  // inner slice s >= 1: A1 + (s-1)*sliceA1
+  int lda1 = 0;
+  int64_t sliceA1 = 0;
+  const float* B = nullptr;  // slice (z*S + s): B + (z*S+s)*sliceB
+  int ldb = 0;
+  int64_t sliceB = 0;
+  int transB = 0;  // 0: B is [Kd,N] row-major; 1: B is [N,Kd] row-major (C = A * B^T)
+  float* C = nullptr;  // output slice z: C + z*sliceC
+  int ldc = 0;
+  int64_t sliceC = 0;
+  const float* bias = nullptr;
+  int act = AGCN_ACT_LINEAR;
+  int accumulate = 0;  // C += result
+};
+int gemm_rows(const GemmArgs& a, cudaStream_t st);
+
+// out[(f*S + s)*N + c] = sum_r A_s[r, f] * D[r, c]     (A_s as in GemmArgs; contraction over the M rows)
+struct GemmTNArgs {
+  int M = 0;   // rows contracted
+  int Kd = 0;  // columns of A_s  (rows of the result per slice)
+  int N = 0;   // columns of D
+  int S = 1;
+  const float* A0 = nullptr;
+  int lda0 = 0;
+  const float* A1 = nullptr;
+  int lda1 = 0;
+  int64_t sliceA1 = 0;
+  const float* D = nullptr;
+  int ldd = 0;
+  float* out = nullptr;  // [Kd*S, N] with row index f*S + s  (the reference's weight layout)
+  float* partial = nullptr;  // scratch, gemm_tn_partial_floats() floats
+};
+size_t gemm_tn_partial_floats(int M, int Kd, int N, int S);
+int gemm_tn(const GemmTNArgs& a, cudaStream_t st);
+
+// dYp = dY * act'(Y) (relu mask), colsum(dYp) -> dbias.  partial: act_bwd_partial_floats() floats.
+size_t act_bwd_partial_floats(int64_t R, int Fo);
+int act_bwd_colsum(const float* dY, const float* Y, float* dYp, float* dbias, float* partial, int64_t R, int Fo, int act,
+                   cudaStream_t st);
+
+// ---------------------------------------------------------------- per-graph kernels (agcn_graph_small.cu)
+struct GraphArgs {
+  const agcn_plan* plan = nullptr;
+  int F = 0, K = 0;
+  int variant = 0, lap_mode = 0, metric_full = 0;
+  // forward inputs
+  const float* X = nullptr;      // [R,F]
+  const float* XW = nullptr;     // [R,F]   X * M_L (needed when the similarity matrix is needed)
+  const float* Lint = nullptr;   // packed
+  const float* Lprev = nullptr;  // packed or null
+  const float* alpha = nullptr;
+  const float* beta = nullptr;
+  // forward outputs / saved
+  float* T = nullptr;       // [K-1][R][F]  Chebyshev terms T_1..T_{K-1}
+  float* Lall = nullptr;    // packed L_all (null in the literal SGC_LL shortcut: L_all = I + Lint)
+  float* Lall_out = nullptr;  // optional second copy of L_all (user output)
+  float* resL = nullptr;    // optional output
+  float* resW = nullptr;    // optional output
+  float* dist = nullptr;    // packed pairwise distances (saved, paper mode)
+  float* dis = nullptr;     // [R] D^-1/2 (saved, paper mode)
+  float* stats = nullptr;   // [B][4]: s1, s2, sum R^2, sum Z^2 (saved)
+  // backward
+  const float* G = nullptr;      // [K][R][F]  dY * W_k^T
+  const float* dLall_in = nullptr;
+  float* dX = nullptr;           // [R,F]
+  float* dL = nullptr;           // packed scratch: dL_all
+  float* dLprev = nullptr;       // packed out
+  float* dXW = nullptr;          // [R,F] out (metric_full)
+  float* dalpha_part = nullptr;  // [B]
+  float* dbeta_part = nullptr;   // [B]
+};
+bool literal_shortcut(int variant, int lap_mode);  // L_all == I + Lint, nothing to build
+int graph_build_laplacian(const GraphArgs& a, bool need_W, cudaStream_t st);
+int graph_chebyshev_fwd(const GraphArgs& a, cudaStream_t st);
+int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st);
+int graph_laplacian_bwd(const GraphArgs& a, cudaStream_t st);
+int reduce_scalar_parts(const float* parts, int B, float* out, cudaStream_t st);
+
+// ---------------------------------------------------------------- helpers
+int fork_streams(const agcn_plan* plan, cudaStream_t main, int n_aux);
+int join_streams(const agcn_plan* plan, cudaStream_t main, int n_aux);
+
+}  // namespace agcn

@@ -1,0 +1,234 @@
+// Batch topology ("plan") and layout conversion between the reference's zero-padded wire layout
+// (models/tf_modules/graph_topology.py:84-135) and the packed HBM layout of this library.
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "agcn_internal.cuh"
+
+namespace agcn {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+
+void set_error(const std::string& msg) { t_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  t_error = std::string(what) + " failed: " + cudaGetErrorString(e) + " (" + file + ":" + std::to_string(line) + ")";
+  return (e == cudaErrorNoDevice || e == cudaErrorNoKernelImageForDevice || e == cudaErrorInsufficientDriver)
+             ? AGCN_ERR_NO_DEVICE
+             : AGCN_ERR_CUDA;
+}
+
+int fork_streams(const agcn_plan* plan, cudaStream_t main, int n_aux) {
+  if (n_aux <= 0) return AGCN_OK;
+  AGCN_CUDA(cudaEventRecord(plan->ev_fork, main));
+  for (int i = 0; i < n_aux && i < 3; ++i) AGCN_CUDA(cudaStreamWaitEvent(plan->aux[i], plan->ev_fork, 0));
+  return AGCN_OK;
+}
+
+int join_streams(const agcn_plan* plan, cudaStream_t main, int n_aux) {
+  for (int i = 0; i < n_aux && i < 3; ++i) {
+    AGCN_CUDA(cudaEventRecord(plan->ev_join[i], plan->aux[i]));
+    AGCN_CUDA(cudaStreamWaitEvent(main, plan->ev_join[i], 0));
+  }
+  return AGCN_OK;
+}
+
+// ------------------------------------------------------------------ pack / unpack kernels
+// One warp per padded row: rows < n_g are copied, rows >= n_g are written as +0.0f (unpack) or
+// skipped (pack).  graphconv.py:153 (tf.slice) and :249-251 (tf.pad).
+__global__ void pack_nodes_kernel(const float* __restrict__ padded, float* __restrict__ packed,
+                                  const int32_t* __restrict__ n_nodes, const int32_t* __restrict__ node_off, int B,
+                                  int Nmax, int F, int to_padded) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (row >= (int64_t)B * Nmax) return;
+  const int lane = threadIdx.x & 31;
+  const int g = (int)(row / Nmax), i = (int)(row % Nmax);
+  const int n = n_nodes[g];
+  const float* pp = padded + row * F;
+  float* ppw = const_cast<float*>(pp);
+  if (i < n) {
+    const int64_t prow = (int64_t)node_off[g] + i;
+    if (to_padded) {
+      for (int c = lane; c < F; c += 32) ppw[c] = packed[prow * F + c];
+    } else {
+      for (int c = lane; c < F; c += 32) packed[prow * F + c] = pp[c];
+    }
+  } else if (to_padded) {
+    for (int c = lane; c < F; c += 32) ppw[c] = 0.0f;
+  }
+}
+
+__global__ void pack_lap_kernel(const float* __restrict__ padded, float* __restrict__ packed,
+                                const int32_t* __restrict__ n_nodes, const int64_t* __restrict__ lap_off, int B,
+                                int Nmax, int to_padded) {
+  const int warps_per_block = blockDim.x >> 5;
+  const int64_t row = (int64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5);
+  if (row >= (int64_t)B * Nmax) return;
+  const int lane = threadIdx.x & 31;
+  const int g = (int)(row / Nmax), i = (int)(row % Nmax);
+  const int n = n_nodes[g];
+  float* ppw = const_cast<float*>(padded) + row * Nmax;
+  if (i < n) {
+    float* pk = packed + lap_off[g] + (int64_t)i * n;
+    if (to_padded) {
+      for (int c = lane; c < Nmax; c += 32) ppw[c] = (c < n) ? pk[c] : 0.0f;
+    } else {
+      for (int c = lane; c < n; c += 32) pk[c] = ppw[c];
+    }
+  } else if (to_padded) {
+    for (int c = lane; c < Nmax; c += 32) ppw[c] = 0.0f;
+  }
+}
+
+}  // namespace agcn
+
+using namespace agcn;
+
+extern "C" {
+
+int agcn_version(void) { return 100; }
+const char* agcn_last_error(void) { return t_error.c_str(); }
+uint64_t agcn_launch_count(void) { return g_launches.load(); }
+
+int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void* stream, agcn_plan** out) {
+  AGCN_REQUIRE(n_nodes_host && out, "null pointer");
+  AGCN_REQUIRE(B >= 1 && Nmax >= 1, "B and Nmax must be positive");
+  agcn_plan* p = new agcn_plan();
+  p->B = B;
+  p->Nmax = Nmax;
+  p->n.assign(n_nodes_host, n_nodes_host + B);
+  p->node_off.resize(B + 1);
+  p->lap_off.resize(B + 1);
+  p->node_off[0] = 0;
+  p->lap_off[0] = 0;
+  for (int g = 0; g < B; ++g) {
+    const int n = p->n[g];
+    if (n < 1 || n > Nmax) {
+      delete p;
+      set_error("invalid argument: n_nodes[g] must be in [1, Nmax]");
+      return AGCN_ERR_INVALID;
+    }
+    p->node_off[g + 1] = p->node_off[g] + n;
+    p->lap_off[g + 1] = p->lap_off[g] + (int64_t)n * n;
+    p->max_n = std::max(p->max_n, n);
+  }
+  p->R = p->node_off[B];
+  p->LL = p->lap_off[B];
+  // largest first: long-running graphs are scheduled first (LPT)
+  p->order.resize(B);
+  std::iota(p->order.begin(), p->order.end(), 0);
+  std::stable_sort(p->order.begin(), p->order.end(), [&](int a, int b) { return p->n[a] > p->n[b]; });
+  int pos = 0;
+  while (pos < B && p->n[p->order[pos]] > AGCN_SMALL_MAX) ++pos;
+  p->large_count = pos;
+  for (int i = 0; i < p->large_count; ++i) {
+    const int g = p->order[i];
+    for (int r = 0; r < p->n[g]; r += 64) {
+      p->tile_graph.push_back(g);
+      p->tile_row.push_back(r);
+    }
+  }
+  p->large_tiles = (int)p->tile_graph.size();
+  static const int limits[] = {AGCN_SMALL_MAX, 64, 32, 16};  // bucket = (limit_next, limit]
+  for (int b = 0; b < 4 && pos < B; ++b) {
+    const int lo = (b + 1 < 4) ? limits[b + 1] : 0;
+    const int start = pos;
+    while (pos < B && p->n[p->order[pos]] > lo) ++pos;
+    if (pos > start) p->buckets.push_back(Bucket{start, pos - start, p->n[p->order[start]]});
+  }
+  // device block: n[B] node_off[B+1] order[B] tile_graph[T] tile_row[T] (int32) then lap_off[B+1] (int64)
+  const size_t T = (size_t)p->large_tiles;
+  const size_t n32 = (size_t)B + (B + 1) + B + 2 * T;
+  const size_t off64 = (n32 * 4 + 15) / 16 * 16;
+  const size_t bytes = off64 + (size_t)(B + 1) * 8;
+  std::vector<char> host(bytes, 0);
+  int32_t* h32 = reinterpret_cast<int32_t*>(host.data());
+  std::memcpy(h32, p->n.data(), (size_t)B * 4);
+  std::memcpy(h32 + B, p->node_off.data(), (size_t)(B + 1) * 4);
+  std::memcpy(h32 + 2 * B + 1, p->order.data(), (size_t)B * 4);
+  if (T) {
+    std::memcpy(h32 + 3 * B + 1, p->tile_graph.data(), T * 4);
+    std::memcpy(h32 + 3 * B + 1 + T, p->tile_row.data(), T * 4);
+  }
+  std::memcpy(host.data() + off64, p->lap_off.data(), (size_t)(B + 1) * 8);
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMalloc(&p->d_block, bytes);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_block, host.data(), bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&p->aux[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    int rc = cuda_fail(e, "agcn_plan_create", __FILE__, __LINE__);
+    agcn_plan_destroy(p);
+    return rc;
+  }
+  int32_t* d32 = reinterpret_cast<int32_t*>(p->d_block);
+  p->d_n = d32;
+  p->d_node_off = d32 + B;
+  p->d_order = d32 + 2 * B + 1;
+  p->d_tile_graph = d32 + 3 * B + 1;
+  p->d_tile_row = d32 + 3 * B + 1 + T;
+  p->d_lap_off = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(p->d_block) + off64);
+  *out = p;
+  return AGCN_OK;
+}
+
+int agcn_plan_destroy(agcn_plan* p) {
+  if (!p) return AGCN_OK;
+  for (int i = 0; i < 3; ++i) {
+    if (p->aux[i]) cudaStreamDestroy(p->aux[i]);
+    if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
+  }
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->d_block) cudaFree(p->d_block);
+  delete p;
+  return AGCN_OK;
+}
+
+int64_t agcn_plan_total_nodes(const agcn_plan* p) { return p ? p->R : -1; }
+int64_t agcn_plan_total_lap(const agcn_plan* p) { return p ? p->LL : -1; }
+const int32_t* agcn_plan_node_off_host(const agcn_plan* p) { return p ? p->node_off.data() : nullptr; }
+const int64_t* agcn_plan_lap_off_host(const agcn_plan* p) { return p ? p->lap_off.data() : nullptr; }
+
+static int pack_nodes_impl(const agcn_plan* plan, const float* padded, float* packed, int32_t F, void* stream,
+                           int to_padded) {
+  AGCN_REQUIRE(plan && padded && packed && F >= 1, "null pointer or F < 1");
+  const int64_t rows = (int64_t)plan->B * plan->Nmax;
+  const int wpb = 8;
+  pack_nodes_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      padded, packed, plan->d_n, plan->d_node_off, plan->B, plan->Nmax, F, to_padded);
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+int agcn_pack_nodes(const agcn_plan* plan, const float* d_padded, float* d_packed, int32_t F, void* stream) {
+  return pack_nodes_impl(plan, d_padded, d_packed, F, stream, 0);
+}
+int agcn_unpack_nodes(const agcn_plan* plan, const float* d_packed, float* d_padded, int32_t F, void* stream) {
+  return pack_nodes_impl(plan, d_padded, const_cast<float*>(d_packed), F, stream, 1);
+}
+
+static int pack_lap_impl(const agcn_plan* plan, const float* padded, float* packed, void* stream, int to_padded) {
+  AGCN_REQUIRE(plan && padded && packed, "null pointer");
+  const int64_t rows = (int64_t)plan->B * plan->Nmax;
+  const int wpb = 8;
+  pack_lap_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
+      padded, packed, plan->d_n, plan->d_lap_off, plan->B, plan->Nmax, to_padded);
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+int agcn_pack_lap(const agcn_plan* plan, const float* d_padded, float* d_packed, void* stream) {
+  return pack_lap_impl(plan, d_padded, d_packed, stream, 0);
+}
+int agcn_unpack_lap(const agcn_plan* plan, const float* d_packed, float* d_padded, void* stream) {
+  return pack_lap_impl(plan, d_padded, const_cast<float*>(d_packed), stream, 1);
+}
+
+}  // extern "C"

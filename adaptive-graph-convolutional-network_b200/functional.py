@@ -1,0 +1,137 @@
+"""torch.autograd bridge to the C ABI: the SGC-LL layer on packed tensors."""
+import ctypes
+
+import torch
+
+from . import _lib
+from .batch import GraphBatch, _ptr, _stream_ptr
+
+
+class _Workspace(object):
+    """Grow-only scratch buffer per device (the `work` area of agcn_sgcll_forward/backward)."""
+    _bufs = {}
+
+    @classmethod
+    def get(cls, device, nbytes):
+        buf = cls._bufs.get(device)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
+            cls._bufs[device] = buf
+        return buf
+
+
+def make_desc(F, Fo, K, variant, laplacian, metric_grad, activation, flags):
+    return _lib.Desc(F, Fo, K, _lib.VARIANT[variant], _lib.LAPLACIAN[laplacian], _lib.METRIC_GRAD[metric_grad],
+                     _lib.ACT[activation], flags)
+
+
+class _SGCLLFunction(torch.autograd.Function):
+    """Forward/backward of SGC_LL.specgraph_LL (graphconv.py:127-252) / specgraph_LL_reslap
+    (graphconv_reslap.py:91-230) for one packed batch."""
+
+    @staticmethod
+    def forward(ctx, X, Lint, Lprev, M_L, weight, bias, alpha, beta, batch, cfg):
+        F, Fo, K = cfg["F"], cfg["Fo"], cfg["K"]
+        flags = _lib.SAVE_FOR_BACKWARD
+        want_resL, want_resW = cfg.get("want_resL", False), cfg.get("want_resW", False)
+        reslap = cfg["variant"] == "SGC_LL_Reslap"
+        if want_resL:
+            flags |= _lib.OUT_RES_L
+        if want_resW:
+            flags |= _lib.OUT_RES_W
+        if reslap:
+            flags |= _lib.OUT_L_ALL
+        desc = make_desc(F, Fo, K, cfg["variant"], cfg["laplacian"], cfg["metric_grad"], cfg["activation"], flags)
+        X = X.contiguous()
+        Lint = Lint.contiguous()
+        if Lprev is not None:
+            Lprev = Lprev.contiguous()
+        assert X.shape == (batch.total_nodes, F) and X.dtype == torch.float32 and X.is_cuda
+        assert Lint.numel() == batch.total_lap
+        dev = X.device
+        saved_b, work_b = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(_lib.lib().agcn_sgcll_workspace_bytes(ctypes.byref(desc), batch.handle, ctypes.byref(saved_b),
+                                                         ctypes.byref(work_b)))
+        saved = torch.empty(saved_b.value, dtype=torch.uint8, device=dev)
+        work = _Workspace.get(dev, work_b.value)
+        Y = torch.empty(batch.total_nodes, Fo, device=dev, dtype=torch.float32)
+        resL = torch.empty(batch.total_lap, device=dev, dtype=torch.float32) if want_resL else None
+        resW = torch.empty(batch.total_lap, device=dev, dtype=torch.float32) if want_resW else None
+        Lall = torch.empty(batch.total_lap, device=dev, dtype=torch.float32) if reslap else None
+        _lib.check(_lib.lib().agcn_sgcll_forward(
+            ctypes.byref(desc), batch.handle, _ptr(X), _ptr(Lint), _ptr(Lprev), _ptr(M_L), _ptr(weight), _ptr(bias),
+            _ptr(alpha), _ptr(beta), _ptr(Y), _ptr(resL), _ptr(resW), _ptr(Lall), _ptr(saved), _ptr(work),
+            work.numel(), _stream_ptr()))
+        ctx.batch, ctx.cfg, ctx.desc = batch, cfg, desc
+        ctx.set_materialize_grads(False)
+        ctx.has_prev = Lprev is not None
+        ctx.has_beta = beta is not None
+        ctx.save_for_backward(X, Lint, Lprev, M_L, weight, alpha, beta, Y, saved)
+        outs = [Y, resL, resW, Lall]
+        nondiff = [t for t in (resL, resW) if t is not None]
+        if nondiff:
+            ctx.mark_non_differentiable(*nondiff)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, dY, _dresL, _dresW, dLall):
+        X, Lint, Lprev, M_L, weight, alpha, beta, Y, saved = ctx.saved_tensors
+        batch, cfg, desc = ctx.batch, ctx.cfg, ctx.desc
+        F, Fo, K = cfg["F"], cfg["Fo"], cfg["K"]
+        dev = X.device
+        if dY is None:
+            dY = torch.zeros_like(Y)
+        dY = dY.contiguous()
+        if dLall is not None:
+            dLall = dLall.contiguous()
+        work_b = ctypes.c_size_t()
+        _lib.check(_lib.lib().agcn_sgcll_workspace_bytes(ctypes.byref(desc), batch.handle, None, ctypes.byref(work_b)))
+        work = _Workspace.get(dev, work_b.value)
+        dX = torch.empty_like(X)
+        dM = torch.empty_like(M_L)
+        dW = torch.empty_like(weight)
+        db = torch.empty(Fo, device=dev, dtype=torch.float32)
+        dalpha = torch.empty(1, device=dev, dtype=torch.float32)
+        dbeta = torch.zeros(1, device=dev, dtype=torch.float32) if ctx.has_beta else None
+        dLprev = torch.empty_like(Lprev) if ctx.has_prev else None
+        _lib.check(_lib.lib().agcn_sgcll_backward(
+            ctypes.byref(desc), batch.handle, _ptr(X), _ptr(Lint), _ptr(Lprev), _ptr(M_L), _ptr(weight), _ptr(alpha),
+            _ptr(beta), _ptr(Y), _ptr(dY), _ptr(dLall), _ptr(saved), _ptr(dX), _ptr(dM), _ptr(dW), _ptr(db),
+            _ptr(dalpha), _ptr(dbeta), _ptr(dLprev), _ptr(work), work.numel(), _stream_ptr()))
+        return dX, None, dLprev, dM, dW, db, dalpha, dbeta, None, None
+
+
+def sgc_ll_packed(X, Lint, Lprev, params, batch, cfg):
+    """X [R,F], Lint packed, Lprev packed or None -> (Y [R,Fo], resL, resW, Lall) packed."""
+    return _SGCLLFunction.apply(X, Lint, Lprev, params["M_L"], params["weight"], params["bias"], params["alpha"],
+                                params.get("beta"), batch, cfg)
+
+
+class _UnpackNodes(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, packed, batch):
+        ctx.batch = batch
+        return batch.unpack_nodes(packed)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.batch.pack_nodes(g), None
+
+
+class _PackNodes(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, padded, batch):
+        ctx.batch = batch
+        return batch.pack_nodes(padded)
+
+    @staticmethod
+    def backward(ctx, g):
+        return ctx.batch.unpack_nodes(g), None
+
+
+def unpack_nodes(packed, batch):
+    return _UnpackNodes.apply(packed, batch)
+
+
+def pack_nodes(padded, batch):
+    return _PackNodes.apply(padded, batch)

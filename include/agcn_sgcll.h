@@ -1,0 +1,149 @@
+/*
+ * agcn_sgcll.h -- C ABI of libagcn_sm100.so: the SGC-LL hot path of
+ * uta-smile/Adaptive-Graph-Convolutional-Network on NVIDIA B200 (sm_100a).
+ *
+ * The reference has no FFI layer (it is 100 % Python on TensorFlow 0.12); the
+ * boundary below is what a maintainer would bind from the Python layer classes
+ * (ctypes stub in INTEGRATION.md).  Each entry point cites the reference code it
+ * replaces, paths relative to the reference root.
+ *
+ * Conventions
+ *   - every pointer named d_* is a DEVICE pointer owned by the caller; nothing is
+ *     allocated inside the compute calls; all work is ordered on `stream`
+ *     (a cudaStream_t passed as void*).
+ *   - return value: 0 = AGCN_OK, negative = AGCN_ERR_*; agcn_last_error() gives
+ *     the text for the calling thread.
+ *   - all floating point data is IEEE fp32, indices int32, Laplacian offsets int64.
+ *   - thread-safe for distinct plans / streams.
+ *
+ * Native HBM layout ("packed"): a batch of B graphs with n_g real nodes is stored
+ * without padding.  Node matrices are [R, F] row-major with R = sum n_g, graph g
+ * owning rows node_off[g] .. node_off[g+1]-1; per-graph n_g x n_g matrices
+ * (Laplacians) are stored back to back, graph g at element offset
+ * lap_off[g] = sum_{h<g} n_h^2 with leading dimension n_g.  The reference's wire
+ * layout (zero-padded [B, Nmax, F] / [B, Nmax, Nmax],
+ * models/tf_modules/graph_topology.py:84-98) is converted at the boundary by
+ * agcn_pack_* / agcn_unpack_*; padded rows come back as exact +0.0f.
+ */
+#ifndef AGCN_SGCLL_H_
+#define AGCN_SGCLL_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AGCN_OK 0
+#define AGCN_ERR_INVALID (-1)   /* bad argument / unsupported shape            */
+#define AGCN_ERR_CUDA (-2)      /* a CUDA runtime call failed                  */
+#define AGCN_ERR_WORKSPACE (-3) /* workspace too small                         */
+#define AGCN_ERR_NO_DEVICE (-4) /* no sm_100 device / kernel image unusable    */
+
+/* layer variant: models/layers/graphconv.py:32 / graphconv_reslap.py:15 */
+#define AGCN_VARIANT_SGC_LL 0
+#define AGCN_VARIANT_SGC_LL_RESLAP 1
+/* what `L = I - D * W * D` means */
+#define AGCN_LAP_REFERENCE_LITERAL 0 /* elementwise on ndarrays => res_L == I (graphconv.py:198-200) */
+#define AGCN_LAP_PAPER 1             /* I - D^-1/2 W D^-1/2                                          */
+/* tf.py_func has no gradient (graphconv.py:211) */
+#define AGCN_METRIC_GRAD_REFERENCE 0 /* stop-gradient through the metric block */
+#define AGCN_METRIC_GRAD_FULL 1      /* differentiable metric (paper)          */
+/* activation fused into the output epilogue (graphconv.py:118-123); others are applied by the host */
+#define AGCN_ACT_LINEAR 0
+#define AGCN_ACT_RELU 1
+
+/* optional outputs (graphconv.py:125 returns res_L and res_W lists; graphconv_reslap.py:89 adds L_all) */
+#define AGCN_OUT_RES_L 1u
+#define AGCN_OUT_RES_W 2u
+#define AGCN_OUT_L_ALL 4u
+#define AGCN_SAVE_FOR_BACKWARD 8u /* forward keeps what backward needs in `d_saved` */
+
+typedef struct agcn_plan agcn_plan; /* opaque: topology of one batch */
+
+typedef struct agcn_sgcll_desc {
+  int32_t F;              /* input features  (n_atom_feature, graphconv.py:58)  */
+  int32_t Fo;             /* output features (nb_filter,      graphconv.py:57)  */
+  int32_t K;              /* Chebyshev order (graphconv.py:61), >= 1            */
+  int32_t variant;        /* AGCN_VARIANT_*                                     */
+  int32_t laplacian_mode; /* AGCN_LAP_*                                         */
+  int32_t metric_grad;    /* AGCN_METRIC_GRAD_*                                 */
+  int32_t activation;     /* AGCN_ACT_*                                         */
+  uint32_t flags;         /* AGCN_OUT_* | AGCN_SAVE_FOR_BACKWARD                */
+} agcn_sgcll_desc;
+
+/* ---- library ---------------------------------------------------------- */
+int agcn_version(void);
+const char* agcn_last_error(void);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches) */
+uint64_t agcn_launch_count(void);
+
+/* ---- batch topology (replaces GraphTopologyMol.batch_to_feed_dict's data_slice / lap_slice,
+ *      models/tf_modules/graph_topology.py:100-135) ----------------------------------------- */
+/* n_nodes_host[B]: real node count of every graph (host memory, 1 <= n_g <= Nmax).
+ * Builds the device-side offset tables and the size-sorted work lists.  Allocates a few KB of
+ * device memory (the only allocation in the library); synchronises `stream` before returning. */
+int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void* stream, agcn_plan** out);
+int agcn_plan_destroy(agcn_plan* plan);
+int64_t agcn_plan_total_nodes(const agcn_plan* plan);    /* R = sum n_g      */
+int64_t agcn_plan_total_lap(const agcn_plan* plan);      /* sum n_g^2        */
+const int32_t* agcn_plan_node_off_host(const agcn_plan* plan); /* [B+1] host   */
+const int64_t* agcn_plan_lap_off_host(const agcn_plan* plan);  /* [B+1] host   */
+
+/* ---- layout conversion (pad_data2sparse / pad_Lap2sparse, graph_topology.py:84-98;
+ *      tf.slice at graphconv.py:153-154; tf.pad at graphconv.py:249-251) ------------------ */
+int agcn_pack_nodes(const agcn_plan* plan, const float* d_padded /*[B,Nmax,F]*/, float* d_packed /*[R,F]*/,
+                    int32_t F, void* stream);
+int agcn_unpack_nodes(const agcn_plan* plan, const float* d_packed, float* d_padded, int32_t F, void* stream);
+int agcn_pack_lap(const agcn_plan* plan, const float* d_padded /*[B,Nmax,Nmax]*/, float* d_packed, void* stream);
+int agcn_unpack_lap(const agcn_plan* plan, const float* d_packed, float* d_padded, void* stream);
+
+/* ---- SGC-LL layer ----------------------------------------------------- */
+/* sizes in BYTES of the two scratch areas: `saved` lives from forward to backward, `work` only
+ * inside one call (max of forward and backward). */
+int agcn_sgcll_workspace_bytes(const agcn_sgcll_desc* desc, const agcn_plan* plan, size_t* saved_bytes,
+                               size_t* work_bytes);
+
+/* SGC_LL.specgraph_LL (graphconv.py:127-252) / SGC_LL_Reslap.specgraph_LL_reslap
+ * (graphconv_reslap.py:91-230) plus the activation of call() (graphconv.py:118-123), whole batch.
+ *   d_X      [R,F]        node features (packed)
+ *   d_Lint   [sum n^2]    intrinsic Laplacians (packed)            'original_laplacian'
+ *   d_Lprev  [sum n^2]    Reslap: previous layer's L_all or NULL   'res_lap'
+ *   d_M_L [F,F], d_weight [F*K,Fo] (row f*K+k), d_bias [Fo], d_alpha [1], d_beta [1] (Reslap, else NULL)
+ *   d_Y      [R,Fo]       activated output (packed)
+ *   d_resL / d_resW / d_Lall [sum n^2]  optional outputs (NULL unless the flag is set; d_Lall is
+ *                                       mandatory for Reslap when AGCN_OUT_L_ALL is set)
+ */
+int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* d_X, const float* d_Lint,
+                       const float* d_Lprev, const float* d_M_L, const float* d_weight, const float* d_bias,
+                       const float* d_alpha, const float* d_beta, float* d_Y, float* d_resL, float* d_resW,
+                       float* d_Lall, void* d_saved, void* d_work, size_t work_bytes, void* stream);
+
+/* Gradient of the above (what tf.gradients builds for graphconv.py:212-251; PyFunc => no gradient
+ * through the metric unless metric_grad == FULL).
+ *   d_dY       [R,Fo]      gradient w.r.t. the activated output
+ *   d_dLall_in [sum n^2]   Reslap: gradient flowing into the returned L_all from later layers, or NULL
+ *   outputs: d_dX [R,F], d_dM_L [F,F], d_dweight [F*K,Fo], d_dbias [Fo], d_dalpha [1], d_dbeta [1] (Reslap),
+ *            d_dLprev [sum n^2] (Reslap with d_Lprev, else NULL).  All outputs are overwritten.
+ */
+int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* d_X, const float* d_Lint,
+                        const float* d_Lprev, const float* d_M_L, const float* d_weight, const float* d_alpha,
+                        const float* d_beta, const float* d_Y, const float* d_dY, const float* d_dLall_in,
+                        const void* d_saved, float* d_dX, float* d_dM_L, float* d_dweight, float* d_dbias,
+                        float* d_dalpha, float* d_dbeta, float* d_dLprev, void* d_work, size_t work_bytes,
+                        void* stream);
+
+/* Host-buffer convenience entry (the end-to-end path): padded HOST arrays in the reference's wire
+ * layout in, padded HOST output out; host<->device copies are issued on `stream` inside the call.
+ * d_scratch must hold agcn_sgcll_host_scratch_bytes() bytes of device memory. */
+int agcn_sgcll_host_scratch_bytes(const agcn_sgcll_desc* desc, const agcn_plan* plan, size_t* bytes);
+int agcn_sgcll_forward_host(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* h_X_padded,
+                            const float* h_L_padded, const float* d_M_L, const float* d_weight, const float* d_bias,
+                            const float* d_alpha, float* h_Y_padded, void* d_scratch, size_t scratch_bytes,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AGCN_SGCLL_H_ */

@@ -1,0 +1,117 @@
+"""Generate the golden vectors under tests/golden/ by EXECUTING THE REFERENCE.
+
+Run once in the build container (needs /root/reference, which does not exist on
+the GPU box; the produced .npz files are committed and travel):
+
+    python tests/golden/make_golden.py
+
+* ``metric_block.npz``: the reference's ``func`` closure (the learned-metric
+  block that runs inside ``tf.py_func``) is pulled out of
+  models/layers/graphconv.py:163-209 and graphconv_reslap.py:136-182 with ``ast``
+  at run time -- no reference source is copied into this repository -- compiled
+  as a free function and executed on seeded inputs.
+* ``graph_laplacian.npz``: ``Graph(...).Laplacian`` from the reference's
+  models/graph_structure.py, imported as a module from its file.
+
+TensorFlow is not installable here, so the TF part of the layer has no
+reference-generated golden; ``layer_regression.npz`` freezes the ORACLE's own
+output (fp64) for drift detection only and is labelled as such.
+"""
+import ast
+import importlib.util
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference"
+sys.path.insert(0, ROOT)
+
+
+def extract_func(path):
+    tree = ast.parse(open(path).read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "func":
+            mod = ast.Module(body=[node], type_ignores=[])
+            ns = {"np": np}
+            exec(compile(mod, path, "exec"), ns)
+            return ns["func"]
+    raise RuntimeError("func not found in " + path)
+
+
+def main():
+    from oracle import sgcll_oracle as O
+
+    func_ll = extract_func(os.path.join(REF, "models/layers/graphconv.py"))
+    func_rl = extract_func(os.path.join(REF, "models/layers/graphconv_reslap.py"))
+    rng = np.random.default_rng(20261017)
+    out = {}
+    cases = [("tox4", 4, 75, "tox"), ("tox5", 5, 75, "tox"), ("tox18", 18, 75, "tox"),
+             ("tox132", 132, 75, "tox"), ("pc50_f3", 50, 3, "xyz"), ("pc13_f4", 13, 4, "xyz"),
+             ("hid20_f64", 20, 64, "relu"), ("far6_f8", 6, 8, "far")]
+    for name, n, F, kind in cases:
+        if kind == "tox":
+            x = O.tox21_like_features(rng, n)
+        elif kind == "xyz":
+            x = rng.standard_normal((n, F)).astype(np.float32)
+        elif kind == "relu":
+            x = np.maximum(rng.standard_normal((n, F)), 0).astype(np.float32)
+        else:  # rows so far apart that exp(-dist) underflows: degree-0 rows
+            x = (rng.standard_normal((n, F)) * 400).astype(np.float32)
+        lim = np.sqrt(6.0 / (2 * F))
+        M = rng.uniform(-lim, lim, (F, F)).astype(np.float32)
+        with np.errstate(all="ignore"):
+            L1, W1 = func_ll(x, M)
+            L2, W2 = func_rl(x, M)
+        out[name + "/x"], out[name + "/M"] = x, M
+        out[name + "/L_ll"], out[name + "/W_ll"] = L1, W1
+        out[name + "/L_rl"], out[name + "/W_rl"] = L2, W2
+        print(name, "L==I:", np.array_equal(L1, np.eye(n, dtype=np.float32)), "W max", W1.max())
+    np.savez_compressed(os.path.join(HERE, "metric_block.npz"), **out)
+
+    spec = importlib.util.spec_from_file_location("ref_graph_structure", os.path.join(REF, "models/graph_structure.py"))
+    gs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gs)
+    out = {}
+    adjs = {
+        "path5": [[1], [0, 2], [1, 3], [2, 4], [3]],
+        "ring6": [[1, 5], [0, 2], [1, 3], [2, 4], [3, 5], [4, 0]],
+        "star5": [[1, 2, 3, 4], [0], [0], [0], [0]],
+        "asym4": [[1], [2], [3], []],                       # one-directional lists are symmetrised
+        "isolated5": [[1], [0], [], [4], [3]],              # a node with no neighbour
+        "mol18": O.molecule_like_adjacency(rng, 18),
+        "mol132": O.molecule_like_adjacency(rng, 132),
+    }
+    for name, adj in adjs.items():
+        n = len(adj)
+        g = gs.MolGraph(np.zeros((n, 3), np.float32), adj)
+        out[name + "/L"] = np.asarray(g.Laplacian.todense())
+        out[name + "/deg"] = g.degree_list
+        flat = np.array([len(a) for a in adj] + [v for a in adj for v in a], np.int64)
+        out[name + "/adj_flat"] = flat
+    g3 = gs.Graph(np.zeros((3, 2), np.float32), [[1], [0, 2], [1]], 4, 0)
+    out["tiny3/has_Lap"] = np.array(g3.has_Lap)
+    np.savez_compressed(os.path.join(HERE, "graph_laplacian.npz"), **out)
+
+    # oracle self-regression (NOT a reference output)
+    import torch
+    reg = {}
+    X, L, n_nodes = O.synthetic_molecule_batch(4, 24, seed=7)
+    n_nodes = np.minimum(n_nodes, 24)
+    for variant in ("SGC_LL", "SGC_LL_Reslap"):
+        for lap in ("reference_literal", "paper"):
+            p = O.make_params(75, 8, 3, variant, seed=3, dtype=torch.float64)
+            Xt, Lt = torch.tensor(X, dtype=torch.float64), torch.tensor(L, dtype=torch.float64)
+            Y, RL, RW, LA = O.sgc_ll_batch(Xt, Lt, n_nodes, p, 3, variant, lap, "reference", None)
+            key = variant + "/" + lap
+            reg[key + "/Y"] = Y.numpy()
+            reg[key + "/L_all0"] = LA[0].numpy()
+    reg["X"], reg["L"], reg["n_nodes"] = X, L, n_nodes
+    np.savez_compressed(os.path.join(HERE, "layer_regression.npz"), **reg)
+    print("golden vectors written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,212 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle.  Tolerance: 1e-4 relative
+(max-abs error over max-abs reference); padding rows must be exactly +0.0."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import sgcll_oracle as O
+from util_cases import TOL, compare, cuda_run, make_batch, oracle_run, random_prev_laps
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [132, 4, 5, 18, 33, 64, 65, 17, 96, 31]
+
+
+def _cot(shape, seed):
+    return np.random.default_rng(seed).standard_normal(shape).astype(np.float32)
+
+
+@pytest.mark.parametrize("laplacian", ["reference_literal", "paper"])
+@pytest.mark.parametrize("K", [1, 2, 3, 5])
+def test_sgc_ll_forward_backward(laplacian, K):
+    F, Fo = 75, 64
+    X, L, n = make_batch(SIZES, F, 132, seed=K, kind="tox")
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=10 + K, dtype=torch.float64)
+    cY = _cot((len(SIZES), 132, Fo), 5)
+    orc = oracle_run(X, L, n, p, K, "SGC_LL", laplacian, "reference", cot_Y=cY)
+    cu = cuda_run(X, L, n, p, K, "SGC_LL", laplacian, "reference", cot_Y=cY)
+    errs = compare(cu, orc)
+    print(laplacian, K, errs)
+
+
+@pytest.mark.parametrize("laplacian", ["reference_literal", "paper"])
+@pytest.mark.parametrize("with_prev", [False, True])
+def test_reslap_forward_backward(laplacian, with_prev):
+    F, Fo, K = 64, 128, 3
+    X, L, n = make_batch(SIZES, F, 132, seed=3, kind="relu")
+    p = O.make_params(F, Fo, K, "SGC_LL_Reslap", seed=21, dtype=torch.float64)
+    Lprev = random_prev_laps(n, 4) if with_prev else None
+    cY = _cot((len(SIZES), 132, Fo), 6)
+    cL = [_cot((int(k), int(k)), 70 + i) for i, k in enumerate(n)]
+    orc = oracle_run(X, L, n, p, K, "SGC_LL_Reslap", laplacian, "reference", Lprev, cot_Y=cY, cot_L=cL)
+    cu = cuda_run(X, L, n, p, K, "SGC_LL_Reslap", laplacian, "reference", Lprev, cot_Y=cY, cot_L=cL)
+    errs = compare(cu, orc)
+    print(laplacian, with_prev, errs)
+
+
+@pytest.mark.parametrize("variant", ["SGC_LL", "SGC_LL_Reslap"])
+def test_paper_full_metric_gradient(variant):
+    F, Fo, K = 32, 16, 3
+    sizes = [40, 4, 9, 23, 64, 70]
+    X, L, n = make_batch(sizes, F, 72, seed=8)
+    X *= 0.5
+    p = O.make_params(F, Fo, K, variant, seed=31, dtype=torch.float64)
+    Lprev = random_prev_laps(n, 5) if variant == "SGC_LL_Reslap" else None
+    cY = _cot((len(sizes), 72, Fo), 7)
+    cL = [_cot((int(k), int(k)), 90 + i) for i, k in enumerate(n)] if variant == "SGC_LL_Reslap" else None
+    orc = oracle_run(X, L, n, p, K, variant, "paper", "full", Lprev, cot_Y=cY, cot_L=cL)
+    cu = cuda_run(X, L, n, p, K, variant, "paper", "full", Lprev, cot_Y=cY, cot_L=cL)
+    errs = compare(cu, orc)
+    assert float(orc["dM_L"].abs().max()) > 0
+    print(variant, errs)
+
+
+def test_full_gradient_with_duplicate_rows():
+    """Exactly duplicated rows (dist == 0): sub-gradient 0, no NaN."""
+    F, Fo, K = 75, 8, 2
+    X, L, n = make_batch([18, 30, 7], F, 30, seed=12, kind="tox")
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=2, dtype=torch.float64)
+    cY = _cot((3, 30, Fo), 9)
+    orc = oracle_run(X, L, n, p, K, "SGC_LL", "paper", "full", cot_Y=cY)
+    cu = cuda_run(X, L, n, p, K, "SGC_LL", "paper", "full", cot_Y=cY)
+    for k, v in cu.items():
+        if isinstance(v, torch.Tensor):
+            assert torch.isfinite(v).all(), k
+    compare(cu, orc)
+
+
+@pytest.mark.parametrize("F,Fo,K", [(3, 32, 3), (4, 16, 2), (128, 128, 3), (256, 32, 2), (64, 617, 2)])
+def test_feature_shapes(F, Fo, K):
+    sizes = [50, 13, 100, 4, 29]
+    X, L, n = make_batch(sizes, F, 100, seed=F)
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=F + 1, dtype=torch.float64)
+    cY = _cot((len(sizes), 100, Fo), 11)
+    for lap in ("reference_literal", "paper"):
+        orc = oracle_run(X, L, n, p, K, "SGC_LL", lap, "reference", cot_Y=cY)
+        cu = cuda_run(X, L, n, p, K, "SGC_LL", lap, "reference", cot_Y=cY)
+        compare(cu, orc)
+
+
+def test_padding_rows_are_positive_zero_and_pack_roundtrip():
+    import agcn_b200
+    F, Fo, K = 75, 64, 3
+    X, L, n = make_batch(SIZES, F, 132, seed=1, kind="tox")
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=1, dtype=torch.float64)
+    cu = cuda_run(X, L, n, p, K, "SGC_LL", "reference_literal", "reference")
+    Y = cu["Y"].numpy()
+    for g, k in enumerate(n):
+        pad = Y[g, k:]
+        assert np.array_equal(pad.view(np.uint32), np.zeros_like(pad).view(np.uint32))  # bit-exact +0.0
+    batch = cu["batch"]
+    Xd, Ld = torch.tensor(X, device="cuda"), torch.tensor(L, device="cuda")
+    assert torch.equal(batch.unpack_nodes(batch.pack_nodes(Xd)), Xd)
+    assert torch.equal(batch.unpack_lap(batch.pack_lap(Ld)), Ld)
+
+
+def test_metric_block_against_reference_golden():
+    """res_W / res_L of the CUDA path against the outputs of the reference's own `func`
+    (tests/golden/metric_block.npz, produced by executing the reference source)."""
+    import os
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "metric_block.npz"))
+    names = sorted({k.split("/")[0] for k in gold.files})
+    for name in names:
+        x, M = gold[name + "/x"], gold[name + "/M"]
+        n, F = x.shape
+        X = x[None].copy()
+        L = np.zeros((1, n, n), np.float32)
+        p = O.make_params(F, 8, 2, "SGC_LL", seed=0, dtype=torch.float64, perturb=False)
+        p["M_L"] = torch.tensor(M, dtype=torch.float64)
+        cu = cuda_run(X, L, np.array([n], np.int32), p, 2, "SGC_LL", "reference_literal", "reference")
+        W_ref, L_ref = gold[name + "/W_ll"], gold[name + "/L_ll"]
+        err = O.rel_err(cu["res_W"][0], W_ref) if W_ref.max() > 0 else float(cu["res_W"][0].abs().max())
+        assert err <= TOL, (name, err)
+        # alpha = 1, clip_by_average_norm(I) = I  => res_L == I exactly
+        assert torch.equal(cu["res_L"][0], torch.tensor(L_ref)), name
+
+
+def test_layer_api_matches_oracle():
+    """SGC_LL / SGC_LL_Reslap called like the reference's graph containers call them
+    (tf_graphs.py:45-54,178-194), with the reference's padded list inputs."""
+    import agcn_b200
+    from agcn_b200.layers import SGC_LL, SGC_LL_Reslap
+    F, Fo, K = 75, 32, 2
+    sizes = [20, 4, 9, 50]
+    X, L, n = make_batch(sizes, F, 50, seed=3, kind="tox")
+    dev = torch.device("cuda:0")
+    x = {"node_features": [torch.tensor(X[g], device=dev) for g in range(4)],
+         "original_laplacian": [torch.tensor(L[g], device=dev) for g in range(4)],
+         "data_slice": np.stack([[k, -1] for k in n]).astype(np.int32),
+         "lap_slice": np.stack([[k, k] for k in n]).astype(np.int32)}
+    layer = SGC_LL(Fo, F, 4, K=K, activation="relu")
+    out, res_L, res_W = layer(x)
+    assert len(out) == 4 and tuple(out[0].shape) == (50, Fo)
+    p = {k: v.detach().double().cpu() for k, v in layer.vars.items()}
+    orc = oracle_run(X, L, n, p, K, "SGC_LL", "reference_literal", "reference")
+    assert O.rel_err(out.padded().detach().cpu(), orc["Y"]) <= TOL
+    assert tuple(res_W[1].shape) == (4, 4) and O.rel_err(res_W[3].cpu(), orc["res_W"][3]) <= TOL
+    assert torch.equal(res_L[0].cpu(), torch.eye(20))
+    # Reslap stack: second layer consumes the first layer's saved Laplacians
+    l1 = SGC_LL_Reslap(Fo, F, 4, K=K, save_lap=True)
+    l2 = SGC_LL_Reslap(16, Fo, 4, K=K)
+    x["res_lap"] = []
+    o1, _, _, La1 = l1(x)
+    x2 = dict(x, node_features=o1, res_lap=list(La1)[-4:])
+    o2, _, _, La2 = l2(x2)
+    p1 = {k: v.detach().double().cpu() for k, v in l1.vars.items()}
+    p2 = {k: v.detach().double().cpu() for k, v in l2.vars.items()}
+    r1 = oracle_run(X, L, n, p1, K, "SGC_LL_Reslap", "reference_literal", "reference")
+    r2 = oracle_run(r1["Y"].numpy(), L, n, p2, K, "SGC_LL_Reslap", "reference_literal", "reference",
+                    [t.numpy() for t in r1["L_all"]])
+    assert O.rel_err(o2.padded().detach().cpu(), r2["Y"]) <= TOL
+    assert O.rel_err(La2[3].detach().cpu(), r2["L_all"][3]) <= TOL
+    (o2.data.sum() + La2.data.sum()).backward()
+    assert l1.vars["beta"].grad is not None and torch.isfinite(l1.vars["weight"].grad).all()
+    with pytest.raises(TypeError):
+        SGC_LL(8, 8, 4, bogus=1)
+    with pytest.raises(ValueError):
+        SGC_LL(8, 8, 4, activation="nope")
+
+
+def test_host_buffer_entry_point():
+    """agcn_sgcll_forward_host: padded host arrays in, padded host array out."""
+    import ctypes
+    import agcn_b200
+    from agcn_b200 import _lib
+    from agcn_b200.functional import make_desc
+    F, Fo, K = 75, 64, 3
+    X, L, n = make_batch([30, 4, 17, 60], F, 64, seed=2, kind="tox")
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=4, dtype=torch.float64)
+    dev = torch.device("cuda:0")
+    batch = agcn_b200.GraphBatch(n, 64, device=dev)
+    desc = make_desc(F, Fo, K, "SGC_LL", "reference_literal", "reference", "relu", 0)
+    nbytes = ctypes.c_size_t()
+    _lib.check(_lib.lib().agcn_sgcll_host_scratch_bytes(ctypes.byref(desc), batch.handle, ctypes.byref(nbytes)))
+    scratch = torch.empty(nbytes.value, dtype=torch.uint8, device=dev)
+    pd = {k: v.float().to(dev) for k, v in p.items()}
+    Xh, Lh = torch.tensor(X).pin_memory(), torch.tensor(L).pin_memory()
+    Yh = torch.empty(4, 64, Fo).pin_memory()
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())
+    _lib.check(_lib.lib().agcn_sgcll_forward_host(ctypes.byref(desc), batch.handle, vp(Xh), vp(Lh), vp(pd["M_L"]),
+                                                  vp(pd["weight"]), vp(pd["bias"]), vp(pd["alpha"]), vp(Yh),
+                                                  vp(scratch), scratch.numel(),
+                                                  ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+    orc = oracle_run(X, L, n, p, K, "SGC_LL", "reference_literal", "reference")
+    assert O.rel_err(Yh, orc["Y"]) <= TOL
+
+
+def test_full_size_properties_toxcast_batch():
+    """BASELINE full size (B = 1024, Nmax = 132, 75 -> 64, K = 3): size-independent properties --
+    linearity in the weights, zero padding, and exact agreement with the oracle on a sample of graphs."""
+    F, Fo, K, B = 75, 64, 3, 1024
+    X, L, n = O.synthetic_molecule_batch(B, 132, seed=1235)
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=5, dtype=torch.float64)
+    p["bias"] = torch.zeros_like(p["bias"])
+    cu1 = cuda_run(X, L, n, p, K, "SGC_LL", "reference_literal", "reference", activation="linear", want_res=False)
+    p2 = dict(p, weight=p["weight"] * 2.0)
+    cu2 = cuda_run(X, L, n, p2, K, "SGC_LL", "reference_literal", "reference", activation="linear", want_res=False)
+    assert O.rel_err(cu2["Y"], 2.0 * cu1["Y"]) <= 1e-6                 # linear in the weights
+    idx = [0, 1, 2, 511, 1023]
+    orc = oracle_run(X[idx], L[idx], n[idx], p, K, "SGC_LL", "reference_literal", "reference", activation="linear")
+    assert O.rel_err(cu1["Y"][idx], orc["Y"]) <= TOL
+    rows = torch.arange(132)[None, :] >= torch.tensor(n.astype(np.int64))[:, None]
+    assert float(cu1["Y"][rows].abs().max()) == 0.0

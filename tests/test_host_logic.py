@@ -1,0 +1,146 @@
+"""CPU-side tests: host logic of the drop-in boundary and the C-ABI library's exports."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    from agcn_b200 import _lib
+    header = open(os.path.join(ROOT, "include", "agcn_sgcll.h")).read()
+    declared = set(re.findall(r"\b(agcn_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations found"
+    handle = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(handle, name), "symbol missing from libagcn_sm100.so: " + name
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    assert _lib.lib().agcn_version() >= 100
+
+
+def test_compute_calls_fail_loudly_without_a_gpu():
+    """No CPU fallback: without a device the plan cannot even be created."""
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from agcn_b200 import _lib
+    n = np.array([4, 5], np.int32)
+    handle = ctypes.c_void_p()
+    rc = _lib.lib().agcn_plan_create(n.ctypes.data_as(ctypes.c_void_p), 2, 8, None, ctypes.byref(handle))
+    assert rc != 0 and _lib.lib().agcn_last_error()
+    with pytest.raises(_lib.AgcnError):
+        _lib.check(rc)
+
+
+def test_plan_rejects_bad_sizes():
+    from agcn_b200 import _lib
+    handle = ctypes.c_void_p()
+    n = np.array([4, 0], np.int32)
+    assert _lib.lib().agcn_plan_create(n.ctypes.data_as(ctypes.c_void_p), 2, 8, None, ctypes.byref(handle)) == -1
+    n = np.array([4, 9], np.int32)
+    assert _lib.lib().agcn_plan_create(n.ctypes.data_as(ctypes.c_void_p), 2, 8, None, ctypes.byref(handle)) == -1
+    assert b"n_nodes" in _lib.lib().agcn_last_error()
+
+
+def test_graph_matches_reference_golden():
+    from agcn_b200 import Graph, MolGraph
+    gold = np.load(os.path.join(GOLD, "graph_laplacian.npz"))
+    names = sorted({k.split("/")[0] for k in gold.files} - {"tiny3"})
+    for name in names:
+        flat = gold[name + "/adj_flat"]
+        n = len(gold[name + "/deg"])
+        lens, vals = flat[:n], flat[n:]
+        adj, pos = [], 0
+        for k in lens:
+            adj.append([int(v) for v in vals[pos:pos + k]])
+            pos += k
+        g = MolGraph(np.zeros((n, 3), np.float32), adj)
+        assert g.has_Lap and g.n_node == n and g.n_feat == 3
+        assert np.array_equal(g.degree_list, gold[name + "/deg"])
+        assert np.abs(np.asarray(g.Laplacian.todense()) - gold[name + "/L"]).max() <= 1e-12, name
+        assert g.Laplacian.dtype == np.float64 and g.Laplacian.format == "csr"
+    tiny = Graph(np.zeros((3, 2), np.float32), [[1], [0, 2], [1]], 4, 0)
+    assert tiny.Laplacian is None and not tiny.has_Lap and bool(gold["tiny3/has_Lap"]) is False
+    assert MolGraph(np.zeros((4, 1), np.float32), [[1], [0], [3], [2]], smiles="CC").smiles == "CC"
+
+
+def test_topology_padding_contract():
+    from agcn_b200 import GraphTopologyMol, MolGraph
+    topo = GraphTopologyMol(3, batch_size=2, max_atom=8, device="cpu")
+    g = MolGraph(np.arange(15, dtype=np.float32).reshape(5, 3), [[1], [0, 2], [1, 3], [2, 4], [3]])
+    feat, sl = topo.pad_data2sparse(g)
+    assert feat.shape == (8, 3) and np.array_equal(feat[:5], g.node_features) and not feat[5:].any()
+    assert sl.tolist() == [5, -1] and sl.dtype == np.int32
+    Lp, ls = topo.pad_Lap2sparse(g)
+    assert Lp.shape == (8, 8) and ls.tolist() == [5, 5] and not Lp[5:].any() and not Lp[:, 5:].any()
+    assert np.allclose(Lp[:5, :5], g.Laplacian.todense())
+
+
+def test_layer_constructor_contract():
+    from agcn_b200.layers import SGC_LL, SGC_LL_Reslap, Layer, Dropout
+    from agcn_b200.operators import model_operatos as model_ops
+    model_ops.reset_uids()
+    a = SGC_LL(64, 75, 256, K=3)
+    b = SGC_LL(64, 75, 256)
+    c = SGC_LL_Reslap(64, 75, 256, save_lap=True, name="mine")
+    assert (a.name, b.name, c.name) == ("sgc_ll_1", "sgc_ll_2", "mine")
+    assert type(a).__name__ == "SGC_LL" and type(c).__name__ == "SGC_LL_Reslap" and isinstance(c, SGC_LL)
+    assert (a.nb_filter, a.n_atom_feature, a.K, b.K, a.save_lap, c.save_lap, a.save_output) == (64, 75, 3, 2, False, True, False)
+    assert a.dropout is None and a.bias is True and a.trainable
+    with pytest.raises(TypeError):
+        SGC_LL(64, 75, 256, unknown_kwarg=1)
+    with pytest.raises(ValueError):
+        SGC_LL(64, 75, 256, activation="not_an_activation")
+    assert Layer(name="x").name == "x" and Dropout(0.5).uses_learning_phase
+
+
+def test_activations_and_leaky_relu():
+    from agcn_b200.operators import activations, model_operatos as model_ops
+    x = torch.tensor([-2.0, 0.0, 3.0])
+    assert activations.get(None)(x) is x
+    assert activations.get("relu")(x).tolist() == [0.0, 0.0, 3.0]
+    assert model_ops.relu(x, alpha=0.5).tolist() == [-1.0, 0.0, 3.0]
+    assert model_ops.relu(x, alpha=torch.tensor([1.0])).tolist() == [-2.0, 0.0, 3.0]   # alpha = 1: identity
+    assert model_ops.relu(x, max_value=2.0).tolist() == [0.0, 0.0, 2.0]
+    assert torch.allclose(activations.get("tanh")(x), torch.tanh(x))
+    f = lambda t: t
+    assert activations.get(f) is f
+
+
+def test_learning_phase_and_dropout():
+    from agcn_b200.layers import Dropout
+    from agcn_b200.operators import model_operatos as model_ops
+    x = torch.ones(1000)
+    model_ops.set_learning_phase(0)
+    assert Dropout(0.5)(x) is x
+    model_ops.set_learning_phase(1)
+    y = Dropout(0.5, seed=1)(x)
+    assert set(y.unique().tolist()) <= {0.0, 2.0} and 300 < int((y == 0).sum()) < 700
+    assert Dropout(0.0)(x) is x
+
+
+def test_initialisers():
+    import agcn_b200.layers.graphconv as gc
+    gc.DEFAULT_DEVICE[0] = "cpu"
+    try:
+        w = gc.glorot([225, 64])
+        lim = np.sqrt(6.0 / (225 + 64))
+        assert w.shape == (225, 64) and float(w.abs().max()) <= lim and w.requires_grad
+        assert float(gc.zeros([64]).abs().max()) == 0.0
+        t = gc.truncate_normal([1000, 4], stddev=1e-3)
+        assert float(t.abs().max()) <= 2e-3 + 1e-9
+        layer = gc.SGC_LL(64, 75, 8, K=3)
+        layer.build()
+        assert set(layer.vars) == {"weight", "bias", "M_L", "alpha"}
+        assert layer.vars["weight"].shape == (225, 64) and layer.vars["M_L"].shape == (75, 75)
+        assert layer.vars["alpha"].tolist() == [1.0] and layer.vars["alpha"].shape == (1,)
+        from agcn_b200.layers import SGC_LL_Reslap
+        r = SGC_LL_Reslap(64, 75, 8)
+        r.build()
+        assert r.vars["beta"].tolist() == [1.0]
+    finally:
+        gc.DEFAULT_DEVICE[0] = "cuda"

@@ -1,0 +1,126 @@
+"""Shared helpers for the parity tests: seeded batches, CUDA calls through the C ABI, oracle calls."""
+import numpy as np
+import torch
+
+from oracle import sgcll_oracle as O
+
+TOL = 1e-4  # north_star: <= 1e-4 relative (max |a-b| / max |b|) on Laplacians, outputs and gradients
+
+
+def make_batch(n_list, F, Nmax=None, seed=0, kind="normal"):
+    """Padded X [B,Nmax,F], L [B,Nmax,Nmax] (float32 numpy) and n_nodes."""
+    rng = np.random.default_rng(seed)
+    n_nodes = np.asarray(n_list, np.int32)
+    Nmax = int(Nmax or n_nodes.max())
+    B = len(n_list)
+    X = np.zeros((B, Nmax, F), np.float32)
+    L = np.zeros((B, Nmax, Nmax), np.float32)
+    for g, n in enumerate(n_nodes):
+        if kind == "tox" and F == 75:
+            X[g, :n] = O.tox21_like_features(rng, n)
+        elif kind == "relu":
+            X[g, :n] = np.maximum(rng.standard_normal((n, F)), 0)
+        else:
+            X[g, :n] = rng.standard_normal((n, F)) * 0.5
+        L[g, :n, :n] = O.compute_laplacian_dense(O.molecule_like_adjacency(rng, n)).astype(np.float32)
+    return X, L, n_nodes
+
+
+def random_prev_laps(n_nodes, seed=0):
+    rng = np.random.default_rng(seed + 99)
+    out = []
+    for n in n_nodes:
+        a = rng.standard_normal((n, n)).astype(np.float32) * 0.2
+        out.append(((a + a.T) / 2).astype(np.float32))
+    return out
+
+
+def oracle_run(X, L, n_nodes, params64, K, variant, laplacian, metric_grad, Lprev=None, activation="relu",
+               cot_Y=None, cot_L=None):
+    """fp64 oracle forward (+ backward when cotangents are given)."""
+    Xt = torch.tensor(X, dtype=torch.float64, requires_grad=True)
+    Lt = torch.tensor(L, dtype=torch.float64)
+    p = {k: v.clone().double().requires_grad_(True) for k, v in params64.items()}
+    Lp = None
+    if Lprev is not None:
+        Lp = [torch.tensor(l, dtype=torch.float64, requires_grad=True) for l in Lprev]
+    Y, RL, RW, LA = O.sgc_ll_batch(Xt, Lt, n_nodes, p, K, variant, laplacian, metric_grad, Lp, activation)
+    res = {"Y": Y.detach(), "res_L": [t.detach() for t in RL], "res_W": [t.detach() for t in RW],
+           "L_all": [t.detach() for t in LA]}
+    if cot_Y is not None:
+        loss = (Y * torch.tensor(cot_Y, dtype=torch.float64)).sum()
+        if cot_L is not None:
+            for la, c in zip(LA, cot_L):
+                loss = loss + (la * torch.tensor(c, dtype=torch.float64)).sum()
+        loss.backward()
+        res["dX"] = Xt.grad
+        for k, v in p.items():
+            res["d" + k] = v.grad if v.grad is not None else torch.zeros_like(v)
+        if Lp is not None:
+            res["dLprev"] = [l.grad if l.grad is not None else torch.zeros_like(l) for l in Lp]
+    return res
+
+
+def cuda_run(X, L, n_nodes, params64, K, variant, laplacian, metric_grad, Lprev=None, activation="relu",
+             cot_Y=None, cot_L=None, want_res=True):
+    """The same through agcn_b200's autograd bridge -> C ABI -> CUDA kernels (fp32)."""
+    import agcn_b200
+    from agcn_b200.functional import sgc_ll_packed
+
+    dev = torch.device("cuda:0")
+    B, Nmax, F = X.shape
+    batch = agcn_b200.GraphBatch(n_nodes, Nmax, device=dev)
+    Xp = batch.pack_nodes(torch.tensor(X, device=dev)).requires_grad_(True)
+    Lp = batch.pack_lap(torch.tensor(L, device=dev))
+    p = {k: v.float().to(dev).requires_grad_(True) for k, v in params64.items()}
+    Lprev_p = None
+    if Lprev is not None:
+        Lprev_p = torch.cat([torch.tensor(l, device=dev).reshape(-1) for l in Lprev]).requires_grad_(True)
+    Fo = p["weight"].shape[1]
+    cfg = {"F": F, "Fo": Fo, "K": K, "variant": variant, "laplacian": laplacian, "metric_grad": metric_grad,
+           "activation": activation, "want_resL": want_res, "want_resW": want_res}
+    Y, resL, resW, Lall = sgc_ll_packed(Xp, Lp, Lprev_p, p, batch, cfg)
+    res = {"Y": batch.unpack_nodes(Y.detach()).cpu(), "batch": batch}
+    if want_res:
+        res["res_L"] = [batch.lap_view(resL, g).cpu() for g in range(B)]
+        res["res_W"] = [batch.lap_view(resW, g).cpu() for g in range(B)]
+    if Lall is not None:
+        res["L_all"] = [batch.lap_view(Lall.detach(), g).cpu() for g in range(B)]
+    if cot_Y is not None:
+        cY = batch.pack_nodes(torch.tensor(cot_Y, device=dev))
+        loss = (Y * cY).sum()
+        if cot_L is not None and Lall is not None:
+            cL = torch.cat([torch.tensor(c, device=dev).reshape(-1) for c in cot_L])
+            loss = loss + (Lall * cL).sum()
+        loss.backward()
+        res["dX"] = batch.unpack_nodes(Xp.grad).cpu()
+        for k, v in p.items():
+            res["d" + k] = v.grad.cpu() if v.grad is not None else torch.zeros_like(v).cpu()
+        if Lprev_p is not None:
+            res["dLprev"] = [batch.lap_view(Lprev_p.grad, g).cpu() for g in range(B)]
+    torch.cuda.synchronize()
+    return res
+
+
+def assert_close(name, got, want, tol=TOL):
+    err = O.rel_err(got, want)
+    assert err <= tol, "%s: relative error %.3e > %.1e" % (name, err, tol)
+    return err
+
+
+def compare(cu, orc, keys_lists=("res_L", "res_W", "L_all"), tol=TOL, skip=()):
+    errs = {}
+    for k in orc:
+        if k in skip or k not in cu:
+            continue
+        if isinstance(orc[k], list):
+            # per-graph matrices: normalise by the largest magnitude over the whole batch
+            scale = max(float(t.abs().max()) for t in orc[k]) if orc[k] else 1.0
+            worst = 0.0
+            for a, b in zip(cu[k], orc[k]):
+                worst = max(worst, float((a.double() - b).abs().max()) / max(scale, 1e-30))
+            assert worst <= tol, "%s: relative error %.3e > %.1e" % (k, worst, tol)
+            errs[k] = worst
+        else:
+            errs[k] = assert_close(k, cu[k], orc[k], tol)
+    return errs
