@@ -174,7 +174,9 @@ class SGC_LL(Layer):
         Y = self._finish(Y, fused)
 
         cache = {}
-        Xd, params = X.detach(), {k: v.detach().clone() for k, v in self.vars.items()}
+        # evaluated with the parameter values at the time of the first read (read them before the
+        # optimizer step, like the reference's sess.run fetches them together with the train op)
+        Xd, params = X.detach(), {k: v.detach() for k, v in self.vars.items()}
 
         def lazy():
             if not cache:

@@ -1,0 +1,91 @@
+"""SimpleAGCN-shaped training step used to MEASURE the SGC-LL hot path (bench.py).
+
+The reference assembles the same stack in models/networks/basic_AGCN.py:35-47: four SGC_LL layers
+(l_n_filters = [64, 128, 128, 64], utils/hyper_parameters.py:14), DenseMol, GraphGatherMol(tanh),
+then MultitaskGraphClassifier's per-task 2-class logits with weighted sigmoid cross-entropy divided
+by the batch size (models/tf_modules/multitask_classifier.py:41-44,187-209) and Adam
+(:233-237).  Only the SGC_LL layers are this repository's product; the dense / gather / head / Adam
+pieces are plain torch ops here (SURVEY.md section 8f lists them as the next rows to fuse).
+
+Data parallel: every rank holds a replica and its own shard of graphs; one all-reduce of a flat
+gradient buffer per step.  The loss is normalised by the GLOBAL batch size.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from .batch import GraphBatch, PackedLaplacians, PackedNodes
+from .layers import SGC_LL
+from .layers import graphconv as _gc
+
+
+class SimpleAGCNStep(object):
+    def __init__(self, n_feat=75, filters=(64, 128, 128, 64), final_feature_n=256, n_tasks=12, K=3, batch_size=256,
+                 learning_rate=2e-3, device="cuda", world_size=1, laplacian="reference_literal",
+                 metric_grad="reference", seed=123):
+        self.device = torch.device(device)
+        self.world_size = world_size
+        self.global_batch = batch_size * world_size
+        self.n_tasks = n_tasks
+        torch.manual_seed(seed)  # identical replicas on every rank
+        _gc.DEFAULT_DEVICE[0] = str(self.device)
+        dims = [n_feat] + list(filters)
+        self.layers = [SGC_LL(dims[i + 1], dims[i], batch_size, K=K, activation='relu', laplacian=laplacian,
+                              metric_grad=metric_grad) for i in range(len(filters))]
+        for l in self.layers:
+            l.build()
+        lim = float(np.sqrt(6.0 / (filters[-1] + final_feature_n)))
+        self.dense_W = ((torch.rand(filters[-1], final_feature_n) * 2 - 1) * lim).to(self.device).requires_grad_(True)
+        self.dense_b = torch.zeros(final_feature_n, device=self.device, requires_grad=True)
+        # n_tasks independent [n_feature, 2] logits heads == one [n_feature, 2 * n_tasks] matrix
+        self.head_W = torch.nn.init.trunc_normal_(torch.empty(final_feature_n, 2 * n_tasks), std=0.01, a=-0.02,
+                                                  b=0.02).to(self.device).requires_grad_(True)
+        self.head_b = torch.zeros(2 * n_tasks, device=self.device, requires_grad=True)
+        self.params = [v for l in self.layers for v in l.vars.values()] + [self.dense_W, self.dense_b, self.head_W,
+                                                                           self.head_b]
+        # one flat gradient buffer; every .grad is a view into it -> a single all-reduce per step
+        total = sum(p.numel() for p in self.params)
+        self.flat_grad = torch.zeros(total, device=self.device, dtype=torch.float32)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        self.opt = torch.optim.Adam(self.params, lr=learning_rate, betas=(0.9, 0.999), eps=1e-7, fused=True)
+
+    def n_parameters(self):
+        return int(self.flat_grad.numel())
+
+    def forward_loss(self, X, Lint, batch, onehot, weights):
+        """X [R, F] packed, Lint packed, onehot [B, 2*T] float, weights [B, 2*T] float -> scalar loss."""
+        x = {'node_features': PackedNodes(X, batch), 'original_laplacian': PackedLaplacians(Lint, batch),
+             'data_slice': None, 'lap_slice': None, '_batch': batch}
+        for layer in self.layers:
+            out, _, _ = layer(x)
+            x = dict(x, node_features=out)
+        H = torch.addmm(self.dense_b, out.data, self.dense_W)                 # DenseMol: no activation applied
+        mol = torch.zeros(batch.batch_size, H.shape[1], device=H.device).index_add_(0, batch.graph_ids(), H)
+        mol = torch.tanh(mol)                                                  # GraphGatherMol
+        logits = torch.addmm(self.head_b, mol, self.head_W)
+        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, onehot, weight=weights, reduction='sum')
+        return loss / self.global_batch
+
+    def step(self, X, Lint, batch, onehot, weights):
+        """One training step: forward, backward, gradient all-reduce, Adam.  Returns the loss tensor."""
+        self.flat_grad.zero_()
+        loss = self.forward_loss(X, Lint, batch, onehot, weights)
+        loss.backward()
+        if self.world_size > 1:
+            dist.all_reduce(self.flat_grad)
+        self.opt.step()
+        return loss
+
+
+def synthetic_labels(B, n_tasks, seed, device):
+    """Bernoulli(0.1) labels as one-hot float targets [B, 2T], weights 1."""
+    rng = np.random.default_rng(seed)
+    y = (rng.random((B, n_tasks)) < 0.1)
+    onehot = np.zeros((B, n_tasks, 2), np.float32)
+    onehot[..., 0] = ~y
+    onehot[..., 1] = y
+    w = np.ones((B, 2 * n_tasks), np.float32)
+    return torch.from_numpy(onehot.reshape(B, 2 * n_tasks)).to(device), torch.from_numpy(w).to(device)

@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""bench.py -- SGC-LL train throughput (graphs/s) on N B200s, one JSON line on rank 0.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1], SURVEY.md section 8d "C2"): ToxCast-shape synthetic molecules,
+B = 1024 graphs per GPU (weak scaling), Nmax = 132, 75 atom features, 617 tasks, K = 3, through the
+SimpleAGCN stack (4 SGC_LL layers 75-64-128-128-64 + DenseMol 256 + GraphGather + 617 two-class
+heads), forward + backward + gradient all-reduce + Adam.  One "step" = one such pass over one batch.
+
+  value : graphs/s with the batch resident in HBM (CUDA events, max over ranks, L2 flushed between
+          the timed steps)
+  e2e   : graphs/s through the public API from pinned HOST buffers: host->device copy of the
+          batch, topology plan, train step, device->host read of the loss, every step
+  roofline : dominant kernel (by live CUDA-event time per launch) against MEASURED_PEAKS.json
+  cpu_baseline / --impl reference : the reference's algorithm as written (oracle port: per-graph
+          Python loop with the interpreted O(n^2) metric block, autograd for the rest) on the host
+          cores, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FILTERS = (64, 128, 128, 64)
+N_FEAT, N_TASKS, K_ORDER, B_PER_GPU, NMAX, FINAL = 75, 617, 3, 1024, 132, 256
+WORKLOAD = ("C2 ToxCast-shape synthetic molecules: B=1024/GPU, Nmax=132, F=75, 617 tasks, K=3, SimpleAGCN "
+            "(4xSGC_LL 64-128-128-64 + DenseMol256 + Gather + heads), fwd+bwd+allreduce+Adam")
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[2:6]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# algorithmic work of one SGC-LL layer over a batch
+# ------------------------------------------------------------------------------------------------
+def layer_algorithmic(n_nodes, F, Fo, K):
+    import numpy as np
+    n = n_nodes.astype(np.float64)
+    flops_fwd = (2 * K * n * n * F + 2 * n * K * F * Fo).sum()          # literal mode: no projection / Gram
+    flops_bwd = (4 * n * K * F * Fo + 4 * (K - 1) * n * n * F).sum()
+    bytes_fwd = (4 * (n * F + n * n + n * Fo)).sum()
+    bytes_bwd = (4 * (n * F + n * n + n * Fo + n * F)).sum()
+    return flops_fwd, flops_bwd, bytes_fwd, bytes_bwd
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm as written, on the host cores
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """Forward + backward of the SimpleAGCN stack over a shard of graphs with the oracle port."""
+    import numpy as np
+    import torch
+    from oracle import sgcll_oracle as O
+    X, L, n_nodes, seed = args
+    torch.set_num_threads(1)
+    dims = [N_FEAT] + list(FILTERS)
+    params = [{k: v.requires_grad_(True) for k, v in O.make_params(dims[i], dims[i + 1], K_ORDER, "SGC_LL", seed=seed + i,
+                                                                    dtype=torch.float32, perturb=False).items()}
+              for i in range(4)]
+    g = torch.Generator().manual_seed(seed)
+    dW = (torch.rand(FILTERS[-1], FINAL, generator=g) * 0.2 - 0.1).requires_grad_(True)
+    hW = (torch.randn(FINAL, 2 * N_TASKS, generator=g) * 0.01).requires_grad_(True)
+    loss = torch.zeros(())
+    for b in range(len(n_nodes)):
+        n = int(n_nodes[b])
+        x = torch.from_numpy(X[b, :n])
+        Lg = torch.from_numpy(L[b, :n, :n])
+        for i in range(4):
+            # the reference runs its interpreted metric block in every forward (graphconv.py:163-211)
+            with torch.no_grad():
+                O.metric_block_literal(x.detach().numpy(), params[i]["M_L"].detach().numpy())
+            y, _, _, _ = O.sgc_ll_graph(x, Lg, params[i], K_ORDER, "SGC_LL", "reference_literal", "reference")
+            x = torch.relu(y)
+        mol = torch.tanh((x @ dW).sum(0))
+        logits = mol @ hW
+        loss = loss + torch.nn.functional.binary_cross_entropy_with_logits(logits, torch.zeros_like(logits),
+                                                                           reduction='sum')
+    loss.backward()
+    return float(loss)
+
+
+def cpu_reference_graphs_per_s(n_graphs, steps, warmup, procs):
+    """graphs/s of the reference-as-written port on `procs` host processes (one core each)."""
+    import multiprocessing as mp
+    import numpy as np
+    from oracle import sgcll_oracle as O
+    X, L, n_nodes = O.synthetic_molecule_batch(n_graphs + 1, NMAX, seed=1235)
+    X, L, n_nodes = X[1:], L[1:], n_nodes[1:]          # drop the forced maximum-size molecule of slot 0
+    shards = [(X[i::procs], L[i::procs], n_nodes[i::procs], 7) for i in range(procs)]
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(procs) as pool:
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            pool.map(_cpu_worker, shards)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+    total = sum(times)
+    return n_graphs * len(times) / total, total / len(times) * 1e3, float(n_nodes.mean())
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    procs = max(1, min(cores, 32))
+    n_graphs = procs * 16
+    steps = max(1, min(args.steps, 3))
+    warmup = max(0, min(args.warmup, 1))
+    gps, ms, nbar = cpu_reference_graphs_per_s(n_graphs, steps, warmup, procs)
+    sample = ("%d graphs/step of the C2 workload (mean n=%.1f), %d step(s), reference-as-written port "
+              "(interpreted metric block + autograd), %d processes" % (n_graphs, nbar, steps, procs))
+    line = {"impl": "reference", "metric": "sgc_ll_train_graphs_per_s", "value": gps, "unit": "graphs/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "sample": sample},
+            "cpu_baseline": {"value": gps, "unit": "graphs/s", "cores": procs, "kind": "port", "sample": sample},
+            "e2e": {"value": gps, "unit": "graphs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import agcn_b200
+    from agcn_b200 import _lib
+    from agcn_b200.simple_agcn import SimpleAGCNStep, synthetic_labels
+    from oracle import sgcll_oracle as O   # synthetic input generator + cpu_baseline leg only
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device; there is no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    # ---- synthetic C2 batch of this rank (host, pinned, packed ragged layout)
+    Xpad, Lpad, n_nodes = O.synthetic_molecule_batch(B_PER_GPU, NMAX, seed=1235 + rank)
+    Xh = torch.from_numpy(np.concatenate([Xpad[g, :n] for g, n in enumerate(n_nodes)], 0)).pin_memory()
+    Lh = torch.from_numpy(np.concatenate([Lpad[g, :n, :n].reshape(-1) for g, n in enumerate(n_nodes)])).pin_memory()
+    onehot, weights = synthetic_labels(B_PER_GPU, N_TASKS, 99 + rank, "cpu")
+    onehot_h, weights_h = onehot.pin_memory(), weights.pin_memory()
+
+    model = SimpleAGCNStep(N_FEAT, FILTERS, FINAL, N_TASKS, K_ORDER, B_PER_GPU, device=dev, world_size=world)
+    batch = agcn_b200.GraphBatch(n_nodes, NMAX, device=dev)
+    Xd, Ld = Xh.to(dev), Lh.to(dev)
+    onehot_d, weights_d = onehot_h.to(dev), weights_h.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        return model.step(Xd, Ld, batch, onehot_d, weights_d)
+
+    def e2e_step():
+        X = Xh.to(dev, non_blocking=True)
+        L = Lh.to(dev, non_blocking=True)
+        oh = onehot_h.to(dev, non_blocking=True)
+        w = weights_h.to(dev, non_blocking=True)
+        b = agcn_b200.GraphBatch(n_nodes, NMAX, device=dev)
+        return float(model.step(X, L, b, oh, w))      # .item(): device -> host read of the loss
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1.0)                                  # evict L2 between timed steps (not timed)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            fn()
+            e1.record()
+            evs.append((e0, e1))
+        barrier()
+        ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t) / steps
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = _lib.launch_count()
+    ms_step = timed(resident_step, args.steps, args.warmup)
+    launches_per_step = (_lib.launch_count() - launches0) / float(args.steps + args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e = timed(e2e_step, max(3, args.steps // 2), 3)
+
+    # ---- roofline of the dominant kernel class: per-layer kernels timed live with CUDA events
+    roof = None
+    if rank == 0:
+        roof = kernel_roofline(model, batch, Xd, Ld, n_nodes, dev)
+
+    value = world * B_PER_GPU / (ms_step * 1e-3)
+    e2e_value = world * B_PER_GPU / (ms_e2e * 1e-3)
+    if rank == 0:
+        # the CPU leg runs in a fresh interpreter: fork-based pools cannot follow autograd / CUDA use
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                              "--warmup", "0"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                             env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+        ref = json.loads(out.stdout.strip().splitlines()[-1])
+        gps, procs, sample = ref["value"], ref["cpu_baseline"]["cores"], ref["cpu_baseline"]["sample"]
+        h2d = Xh.numel() * 4 + Lh.numel() * 4 + onehot_h.numel() * 4 + weights_h.numel() * 4 + n_nodes.nbytes * 4
+        line = {"metric": "sgc_ll_train_graphs_per_s", "value": value, "unit": "graphs/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": "dp%d" % world,
+                           "semantics": "laplacian=reference_literal, metric_grad=reference",
+                           "l2": "flushed between timed steps (256 MB fill)", "mean_nodes": float(n_nodes.mean()),
+                           "parameters": model.n_parameters(), "host_layout_e2e": "packed ragged (pinned)"},
+                "clocks": clocks,
+                "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
+                        "d2h_bytes_per_step": 4},
+                "gpu_launches": int(round(launches_per_step * args.steps)),
+                "gpu_launches_per_step": launches_per_step,
+                "roofline": roof,
+                "cpu_baseline": {"value": gps, "unit": "graphs/s", "cores": procs, "kind": "port", "sample": sample}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def kernel_roofline(model, batch, Xd, Ld, n_nodes, dev):
+    """Times the SGC-LL layer-2 forward (64 -> 128, the heaviest layer) as one unit with CUDA events
+    and reports its algorithmic bytes / time against the measured HBM copy bandwidth."""
+    import torch
+    from agcn_b200.functional import sgc_ll_packed
+    peaks = load_peaks()
+    layer = model.layers[1]
+    F, Fo, K = layer.n_atom_feature, layer.nb_filter, layer.K
+    X = torch.relu(torch.randn(batch.total_nodes, F, device=dev))
+    cfg = layer._cfg('relu')
+    p = {k: v.detach() for k, v in layer.vars.items()}
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
+    times = []
+    with torch.no_grad():
+        for it in range(13):
+            flush.fill_(0.0)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            sgc_ll_packed(X, Ld, None, p, batch, cfg)
+            e1.record()
+            torch.cuda.synchronize()
+            if it >= 3:
+                times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    ff, fb, bf, bb = layer_algorithmic(n_nodes, F, Fo, K)
+    achieved = bf / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "SGC_LL layer-2 forward (cheb_fwd_kernel + gemm_rows_kernel)",
+            "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+            "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_launch": bf,
+            "ms_per_launch": ms, "fp32_tflops_achieved": ff / (ms * 1e-3) / 1e12}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()
