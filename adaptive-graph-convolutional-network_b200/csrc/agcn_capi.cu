@@ -11,6 +11,12 @@ namespace {
 
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
+// node-level GEMM: tensor cores when the operands are TMA-compatible, CUDA cores otherwise (F = 75)
+int node_gemm(const GemmArgs& g, float* tc_scratch, cudaStream_t st) {
+  if (tc_gemm_supported(g)) return tc_gemm(g, tc_scratch, st);
+  return gemm_rows(g, st);
+}
+
 struct Carver {
   char* base;
   size_t off = 0;
@@ -57,7 +63,7 @@ Saved carve_saved(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
 }
 
 struct Work {
-  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part;
+  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tc;
   size_t bytes;
 };
 
@@ -76,6 +82,9 @@ Work carve_work(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
   w.dXW = m.full ? c.take((size_t)p->R * d->F) : nullptr;
   w.dalpha_part = c.take((size_t)p->B);
   w.dbeta_part = c.take((size_t)p->B);
+  size_t tcf = std::max(tc_gemm_scratch_floats(d->Fo, d->F, d->K, 1), tc_gemm_scratch_floats(d->F, d->Fo, 1, d->K));
+  tcf = std::max(tcf, tc_gemm_scratch_floats(d->F, d->F, 1, 1));
+  w.tc = c.take(tcf);  // hi / lo copies of the parameter operand of the tensor-core GEMMs
   w.bytes = c.off;
   return w;
 }
@@ -143,7 +152,7 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
     g.A0 = d_X; g.lda0 = F;
     g.B = d_M_L; g.ldb = F;
     g.C = XW; g.ldc = F;
-    if ((rc = gemm_rows(g, st))) return rc;
+    if ((rc = node_gemm(g, wk.tc, st))) return rc;
   }
   GraphArgs ga;
   ga.plan = plan; ga.F = F; ga.K = K;
@@ -169,7 +178,7 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
     g.B = d_weight; g.ldb = K * Fo; g.sliceB = Fo;
     g.C = d_Y; g.ldc = Fo;
     g.bias = d_bias; g.act = desc->activation;
-    if ((rc = gemm_rows(g, st))) return rc;
+    if ((rc = node_gemm(g, wk.tc, st))) return rc;
   }
   return AGCN_OK;
 }
@@ -184,7 +193,7 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   if (rc) return rc;
   AGCN_REQUIRE(d_X && d_Lint && d_M_L && d_weight && d_alpha && d_Y && d_dY && d_saved && d_work,
                "backward: null input pointer");
-  AGCN_REQUIRE(d_dX && d_dM_L && d_dweight && d_dbias && d_dalpha, "backward: null output pointer");
+  AGCN_REQUIRE(d_dM_L && d_dweight && d_dbias && d_dalpha, "backward: null output pointer");
   const Modes m = modes_of(desc);
   AGCN_REQUIRE(!m.reslap || (d_beta && d_dbeta), "backward: beta / dbeta required for SGC_LL_Reslap");
   cudaStream_t st = (cudaStream_t)stream;
@@ -201,13 +210,17 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   // dYpre = dY * act'(Y);  dbias = colsum(dYpre)
   const float* dYp = (desc->activation == AGCN_ACT_RELU) ? wk.dYp : d_dY;
   if ((rc = act_bwd_colsum(d_dY, d_Y, wk.dYp, d_dbias, wk.act_part, R, Fo, desc->activation, st))) return rc;
-  {  // G_k = dYpre W_k^T   (K == 1: this is dX)
+  // d_dX == NULL: the caller does not need the gradient w.r.t. the node features (first layer)
+  const bool need_G = d_dX != nullptr || (m.need_dL && K >= 2);
+  float* dXbuf = d_dX ? d_dX : wk.G;  // scratch target when dX itself is not wanted (K >= 2 only)
+  AGCN_REQUIRE(d_dX || !m.full, "backward: d_dX is required with metric_grad = full");
+  if (need_G) {  // G_k = dYpre W_k^T   (K == 1: this is dX)
     GemmArgs g;
     g.M = R; g.N = F; g.Kd = Fo; g.Z = K;
     g.A0 = dYp; g.lda0 = Fo;
     g.B = d_weight; g.ldb = K * Fo; g.sliceB = Fo; g.transB = 1;
     g.C = (K == 1) ? d_dX : wk.G; g.ldc = F; g.sliceC = (int64_t)R * F;
-    if ((rc = gemm_rows(g, st))) return rc;
+    if ((rc = node_gemm(g, wk.tc, st))) return rc;
   }
   GraphArgs ga;
   ga.plan = plan; ga.F = F; ga.K = K;
@@ -216,11 +229,11 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   ga.alpha = d_alpha; ga.beta = d_beta;
   ga.T = sv.T; ga.Lall = m.shortcut ? nullptr : sv.Lall;
   ga.dist = sv.dist; ga.dis = sv.dis; ga.stats = sv.stats;
-  ga.G = wk.G; ga.dLall_in = d_dLall_in; ga.dX = d_dX; ga.dL = wk.dL;
+  ga.G = wk.G; ga.dLall_in = d_dLall_in; ga.dX = dXbuf; ga.dL = wk.dL;
   ga.dLprev = has_prev ? d_dLprev : nullptr;
   ga.dXW = wk.dXW; ga.dalpha_part = wk.dalpha_part; ga.dbeta_part = m.reslap ? wk.dbeta_part : nullptr;
   if (K >= 2) {
-    if ((rc = graph_recurrence_bwd(ga, m.need_dL, st))) return rc;
+    if (need_G && (rc = graph_recurrence_bwd(ga, m.need_dL, st))) return rc;
   } else if (m.need_dL) {
     if (d_dLall_in)
       AGCN_CUDA(cudaMemcpyAsync(wk.dL, d_dLall_in, (size_t)plan->LL * sizeof(float), cudaMemcpyDeviceToDevice, st));
@@ -257,7 +270,7 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
     g.A0 = wk.dXW; g.lda0 = F;
     g.B = d_M_L; g.ldb = F; g.transB = 1;
     g.C = d_dX; g.ldc = F; g.accumulate = 1;
-    if ((rc = gemm_rows(g, st))) return rc;
+    if ((rc = node_gemm(g, wk.tc, st))) return rc;
   } else {
     // tf.py_func has no gradient: M_L receives none (graphconv.py:211)
     AGCN_CUDA(cudaMemsetAsync(d_dM_L, 0, (size_t)F * F * sizeof(float), st));

@@ -119,26 +119,58 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 __device__ __forceinline__ float leaky(float x, float alpha) { return fmaxf(x, 0.f) - alpha * fmaxf(-x, 0.f); }
 __device__ __forceinline__ float leaky_grad(float x, float alpha) { return x > 0.f ? 1.f : (x < 0.f ? alpha : 0.f); }
 
-// load an n x n packed matrix into an n4 x pl zero-padded shared tile (optionally + I)
-__device__ __forceinline__ void load_square(float* sM, int pl, int n, int n4, const float* __restrict__ src,
-                                            bool add_identity) {
+// ---- asynchronous global -> shared copies (LDGSTS): every element of a tile is in flight at once, so a
+// CTA pays one memory latency per tile instead of one per loop iteration.
+__device__ __forceinline__ void cp_async4(float* sdst, const float* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* sdst, const float* gsrc) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(sdst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// n x n packed matrix -> n4 x pl zero-padded shared tile (async; finish with cp_async_wait_all + barrier)
+__device__ __forceinline__ void load_square(float* sM, int pl, int n, int n4, const float* __restrict__ src) {
   for (int idx = threadIdx.x; idx < n4 * pl; idx += blockDim.x) {
     const int i = idx / pl, j = idx - i * pl;
-    float v = 0.f;
-    if (i < n && j < n) {
-      v = src ? src[i * n + j] : 0.f;
-      if (add_identity && i == j) v += 1.f;
-    }
-    sM[idx] = v;
+    if (src != nullptr && i < n && j < n)
+      cp_async4(&sM[idx], src + i * n + j);
+    else
+      sM[idx] = 0.f;
   }
 }
 
-// load rows [row0, row0+n) x cols [f0, f0+fc) of a [R, ld] matrix into an n4 x pf zero padded tile
+__device__ __forceinline__ void add_identity(float* sM, int pl, int n) {
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sM[i * pl + i] += 1.f;
+}
+
+// rows [row0, row0+n) x cols [f0, f0+fc) of a [R, ld] matrix -> n4 x pf zero padded tile (async)
 __device__ __forceinline__ void load_chunk(float* sT, int pf, int n, int n4, const float* __restrict__ src, int ld,
                                            int64_t row0, int f0, int fc) {
-  for (int idx = threadIdx.x; idx < n4 * pf; idx += blockDim.x) {
-    const int i = idx / pf, c = idx - i * pf;
-    sT[idx] = (i < n && c < fc) ? src[(row0 + i) * ld + f0 + c] : 0.f;
+  const bool vec = ((ld & 3) == 0) && ((f0 & 3) == 0) && ((fc & 3) == 0) &&
+                   ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+  if (vec) {
+    const int pf4 = pf >> 2, fc4 = fc >> 2;
+    for (int idx = threadIdx.x; idx < n4 * pf4; idx += blockDim.x) {
+      const int i = idx / pf4, c4 = idx - i * pf4;
+      float* d = &sT[i * pf + c4 * 4];
+      if (i < n && c4 < fc4)
+        cp_async16(d, src + (row0 + i) * ld + f0 + c4 * 4);
+      else
+        *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < n4 * pf; idx += blockDim.x) {
+      const int i = idx / pf, c = idx - i * pf;
+      if (i < n && c < fc)
+        cp_async4(&sT[idx], src + (row0 + i) * ld + f0 + c);
+      else
+        sT[idx] = 0.f;
+    }
   }
 }
 
@@ -167,10 +199,15 @@ __global__ void cheb_fwd_kernel(ChebArgs p) {
   float* sA = sL + n4 * pl;
   float* sB = sA + n4 * pf;
   const int64_t row0 = p.pp.node_off[g];
-  load_square(sL, pl, n, n4, p.L + p.pp.lap_off[g], p.add_identity != 0);
+  load_square(sL, pl, n, n4, p.L + p.pp.lap_off[g]);
   load_chunk(sA, pf, n, n4, p.X, p.F, row0, f0, fc);
   for (int idx = threadIdx.x; idx < n4 * pf; idx += blockDim.x) sB[idx] = 0.f;
+  cp_async_wait_all();
   __syncthreads();
+  if (p.add_identity) {
+    add_identity(sL, pl, n);
+    __syncthreads();
+  }
   const int tc = (fc + 3) / 4, tiles = (n4 / 4) * tc;
   float* src = sA;
   float* dst = sB;
@@ -237,8 +274,11 @@ __global__ void recur_bwd_kernel(RecurArgs p) {
   const int64_t row0 = p.pp.node_off[g];
   const int64_t loff = p.pp.lap_off[g];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-  load_square(sL, pl, n, n4, p.L + loff, p.add_identity != 0);
-  if (p.need_dL) load_square(sdL, pl, n, n4, p.dLall_in ? p.dLall_in + loff : nullptr, false);
+  load_square(sL, pl, n, n4, p.L + loff);
+  if (p.need_dL) load_square(sdL, pl, n, n4, p.dLall_in ? p.dLall_in + loff : nullptr);
+  cp_async_wait_all();
+  __syncthreads();
+  if (p.add_identity) add_identity(sL, pl, n);
   const int f_begin = p.need_dL ? 0 : ch * p.FC;
   const int f_end = p.need_dL ? p.F : min(p.F, f_begin + p.FC);
   for (int f0 = f_begin; f0 < f_end; f0 += p.FC) {
@@ -255,6 +295,7 @@ __global__ void recur_bwd_kernel(RecurArgs p) {
         // dL += c_{j+1} U_{j+1} T_j^T
         const float* Tj = (j == 0) ? p.X : p.T + (int64_t)(j - 1) * p.tslice;
         load_chunk(sT, pf, n, n4, Tj, p.F, row0, f0, fc);
+        cp_async_wait_all();
         __syncthreads();
         for (int rb = wid; rb < n4 / 4; rb += nw) {
           float acc[4][NT_COLS];
@@ -274,6 +315,7 @@ __global__ void recur_bwd_kernel(RecurArgs p) {
           }
         }
       } else {
+        cp_async_wait_all();
         __syncthreads();
       }
       const float* __restrict__ Gj = p.G + (int64_t)j * p.gslice;
@@ -360,6 +402,7 @@ __global__ void build_lap_kernel(BuildArgs p) {
       const int fc = min(p.FCD, p.F - f0);
       __syncthreads();
       load_chunk(sS, pc, n, n4, p.XW, p.F, row0, f0, fc);
+      cp_async_wait_all();
       __syncthreads();
       for (int rb = wid; rb < n4 / 4; rb += nw) {
         float acc[4][NT_COLS];
@@ -634,6 +677,7 @@ __global__ void lap_bwd_kernel(LapBwdArgs p) {
     const int fc = min(p.FCD, p.F - f0);
     __syncthreads();
     load_chunk(sS, pc, n, n4, p.XW, p.F, row0, f0, fc);
+    cp_async_wait_all();
     __syncthreads();
     const int tc = (fc + 3) / 4, tiles = (n4 / 4) * tc;
     for (int t = threadIdx.x; t < tiles; t += blockDim.x) {
@@ -717,13 +761,15 @@ static ChunkCfg chunk_cfg(int max_n, int F, int nbuf, int nsq, bool single_chunk
   else if (max_n <= 64)
     FC = std::min(F4, 64);
   else
-    FC = std::min(F4, F <= 64 ? 16 : 32);
+    FC = std::min(F4, 16);  // big graphs: many narrow feature chunks = many CTAs per graph
   if (single_chunk) FC = std::min(F4, max_n <= 64 ? 32 : 16);
   FC = (FC + 7) & ~7;  // (FC + 4) / 4 odd: conflict-free float4 rows
   ChunkCfg c;
   c.FC = FC;
   c.chunks = single_chunk ? 1 : (F + FC - 1) / FC;
-  c.threads = (max_n <= 32) ? 128 : 256;
+  // one 4x4 output tile per thread where possible
+  const int tiles = (n4 / 4) * (std::min(FC, F4) / 4);
+  c.threads = std::min(512, std::max(64, (tiles + 31) / 32 * 32));
   c.smem = ((size_t)nsq * n4 * pl + (size_t)nbuf * n4 * (FC + 4)) * sizeof(float);
   return c;
 }

@@ -99,6 +99,10 @@ struct GemmArgs {
   int accumulate = 0;  // C += result
 };
 int gemm_rows(const GemmArgs& a, cudaStream_t st);
+// tcgen05 (3xTF32) implementation of the same contraction for TMA-compatible shapes (agcn_tc_gemm.cu)
+bool tc_gemm_supported(const GemmArgs& a);
+size_t tc_gemm_scratch_floats(int N, int Kd, int S, int Z);
+int tc_gemm(const GemmArgs& a, float* scratch, cudaStream_t st);
 
 // out[(f*S + s)*N + c] = sum_r A_s[r, f] * D[r, c]     (A_s as in GemmArgs; contraction over the M rows)
 struct GemmTNArgs {

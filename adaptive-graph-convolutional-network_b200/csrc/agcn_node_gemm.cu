@@ -17,7 +17,7 @@ constexpr int BM = 64, BN = 64, BK = 16, PK = BK + 4;
 template <bool VEC, bool TB>
 __global__ void __launch_bounds__(256) gemm_rows_kernel(GemmArgs p) {
   __shared__ __align__(16) float As[BM][PK];
-  __shared__ __align__(16) float Bs[TB ? BN : BK][TB ? PK : (BN + 4)];
+  __shared__ __align__(16) float Bs[BK][BN + 4];  // always [k][col]; B^T tiles are transposed on the way in
   const int tid = threadIdx.x;
   const int ty = tid >> 4, tx = tid & 15;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN, z = blockIdx.z;
@@ -69,13 +69,13 @@ __global__ void __launch_bounds__(256) gemm_rows_kernel(GemmArgs p) {
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
           const int c = n0 + col, k = k0 + k4;
           if (c < p.N && k < p.Kd) v = *reinterpret_cast<const float4*>(Bm + (int64_t)c * p.ldb + k);
-          *reinterpret_cast<float4*>(&Bs[col][k4]) = v;
+          Bs[k4 + 0][col] = v.x; Bs[k4 + 1][col] = v.y; Bs[k4 + 2][col] = v.z; Bs[k4 + 3][col] = v.w;
         } else {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             const int e = tid + 256 * u, col = e / BK, kk = e % BK;
             const int c = n0 + col, k = k0 + kk;
-            Bs[col][kk] = (c < p.N && k < p.Kd) ? Bm[(int64_t)c * p.ldb + k] : 0.f;
+            Bs[kk][col] = (c < p.N && k < p.Kd) ? Bm[(int64_t)c * p.ldb + k] : 0.f;
           }
         }
       }
@@ -85,24 +85,14 @@ __global__ void __launch_bounds__(256) gemm_rows_kernel(GemmArgs p) {
         float4 a[4], b[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const float4*>(&As[ty * 4 + q][kk]);
-        if (!TB) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) b[u] = *reinterpret_cast<const float4*>(&Bs[kk + u][tx * 4]);
+        for (int u = 0; u < 4; ++u) b[u] = *reinterpret_cast<const float4*>(&Bs[kk + u][tx * 4]);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            acc[q][0] += a[q].x * b[0].x + a[q].y * b[1].x + a[q].z * b[2].x + a[q].w * b[3].x;
-            acc[q][1] += a[q].x * b[0].y + a[q].y * b[1].y + a[q].z * b[2].y + a[q].w * b[3].y;
-            acc[q][2] += a[q].x * b[0].z + a[q].y * b[1].z + a[q].z * b[2].z + a[q].w * b[3].z;
-            acc[q][3] += a[q].x * b[0].w + a[q].y * b[1].w + a[q].z * b[2].w + a[q].w * b[3].w;
-          }
-        } else {
-#pragma unroll
-          for (int t = 0; t < 4; ++t) b[t] = *reinterpret_cast<const float4*>(&Bs[tx * 4 + t][kk]);
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-#pragma unroll
-            for (int t = 0; t < 4; ++t)
-              acc[q][t] += a[q].x * b[t].x + a[q].y * b[t].y + a[q].z * b[t].z + a[q].w * b[t].w;
+        for (int q = 0; q < 4; ++q) {
+          acc[q][0] += a[q].x * b[0].x + a[q].y * b[1].x + a[q].z * b[2].x + a[q].w * b[3].x;
+          acc[q][1] += a[q].x * b[0].y + a[q].y * b[1].y + a[q].z * b[2].y + a[q].w * b[3].y;
+          acc[q][2] += a[q].x * b[0].z + a[q].y * b[1].z + a[q].z * b[2].z + a[q].w * b[3].z;
+          acc[q][3] += a[q].x * b[0].w + a[q].y * b[1].w + a[q].z * b[2].w + a[q].w * b[3].w;
         }
       }
       __syncthreads();

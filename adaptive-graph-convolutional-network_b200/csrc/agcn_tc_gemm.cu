@@ -1,0 +1,378 @@
+// Node-level GEMMs on the 5th-generation tensor cores (tcgen05), fp32 in / fp32 out with 3xTF32
+// split-precision accumulation in TMEM.
+//
+//   C_z[M,N] (+)= act( sum_{s<S} A_s[M,Kd] * B_{z,s}[N,Kd]^T + bias )
+//
+// A_s are row-major node matrices (K-major operands, streamed by TMA with 128-byte swizzle);
+// B is a small parameter matrix that a prep kernel rearranges to [N,Kd] K-major and splits into
+// hi/lo TF32 halves once per call.  Every A tile is split in shared memory by four warps:
+//   x = hi + lo,  hi = x with the 13 low mantissa bits cleared (exact in TF32),  lo = x - hi
+//   D += A_lo B_hi + A_hi B_lo + A_hi B_hi        (error ~2^-21 relative: inside the 1e-4 budget,
+//                                                  a single TF32 pass, ~5e-4, is not)
+// One CTA per 128-row tile: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner), warps 2-5 =
+// operand splitter, then epilogue (TMEM -> registers -> global, bias + activation fused).
+//
+// Used for Y = act(sum_k T_k W_k + b) (graphconv.py:238-247), G_k = dY W_k^T, XW = X M_L
+// (graphconv.py:164) and dX += dXW M_L^T.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+#include "agcn_internal.cuh"
+
+namespace agcn {
+
+namespace tc {
+
+constexpr int BM = 128;      // rows per CTA tile (UMMA M)
+constexpr int BK = 32;       // fp32 elements per k-block = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;    // tf32
+constexpr int A_TILE_BYTES = BM * BK * 4;  // 16 KB
+constexpr uint32_t SPIN_LIMIT = 1u << 24;  // converts a protocol bug into a trap instead of a hang
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms of 1024 bytes
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);  // start address, 16-byte units
+  d |= (uint64_t)1 << 16;                    // leading byte offset (unused with swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32;          // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;                    // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                    // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+struct Args {
+  int M, N, Kd, S;
+  int kb_per_slice;   // ceil(Kd / 32)
+  int rows_slice1;    // row offset between A1 slices in the stacked 2-D view
+  int b_rows_slice;   // rows of one B slice in the stacked [Z*S*Npad, Kd] view (= Npad)
+  float* C;
+  int ldc;
+  long long sliceC;
+  const float* bias;
+  int act, accumulate;
+};
+
+template <int BN>
+struct Smem {
+  static constexpr int B_TILE_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
+  static constexpr int STAGES = (BN <= 64) ? 4 : 3;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, Args p) {
+  using SM = Smem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::STAGES * SM::STAGE_BYTES);
+  uint64_t* full_bar = bars;                     // TMA landed
+  uint64_t* split_bar = bars + SM::STAGES;       // operand split done
+  uint64_t* empty_bar = bars + 2 * SM::STAGES;   // MMAs that read the stage retired
+  uint64_t* tmem_full_bar = bars + 3 * SM::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * SM::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * BM;
+  const int z = blockIdx.y;   // output slice
+  const int nb = blockIdx.z;  // 128-column block of wide outputs
+  const int num_kb = p.S * p.kb_per_slice;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SM::STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: BN fp32 accumulator columns x 128 lanes
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % SM::STAGES, phase = (kb / SM::STAGES) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = base + stage * SM::STAGE_BYTES;
+        const int s = kb / p.kb_per_slice, k0 = (kb - s * p.kb_per_slice) * BK;
+        mbar_expect_tx(&full_bar[stage], A_TILE_BYTES + 2 * SM::B_TILE_BYTES);
+        if (s == 0)
+          tma_load_2d(st, &tmA0, &full_bar[stage], k0, m0);
+        else
+          tma_load_2d(st, &tmA1, &full_bar[stage], k0, (s - 1) * p.rows_slice1 + m0);
+        const int brow = (z * p.S + s) * p.b_rows_slice + nb * BN;
+        tma_load_2d(st + 2 * A_TILE_BYTES, &tmBhi, &full_bar[stage], k0, brow);
+        tma_load_2d(st + 2 * A_TILE_BYTES + SM::B_TILE_BYTES, &tmBlo, &full_bar[stage], k0, brow);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      // instruction descriptor: D = f32, A = B = tf32, both K-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % SM::STAGES, phase = (kb / SM::STAGES) & 1;
+        mbar_wait(&split_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(base + stage * SM::STAGE_BYTES);
+        const uint32_t sa_lo = sa + A_TILE_BYTES;
+        const uint32_t sb_hi = sa + 2 * A_TILE_BYTES, sb_lo = sb_hi + SM::B_TILE_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint32_t koff = k * UMMA_K * 4;  // bytes inside the 128-byte swizzle row
+          const uint64_t a_hi = make_desc(sa + koff), a_lo = make_desc(sa_lo + koff);
+          const uint64_t b_hi = make_desc(sb_hi + koff), b_lo = make_desc(sb_lo + koff);
+          umma_tf32(tmem_base, a_lo, b_hi, idesc, (kb | k) != 0);
+          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+          umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+        }
+        umma_commit(&empty_bar[stage]);  // frees the stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ================= operand splitter, then epilogue =================
+    const int t = threadIdx.x - 64;  // 0..127
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int stage = kb % SM::STAGES, phase = (kb / SM::STAGES) & 1;
+      mbar_wait(&full_bar[stage], phase);
+      float4* a = reinterpret_cast<float4*>(base + stage * SM::STAGE_BYTES);
+      float4* alo = reinterpret_cast<float4*>(base + stage * SM::STAGE_BYTES + A_TILE_BYTES);
+#pragma unroll
+      for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
+        const int idx = t + 128 * i;
+        const float4 v = a[idx];
+        float4 hi, lo;
+        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        lo.x = __uint_as_float(__float_as_uint(v.x - hi.x) & 0xffffe000u);
+        lo.y = __uint_as_float(__float_as_uint(v.y - hi.y) & 0xffffe000u);
+        lo.z = __uint_as_float(__float_as_uint(v.z - hi.z) & 0xffffe000u);
+        lo.w = __uint_as_float(__float_as_uint(v.w - hi.w) & 0xffffe000u);
+        a[idx] = hi;
+        alo[idx] = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor core reads
+      mbar_arrive(&split_bar[stage]);
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int m = m0 + q * 32 + lane;     // output row of this thread
+    float* __restrict__ Crow = p.C + (long long)z * p.sliceC + (long long)m * p.ldc;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t v[16];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+      if (m < p.M) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int c = nb * BN + c0 + u;
+          if (c < p.N) {
+            float o = __uint_as_float(v[u]);
+            if (p.bias) o += p.bias[c];
+            if (p.accumulate) o += Crow[c];
+            if (p.act == AGCN_ACT_RELU) o = fmaxf(o, 0.f);
+            Crow[c] = o;
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
+// B prep: out_{hi,lo}[(slice*Npad + n)*Kd + k] = split(src[n*sn + k*sk + slice*ss]),  zero rows for n >= N
+__global__ void split_b_kernel(const float* __restrict__ src, long long sn, long long sk, long long ss, int N, int Npad,
+                               int Kd, int slices, float* __restrict__ hi, float* __restrict__ lo) {
+  const long long total = (long long)slices * Npad * Kd;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % Kd);
+    const long long r = e / Kd;
+    const int n = (int)(r % Npad), sl = (int)(r / Npad);
+    float x = 0.f;
+    if (n < N) x = src[n * sn + k * sk + sl * ss];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    hi[e] = h;
+    lo[e] = __uint_as_float(__float_as_uint(x - h) & 0xffffe000u);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// 2-D fp32 row-major [rows, cols] with leading dimension ld; box = 32 columns x box_rows, 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return AGCN_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return AGCN_ERR_CUDA;
+  }
+  return AGCN_OK;
+}
+
+}  // namespace tc
+
+static int tc_npad(int N) { return N <= 64 ? 64 : (N + 127) / 128 * 128; }
+
+bool tc_gemm_supported(const GemmArgs& a) {
+  if (getenv("AGCN_DISABLE_TCGEN05")) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (a.M < 1 || a.Kd < 32 || a.Kd % 4 != 0) return false;
+  if (a.lda0 % 4 != 0 || !al16(a.A0)) return false;
+  if (a.S > 1 && (a.lda1 % 4 != 0 || !al16(a.A1) || a.sliceA1 % a.lda1 != 0)) return false;
+  if (a.S > 1 && a.lda1 != a.Kd) return false;  // slices are stacked as one [(S-1)*rows, Kd] matrix
+  return true;
+}
+
+size_t tc_gemm_scratch_floats(int N, int Kd, int S, int Z) { return 2 * (size_t)Z * S * tc_npad(N) * Kd; }
+
+// scratch holds the rearranged hi / lo copies of B (tc_gemm_scratch_floats floats).
+int tc_gemm(const GemmArgs& a, float* scratch, cudaStream_t st) {
+  using namespace tc;
+  // B element (slice, n, k): row-major [Kd, N] (ldb) or, transposed, [N, Kd]
+  const long long sn = a.transB ? a.ldb : 1, sk = a.transB ? 1 : a.ldb, ss = a.sliceB;
+  const int Npad = tc_npad(a.N);
+  const int slices = a.Z * a.S;
+  float* Bhi = scratch;
+  float* Blo = scratch + (size_t)slices * Npad * a.Kd;
+  {
+    const long long total = (long long)slices * Npad * a.Kd;
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 1184);
+    split_b_kernel<<<blocks, 256, 0, st>>>(a.B, sn, sk, ss, a.N, Npad, a.Kd, slices, Bhi, Blo);
+    AGCN_LAUNCH_CHECK();
+  }
+  CUtensorMap mA0, mA1, mBhi, mBlo;
+  int rc;
+  if ((rc = make_map(&mA0, a.A0, (uint64_t)a.M, (uint64_t)a.Kd, (uint64_t)a.lda0, BM))) return rc;
+  const int rows_slice1 = a.S > 1 ? (int)(a.sliceA1 / a.lda1) : 0;
+  if (a.S > 1) {
+    if ((rc = make_map(&mA1, a.A1, (uint64_t)(a.S - 2) * rows_slice1 + a.M, (uint64_t)a.Kd, (uint64_t)a.lda1, BM)))
+      return rc;
+  } else {
+    mA1 = mA0;
+  }
+  const int BN = Npad <= 64 ? 64 : 128;
+  if ((rc = make_map(&mBhi, Bhi, (uint64_t)slices * Npad, (uint64_t)a.Kd, (uint64_t)a.Kd, BN))) return rc;
+  if ((rc = make_map(&mBlo, Blo, (uint64_t)slices * Npad, (uint64_t)a.Kd, (uint64_t)a.Kd, BN))) return rc;
+  Args p;
+  p.M = a.M; p.N = a.N; p.Kd = a.Kd; p.S = a.S;
+  p.kb_per_slice = (a.Kd + BK - 1) / BK;
+  p.rows_slice1 = rows_slice1;
+  p.b_rows_slice = Npad;
+  p.C = a.C; p.ldc = a.ldc; p.sliceC = a.sliceC;
+  p.bias = a.bias; p.act = a.act; p.accumulate = a.accumulate;
+  dim3 grid((a.M + BM - 1) / BM, a.Z, Npad / BN);
+  static std::once_flag once64, once128;
+  if (BN == 64) {
+    std::call_once(once64, [] {
+      cudaFuncSetAttribute(tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64>::TOTAL);
+    });
+    tc_gemm_kernel<64><<<grid, 192, Smem<64>::TOTAL, st>>>(mA0, mA1, mBhi, mBlo, p);
+  } else {
+    std::call_once(once128, [] {
+      cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128>::TOTAL);
+    });
+    tc_gemm_kernel<128><<<grid, 192, Smem<128>::TOTAL, st>>>(mA0, mA1, mBhi, mBlo, p);
+  }
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+}  // namespace agcn

@@ -87,7 +87,8 @@ class _SGCLLFunction(torch.autograd.Function):
         work_b = ctypes.c_size_t()
         _lib.check(_lib.lib().agcn_sgcll_workspace_bytes(ctypes.byref(desc), batch.handle, None, ctypes.byref(work_b)))
         work = _Workspace.get(dev, work_b.value)
-        dX = torch.empty_like(X)
+        need_dX = ctx.needs_input_grad[0] or cfg["metric_grad"] == "full"
+        dX = torch.empty_like(X) if need_dX else None
         dM = torch.empty_like(M_L)
         dW = torch.empty_like(weight)
         db = torch.empty(Fo, device=dev, dtype=torch.float32)

@@ -50,7 +50,7 @@ class SimpleAGCNStep(object):
         for p in self.params:
             p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
             off += p.numel()
-        self.opt = torch.optim.Adam(self.params, lr=learning_rate, betas=(0.9, 0.999), eps=1e-7, fused=True)
+        self.opt = torch.optim.Adam(self.params, lr=learning_rate, betas=(0.9, 0.999), eps=1e-7, fused=True, capturable=True)
 
     def n_parameters(self):
         return int(self.flat_grad.numel())

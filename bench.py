@@ -252,12 +252,35 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t) / steps
 
+    # eager launches first (also warms every kernel up), then the same step captured in a CUDA graph:
+    # a step is ~100 small launches, so replaying the graph removes the host launch path from the timing
+    launches0 = _lib.launch_count()
+    ms_eager = timed(resident_step, args.steps, args.warmup)
+    launches_per_step = (_lib.launch_count() - launches0) / float(args.steps + args.warmup)
+    launch_mode, graph = "eager", None
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(3):
+                    resident_step()
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                resident_step()
+            launch_mode = "cuda_graph"
+        except Exception as exc:  # stay on eager launches, say so in the line
+            graph, launch_mode = None, "eager (graph capture failed: %s)" % str(exc)[:120]
+            torch.cuda.synchronize()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    launches0 = _lib.launch_count()
-    ms_step = timed(resident_step, args.steps, args.warmup)
-    launches_per_step = (_lib.launch_count() - launches0) / float(args.steps + args.warmup)
+    if graph is not None:
+        ms_step = timed(graph.replay, args.steps, args.warmup)
+    else:
+        ms_step = timed(resident_step, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(e2e_step, max(3, args.steps // 2), 3)
 
@@ -277,9 +300,10 @@ def run_ours(args):
         gps, procs, sample = ref["value"], ref["cpu_baseline"]["cores"], ref["cpu_baseline"]["sample"]
         h2d = Xh.numel() * 4 + Lh.numel() * 4 + onehot_h.numel() * 4 + weights_h.numel() * 4 + n_nodes.nbytes * 4
         line = {"metric": "sgc_ll_train_graphs_per_s", "value": value, "unit": "graphs/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_step_eager": ms_eager,
+                "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": "dp%d" % world,
+                "config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": "dp%d" % world, "launch": launch_mode,
                            "semantics": "laplacian=reference_literal, metric_grad=reference",
                            "l2": "flushed between timed steps (256 MB fill)", "mean_nodes": float(n_nodes.mean()),
                            "parameters": model.n_parameters(), "host_layout_e2e": "packed ragged (pinned)"},
@@ -333,6 +357,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
