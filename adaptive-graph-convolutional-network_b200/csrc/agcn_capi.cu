@@ -99,8 +99,9 @@ int check_desc(const agcn_sgcll_desc* d, const agcn_plan* p) {
                "unknown metric_grad");
   AGCN_REQUIRE(d->activation == AGCN_ACT_LINEAR || d->activation == AGCN_ACT_RELU, "unknown activation");
   AGCN_REQUIRE(p->R < (1ll << 31) / std::max(d->F, d->Fo), "batch too large for 32-bit row indexing");
-  if (p->large_count > 0) {
-    set_error("graphs with more than AGCN_SMALL_MAX nodes need the row-tiled path, which this build lacks");
+  if (p->large_count > 0 && !literal_shortcut(d->variant, d->laplacian_mode)) {
+    set_error("graphs with more than 144 nodes are supported for SGC_LL / reference_literal only in this build "
+              "(the row-tiled Laplacian construction for paper / Reslap modes is not built yet)");
     return AGCN_ERR_INVALID;
   }
   return AGCN_OK;
@@ -145,6 +146,10 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
   const bool need_W = m.paper || want_resW;
   const bool need_build = !m.shortcut || want_resL || want_resW || want_Lall;
   float* XW = m.full ? sv.XW : wk.XW;
+  if (plan->large_count > 0 && need_build) {
+    set_error("res_L / res_W / L_all outputs are not built for graphs with more than 144 nodes yet");
+    return AGCN_ERR_INVALID;
+  }
 
   if (need_W) {  // x_w = np.dot(x, M)   graphconv.py:164
     GemmArgs g;

@@ -1,0 +1,173 @@
+// Row-tiled path for graphs with more than AGCN_SMALL_MAX nodes (point clouds: ModelNet40-shape
+// N = 1024, Sydney-shape ragged N, the N <= 4096 sweep): the n x n Laplacian does not fit in shared
+// memory, so every Chebyshev step is a grouped GEMM over (graph, 64-row tile) work items,
+//     Out = cmul * op(L_g) * In  (+ Add)  (- Sub),        op(L) = L + I | L | L^T (+ I)
+// with L streamed from HBM/L2 in 64 x 16 tiles.  Forward: graphconv.py:221-236; backward: its
+// reverse recurrence (see agcn_graph_small.cu).
+#include "agcn_internal.cuh"
+
+namespace agcn {
+
+struct GroupedArgs {
+  const int32_t* n_nodes;
+  const int32_t* node_off;
+  const int64_t* lap_off;
+  const int32_t* tile_graph;
+  const int32_t* tile_row;
+  const float* L;
+  int add_identity, transL;
+  const float* In;
+  const float* Sub;
+  const float* Add;
+  float* Out;
+  float* Out2;
+  float cmul;
+  int F;
+};
+
+constexpr int GM = 64, GN = 64, GK = 16;
+
+__global__ void __launch_bounds__(256) grouped_lap_gemm_kernel(GroupedArgs p) {
+  __shared__ __align__(16) float As[GM][GK + 4];
+  __shared__ __align__(16) float Bs[GK][GN + 4];
+  const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+  const int g = p.tile_graph[blockIdx.x], m0 = p.tile_row[blockIdx.x];
+  const int n = p.n_nodes[g];
+  const int64_t row0 = p.node_off[g];
+  const float* __restrict__ Lg = p.L + p.lap_off[g];
+  const int c0 = blockIdx.y * GN;
+  float acc[4][4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+#pragma unroll
+    for (int t = 0; t < 4; ++t) acc[q][t] = 0.f;
+  for (int k0 = 0; k0 < n; k0 += GK) {
+    // ---- op(L) tile: rows m0..m0+63, columns k0..k0+15
+    if (!p.transL) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = tid + 256 * u, row = e / GK, kk = e % GK;
+        const int i = m0 + row, j = k0 + kk;
+        float v = 0.f;
+        if (i < n && j < n) {
+          v = Lg[(int64_t)i * n + j];
+          if (p.add_identity && i == j) v += 1.f;
+        }
+        As[row][kk] = v;
+      }
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int e = tid + 256 * u, kk = e / GM, row = e % GM;  // consecutive threads walk a row of L
+        const int i = m0 + row, j = k0 + kk;
+        float v = 0.f;
+        if (i < n && j < n) {
+          v = Lg[(int64_t)j * n + i];
+          if (p.add_identity && i == j) v += 1.f;
+        }
+        As[row][kk] = v;
+      }
+    }
+    // ---- In tile: rows k0..k0+15 of the graph, columns c0..c0+63
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = tid + 256 * u, kk = e / GN, cc = e % GN;
+      const int j = k0 + kk, c = c0 + cc;
+      Bs[kk][cc] = (j < n && c < p.F) ? p.In[(row0 + j) * p.F + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < GK; kk += 4) {
+      float4 a[4], b[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) a[q] = *reinterpret_cast<const float4*>(&As[ty * 4 + q][kk]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) b[u] = *reinterpret_cast<const float4*>(&Bs[kk + u][tx * 4]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        acc[q][0] += a[q].x * b[0].x + a[q].y * b[1].x + a[q].z * b[2].x + a[q].w * b[3].x;
+        acc[q][1] += a[q].x * b[0].y + a[q].y * b[1].y + a[q].z * b[2].y + a[q].w * b[3].y;
+        acc[q][2] += a[q].x * b[0].z + a[q].y * b[1].z + a[q].z * b[2].z + a[q].w * b[3].z;
+        acc[q][3] += a[q].x * b[0].w + a[q].y * b[1].w + a[q].z * b[2].w + a[q].w * b[3].w;
+      }
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int i = m0 + ty * 4 + q;
+    if (i >= n) continue;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const int c = c0 + tx * 4 + t;
+      if (c >= p.F) continue;
+      const int64_t o = (row0 + i) * p.F + c;
+      float v = p.cmul * acc[q][t];
+      if (p.Add) v += p.Add[o];
+      if (p.Sub) v -= p.Sub[o];
+      p.Out[o] = v;
+      if (p.Out2) p.Out2[o] = v;
+    }
+  }
+}
+
+static GroupedArgs base_args(const agcn_plan* plan) {
+  GroupedArgs k{};
+  k.n_nodes = plan->d_n;
+  k.node_off = plan->d_node_off;
+  k.lap_off = plan->d_lap_off;
+  k.tile_graph = plan->d_tile_graph;
+  k.tile_row = plan->d_tile_row;
+  return k;
+}
+
+int large_chebyshev_fwd(const GraphArgs& a, cudaStream_t st) {
+  const agcn_plan* plan = a.plan;
+  if (plan->large_tiles == 0 || a.K <= 1) return AGCN_OK;
+  const bool shortcut = (a.Lall == nullptr);
+  const int64_t slice = (int64_t)plan->R * a.F;
+  dim3 grid(plan->large_tiles, (a.F + GN - 1) / GN);
+  for (int k = 1; k < a.K; ++k) {
+    GroupedArgs g = base_args(plan);
+    g.L = shortcut ? a.Lint : a.Lall;
+    g.add_identity = shortcut ? 1 : 0;
+    g.transL = 0;
+    g.In = (k == 1) ? a.X : a.T + (int64_t)(k - 2) * slice;
+    g.Sub = (k >= 2) ? ((k == 2) ? a.X : a.T + (int64_t)(k - 3) * slice) : nullptr;
+    g.Add = nullptr;
+    g.Out = a.T + (int64_t)(k - 1) * slice;
+    g.Out2 = nullptr;
+    g.cmul = (k == 1) ? 1.f : 2.f;
+    g.F = a.F;
+    grouped_lap_gemm_kernel<<<grid, 256, 0, st>>>(g);
+    AGCN_LAUNCH_CHECK();
+  }
+  return AGCN_OK;
+}
+
+// U_j overwrites G_j in place (slice j of a.G); dX receives U_0.
+int large_recurrence_bwd(const GraphArgs& a, float* G, cudaStream_t st) {
+  const agcn_plan* plan = a.plan;
+  if (plan->large_tiles == 0 || a.K <= 1) return AGCN_OK;
+  const bool shortcut = (a.Lall == nullptr);
+  const int64_t slice = (int64_t)plan->R * a.F;
+  dim3 grid(plan->large_tiles, (a.F + GN - 1) / GN);
+  for (int j = a.K - 2; j >= 0; --j) {
+    GroupedArgs g = base_args(plan);
+    g.L = shortcut ? a.Lint : a.Lall;
+    g.add_identity = shortcut ? 1 : 0;
+    g.transL = 1;
+    g.In = G + (int64_t)(j + 1) * slice;
+    g.Add = G + (int64_t)j * slice;
+    g.Sub = (j + 2 <= a.K - 1) ? G + (int64_t)(j + 2) * slice : nullptr;
+    g.Out = G + (int64_t)j * slice;
+    g.Out2 = (j == 0) ? a.dX : nullptr;
+    g.cmul = (j + 1 >= 2) ? 2.f : 1.f;
+    g.F = a.F;
+    grouped_lap_gemm_kernel<<<grid, 256, 0, st>>>(g);
+    AGCN_LAUNCH_CHECK();
+  }
+  return AGCN_OK;
+}
+
+}  // namespace agcn

@@ -792,6 +792,7 @@ int graph_chebyshev_fwd(const GraphArgs& a, cudaStream_t st) {
     cheb_fwd_kernel<<<bk.count * c.chunks, c.threads, c.smem, s>>>(k);
     AGCN_LAUNCH_CHECK();
   }
+  if ((rc = large_chebyshev_fwd(a, st))) return rc;  // graphs that do not fit in shared memory
   return join_streams(plan, st, nb - 1);
 }
 
@@ -812,6 +813,7 @@ int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st) {
     recur_bwd_kernel<<<bk.count * c.chunks, c.threads, c.smem, s>>>(k);
     AGCN_LAUNCH_CHECK();
   }
+  if ((rc = large_recurrence_bwd(a, const_cast<float*>(a.G), st))) return rc;
   return join_streams(plan, st, nb - 1);
 }
 

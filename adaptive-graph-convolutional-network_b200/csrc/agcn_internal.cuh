@@ -165,6 +165,9 @@ int graph_chebyshev_fwd(const GraphArgs& a, cudaStream_t st);
 int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st);
 int graph_laplacian_bwd(const GraphArgs& a, cudaStream_t st);
 int reduce_scalar_parts(const float* parts, int B, float* out, cudaStream_t st);
+// graphs with more than AGCN_SMALL_MAX nodes (agcn_graph_large.cu)
+int large_chebyshev_fwd(const GraphArgs& a, cudaStream_t st);
+int large_recurrence_bwd(const GraphArgs& a, float* G, cudaStream_t st);
 
 // ---------------------------------------------------------------- helpers
 int fork_streams(const agcn_plan* plan, cudaStream_t main, int n_aux);

@@ -241,25 +241,57 @@ int gemm_tn(const GemmTNArgs& a, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------------------------------------
-constexpr int ACT_ROWS = 128;  // rows per CTA
+constexpr int ACT_ROWS = 64;  // rows per CTA
 
+// dYp = dY * relu'(Y); per-CTA column sums.  Threads are laid out [row lane][column]: consecutive threads
+// walk consecutive columns (coalesced), the row lanes of a column are combined through shared memory.
 __global__ void __launch_bounds__(256) act_bwd_colsum_kernel(const float* __restrict__ dY, const float* __restrict__ Y,
                                                              float* __restrict__ dYp, float* __restrict__ partial,
                                                              int64_t R, int Fo, int act) {
+  __shared__ float red[256];
   const int64_t r0 = (int64_t)blockIdx.x * ACT_ROWS;
   const int64_t r1 = min(R, r0 + ACT_ROWS);
-  // thread t owns columns t, t+256, ...; rows are walked sequentially: coalesced along the row
-  for (int c = threadIdx.x; c < Fo; c += blockDim.x) {
+  const int cols = min(Fo, 256);             // columns handled per pass
+  const int lanes = 256 / cols > 0 ? 256 / cols : 1;  // row lanes per column
+  for (int cbase = 0; cbase < Fo; cbase += cols) {
+    const int c = cbase + (int)(threadIdx.x % cols), rl = threadIdx.x / cols;
     float s = 0.f;
-    for (int64_t r = r0; r < r1; ++r) {
-      float g = dY[r * Fo + c];
-      if (act == AGCN_ACT_RELU) {
-        g = (Y[r * Fo + c] > 0.f) ? g : 0.f;
-        dYp[r * Fo + c] = g;
+    if (c < Fo && rl < lanes) {
+      for (int64_t r = r0 + rl; r < r1; r += lanes) {
+        float g = dY[r * Fo + c];
+        if (act == AGCN_ACT_RELU) {
+          g = (Y[r * Fo + c] > 0.f) ? g : 0.f;
+          dYp[r * Fo + c] = g;
+        }
+        s += g;
       }
-      s += g;
     }
-    partial[(int64_t)blockIdx.x * Fo + c] = s;
+    red[threadIdx.x] = s;
+    __syncthreads();
+    if (rl == 0 && c < Fo) {
+      for (int l = 1; l < lanes; ++l) s += red[l * cols + (threadIdx.x % cols)];
+      partial[(int64_t)blockIdx.x * Fo + c] = s;
+    }
+    __syncthreads();
+  }
+}
+
+// out[c] = sum_k partial[k][c]: 32 columns per CTA, the k range split over 8 warps, fixed summation order
+__global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restrict__ partial, float* __restrict__ out,
+                                                            int n_part, int Fo) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (c < Fo)
+    for (int k = w; k < n_part; k += 8) s += partial[(int64_t)k * Fo + c];
+  red[w][lane] = s;
+  __syncthreads();
+  if (w == 0 && c < Fo) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    out[c] = t;
   }
 }
 
@@ -274,7 +306,7 @@ int act_bwd_colsum(const float* dY, const float* Y, float* dYp, float* dbias, fl
   const int blocks = (int)((R + ACT_ROWS - 1) / ACT_ROWS);
   act_bwd_colsum_kernel<<<blocks, 256, 0, st>>>(dY, Y, dYp, partial, R, Fo, act);
   AGCN_LAUNCH_CHECK();
-  reduce_partials_kernel<<<(Fo + 255) / 256, 256, 0, st>>>(partial, dbias, Fo, blocks);
+  colsum_reduce_kernel<<<(Fo + 31) / 32, 256, 0, st>>>(partial, dbias, blocks, Fo);
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }

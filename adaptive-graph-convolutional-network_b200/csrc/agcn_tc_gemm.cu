@@ -218,32 +218,73 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     mbar_wait(tmem_full_bar, 0);
     tc_fence_after();
-    const int q = warp & 3;               // TMEM lane quarter this warp may access
-    const int m = m0 + q * 32 + lane;     // output row of this thread
-    float* __restrict__ Crow = p.C + (long long)z * p.sliceC + (long long)m * p.ldc;
+    const int q = warp & 3;  // TMEM lane quarter this warp may access: tile rows 32q .. 32q+31
+    // Each thread owns one accumulator row.  32-column chunks are staged through shared memory (the
+    // pipeline stages are free now) so that the global stores are row-contiguous 128-byte segments.
+    float* stg = reinterpret_cast<float*>(base) + (warp - 2) * (32 * 36);
+    float* __restrict__ Cz = p.C + (long long)z * p.sliceC;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16];
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (nb * BN + c0 >= p.N) break;
+      uint32_t v[32];
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
       asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+          "%29,%30,%31}, [%32];\n"
           : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
-      if (m < p.M) {
 #pragma unroll
-        for (int u = 0; u < 16; ++u) {
-          const int c = nb * BN + c0 + u;
-          if (c < p.N) {
-            float o = __uint_as_float(v[u]);
-            if (p.bias) o += p.bias[c];
-            if (p.accumulate) o += Crow[c];
-            if (p.act == AGCN_ACT_RELU) o = fmaxf(o, 0.f);
-            Crow[c] = o;
+      for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<float4*>(&stg[lane * 36 + 4 * u]) =
+            make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]),
+                        __uint_as_float(v[4 * u + 3]));
+      __syncwarp();
+      const int cc = nb * BN + c0 + 4 * (lane & 7);  // first of this lane's 4 output columns
+      float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.bias) {
+        if (cc + 0 < p.N) bv.x = p.bias[cc + 0];
+        if (cc + 1 < p.N) bv.y = p.bias[cc + 1];
+        if (cc + 2 < p.N) bv.z = p.bias[cc + 2];
+        if (cc + 3 < p.N) bv.w = p.bias[cc + 3];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + (lane >> 3);
+        const int m = m0 + q * 32 + r;
+        float4 o = *reinterpret_cast<const float4*>(&stg[r * 36 + 4 * (lane & 7)]);
+        if (m < p.M && cc < p.N) {
+          float* dst = Cz + (long long)m * p.ldc + cc;
+          o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          if (vec_ok && cc + 3 < p.N) {
+            if (p.accumulate) {
+              const float4 old = *reinterpret_cast<const float4*>(dst);
+              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            }
+            if (p.act == AGCN_ACT_RELU) {
+              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            *reinterpret_cast<float4*>(dst) = o;
+          } else {
+            const float ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (cc + e < p.N) {
+                float x = ov[e];
+                if (p.accumulate) x += dst[e];
+                if (p.act == AGCN_ACT_RELU) x = fmaxf(x, 0.f);
+                dst[e] = x;
+              }
+            }
           }
         }
       }
+      __syncwarp();
     }
   }
   tc_fence_before();

@@ -15,6 +15,7 @@ import torch
 import torch.distributed as dist
 
 from .batch import GraphBatch, PackedLaplacians, PackedNodes
+from .data_parallel import FlatGradBuffer
 from .layers import SGC_LL
 from .layers import graphconv as _gc
 
@@ -44,13 +45,16 @@ class SimpleAGCNStep(object):
         self.params = [v for l in self.layers for v in l.vars.values()] + [self.dense_W, self.dense_b, self.head_W,
                                                                            self.head_b]
         # one flat gradient buffer; every .grad is a view into it -> a single all-reduce per step
-        total = sum(p.numel() for p in self.params)
-        self.flat_grad = torch.zeros(total, device=self.device, dtype=torch.float32)
-        off = 0
-        for p in self.params:
-            p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
-            off += p.numel()
+        self.grads = FlatGradBuffer(self.params)
+        self.flat_grad = self.grads.flat
         self.opt = torch.optim.Adam(self.params, lr=learning_rate, betas=(0.9, 0.999), eps=1e-7, fused=True, capturable=True)
+
+    def _n_nodes_f(self, batch):
+        t = getattr(batch, "_n_nodes_float", None)
+        if t is None:
+            t = torch.from_numpy(batch.n_nodes.astype(np.float32)).to(self.device)
+            batch._n_nodes_float = t
+        return t
 
     def n_parameters(self):
         return int(self.flat_grad.numel())
@@ -62,8 +66,12 @@ class SimpleAGCNStep(object):
         for layer in self.layers:
             out, _, _ = layer(x)
             x = dict(x, node_features=out)
-        H = torch.addmm(self.dense_b, out.data, self.dense_W)                 # DenseMol: no activation applied
-        mol = torch.zeros(batch.batch_size, H.shape[1], device=H.device).index_add_(0, batch.graph_ids(), H)
+        # DenseMol applies no activation (dense_layer.py:42-50), so the per-graph row sum of GraphGatherMol
+        # (graphgather.py:68-77) commutes with it: sum_i (h_i W + b) = (sum_i h_i) W + n_g b.  Gathering first
+        # shrinks the dense GEMM from R = sum n_g rows to B rows.
+        hsum = torch.zeros(batch.batch_size, out.data.shape[1], device=out.data.device).index_add_(
+            0, batch.graph_ids(), out.data)
+        mol = torch.addmm(self._n_nodes_f(batch)[:, None] * self.dense_b[None, :], hsum, self.dense_W)
         mol = torch.tanh(mol)                                                  # GraphGatherMol
         logits = torch.addmm(self.head_b, mol, self.head_W)
         loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, onehot, weight=weights, reduction='sum')
@@ -71,11 +79,11 @@ class SimpleAGCNStep(object):
 
     def step(self, X, Lint, batch, onehot, weights):
         """One training step: forward, backward, gradient all-reduce, Adam.  Returns the loss tensor."""
-        self.flat_grad.zero_()
+        self.grads.zero()
         loss = self.forward_loss(X, Lint, batch, onehot, weights)
         loss.backward()
         if self.world_size > 1:
-            dist.all_reduce(self.flat_grad)
+            self.grads.all_reduce()
         self.opt.step()
         return loss
 

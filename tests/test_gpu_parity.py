@@ -210,3 +210,33 @@ def test_full_size_properties_toxcast_batch():
     assert O.rel_err(cu1["Y"][idx], orc["Y"]) <= TOL
     rows = torch.arange(132)[None, :] >= torch.tensor(n.astype(np.int64))[:, None]
     assert float(cu1["Y"][rows].abs().max()) == 0.0
+
+
+def _dense_laplacians(n_list, Nmax, seed):
+    """Dense symmetric normalised Laplacians like the thresholded point-cloud graphs (~50 % fill)."""
+    rng = np.random.default_rng(seed)
+    L = np.zeros((len(n_list), Nmax, Nmax), np.float32)
+    for g, n in enumerate(n_list):
+        A = (rng.random((n, n)) < 0.5).astype(np.float64)
+        A = np.triu(A, 1); A = A + A.T + np.eye(n)
+        d = 1.0 / np.sqrt(A.sum(1))
+        L[g, :n, :n] = (np.eye(n) - d[:, None] * A * d[None, :]).astype(np.float32)
+    return L
+
+
+@pytest.mark.parametrize("sizes,F,Fo,K", [([1024, 1024, 1024], 3, 32, 3),          # ModelNet40-shape
+                                          ([13, 700, 145, 1024, 64, 144, 333], 4, 26, 3),   # Sydney-shape, ragged
+                                          ([2048, 150], 32, 32, 2),              # sweep point
+                                          ([513, 200], 64, 128, 5)])
+def test_large_graphs_row_tiled_path(sizes, F, Fo, K):
+    """Graphs that do not fit in shared memory (n > 144) run through the grouped-GEMM path; small and large
+    graphs mix freely in one batch."""
+    Nmax = max(sizes)
+    X, _, n = make_batch(sizes, F, Nmax, seed=F + K)
+    L = _dense_laplacians(sizes, Nmax, seed=K)
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=F, dtype=torch.float64)
+    cY = _cot((len(sizes), Nmax, Fo), 13)
+    orc = oracle_run(X, L, n, p, K, "SGC_LL", "reference_literal", "reference", cot_Y=cY)
+    cu = cuda_run(X, L, n, p, K, "SGC_LL", "reference_literal", "reference", cot_Y=cY, want_res=False)
+    errs = compare(cu, orc, skip=("res_L", "res_W", "L_all"))
+    print(sizes, errs)
