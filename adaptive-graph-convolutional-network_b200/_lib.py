@@ -46,6 +46,9 @@ _SIGNATURES = {
                                                   ctypes.POINTER(ctypes.c_size_t)]),
     "agcn_sgcll_forward": (ctypes.c_int, [ctypes.POINTER(Desc), _P] + [_P] * 14 + [ctypes.c_size_t, _P]),
     "agcn_sgcll_backward": (ctypes.c_int, [ctypes.POINTER(Desc), _P] + [_P] * 19 + [ctypes.c_size_t, _P]),
+    "agcn_gemm_tn_scratch_bytes": (ctypes.c_size_t, [ctypes.c_int32] * 4),
+    "agcn_gemm_tn": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                    _P, ctypes.c_int32, _P]),
     "agcn_sgcll_host_scratch_bytes": (ctypes.c_int, [ctypes.POINTER(Desc), _P, ctypes.POINTER(ctypes.c_size_t)]),
     "agcn_sgcll_forward_host": (ctypes.c_int, [ctypes.POINTER(Desc), _P] + [_P] * 8 + [ctypes.c_size_t, _P]),
 }

@@ -12,6 +12,11 @@ namespace {
 inline size_t align256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // node-level GEMM: tensor cores when the operands are TMA-compatible, CUDA cores otherwise (F = 75)
+int node_gemm_tn(const GemmTNArgs& t, cudaStream_t st) {
+  if (tc_gemm_tn_supported(t)) return tc_gemm_tn(t, st);
+  return gemm_tn(t, st);
+}
+
 int node_gemm(const GemmArgs& g, float* tc_scratch, cudaStream_t st) {
   if (tc_gemm_supported(g)) return tc_gemm(g, tc_scratch, st);
   return gemm_rows(g, st);
@@ -76,6 +81,13 @@ Work carve_work(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
   w.G = c.take((size_t)d->K * p->R * d->F);
   size_t tn = gemm_tn_partial_floats((int)p->R, d->F, d->Fo, d->K);
   if (m.full) tn = std::max(tn, gemm_tn_partial_floats((int)p->R, d->F, d->F, 1));
+  {
+    GemmTNArgs t;
+    t.M = (int)p->R; t.Kd = d->F; t.N = d->Fo; t.S = d->K;
+    tn = std::max(tn, tc_gemm_tn_partial_floats(t));
+    t.N = d->F; t.S = 1;
+    tn = std::max(tn, tc_gemm_tn_partial_floats(t));
+  }
   w.tn_part = c.take(tn);
   w.act_part = c.take(act_bwd_partial_floats(p->R, d->Fo));
   w.dL = m.need_dL ? c.take((size_t)p->LL) : nullptr;
@@ -237,6 +249,19 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   ga.G = wk.G; ga.dLall_in = d_dLall_in; ga.dX = dXbuf; ga.dL = wk.dL;
   ga.dLprev = has_prev ? d_dLprev : nullptr;
   ga.dXW = wk.dXW; ga.dalpha_part = wk.dalpha_part; ga.dbeta_part = m.reslap ? wk.dbeta_part : nullptr;
+  // dweight[f*K + k, :] = T_k^T dYpre: depends on dYpre only -> side stream, overlapping the dX chain
+  AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
+  AGCN_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_side_fork, 0));
+  {
+    GemmTNArgs t;
+    t.M = R; t.Kd = F; t.N = Fo; t.S = K;
+    t.A0 = d_X; t.lda0 = F;
+    t.A1 = sv.T; t.lda1 = F; t.sliceA1 = (int64_t)R * F;
+    t.D = dYp; t.ldd = Fo;
+    t.out = d_dweight; t.partial = wk.tn_part;
+    if ((rc = node_gemm_tn(t, plan->side))) return rc;
+  }
+  AGCN_CUDA(cudaEventRecord(plan->ev_side_join, plan->side));
   if (K >= 2) {
     if (need_G && (rc = graph_recurrence_bwd(ga, m.need_dL, st))) return rc;
   } else if (m.need_dL) {
@@ -245,15 +270,7 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
     else
       AGCN_CUDA(cudaMemsetAsync(wk.dL, 0, (size_t)plan->LL * sizeof(float), st));
   }
-  {  // dweight[f*K + k, :] = T_k^T dYpre
-    GemmTNArgs t;
-    t.M = R; t.Kd = F; t.N = Fo; t.S = K;
-    t.A0 = d_X; t.lda0 = F;
-    t.A1 = sv.T; t.lda1 = F; t.sliceA1 = (int64_t)R * F;
-    t.D = dYp; t.ldd = Fo;
-    t.out = d_dweight; t.partial = wk.tn_part;
-    if ((rc = gemm_tn(t, st))) return rc;
-  }
+  AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
   if (m.need_dL) {
     if ((rc = graph_laplacian_bwd(ga, st))) return rc;
     if ((rc = reduce_scalar_parts(wk.dalpha_part, plan->B, d_dalpha, st))) return rc;
@@ -269,7 +286,7 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
     t.A0 = d_X; t.lda0 = F;
     t.D = wk.dXW; t.ldd = F;
     t.out = d_dM_L; t.partial = wk.tn_part;
-    if ((rc = gemm_tn(t, st))) return rc;
+    if ((rc = node_gemm_tn(t, st))) return rc;
     GemmArgs g;  // dX += dXW M_L^T
     g.M = R; g.N = F; g.Kd = F;
     g.A0 = wk.dXW; g.lda0 = F;
@@ -281,6 +298,33 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
     AGCN_CUDA(cudaMemsetAsync(d_dM_L, 0, (size_t)F * F * sizeof(float), st));
   }
   return AGCN_OK;
+}
+
+/* Building block exported for tests and tuning: out[(f*S + s)*N + c] = sum_r A_s[r, f] * D[r, c].
+ * use_tensor_cores = 0 forces the CUDA-core kernel.  scratch: agcn_gemm_tn_scratch_bytes() bytes. */
+size_t agcn_gemm_tn_scratch_bytes(int32_t M, int32_t Kd, int32_t N, int32_t S) {
+  GemmTNArgs t;
+  t.M = M; t.Kd = Kd; t.N = N; t.S = S;
+  return 4 * std::max(gemm_tn_partial_floats(M, Kd, N, S), tc_gemm_tn_partial_floats(t)) + 256;
+}
+
+int agcn_gemm_tn(const float* d_A0, const float* d_A1, const float* d_D, float* d_out, int32_t M, int32_t Kd,
+                 int32_t N, int32_t S, void* d_scratch, int32_t use_tensor_cores, void* stream) {
+  AGCN_REQUIRE(d_A0 && d_D && d_out && d_scratch && M >= 1 && Kd >= 1 && N >= 1 && S >= 1, "gemm_tn: bad arguments");
+  GemmTNArgs t;
+  t.M = M; t.Kd = Kd; t.N = N; t.S = S;
+  t.A0 = d_A0; t.lda0 = Kd;
+  t.A1 = d_A1; t.lda1 = Kd; t.sliceA1 = (int64_t)M * Kd;
+  t.D = d_D; t.ldd = N;
+  t.out = d_out; t.partial = reinterpret_cast<float*>(d_scratch);
+  if (use_tensor_cores) {
+    if (!tc_gemm_tn_supported(t)) {
+      set_error("gemm_tn: shape not supported by the tensor-core kernel");
+      return AGCN_ERR_INVALID;
+    }
+    return tc_gemm_tn(t, (cudaStream_t)stream);
+  }
+  return gemm_tn(t, (cudaStream_t)stream);
 }
 
 int agcn_sgcll_host_scratch_bytes(const agcn_sgcll_desc* desc, const agcn_plan* plan, size_t* bytes) {

@@ -41,41 +41,46 @@ __global__ void __launch_bounds__(256) grouped_lap_gemm_kernel(GroupedArgs p) {
   for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int t = 0; t < 4; ++t) acc[q][t] = 0.f;
-  for (int k0 = 0; k0 < n; k0 += GK) {
-    // ---- op(L) tile: rows m0..m0+63, columns k0..k0+15
-    if (!p.transL) {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = tid + 256 * u, row = e / GK, kk = e % GK;
-        const int i = m0 + row, j = k0 + kk;
-        float v = 0.f;
-        if (i < n && j < n) {
-          v = Lg[(int64_t)i * n + j];
-          if (p.add_identity && i == j) v += 1.f;
-        }
-        As[row][kk] = v;
-      }
-    } else {
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int e = tid + 256 * u, kk = e / GM, row = e % GM;  // consecutive threads walk a row of L
-        const int i = m0 + row, j = k0 + kk;
-        float v = 0.f;
-        if (i < n && j < n) {
-          v = Lg[(int64_t)j * n + i];
-          if (p.add_identity && i == j) v += 1.f;
-        }
-        As[row][kk] = v;
-      }
-    }
-    // ---- In tile: rows k0..k0+15 of the graph, columns c0..c0+63
+  // register-staged double buffering: the global loads of tile k+1 are in flight while tile k is multiplied
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int e = tid + 256 * u, kk = e / GN, cc = e % GN;
-      const int j = k0 + kk, c = c0 + cc;
-      Bs[kk][cc] = (j < n && c < p.F) ? p.In[(row0 + j) * p.F + c] : 0.f;
+      const int e = tid + 256 * u;
+      int row, kk;
+      if (!p.transL) {
+        row = e / GK; kk = e % GK;
+      } else {
+        kk = e / GM; row = e % GM;  // consecutive threads walk a row of L
+      }
+      const int i = m0 + row, j = k0 + kk;
+      float v = 0.f;
+      if (i < n && j < n) {
+        v = p.transL ? Lg[(int64_t)j * n + i] : Lg[(int64_t)i * n + j];
+        if (p.add_identity && i == j) v += 1.f;
+      }
+      ra[u] = v;
+      const int bk = e / GN, cc = e % GN;
+      const int jj = k0 + bk, c = c0 + cc;
+      rb[u] = (jj < n && c < p.F) ? p.In[(row0 + jj) * p.F + c] : 0.f;
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = tid + 256 * u;
+      if (!p.transL)
+        As[e / GK][e % GK] = ra[u];
+      else
+        As[e % GM][e / GM] = ra[u];
+      Bs[e / GN][e % GN] = rb[u];
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < n; k0 += GK) {
+    stash();
     __syncthreads();
+    if (k0 + GK < n) fetch(k0 + GK);
 #pragma unroll
     for (int kk = 0; kk < GK; kk += 4) {
       float4 a[4], b[4];

@@ -13,6 +13,9 @@
 // Largest graph handled by the one-CTA-per-(graph, feature chunk) shared-memory kernels; bigger
 // graphs go through the row-tiled kernels (agcn_graph_large.cu).
 #define AGCN_SMALL_MAX 144
+// Graphs above this size run their Chebyshev recurrences as row-tiled grouped GEMMs (one launch per step,
+// several CTAs per graph) instead of one CTA per (graph, feature chunk).
+#define AGCN_CHEB_SMALL_MAX 64
 
 namespace agcn {
 
@@ -57,7 +60,8 @@ struct agcn_plan {
   std::vector<int64_t> lap_off;
   std::vector<agcn::Bucket> buckets;  // graphs with n <= AGCN_SMALL_MAX, biggest bucket first
   int large_count = 0;                // graphs with n > AGCN_SMALL_MAX are order[0 .. large_count)
-  // row tiles of the large graphs: tile t covers rows [tile_row[t], tile_row[t]+64) of graph tile_graph[t]
+  // row tiles of the graphs with n > AGCN_CHEB_SMALL_MAX: tile t covers rows [tile_row[t], tile_row[t]+64) of
+  // graph tile_graph[t]
   std::vector<int32_t> tile_graph, tile_row;
   int large_tiles = 0;
   // device copies (one allocation)
@@ -72,6 +76,10 @@ struct agcn_plan {
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
   cudaEvent_t ev_join[3] = {nullptr, nullptr, nullptr};
+  // a fourth side stream for the parameter-gradient contraction of the backward pass (dW = T^T dY), which
+  // only depends on dY and overlaps with the dX chain
+  cudaStream_t side = nullptr;
+  cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;
 };
 
 namespace agcn {
@@ -122,6 +130,10 @@ struct GemmTNArgs {
 };
 size_t gemm_tn_partial_floats(int M, int Kd, int N, int S);
 int gemm_tn(const GemmTNArgs& a, cudaStream_t st);
+// tcgen05 (3xTF32, MN-major operands) implementation of the same contraction (agcn_tc_gemm.cu)
+bool tc_gemm_tn_supported(const GemmTNArgs& a);
+size_t tc_gemm_tn_partial_floats(const GemmTNArgs& a);
+int tc_gemm_tn(const GemmTNArgs& a, cudaStream_t st);
 
 // dYp = dY * act'(Y) (relu mask), colsum(dYp) -> dbias.  partial: act_bwd_partial_floats() floats.
 size_t act_bwd_partial_floats(int64_t R, int Fo);

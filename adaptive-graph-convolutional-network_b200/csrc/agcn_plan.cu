@@ -124,7 +124,7 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   int pos = 0;
   while (pos < B && p->n[p->order[pos]] > AGCN_SMALL_MAX) ++pos;
   p->large_count = pos;
-  for (int i = 0; i < p->large_count; ++i) {
+  for (int i = 0; i < B && p->n[p->order[i]] > AGCN_CHEB_SMALL_MAX; ++i) {
     const int g = p->order[i];
     for (int r = 0; r < p->n[g]; r += 64) {
       p->tile_graph.push_back(g);
@@ -163,6 +163,9 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming);
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_side_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_side_join, cudaEventDisableTiming);
   if (e != cudaSuccess) {
     int rc = cuda_fail(e, "agcn_plan_create", __FILE__, __LINE__);
     agcn_plan_destroy(p);
@@ -186,6 +189,9 @@ int agcn_plan_destroy(agcn_plan* p) {
     if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
   }
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  if (p->side) cudaStreamDestroy(p->side);
+  if (p->ev_side_fork) cudaEventDestroy(p->ev_side_fork);
+  if (p->ev_side_join) cudaEventDestroy(p->ev_side_join);
   if (p->d_block) cudaFree(p->d_block);
   delete p;
   return AGCN_OK;

@@ -15,6 +15,7 @@
 // Used for Y = act(sum_k T_k W_k + b) (graphconv.py:238-247), G_k = dY W_k^T, XW = X M_L
 // (graphconv.py:164) and dX += dXW M_L^T.
 #include <cuda.h>
+#include <cstdio>
 
 #include <algorithm>
 #include <cstdlib>
@@ -294,6 +295,234 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// TN contraction over the node dimension on the tensor cores:
+//     P_chunk[(f*S + s)*N + c] = sum_{r in chunk} A_s[r, f] * D[r, c]
+// Both operands are row-major node matrices, i.e. MN-major for the MMA (the contraction index r is the
+// slow one).  MN-major TF32 operands must use the "128B swizzle, 32B atom" shared-memory layout (UMMA layout
+// type 1 / CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B): TMA brings 32-row x 32-column boxes, four rows form one
+// 512-byte swizzle atom (stride byte offset), a k-step of 8 rows is 1024 bytes, and the 32-column groups of
+// one operand are 4096 bytes apart (leading byte offset).
+// Both operands are activations, so both are split hi/lo in shared memory.
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;  // leading byte offset: next group of 32 M/N elements
+  d |= (uint64_t)(512 >> 4) << 32;   // stride byte offset: next group of 4 K rows
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;            // SWIZZLE_128B_BASE32B
+  return d;
+}
+
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+
+struct TnArgs {
+  int M;        // rows contracted (nodes)
+  int Kd;       // columns of A_s = rows of the result (<= 128)
+  int N;        // columns of D
+  int S;
+  int kb_per_chunk;
+  float* partial;   // [chunks][Kd*S*N]
+};
+
+template <int BN>
+struct SmemTn {
+  static constexpr int A_BYTES = 128 * BK * 4;   // 4 boxes of 32 rows x 128 bytes
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = (BN <= 64) ? 4 : 3;
+  static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 + 256;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(192, 1)
+tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+                  const __grid_constant__ CUtensorMap tmD, TnArgs p) {
+  using SM = SmemTn<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::STAGES * SM::STAGE_BYTES);
+  uint64_t* full_bar = bars;
+  uint64_t* split_bar = bars + SM::STAGES;
+  uint64_t* empty_bar = bars + 2 * SM::STAGES;
+  uint64_t* tmem_full_bar = bars + 3 * SM::STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * SM::STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int chunk = blockIdx.x, s = blockIdx.y, nb = blockIdx.z;
+  const int total_kb = (p.M + BK - 1) / BK;
+  const int kb_begin = chunk * p.kb_per_chunk;
+  const int num_kb = min(p.kb_per_chunk, total_kb - kb_begin);
+  const int a_boxes = (p.Kd + 31) / 32;                       // 32-column groups of A that exist
+  const int b_boxes = min(BN / 32, (p.N - nb * BN + 31) / 32);  // of this column block of D
+
+  // boxes that are never loaded stay zero for the whole kernel
+  for (int i = threadIdx.x; i < SM::STAGES * SM::STAGE_BYTES / 16; i += blockDim.x)
+    reinterpret_cast<float4*>(base)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < SM::STAGES; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&split_bar[i], 128);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(BN)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // zero fill above vs. TMA / tensor-core reads
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % SM::STAGES, phase = (kb / SM::STAGES) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = base + stage * SM::STAGE_BYTES;
+        const int r0 = (kb_begin + kb) * BK;
+        mbar_expect_tx(&full_bar[stage], (a_boxes + b_boxes) * 4096);
+        for (int b = 0; b < a_boxes; ++b) {
+          if (s == 0)
+            tma_load_3d(st + b * 4096, &tmA0, &full_bar[stage], 32 * b, r0, 0);
+          else
+            tma_load_3d(st + b * 4096, &tmA1, &full_bar[stage], 32 * b, r0, s - 1);
+        }
+        for (int b = 0; b < b_boxes; ++b)
+          tma_load_3d(st + 2 * SM::A_BYTES + b * 4096, &tmD, &full_bar[stage], nb * BN + 32 * b, r0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = f32, A = B = tf32, both MN-major, N = BN, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % SM::STAGES, phase = (kb / SM::STAGES) & 1;
+        mbar_wait(&split_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(base + stage * SM::STAGE_BYTES);
+        const uint32_t sa_lo = sa + SM::A_BYTES;
+        const uint32_t sb = sa + 2 * SM::A_BYTES, sb_lo = sb + SM::B_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint32_t koff = k * 1024;  // 8 contraction rows = one swizzle atom
+          const uint64_t a_hi = make_desc_mn(sa + koff), a_lo = make_desc_mn(sa_lo + koff);
+          const uint64_t b_hi = make_desc_mn(sb + koff), b_lo = make_desc_mn(sb_lo + koff);
+          umma_tf32(tmem_base, a_lo, b_hi, idesc, (kb | k) != 0);
+          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+          umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int t = threadIdx.x - 64;
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int stage = kb % SM::STAGES, phase = (kb / SM::STAGES) & 1;
+      mbar_wait(&full_bar[stage], phase);
+      uint8_t* st = base + stage * SM::STAGE_BYTES;
+      auto split = [&](float4* hi_p, float4* lo_p, int n16) {
+        for (int idx = t; idx < n16; idx += 128) {
+          const float4 v = hi_p[idx];
+          float4 hi, lo;
+          hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+          hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+          hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+          hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+          lo.x = __uint_as_float(__float_as_uint(v.x - hi.x) & 0xffffe000u);
+          lo.y = __uint_as_float(__float_as_uint(v.y - hi.y) & 0xffffe000u);
+          lo.z = __uint_as_float(__float_as_uint(v.z - hi.z) & 0xffffe000u);
+          lo.w = __uint_as_float(__float_as_uint(v.w - hi.w) & 0xffffe000u);
+          hi_p[idx] = hi;
+          lo_p[idx] = lo;
+        }
+      };
+#ifdef AGCN_TN_DEBUG
+      if (t == 0 && blockIdx.x == 0 && kb == 0) {
+        const float* fa = reinterpret_cast<const float*>(st);
+        const float* fb = reinterpret_cast<const float*>(st + 2 * SM::A_BYTES);
+        printf("TNDBG a_boxes %d b_boxes %d num_kb %d A: %f %f %f %f | row1 %f %f %f %f | B: %f %f %f %f row1 %f %f\n", a_boxes,
+               b_boxes, num_kb, fa[0], fa[1], fa[2], fa[3], fa[32], fa[33], fa[34], fa[35], fb[0], fb[1], fb[2], fb[3],
+               fb[32], fb[33]);
+      }
+#endif
+      split(reinterpret_cast<float4*>(st), reinterpret_cast<float4*>(st + SM::A_BYTES), a_boxes * 256);
+      split(reinterpret_cast<float4*>(st + 2 * SM::A_BYTES),
+            reinterpret_cast<float4*>(st + 2 * SM::A_BYTES + SM::B_BYTES), b_boxes * 256);
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      mbar_arrive(&split_bar[stage]);
+    }
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    float* stg = reinterpret_cast<float*>(base) + (warp - 2) * (32 * 36);
+    float* __restrict__ P = p.partial + (long long)chunk * p.Kd * p.S * p.N;
+#pragma unroll 1
+    for (int c0 = 0; c0 < BN; c0 += 32) {
+      if (nb * BN + c0 >= p.N) break;
+      uint32_t v[32];
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+          "%29,%30,%31}, [%32];\n"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+            "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+            "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+            "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#ifdef AGCN_TN_DEBUG
+      if (blockIdx.x == 0 && c0 == 0 && lane < 2)
+        printf("TNDBG tmem q %d lane %d: %f %f %f %f\n", q, lane, __uint_as_float(v[0]), __uint_as_float(v[1]),
+               __uint_as_float(v[2]), __uint_as_float(v[3]));
+#endif
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<float4*>(&stg[lane * 36 + 4 * u]) =
+            make_float4(__uint_as_float(v[4 * u]), __uint_as_float(v[4 * u + 1]), __uint_as_float(v[4 * u + 2]),
+                        __uint_as_float(v[4 * u + 3]));
+      __syncwarp();
+      const int cc = nb * BN + c0 + 4 * (lane & 7);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = 4 * i + (lane >> 3);
+        const int f = q * 32 + r;  // result row = column of A_s
+        if (f < p.Kd && cc < p.N) {
+          const float4 o = *reinterpret_cast<const float4*>(&stg[r * 36 + 4 * (lane & 7)]);
+          float* dst = P + ((long long)f * p.S + s) * p.N + cc;
+          if ((p.N & 3) == 0) {
+            *reinterpret_cast<float4*>(dst) = o;
+          } else {
+            const float ov[4] = {o.x, o.y, o.z, o.w};
+            for (int e = 0; e < 4; ++e)
+              if (cc + e < p.N) dst[e] = ov[e];
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(BN) : "memory");
+  }
+}
+
 // B prep: out_{hi,lo}[(slice*Npad + n)*Kd + k] = split(src[n*sn + k*sk + slice*ss]),  zero rows for n >= N
 __global__ void split_b_kernel(const float* __restrict__ src, long long sn, long long sk, long long ss, int N, int Npad,
                                int Kd, int slices, float* __restrict__ hi, float* __restrict__ lo) {
@@ -343,6 +572,28 @@ static int make_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t 
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return AGCN_ERR_CUDA;
+  }
+  return AGCN_OK;
+}
+
+// 3-D fp32 [slices, rows, cols] (cols contiguous, row pitch ld, slice pitch slice_elems); box = 32 x 32 x 1
+static int make_map3(CUtensorMap* map, const float* ptr, uint64_t slices, uint64_t rows, uint64_t cols, uint64_t ld,
+                     uint64_t slice_elems) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return AGCN_ERR_CUDA;
+  }
+  cuuint64_t gdim[3] = {cols, rows, slices};
+  cuuint64_t gstride[2] = {ld * sizeof(float), slice_elems * sizeof(float)};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (3d) failed with code " + std::to_string((int)r));
     return AGCN_ERR_CUDA;
   }
   return AGCN_OK;
@@ -412,6 +663,83 @@ int tc_gemm(const GemmArgs& a, float* scratch, cudaStream_t st) {
     });
     tc_gemm_kernel<128><<<grid, 192, Smem<128>::TOTAL, st>>>(mA0, mA1, mBhi, mBlo, p);
   }
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+}  // namespace agcn
+
+namespace agcn {
+
+bool tc_gemm_tn_supported(const GemmTNArgs& a) {
+  if (getenv("AGCN_DISABLE_TCGEN05") || getenv("AGCN_DISABLE_TCGEN05_TN")) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (a.M < 32 || a.Kd > 128 || a.Kd % 4 != 0 || a.N % 4 != 0) return false;
+  if (a.lda0 % 4 != 0 || a.ldd % 4 != 0 || !al16(a.A0) || !al16(a.D)) return false;
+  if (a.S > 1 && (a.lda1 % 4 != 0 || !al16(a.A1) || a.sliceA1 % 4 != 0)) return false;
+  return true;
+}
+
+static void tn_chunks(const GemmTNArgs& a, int* chunks, int* kb_per_chunk) {
+  const int total_kb = (a.M + tc::BK - 1) / tc::BK;
+  const int nblk = (a.N + 127) / 128;
+  int want = std::max(1, 148 / std::max(1, a.S * nblk));
+  int per = std::max(4, (total_kb + want - 1) / want);
+  *kb_per_chunk = per;
+  *chunks = (total_kb + per - 1) / per;
+}
+
+size_t tc_gemm_tn_partial_floats(const GemmTNArgs& a) {
+  int chunks, per;
+  tn_chunks(a, &chunks, &per);
+  return (size_t)chunks * a.Kd * a.S * a.N;
+}
+
+__global__ void reduce_chunks_kernel(const float* __restrict__ partial, float* __restrict__ out, long long elems,
+                                     int chunks) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= elems) return;
+  float s = 0.f;
+  for (int k = 0; k < chunks; ++k) s += partial[(long long)k * elems + e];
+  out[e] = s;
+}
+
+int tc_gemm_tn(const GemmTNArgs& a, cudaStream_t st) {
+  using namespace tc;
+  int chunks, per;
+  tn_chunks(a, &chunks, &per);
+  CUtensorMap mA0, mA1, mD;
+  int rc;
+  if ((rc = make_map3(&mA0, a.A0, 1, (uint64_t)a.M, (uint64_t)a.Kd, (uint64_t)a.lda0, (uint64_t)a.M * a.lda0))) return rc;
+  if (a.S > 1) {
+    if ((rc = make_map3(&mA1, a.A1, (uint64_t)(a.S - 1), (uint64_t)a.M, (uint64_t)a.Kd, (uint64_t)a.lda1,
+                        (uint64_t)a.sliceA1)))
+      return rc;
+  } else {
+    mA1 = mA0;
+  }
+  if ((rc = make_map3(&mD, a.D, 1, (uint64_t)a.M, (uint64_t)a.N, (uint64_t)a.ldd, (uint64_t)a.M * a.ldd))) return rc;
+  TnArgs p;
+  p.M = a.M; p.Kd = a.Kd; p.N = a.N; p.S = a.S;
+  p.kb_per_chunk = per;
+  p.partial = a.partial;
+  const int BN = a.N <= 64 ? 64 : 128;
+  dim3 grid(chunks, a.S, (a.N + BN - 1) / BN);
+  static std::once_flag once64, once128;
+  if (BN == 64) {
+    std::call_once(once64, [] {
+      cudaFuncSetAttribute(tc_gemm_tn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemTn<64>::TOTAL);
+    });
+    tc_gemm_tn_kernel<64><<<grid, 192, SmemTn<64>::TOTAL, st>>>(mA0, mA1, mD, p);
+  } else {
+    std::call_once(once128, [] {
+      cudaFuncSetAttribute(tc_gemm_tn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemTn<128>::TOTAL);
+    });
+    tc_gemm_tn_kernel<128><<<grid, 192, SmemTn<128>::TOTAL, st>>>(mA0, mA1, mD, p);
+  }
+  AGCN_LAUNCH_CHECK();
+  const long long elems = (long long)a.Kd * a.S * a.N;
+  reduce_chunks_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(a.partial, a.out, elems, chunks);
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }

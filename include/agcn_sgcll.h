@@ -135,6 +135,14 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
                         float* d_dalpha, float* d_dbeta, float* d_dLprev, void* d_work, size_t work_bytes,
                         void* stream);
 
+/* Building block of the backward pass, exported for unit tests and tuning (no reference counterpart: it is
+ * the dW = T^T dY contraction that tf.gradients derives from graphconv.py:245-247):
+ *   out[(f*S + s)*N + c] = sum_r A_s[r, f] * D[r, c],  A_0 = d_A0 [M,Kd], A_s = d_A1 + (s-1)*M*Kd, D [M,N].
+ * use_tensor_cores: 1 = tcgen05 3xTF32 kernel (needs Kd <= 128, Kd % 4 == 0, N % 4 == 0), 0 = CUDA cores. */
+size_t agcn_gemm_tn_scratch_bytes(int32_t M, int32_t Kd, int32_t N, int32_t S);
+int agcn_gemm_tn(const float* d_A0, const float* d_A1, const float* d_D, float* d_out, int32_t M, int32_t Kd,
+                 int32_t N, int32_t S, void* d_scratch, int32_t use_tensor_cores, void* stream);
+
 /* Host-buffer convenience entry (the end-to-end path): padded HOST arrays in the reference's wire
  * layout in, padded HOST output out; host<->device copies are issued on `stream` inside the call.
  * d_scratch must hold agcn_sgcll_host_scratch_bytes() bytes of device memory. */
