@@ -68,7 +68,7 @@ Saved carve_saved(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
 }
 
 struct Work {
-  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tc;
+  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tc, *big;
   size_t bytes;
 };
 
@@ -97,6 +97,7 @@ Work carve_work(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
   size_t tcf = std::max(tc_gemm_scratch_floats(d->Fo, d->F, d->K, 1), tc_gemm_scratch_floats(d->F, d->Fo, 1, d->K));
   tcf = std::max(tcf, tc_gemm_scratch_floats(d->F, d->F, 1, 1));
   w.tc = c.take(tcf);  // hi / lo copies of the parameter operand of the tensor-core GEMMs
+  w.big = c.take(big_work_floats(p, m.full));  // sweeps of the graphs with n > AGCN_SMALL_MAX
   w.bytes = c.off;
   return w;
 }
@@ -111,11 +112,6 @@ int check_desc(const agcn_sgcll_desc* d, const agcn_plan* p) {
                "unknown metric_grad");
   AGCN_REQUIRE(d->activation == AGCN_ACT_LINEAR || d->activation == AGCN_ACT_RELU, "unknown activation");
   AGCN_REQUIRE(p->R < (1ll << 31) / std::max(d->F, d->Fo), "batch too large for 32-bit row indexing");
-  if (p->large_count > 0 && !literal_shortcut(d->variant, d->laplacian_mode)) {
-    set_error("graphs with more than 144 nodes are supported for SGC_LL / reference_literal only in this build "
-              "(the row-tiled Laplacian construction for paper / Reslap modes is not built yet)");
-    return AGCN_ERR_INVALID;
-  }
   return AGCN_OK;
 }
 
@@ -158,10 +154,6 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
   const bool need_W = m.paper || want_resW;
   const bool need_build = !m.shortcut || want_resL || want_resW || want_Lall;
   float* XW = m.full ? sv.XW : wk.XW;
-  if (plan->large_count > 0 && need_build) {
-    set_error("res_L / res_W / L_all outputs are not built for graphs with more than 144 nodes yet");
-    return AGCN_ERR_INVALID;
-  }
 
   if (need_W) {  // x_w = np.dot(x, M)   graphconv.py:164
     GemmArgs g;
@@ -183,6 +175,7 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
     ga.resL = want_resL ? d_resL : nullptr;
     ga.resW = want_resW ? d_resW : nullptr;
     ga.dist = sv.dist; ga.dis = sv.dis; ga.stats = sv.stats;
+    ga.big_work = wk.big;
     if ((rc = graph_build_laplacian(ga, need_W, st))) return rc;
   }
   ga.Lall = m.shortcut ? nullptr : sv.Lall;
@@ -249,6 +242,7 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   ga.G = wk.G; ga.dLall_in = d_dLall_in; ga.dX = dXbuf; ga.dL = wk.dL;
   ga.dLprev = has_prev ? d_dLprev : nullptr;
   ga.dXW = wk.dXW; ga.dalpha_part = wk.dalpha_part; ga.dbeta_part = m.reslap ? wk.dbeta_part : nullptr;
+  ga.big_work = wk.big;
   // dweight[f*K + k, :] = T_k^T dYpre: depends on dYpre only -> side stream, overlapping the dX chain
   AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
   AGCN_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_side_fork, 0));

@@ -23,6 +23,8 @@ struct GroupedArgs {
   float* Out2;
   float cmul;
   int F;
+  const float* RowScale;  // optional: Out += RowScale[row] * ScaleIn[row, c]
+  const float* ScaleIn;
 };
 
 constexpr int GM = 64, GN = 64, GK = 16;
@@ -110,6 +112,7 @@ __global__ void __launch_bounds__(256) grouped_lap_gemm_kernel(GroupedArgs p) {
       float v = p.cmul * acc[q][t];
       if (p.Add) v += p.Add[o];
       if (p.Sub) v -= p.Sub[o];
+      if (p.RowScale) v += p.RowScale[row0 + i] * p.ScaleIn[o];
       p.Out[o] = v;
       if (p.Out2) p.Out2[o] = v;
     }
@@ -150,13 +153,15 @@ int large_chebyshev_fwd(const GraphArgs& a, cudaStream_t st) {
   return AGCN_OK;
 }
 
-// U_j overwrites G_j in place (slice j of a.G); dX receives U_0.
-int large_recurrence_bwd(const GraphArgs& a, float* G, cudaStream_t st) {
+// U_j overwrites G_j in place (slice j of a.G); dX receives U_0.  big_only: only the graphs with
+// n > AGCN_SMALL_MAX (the others accumulate dL in shared memory inside recur_bwd_kernel).
+int large_recurrence_bwd(const GraphArgs& a, float* G, bool big_only, cudaStream_t st) {
   const agcn_plan* plan = a.plan;
-  if (plan->large_tiles == 0 || a.K <= 1) return AGCN_OK;
+  const int tiles = big_only ? plan->big_tiles : plan->large_tiles;
+  if (tiles == 0 || a.K <= 1) return AGCN_OK;
   const bool shortcut = (a.Lall == nullptr);
   const int64_t slice = (int64_t)plan->R * a.F;
-  dim3 grid(plan->large_tiles, (a.F + GN - 1) / GN);
+  dim3 grid(tiles, (a.F + GN - 1) / GN);
   for (int j = a.K - 2; j >= 0; --j) {
     GroupedArgs g = base_args(plan);
     g.L = shortcut ? a.Lint : a.Lall;
@@ -172,6 +177,21 @@ int large_recurrence_bwd(const GraphArgs& a, float* G, cudaStream_t st) {
     grouped_lap_gemm_kernel<<<grid, 256, 0, st>>>(g);
     AGCN_LAUNCH_CHECK();
   }
+  return AGCN_OK;
+}
+
+// Out[rows of the first `tiles` tiles] = cmul * M_g In + row_scale[row] * scale_in[row, :]
+int grouped_rows_gemm(const agcn_plan* plan, int tiles, const float* Lmat, const float* In, float cmul,
+                      const float* row_scale, const float* scale_in, float* Out, int F, cudaStream_t st) {
+  if (tiles == 0) return AGCN_OK;
+  GroupedArgs g = base_args(plan);
+  g.L = Lmat; g.add_identity = 0; g.transL = 0;
+  g.In = In; g.Sub = nullptr; g.Add = nullptr;
+  g.Out = Out; g.Out2 = nullptr; g.cmul = cmul; g.F = F;
+  g.RowScale = row_scale; g.ScaleIn = scale_in;
+  dim3 grid(tiles, (F + GN - 1) / GN);
+  grouped_lap_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }
 

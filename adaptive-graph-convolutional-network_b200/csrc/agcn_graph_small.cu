@@ -815,7 +815,10 @@ int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st) {
     recur_bwd_kernel<<<bk.count * c.chunks, c.threads, c.smem, s>>>(k);
     AGCN_LAUNCH_CHECK();
   }
-  if (!need_dL && (rc = large_recurrence_bwd(a, const_cast<float*>(a.G), st))) return rc;
+  // row-tiled reverse recurrence: every graph above AGCN_CHEB_SMALL_MAX, or, when dL is needed, only those
+  // above AGCN_SMALL_MAX (the mid-size ones accumulated dL in shared memory above)
+  if ((rc = large_recurrence_bwd(a, const_cast<float*>(a.G), need_dL, st))) return rc;
+  if (need_dL && (rc = big_dL(a, a.G, st))) return rc;
   return join_streams(plan, st, nb - 1);
 }
 
@@ -840,6 +843,7 @@ int graph_build_laplacian(const GraphArgs& a, bool need_W, cudaStream_t st) {
     build_lap_kernel<<<bk.count, threads, smem, s>>>(k);
     AGCN_LAUNCH_CHECK();
   }
+  if ((rc = big_build_laplacian(a, need_W, a.big_work, st))) return rc;
   return join_streams(plan, st, nb - 1);
 }
 
@@ -865,6 +869,7 @@ int graph_laplacian_bwd(const GraphArgs& a, cudaStream_t st) {
     lap_bwd_kernel<<<bk.count, threads, smem, s>>>(k);
     AGCN_LAUNCH_CHECK();
   }
+  if ((rc = big_laplacian_bwd(a, a.big_work, st))) return rc;
   return join_streams(plan, st, nb - 1);
 }
 

@@ -64,6 +64,10 @@ struct agcn_plan {
   // graph tile_graph[t]
   std::vector<int32_t> tile_graph, tile_row;
   int large_tiles = 0;
+  // graphs with n > AGCN_SMALL_MAX ("big": their n x n matrices never fit in shared memory) own the first
+  // big_tiles entries of the tile list; big_tile_start[i] .. big_tile_start[i+1] are the tiles of order[i]
+  int big_tiles = 0;
+  std::vector<int32_t> big_tile_start;
   // device copies (one allocation)
   void* d_block = nullptr;
   int32_t* d_n = nullptr;
@@ -72,6 +76,7 @@ struct agcn_plan {
   int64_t* d_lap_off = nullptr;
   int32_t* d_tile_graph = nullptr;
   int32_t* d_tile_row = nullptr;
+  int32_t* d_big_tile_start = nullptr;
   // side streams so the per-bucket launches of one phase overlap on the device
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
@@ -170,6 +175,7 @@ struct GraphArgs {
   float* dXW = nullptr;          // [R,F] out (metric_full)
   float* dalpha_part = nullptr;  // [B]
   float* dbeta_part = nullptr;   // [B]
+  float* big_work = nullptr;     // scratch of the big-graph sweeps (big_work_floats() floats)
 };
 bool literal_shortcut(int variant, int lap_mode);  // L_all == I + Lint, nothing to build
 int graph_build_laplacian(const GraphArgs& a, bool need_W, cudaStream_t st);
@@ -179,7 +185,12 @@ int graph_laplacian_bwd(const GraphArgs& a, cudaStream_t st);
 int reduce_scalar_parts(const float* parts, int B, float* out, cudaStream_t st);
 // graphs with more than AGCN_SMALL_MAX nodes (agcn_graph_large.cu)
 int large_chebyshev_fwd(const GraphArgs& a, cudaStream_t st);
-int large_recurrence_bwd(const GraphArgs& a, float* G, cudaStream_t st);
+int large_recurrence_bwd(const GraphArgs& a, float* G, bool big_only, cudaStream_t st);
+// Laplacian construction / gradient for graphs with more than AGCN_SMALL_MAX nodes (agcn_graph_big.cu)
+size_t big_work_floats(const agcn_plan* plan, bool full);
+int big_build_laplacian(const GraphArgs& a, bool need_W, float* big_work, cudaStream_t st);
+int big_dL(const GraphArgs& a, const float* U, cudaStream_t st);
+int big_laplacian_bwd(const GraphArgs& a, float* big_work, cudaStream_t st);
 
 // ---------------------------------------------------------------- helpers
 int fork_streams(const agcn_plan* plan, cudaStream_t main, int n_aux);

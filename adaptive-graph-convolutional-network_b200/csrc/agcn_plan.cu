@@ -126,12 +126,18 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   p->large_count = pos;
   for (int i = 0; i < B && p->n[p->order[i]] > AGCN_CHEB_SMALL_MAX; ++i) {
     const int g = p->order[i];
+    if (i <= p->large_count) p->big_tile_start.push_back((int32_t)p->tile_graph.size());
+    if (i == p->large_count) p->big_tiles = (int)p->tile_graph.size();
     for (int r = 0; r < p->n[g]; r += 64) {
       p->tile_graph.push_back(g);
       p->tile_row.push_back(r);
     }
   }
   p->large_tiles = (int)p->tile_graph.size();
+  if ((int)p->big_tile_start.size() <= p->large_count) {  // every tiled graph is a big one
+    p->big_tile_start.push_back(p->large_tiles);
+    p->big_tiles = p->large_tiles;
+  }
   static const int limits[] = {AGCN_SMALL_MAX, 64, 32, 16};  // bucket = (limit_next, limit]
   for (int b = 0; b < 4 && pos < B; ++b) {
     const int lo = (b + 1 < 4) ? limits[b + 1] : 0;
@@ -141,7 +147,8 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   }
   // device block: n[B] node_off[B+1] order[B] tile_graph[T] tile_row[T] (int32) then lap_off[B+1] (int64)
   const size_t T = (size_t)p->large_tiles;
-  const size_t n32 = (size_t)B + (B + 1) + B + 2 * T;
+  const size_t NB = p->big_tile_start.size();
+  const size_t n32 = (size_t)B + (B + 1) + B + 2 * T + NB;
   const size_t off64 = (n32 * 4 + 15) / 16 * 16;
   const size_t bytes = off64 + (size_t)(B + 1) * 8;
   std::vector<char> host(bytes, 0);
@@ -153,6 +160,7 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
     std::memcpy(h32 + 3 * B + 1, p->tile_graph.data(), T * 4);
     std::memcpy(h32 + 3 * B + 1 + T, p->tile_row.data(), T * 4);
   }
+  std::memcpy(h32 + 3 * B + 1 + 2 * T, p->big_tile_start.data(), NB * 4);
   std::memcpy(host.data() + off64, p->lap_off.data(), (size_t)(B + 1) * 8);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMalloc(&p->d_block, bytes);
@@ -177,6 +185,7 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   p->d_order = d32 + 2 * B + 1;
   p->d_tile_graph = d32 + 3 * B + 1;
   p->d_tile_row = d32 + 3 * B + 1 + T;
+  p->d_big_tile_start = d32 + 3 * B + 1 + 2 * T;
   p->d_lap_off = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(p->d_block) + off64);
   *out = p;
   return AGCN_OK;

@@ -240,3 +240,44 @@ def test_large_graphs_row_tiled_path(sizes, F, Fo, K):
     cu = cuda_run(X, L, n, p, K, "SGC_LL", "reference_literal", "reference", cot_Y=cY, want_res=False)
     errs = compare(cu, orc, skip=("res_L", "res_W", "L_all"))
     print(sizes, errs)
+
+
+@pytest.mark.parametrize("variant,laplacian,metric_grad,with_prev", [
+    ("SGC_LL", "paper", "reference", False),
+    ("SGC_LL", "paper", "full", False),
+    ("SGC_LL", "reference_literal", "reference", False),      # shortcut + optional outputs
+    ("SGC_LL_Reslap", "reference_literal", "reference", True),
+    ("SGC_LL_Reslap", "paper", "reference", False),
+    ("SGC_LL_Reslap", "paper", "full", True)])
+def test_big_graphs_all_modes(variant, laplacian, metric_grad, with_prev):
+    """Graphs with more than 144 nodes (row-tiled sweeps, agcn_graph_big.cu) mixed with small ones, in every
+    variant / semantics, including the optional res_L / res_W / L_all outputs and all gradients."""
+    F, Fo, K = 16, 24, 3
+    sizes = [150, 333, 20, 513, 64, 145, 4]
+    Nmax = max(sizes)
+    X, _, n = make_batch(sizes, F, Nmax, seed=41)
+    X *= 0.6
+    L = _dense_laplacians(sizes, Nmax, seed=5)
+    p = O.make_params(F, Fo, K, variant, seed=17, dtype=torch.float64)
+    Lprev = random_prev_laps(n, 6) if with_prev else None
+    cY = _cot((len(sizes), Nmax, Fo), 3)
+    cL = [_cot((int(k), int(k)), 50 + i) * 0.1 for i, k in enumerate(n)] if variant == "SGC_LL_Reslap" else None
+    orc = oracle_run(X, L, n, p, K, variant, laplacian, metric_grad, Lprev, cot_Y=cY, cot_L=cL)
+    cu = cuda_run(X, L, n, p, K, variant, laplacian, metric_grad, Lprev, cot_Y=cY, cot_L=cL)
+    errs = compare(cu, orc)
+    if metric_grad == "full":
+        assert float(orc["dM_L"].abs().max()) > 0
+    print(variant, laplacian, metric_grad, errs)
+
+
+def test_big_graph_point_cloud_shape_paper_full():
+    """ModelNet40-like first layer (xyz features, F = 3, n = 1024) with the differentiable metric, K = 2."""
+    sizes = [1024, 700]
+    F, Fo, K = 3, 32, 2
+    X, _, n = make_batch(sizes, F, 1024, seed=2)
+    L = _dense_laplacians(sizes, 1024, seed=9)
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=4, dtype=torch.float64)
+    cY = _cot((2, 1024, Fo), 1)
+    orc = oracle_run(X, L, n, p, K, "SGC_LL", "paper", "full", cot_Y=cY)
+    cu = cuda_run(X, L, n, p, K, "SGC_LL", "paper", "full", cot_Y=cY)
+    print(compare(cu, orc))
