@@ -17,9 +17,39 @@ int node_gemm_tn(const GemmTNArgs& t, cudaStream_t st) {
   return gemm_tn(t, st);
 }
 
-int node_gemm(const GemmArgs& g, float* tc_scratch, cudaStream_t st) {
-  if (tc_gemm_supported(g)) return tc_gemm(g, tc_scratch, st);
+// presplit: the hi / lo copies of B in tc_scratch were already produced by tc_gemm_split_b (side stream)
+int node_gemm(const GemmArgs& g, float* tc_scratch, cudaStream_t st, bool presplit = false) {
+  if (tc_gemm_supported(g)) {
+    if (!presplit) {
+      int rc = tc_gemm_split_b(g, tc_scratch, st);
+      if (rc) return rc;
+    }
+    return tc_gemm(g, tc_scratch, st);
+  }
   return gemm_rows(g, st);
+}
+
+// Y = act(sum_k T_k W_k + b)   graphconv.py:238-247, :118-123
+GemmArgs y_gemm_args(const agcn_sgcll_desc* d, int R, const float* X, const float* T, const float* weight,
+                     const float* bias, float* Y) {
+  GemmArgs g;
+  g.M = R; g.N = d->Fo; g.Kd = d->F; g.S = d->K;
+  g.A0 = X; g.lda0 = d->F;
+  g.A1 = T; g.lda1 = d->F; g.sliceA1 = (int64_t)R * d->F;
+  g.B = weight; g.ldb = d->K * d->Fo; g.sliceB = d->Fo;
+  g.C = Y; g.ldc = d->Fo;
+  g.bias = bias; g.act = d->activation;
+  return g;
+}
+
+// G_k = dYpre W_k^T   (K == 1: this is dX)
+GemmArgs g_gemm_args(const agcn_sgcll_desc* d, int R, const float* dYp, const float* weight, float* C) {
+  GemmArgs g;
+  g.M = R; g.N = d->F; g.Kd = d->Fo; g.Z = d->K;
+  g.A0 = dYp; g.lda0 = d->Fo;
+  g.B = weight; g.ldb = d->K * d->Fo; g.sliceB = d->Fo; g.transB = 1;
+  g.C = C; g.ldc = d->F; g.sliceC = (int64_t)R * d->F;
+  return g;
 }
 
 struct Carver {
@@ -49,7 +79,7 @@ Modes modes_of(const agcn_sgcll_desc* d) {
 
 // saved area layout (forward -> backward)
 struct Saved {
-  float *T, *Lall, *dist, *dis, *stats, *XW;
+  float *T, *Lall, *dist, *dis, *stats, *XW, *tcG;
   size_t bytes;
 };
 
@@ -63,12 +93,13 @@ Saved carve_saved(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
   s.dis = m.paper ? c.take((size_t)p->R) : nullptr;
   s.stats = m.shortcut ? nullptr : c.take((size_t)4 * p->B);
   s.XW = m.full ? c.take((size_t)p->R * d->F) : nullptr;
+  s.tcG = c.take(tc_gemm_scratch_floats(d->F, d->Fo, 1, d->K));  // hi / lo of W_k^T for the backward G GEMM
   s.bytes = c.off;
   return s;
 }
 
 struct Work {
-  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tc, *big;
+  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tcY, *tcM, *big;
   size_t bytes;
 };
 
@@ -94,9 +125,9 @@ Work carve_work(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
   w.dXW = m.full ? c.take((size_t)p->R * d->F) : nullptr;
   w.dalpha_part = c.take((size_t)p->B);
   w.dbeta_part = c.take((size_t)p->B);
-  size_t tcf = std::max(tc_gemm_scratch_floats(d->Fo, d->F, d->K, 1), tc_gemm_scratch_floats(d->F, d->Fo, 1, d->K));
-  tcf = std::max(tcf, tc_gemm_scratch_floats(d->F, d->F, 1, 1));
-  w.tc = c.take(tcf);  // hi / lo copies of the parameter operand of the tensor-core GEMMs
+  // hi / lo copies of the parameter operands of the tensor-core GEMMs
+  w.tcY = c.take(tc_gemm_scratch_floats(d->Fo, d->F, d->K, 1));
+  w.tcM = c.take(tc_gemm_scratch_floats(d->F, d->F, 1, 1));
   w.big = c.take(big_work_floats(p, m.full));  // sweeps of the graphs with n > AGCN_SMALL_MAX
   w.bytes = c.off;
   return w;
@@ -155,13 +186,26 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
   const bool need_build = !m.shortcut || want_resL || want_resW || want_Lall;
   float* XW = m.full ? sv.XW : wk.XW;
 
+  // the parameter operands of the two big node-level GEMMs (this forward's Y and the backward's G) are
+  // rearranged / split on the side stream while the per-graph kernels run
+  GemmArgs gy = y_gemm_args(desc, R, d_X, sv.T, d_weight, d_bias, d_Y);
+  const bool y_tc = tc_gemm_supported(gy);
+  GemmArgs gg = g_gemm_args(desc, R, d_Y /* placeholder with the alignment of dYpre */, d_weight, wk.G);
+  const bool g_tc = (desc->flags & AGCN_SAVE_FOR_BACKWARD) && tc_gemm_supported(gg);
+  if (y_tc || g_tc) {
+    AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
+    AGCN_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_side_fork, 0));
+    if (y_tc && (rc = tc_gemm_split_b(gy, wk.tcY, plan->side))) return rc;
+    if (g_tc && (rc = tc_gemm_split_b(gg, sv.tcG, plan->side))) return rc;
+    AGCN_CUDA(cudaEventRecord(plan->ev_side_join, plan->side));
+  }
   if (need_W) {  // x_w = np.dot(x, M)   graphconv.py:164
     GemmArgs g;
     g.M = R; g.N = F; g.Kd = F;
     g.A0 = d_X; g.lda0 = F;
     g.B = d_M_L; g.ldb = F;
     g.C = XW; g.ldc = F;
-    if ((rc = node_gemm(g, wk.tc, st))) return rc;
+    if ((rc = node_gemm(g, wk.tcM, st))) return rc;
   }
   GraphArgs ga;
   ga.plan = plan; ga.F = F; ga.K = K;
@@ -180,16 +224,9 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
   }
   ga.Lall = m.shortcut ? nullptr : sv.Lall;
   if ((rc = graph_chebyshev_fwd(ga, st))) return rc;  // graphconv.py:221-236
-  {  // x = reshape(transpose(stack T)) . weight + bias, activation   graphconv.py:238-247, :118-123
-    GemmArgs g;
-    g.M = R; g.N = Fo; g.Kd = F; g.S = K;
-    g.A0 = d_X; g.lda0 = F;
-    g.A1 = sv.T; g.lda1 = F; g.sliceA1 = (int64_t)R * F;
-    g.B = d_weight; g.ldb = K * Fo; g.sliceB = Fo;
-    g.C = d_Y; g.ldc = Fo;
-    g.bias = d_bias; g.act = desc->activation;
-    if ((rc = node_gemm(g, wk.tc, st))) return rc;
-  }
+  if (y_tc || g_tc) AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
+  // x = reshape(transpose(stack T)) . weight + bias, activation   graphconv.py:238-247, :118-123
+  if ((rc = node_gemm(gy, wk.tcY, st, /*presplit=*/true))) return rc;
   return AGCN_OK;
 }
 
@@ -217,20 +254,22 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   const int R = (int)plan->R;
   const bool has_prev = m.reslap && d_Lprev;
 
-  // dYpre = dY * act'(Y);  dbias = colsum(dYpre)
+  // dYpre = dY * act'(Y) and per-CTA column sums; dbias = colsum(dYpre) is folded on the side stream
   const float* dYp = (desc->activation == AGCN_ACT_RELU) ? wk.dYp : d_dY;
-  if ((rc = act_bwd_colsum(d_dY, d_Y, wk.dYp, d_dbias, wk.act_part, R, Fo, desc->activation, st))) return rc;
+  if ((rc = act_bwd_partials(d_dY, d_Y, wk.dYp, wk.act_part, R, Fo, desc->activation, st))) return rc;
+  // the parameter gradients depend on dYpre only -> side stream, overlapping the dX chain
+  AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
+  AGCN_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_side_fork, 0));
+  if ((rc = act_bwd_reduce(wk.act_part, d_dbias, R, Fo, plan->side))) return rc;
   // d_dX == NULL: the caller does not need the gradient w.r.t. the node features (first layer)
   const bool need_G = d_dX != nullptr || (m.need_dL && K >= 2);
   float* dXbuf = d_dX ? d_dX : wk.G;  // scratch target when dX itself is not wanted (K >= 2 only)
   AGCN_REQUIRE(d_dX || !m.full, "backward: d_dX is required with metric_grad = full");
-  if (need_G) {  // G_k = dYpre W_k^T   (K == 1: this is dX)
-    GemmArgs g;
-    g.M = R; g.N = F; g.Kd = Fo; g.Z = K;
-    g.A0 = dYp; g.lda0 = Fo;
-    g.B = d_weight; g.ldb = K * Fo; g.sliceB = Fo; g.transB = 1;
-    g.C = (K == 1) ? d_dX : wk.G; g.ldc = F; g.sliceC = (int64_t)R * F;
-    if ((rc = node_gemm(g, wk.tc, st))) return rc;
+  if (need_G) {  // G_k = dYpre W_k^T   (K == 1: this is dX); W_k^T was split by the forward pass
+    GemmArgs g = g_gemm_args(desc, R, dYp, d_weight, (K == 1) ? d_dX : wk.G);
+    GemmArgs probe = g_gemm_args(desc, R, d_Y, d_weight, wk.G);
+    const bool presplit = (desc->flags & AGCN_SAVE_FOR_BACKWARD) && tc_gemm_supported(probe);
+    if ((rc = node_gemm(g, sv.tcG, st, presplit))) return rc;
   }
   GraphArgs ga;
   ga.plan = plan; ga.F = F; ga.K = K;
@@ -243,9 +282,7 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   ga.dLprev = has_prev ? d_dLprev : nullptr;
   ga.dXW = wk.dXW; ga.dalpha_part = wk.dalpha_part; ga.dbeta_part = m.reslap ? wk.dbeta_part : nullptr;
   ga.big_work = wk.big;
-  // dweight[f*K + k, :] = T_k^T dYpre: depends on dYpre only -> side stream, overlapping the dX chain
-  AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
-  AGCN_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_side_fork, 0));
+  // dweight[f*K + k, :] = T_k^T dYpre
   {
     GemmTNArgs t;
     t.M = R; t.Kd = F; t.N = Fo; t.S = K;
@@ -286,7 +323,7 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
     g.A0 = wk.dXW; g.lda0 = F;
     g.B = d_M_L; g.ldb = F; g.transB = 1;
     g.C = d_dX; g.ldc = F; g.accumulate = 1;
-    if ((rc = node_gemm(g, wk.tc, st))) return rc;
+    if ((rc = node_gemm(g, wk.tcM, st))) return rc;
   } else {
     // tf.py_func has no gradient: M_L receives none (graphconv.py:211)
     AGCN_CUDA(cudaMemsetAsync(d_dM_L, 0, (size_t)F * F * sizeof(float), st));

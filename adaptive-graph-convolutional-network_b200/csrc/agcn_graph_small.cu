@@ -783,7 +783,7 @@ int graph_chebyshev_fwd(const GraphArgs& a, cudaStream_t st) {
   if (rc) return rc;
   for (int b = 0; b < nb; ++b) {
     const Bucket& bk = plan->buckets[b];
-    if (bk.max_n > AGCN_CHEB_SMALL_MAX) continue;  // row-tiled below
+    if (bk.max_n > plan->cheb_small_max) continue;  // row-tiled below
     ChunkCfg c = chunk_cfg(bk.max_n, a.F, 2, 1, false);
     rc = set_smem(cheb_fwd_kernel, c.smem);
     if (rc) return rc;
@@ -805,7 +805,7 @@ int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st) {
   if (rc) return rc;
   for (int b = 0; b < nb; ++b) {
     const Bucket& bk = plan->buckets[b];
-    if (!need_dL && bk.max_n > AGCN_CHEB_SMALL_MAX) continue;  // row-tiled below
+    if (!need_dL && bk.max_n > plan->cheb_small_max) continue;  // row-tiled below
     ChunkCfg c = chunk_cfg(bk.max_n, a.F, need_dL ? 3 : 2, need_dL ? 2 : 1, need_dL);
     rc = set_smem(recur_bwd_kernel, c.smem);
     if (rc) return rc;

@@ -15,7 +15,7 @@
 #define AGCN_SMALL_MAX 144
 // Graphs above this size run their Chebyshev recurrences as row-tiled grouped GEMMs (one launch per step,
 // several CTAs per graph) instead of one CTA per (graph, feature chunk).
-#define AGCN_CHEB_SMALL_MAX 64
+#define AGCN_CHEB_SMALL_MAX 144
 
 namespace agcn {
 
@@ -54,6 +54,7 @@ extern std::atomic<uint64_t> g_launches;
 
 struct agcn_plan {
   int32_t B = 0, Nmax = 0, max_n = 0;
+  int32_t cheb_small_max = AGCN_CHEB_SMALL_MAX;  // overridable with the environment variable of the same name
   int64_t R = 0;   // total nodes
   int64_t LL = 0;  // total n^2
   std::vector<int32_t> n, node_off, order;
@@ -110,12 +111,20 @@ struct GemmArgs {
   const float* bias = nullptr;
   int act = AGCN_ACT_LINEAR;
   int accumulate = 0;  // C += result
+  // tensor-core kernel only: fused weighted sigmoid cross-entropy epilogue (C = d loss / d logits, see agcn_head.cu);
+  // bce_y / bce_w are laid out like C, loss_part holds tc_gemm_loss_parts() floats
+  const float* bce_y = nullptr;
+  const float* bce_w = nullptr;
+  float bce_scale = 1.f;
+  float* loss_part = nullptr;
 };
+int tc_gemm_loss_parts(const GemmArgs& a);  // number of partial loss sums tc_gemm writes
 int gemm_rows(const GemmArgs& a, cudaStream_t st);
 // tcgen05 (3xTF32) implementation of the same contraction for TMA-compatible shapes (agcn_tc_gemm.cu)
 bool tc_gemm_supported(const GemmArgs& a);
 size_t tc_gemm_scratch_floats(int N, int Kd, int S, int Z);
-int tc_gemm(const GemmArgs& a, float* scratch, cudaStream_t st);
+int tc_gemm_split_b(const GemmArgs& a, float* scratch, cudaStream_t st);
+int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st);
 
 // out[(f*S + s)*N + c] = sum_r A_s[r, f] * D[r, c]     (A_s as in GemmArgs; contraction over the M rows)
 struct GemmTNArgs {
@@ -142,8 +151,9 @@ int tc_gemm_tn(const GemmTNArgs& a, cudaStream_t st);
 
 // dYp = dY * act'(Y) (relu mask), colsum(dYp) -> dbias.  partial: act_bwd_partial_floats() floats.
 size_t act_bwd_partial_floats(int64_t R, int Fo);
-int act_bwd_colsum(const float* dY, const float* Y, float* dYp, float* dbias, float* partial, int64_t R, int Fo, int act,
-                   cudaStream_t st);
+int act_bwd_partials(const float* dY, const float* Y, float* dYp, float* partial, int64_t R, int Fo, int act,
+                     cudaStream_t st);
+int act_bwd_reduce(const float* partial, float* dbias, int64_t R, int Fo, cudaStream_t st);
 
 // ---------------------------------------------------------------- per-graph kernels (agcn_graph_small.cu)
 struct GraphArgs {

@@ -297,15 +297,23 @@ __global__ void __launch_bounds__(256) colsum_reduce_kernel(const float* __restr
 
 size_t act_bwd_partial_floats(int64_t R, int Fo) { return (size_t)((R + ACT_ROWS - 1) / ACT_ROWS) * Fo; }
 
-int act_bwd_colsum(const float* dY, const float* Y, float* dYp, float* dbias, float* partial, int64_t R, int Fo, int act,
-                   cudaStream_t st) {
+// stage 1 (stream st): dYp and the per-CTA column sums; stage 2 (stream st2, ordered after stage 1 by the
+// caller): dbias.  Split so that the reduction can leave the critical path of the backward pass.
+int act_bwd_partials(const float* dY, const float* Y, float* dYp, float* partial, int64_t R, int Fo, int act,
+                     cudaStream_t st) {
+  if (R <= 0) return AGCN_OK;
+  const int blocks = (int)((R + ACT_ROWS - 1) / ACT_ROWS);
+  act_bwd_colsum_kernel<<<blocks, 256, 0, st>>>(dY, Y, dYp, partial, R, Fo, act);
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+int act_bwd_reduce(const float* partial, float* dbias, int64_t R, int Fo, cudaStream_t st) {
   if (R <= 0) {
     AGCN_CUDA(cudaMemsetAsync(dbias, 0, Fo * sizeof(float), st));
     return AGCN_OK;
   }
   const int blocks = (int)((R + ACT_ROWS - 1) / ACT_ROWS);
-  act_bwd_colsum_kernel<<<blocks, 256, 0, st>>>(dY, Y, dYp, partial, R, Fo, act);
-  AGCN_LAUNCH_CHECK();
   colsum_reduce_kernel<<<(Fo + 31) / 32, 256, 0, st>>>(partial, dbias, blocks, Fo);
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;

@@ -1,6 +1,7 @@
 // Batch topology ("plan") and layout conversion between the reference's zero-padded wire layout
 // (models/tf_modules/graph_topology.py:84-135) and the packed HBM layout of this library.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 
@@ -124,7 +125,8 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   int pos = 0;
   while (pos < B && p->n[p->order[pos]] > AGCN_SMALL_MAX) ++pos;
   p->large_count = pos;
-  for (int i = 0; i < B && p->n[p->order[i]] > AGCN_CHEB_SMALL_MAX; ++i) {
+  if (const char* e = getenv("AGCN_CHEB_SMALL_MAX")) p->cheb_small_max = std::min(AGCN_SMALL_MAX, std::max(16, atoi(e)));
+  for (int i = 0; i < B && p->n[p->order[i]] > p->cheb_small_max; ++i) {
     const int g = p->order[i];
     if (i <= p->large_count) p->big_tile_start.push_back((int32_t)p->tile_graph.size());
     if (i == p->large_count) p->big_tiles = (int)p->tile_graph.size();

@@ -98,6 +98,11 @@ struct Args {
   long long sliceC;
   const float* bias;
   int act, accumulate;
+  // fused weighted sigmoid cross-entropy epilogue (multitask head): C receives d loss / d logits
+  const float* bce_y;
+  const float* bce_w;
+  float bce_scale;
+  float* loss_part;  // [CTAs][4]
 };
 
 template <int BN>
@@ -225,6 +230,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     float* stg = reinterpret_cast<float*>(base) + (warp - 2) * (32 * 36);
     float* __restrict__ Cz = p.C + (long long)z * p.sliceC;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
+    float loss_acc = 0.f;
+    // bias has been added; accumulate / activation / loss epilogue of one element
+    auto finish = [&](float x, float old, long long off) -> float {
+      if (p.accumulate) x += old;
+      if (p.bce_y) {
+        // weighted sigmoid cross-entropy with logits (multitask_classifier.py:41-44): loss and its gradient
+        const float y = p.bce_y[off], w = p.bce_w[off];
+        loss_acc += w * (fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x))));
+        return w * (1.f / (1.f + expf(-x)) - y) * p.bce_scale;
+      }
+      return (p.act == AGCN_ACT_RELU) ? fmaxf(x, 0.f) : x;
+    };
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       if (nb * BN + c0 >= p.N) break;
@@ -260,32 +277,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int m = m0 + q * 32 + r;
         float4 o = *reinterpret_cast<const float4*>(&stg[r * 36 + 4 * (lane & 7)]);
         if (m < p.M && cc < p.N) {
-          float* dst = Cz + (long long)m * p.ldc + cc;
+          const long long off = (long long)m * p.ldc + cc;
+          float* dst = Cz + off;
           o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
           if (vec_ok && cc + 3 < p.N) {
-            if (p.accumulate) {
-              const float4 old = *reinterpret_cast<const float4*>(dst);
-              o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-            }
-            if (p.act == AGCN_ACT_RELU) {
-              o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-            }
+            float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.accumulate) old = *reinterpret_cast<const float4*>(dst);
+            o.x = finish(o.x, old.x, off); o.y = finish(o.y, old.y, off + 1);
+            o.z = finish(o.z, old.z, off + 2); o.w = finish(o.w, old.w, off + 3);
             *reinterpret_cast<float4*>(dst) = o;
           } else {
             const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              if (cc + e < p.N) {
-                float x = ov[e];
-                if (p.accumulate) x += dst[e];
-                if (p.act == AGCN_ACT_RELU) x = fmaxf(x, 0.f);
-                dst[e] = x;
-              }
+              if (cc + e < p.N) dst[e] = finish(ov[e], p.accumulate ? dst[e] : 0.f, off + e);
             }
           }
         }
       }
       __syncwarp();
+    }
+    if (p.loss_part) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) loss_acc += __shfl_xor_sync(0xffffffffu, loss_acc, o);
+      const int cta = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z);
+      if (lane == 0) p.loss_part[cta * 4 + (warp - 2)] = loss_acc * p.bce_scale;
     }
   }
   tc_fence_before();
@@ -613,10 +629,16 @@ bool tc_gemm_supported(const GemmArgs& a) {
   return true;
 }
 
+int tc_gemm_loss_parts(const GemmArgs& a) {
+  const int Npad = tc_npad(a.N), BN = Npad <= 64 ? 64 : 128;
+  return 4 * ((a.M + tc::BM - 1) / tc::BM) * a.Z * (Npad / BN);
+}
+
 size_t tc_gemm_scratch_floats(int N, int Kd, int S, int Z) { return 2 * (size_t)Z * S * tc_npad(N) * Kd; }
 
-// scratch holds the rearranged hi / lo copies of B (tc_gemm_scratch_floats floats).
-int tc_gemm(const GemmArgs& a, float* scratch, cudaStream_t st) {
+// Rearranges the parameter operand B to [slice][Npad][Kd] (K-major) and splits it into hi / lo TF32 halves.
+// It depends on the parameters only, so callers run it on a side stream (or once per forward/backward pair).
+int tc_gemm_split_b(const GemmArgs& a, float* scratch, cudaStream_t st) {
   using namespace tc;
   // B element (slice, n, k): row-major [Kd, N] (ldb) or, transposed, [N, Kd]
   const long long sn = a.transB ? a.ldb : 1, sk = a.transB ? 1 : a.ldb, ss = a.sliceB;
@@ -624,12 +646,20 @@ int tc_gemm(const GemmArgs& a, float* scratch, cudaStream_t st) {
   const int slices = a.Z * a.S;
   float* Bhi = scratch;
   float* Blo = scratch + (size_t)slices * Npad * a.Kd;
-  {
-    const long long total = (long long)slices * Npad * a.Kd;
-    const int blocks = (int)std::min<long long>((total + 255) / 256, 1184);
-    split_b_kernel<<<blocks, 256, 0, st>>>(a.B, sn, sk, ss, a.N, Npad, a.Kd, slices, Bhi, Blo);
-    AGCN_LAUNCH_CHECK();
-  }
+  const long long total = (long long)slices * Npad * a.Kd;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 1184);
+  split_b_kernel<<<blocks, 256, 0, st>>>(a.B, sn, sk, ss, a.N, Npad, a.Kd, slices, Bhi, Blo);
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+// scratch holds the hi / lo copies of B written by tc_gemm_split_b (tc_gemm_scratch_floats floats).
+int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
+  using namespace tc;
+  const int Npad = tc_npad(a.N);
+  const int slices = a.Z * a.S;
+  const float* Bhi = scratch;
+  const float* Blo = scratch + (size_t)slices * Npad * a.Kd;
   CUtensorMap mA0, mA1, mBhi, mBlo;
   int rc;
   if ((rc = make_map(&mA0, a.A0, (uint64_t)a.M, (uint64_t)a.Kd, (uint64_t)a.lda0, BM))) return rc;
@@ -650,6 +680,7 @@ int tc_gemm(const GemmArgs& a, float* scratch, cudaStream_t st) {
   p.b_rows_slice = Npad;
   p.C = a.C; p.ldc = a.ldc; p.sliceC = a.sliceC;
   p.bias = a.bias; p.act = a.act; p.accumulate = a.accumulate;
+  p.bce_y = a.bce_y; p.bce_w = a.bce_w; p.bce_scale = a.bce_scale; p.loss_part = a.loss_part;
   dim3 grid((a.M + BM - 1) / BM, a.Z, Npad / BN);
   static std::once_flag once64, once128;
   if (BN == 64) {

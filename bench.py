@@ -293,11 +293,14 @@ def run_ours(args):
     e2e_value = world * B_PER_GPU / (ms_e2e * 1e-3)
     if rank == 0:
         # the CPU leg runs in a fresh interpreter: fork-based pools cannot follow autograd / CUDA use
-        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
-                              "--warmup", "0"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
-                             env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
-        ref = json.loads(out.stdout.strip().splitlines()[-1])
-        gps, procs, sample = ref["value"], ref["cpu_baseline"]["cores"], ref["cpu_baseline"]["sample"]
+        if args.skip_cpu:    # quick experiments only: the driver's runs always carry the CPU leg
+            gps, procs, sample = None, 0, "skipped (--skip-cpu)"
+        else:
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
+                                  "--warmup", "0"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+                                 env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
+            ref = json.loads(out.stdout.strip().splitlines()[-1])
+            gps, procs, sample = ref["value"], ref["cpu_baseline"]["cores"], ref["cpu_baseline"]["sample"]
         h2d = Xh.numel() * 4 + Lh.numel() * 4 + onehot_h.numel() * 4 + weights_h.numel() * 4 + n_nodes.nbytes * 4
         line = {"metric": "sgc_ll_train_graphs_per_s", "value": value, "unit": "graphs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_step_eager": ms_eager,
@@ -358,6 +361,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
+    ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (quick experiments)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
