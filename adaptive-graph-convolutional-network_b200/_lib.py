@@ -38,6 +38,7 @@ _SIGNATURES = {
     "agcn_plan_total_lap": (ctypes.c_int64, [_P]),
     "agcn_plan_node_off_host": (_P, [_P]),
     "agcn_plan_lap_off_host": (_P, [_P]),
+    "agcn_fused_tiles_host": (ctypes.c_int, [_P, ctypes.c_int32, _P, ctypes.c_int32, _P, ctypes.c_int32, _P, _P]),
     "agcn_pack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
     "agcn_unpack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
     "agcn_pack_lap": (ctypes.c_int, [_P, _P, _P, _P]),

@@ -79,7 +79,7 @@ Modes modes_of(const agcn_sgcll_desc* d) {
 
 // saved area layout (forward -> backward)
 struct Saved {
-  float *T, *Lall, *dist, *dis, *stats, *XW, *tcG;
+  float *T, *Lall, *dist, *dis, *stats, *XW, *tcG, *ftG;
   size_t bytes;
 };
 
@@ -94,12 +94,13 @@ Saved carve_saved(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
   s.stats = m.shortcut ? nullptr : c.take((size_t)4 * p->B);
   s.XW = m.full ? c.take((size_t)p->R * d->F) : nullptr;
   s.tcG = c.take(tc_gemm_scratch_floats(d->F, d->Fo, 1, d->K));  // hi / lo of W_k^T for the backward G GEMM
+  s.ftG = c.take(fused_w_floats(d->F, d->Fo, d->K));             // the same operand in the fused backward's layout
   s.bytes = c.off;
   return s;
 }
 
 struct Work {
-  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tcY, *tcM, *big;
+  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tcY, *tcM, *big, *ftY;
   size_t bytes;
 };
 
@@ -129,6 +130,7 @@ Work carve_work(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
   w.tcY = c.take(tc_gemm_scratch_floats(d->Fo, d->F, d->K, 1));
   w.tcM = c.take(tc_gemm_scratch_floats(d->F, d->F, 1, 1));
   w.big = c.take(big_work_floats(p, m.full));  // sweeps of the graphs with n > AGCN_SMALL_MAX
+  w.ftY = c.take(fused_w_floats(d->Fo, d->F, d->K));  // pre-split W_k of the fused forward kernel
   w.bytes = c.off;
   return w;
 }
@@ -188,14 +190,19 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
 
   // the parameter operands of the two big node-level GEMMs (this forward's Y and the backward's G) are
   // rearranged / split on the side stream while the per-graph kernels run
+  // Fused tile path: recurrence + transform in one tensor-core kernel (agcn_fused_tile.cu)
+  const bool fuse_f = fused_fwd_supported(plan, F, Fo, K);
+  const bool fuse_b = (desc->flags & AGCN_SAVE_FOR_BACKWARD) && !m.need_dL && fused_bwd_supported(plan, F, Fo, K);
   GemmArgs gy = y_gemm_args(desc, R, d_X, sv.T, d_weight, d_bias, d_Y);
-  const bool y_tc = tc_gemm_supported(gy);
+  const bool y_tc = !fuse_f && tc_gemm_supported(gy);
   GemmArgs gg = g_gemm_args(desc, R, d_Y /* placeholder with the alignment of dYpre */, d_weight, wk.G);
   const bool g_tc = (desc->flags & AGCN_SAVE_FOR_BACKWARD) && tc_gemm_supported(gg);
-  if (y_tc || g_tc) {
+  if (y_tc || g_tc || fuse_f || fuse_b) {
     AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
     AGCN_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_side_fork, 0));
+    if (fuse_f && (rc = fused_fwd_prep(d_weight, F, Fo, K, wk.ftY, plan->side))) return rc;
     if (y_tc && (rc = tc_gemm_split_b(gy, wk.tcY, plan->side))) return rc;
+    if (fuse_b && (rc = fused_bwd_prep(d_weight, F, Fo, K, sv.ftG, plan->side))) return rc;
     if (g_tc && (rc = tc_gemm_split_b(gg, sv.tcG, plan->side))) return rc;
     AGCN_CUDA(cudaEventRecord(plan->ev_side_join, plan->side));
   }
@@ -223,8 +230,15 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
     if ((rc = graph_build_laplacian(ga, need_W, st))) return rc;
   }
   ga.Lall = m.shortcut ? nullptr : sv.Lall;
+  if (fuse_f) {
+    // graphs above AGCN_FUSE_MAX_N keep their per-graph / row-tiled recurrences; the tile kernel reads their T_k
+    if (plan->max_n > AGCN_FUSE_MAX_N && (rc = graph_chebyshev_fwd(ga, st, AGCN_FUSE_MAX_N))) return rc;
+    AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
+    return fused_forward(plan, d_X, m.shortcut ? d_Lint : sv.Lall, m.shortcut ? 1 : 0, wk.ftY, d_bias,
+                         desc->activation, F, Fo, K, sv.T, d_Y, st);
+  }
   if ((rc = graph_chebyshev_fwd(ga, st))) return rc;  // graphconv.py:221-236
-  if (y_tc || g_tc) AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
+  if (y_tc || g_tc || fuse_b) AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
   // x = reshape(transpose(stack T)) . weight + bias, activation   graphconv.py:238-247, :118-123
   if ((rc = node_gemm(gy, wk.tcY, st, /*presplit=*/true))) return rc;
   return AGCN_OK;
@@ -262,7 +276,9 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   AGCN_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_side_fork, 0));
   if ((rc = act_bwd_reduce(wk.act_part, d_dbias, R, Fo, plan->side))) return rc;
   // d_dX == NULL: the caller does not need the gradient w.r.t. the node features (first layer)
-  const bool need_G = d_dX != nullptr || (m.need_dL && K >= 2);
+  const bool fuse_b = (desc->flags & AGCN_SAVE_FOR_BACKWARD) && !m.need_dL && d_dX != nullptr &&
+                      fused_bwd_supported(plan, F, Fo, K);
+  const bool need_G = !fuse_b && (d_dX != nullptr || (m.need_dL && K >= 2));
   float* dXbuf = d_dX ? d_dX : wk.G;  // scratch target when dX itself is not wanted (K >= 2 only)
   AGCN_REQUIRE(d_dX || !m.full, "backward: d_dX is required with metric_grad = full");
   if (need_G) {  // G_k = dYpre W_k^T   (K == 1: this is dX); W_k^T was split by the forward pass
@@ -293,7 +309,14 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
     if ((rc = node_gemm_tn(t, plan->side))) return rc;
   }
   AGCN_CUDA(cudaEventRecord(plan->ev_side_join, plan->side));
-  if (K >= 2) {
+  if (fuse_b) {
+    // G_z = dYpre W_z^T and the reverse recurrence in one kernel; graphs above AGCN_FUSE_MAX_N get their G_z
+    // rows in wk.G and finish in the per-graph / row-tiled kernels
+    if ((rc = fused_backward(plan, dYp, m.shortcut ? d_Lint : sv.Lall, m.shortcut ? 1 : 0, sv.ftG, F, Fo, K, wk.G,
+                             d_dX, st)))
+      return rc;
+    if (plan->max_n > AGCN_FUSE_MAX_N && (rc = graph_recurrence_bwd(ga, false, st, AGCN_FUSE_MAX_N))) return rc;
+  } else if (K >= 2) {
     if (need_G && (rc = graph_recurrence_bwd(ga, m.need_dL, st))) return rc;
   } else if (m.need_dL) {
     if (d_dLall_in)

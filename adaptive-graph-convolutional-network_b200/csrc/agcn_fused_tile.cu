@@ -1,0 +1,896 @@
+// Fused SGC-LL tile kernels: the Chebyshev recurrence and the feature transform of one layer in ONE
+// kernel per direction (north_star item 3), for the molecule-sized graphs that dominate the Tox21 /
+// ToxCast shapes.
+//
+// A "tile" is 128 rows of the packed node matrix that belong to whole graphs (agcn_plan.cu packs graphs
+// with n <= AGCN_FUSE_MAX_N into tiles, first-fit decreasing).  One CTA owns one tile:
+//
+//   forward  (graphconv.py:221-247, :118-123)
+//     warps 2-5 (one thread per tile row): T_0 chunk (32 feature columns) -> shared memory, then
+//       T_1 = L T_0, T_k = 2 L T_{k-1} - T_{k-2} on the CUDA cores in exact fp32 with the per-graph L
+//       matrices of the tile resident in shared memory; every T_k chunk is written once to HBM (saved for
+//       backward) and, split into hi/lo TF32 halves, into a 128x32 K-major swizzled operand stage;
+//     warp 1: tcgen05.mma (3xTF32) Y += T_k[:, chunk] W_k[chunk, :] into a TMEM accumulator;
+//     warp 0: TMA producer of the pre-split W tiles;
+//     epilogue: TMEM -> registers -> bias + activation -> Y.
+//   backward (reverse mode of the same lines, dX chain only)
+//     mainloop: G_z = dYpre W_z^T for z = 0..K-1 into K TMEM accumulators (A = dYpre chunks split by the
+//       workers, B = W_z by TMA);
+//     epilogue: U_{K-1} = G_{K-1}, U_j = G_j + c_{j+1} L^T U_{j+1} - U_{j+2} per 32-column chunk, reading
+//       G_j straight from TMEM; dX = U_0.  The K [R,F] G matrices never touch HBM.
+//
+// Graphs with n > AGCN_FUSE_MAX_N own "pre" tiles (128-row ranges of one graph): their recurrences run in
+// the per-graph / row-tiled kernels (agcn_graph_small.cu, agcn_graph_large.cu) and the tile kernel only
+// does the tensor-core part for those rows (forward: T_k read from HBM; backward: G_z written to HBM).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+#include "agcn_internal.cuh"
+
+namespace agcn {
+namespace ft {
+
+constexpr int TM = 128;            // rows per tile (UMMA M)
+constexpr int CH = 32;             // feature columns per k-block = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;          // tf32
+constexpr int A_BYTES = TM * CH * 4;  // 16 KB: one operand half (hi or lo) of a k-block
+constexpr int LCAP = AGCN_FUSE_LCAP;  // floats of per-graph L matrices per tile
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > SPIN_LIMIT) __trap();  // a protocol bug becomes an error, not a hang
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms of 1024 bytes
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, int cols) {
+  const uint32_t s = smem_u32(slot);
+  switch (cols) {
+    case 32: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;\n" ::"r"(s) : "memory"); break;
+    case 64: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;\n" ::"r"(s) : "memory"); break;
+    case 128: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n" ::"r"(s) : "memory"); break;
+    case 256: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" ::"r"(s) : "memory"); break;
+    default: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;\n" ::"r"(s) : "memory"); break;
+  }
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t base, int cols) {
+  switch (cols) {
+    case 32: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;\n" ::"r"(base) : "memory"); break;
+    case 64: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;\n" ::"r"(base) : "memory"); break;
+    case 128: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" ::"r"(base) : "memory"); break;
+    case 256: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(base) : "memory"); break;
+    default: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;\n" ::"r"(base) : "memory"); break;
+  }
+}
+// 32 consecutive fp32 accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t u[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];\n"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+}
+
+__device__ __forceinline__ void cp_async4(float* sdst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* sdst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+// ---- fp32 chunk buffers: [128 rows][32 floats], 16-byte groups XOR-swizzled by (row & 7) (same pattern as
+// the operand stages, so rows of different graphs read by one warp fall into different banks)
+__device__ __forceinline__ float* chunk_ptr(float* buf, int row, int group) {
+  return buf + row * CH + ((group ^ (row & 7)) << 2);
+}
+
+// This warp's 32 rows (quarter q) of a 32-column chunk: global [.., ld] rows s_grow[row] -> buf, asynchronously.
+__device__ __forceinline__ void load_rows_async(float* buf, const float* __restrict__ M, int ld, int ncols, int c,
+                                                const int* s_grow, int q, int lane, bool vec) {
+  if (vec) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = q * 32 + 4 * i + (lane >> 3), grp = lane & 7, col = c * CH + grp * 4;
+      const int grow = s_grow[row];
+      float* d = chunk_ptr(buf, row, grp);
+      if (grow >= 0 && col < ncols)
+        cp_async16(d, M + (int64_t)grow * ld + col);
+      else
+        *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  } else {
+    for (int i = 0; i < 32; ++i) {
+      const int row = q * 32 + i, col = c * CH + lane;
+      const int grow = s_grow[row];
+      float* d = chunk_ptr(buf, row, lane >> 2) + (lane & 3);
+      if (grow >= 0 && col < ncols)
+        cp_async4(d, M + (int64_t)grow * ld + col);
+      else
+        *d = 0.f;
+    }
+  }
+}
+
+// This warp's 32 rows of a chunk: buf -> global rows (coalesced).  Callers bracket with __syncwarp.
+__device__ __forceinline__ void store_rows(const float* buf, float* __restrict__ M, int ld, int ncols, int c,
+                                           const int* s_grow, int q, int lane, bool vec) {
+  if (vec) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = q * 32 + 4 * i + (lane >> 3), grp = lane & 7, col = c * CH + grp * 4;
+      const int grow = s_grow[row];
+      if (grow >= 0 && col < ncols)
+        *reinterpret_cast<float4*>(M + (int64_t)grow * ld + col) =
+            *reinterpret_cast<const float4*>(chunk_ptr(const_cast<float*>(buf), row, grp));
+    }
+  } else {
+    for (int i = 0; i < 32; ++i) {
+      const int row = q * 32 + i, col = c * CH + lane;
+      const int grow = s_grow[row];
+      if (grow >= 0 && col < ncols) M[(int64_t)grow * ld + col] = *(chunk_ptr(const_cast<float*>(buf), row, lane >> 2) + (lane & 3));
+    }
+  }
+}
+
+__device__ __forceinline__ void read_row(const float* buf, int row, float v[32]) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 x = *reinterpret_cast<const float4*>(chunk_ptr(const_cast<float*>(buf), row, g));
+    v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
+  }
+}
+__device__ __forceinline__ void write_row(float* buf, int row, const float v[32]) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g)
+    *reinterpret_cast<float4*>(chunk_ptr(buf, row, g)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+}
+
+// acc[:] = sum_j Lrow[j * lstride] * src[r0 + j][:]
+__device__ __forceinline__ void lap_times_rows(const float* __restrict__ Lrow, int lstride, const float* src, int r0, int n,
+                                               float acc[32]) {
+#pragma unroll
+  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
+  for (int j = 0; j < n; ++j) {
+    const float a = Lrow[j * lstride];
+    const int row = r0 + j;
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      const float4 b = *reinterpret_cast<const float4*>(chunk_ptr(const_cast<float*>(src), row, g));
+      acc[4 * g] = fmaf(a, b.x, acc[4 * g]);
+      acc[4 * g + 1] = fmaf(a, b.y, acc[4 * g + 1]);
+      acc[4 * g + 2] = fmaf(a, b.z, acc[4 * g + 2]);
+      acc[4 * g + 3] = fmaf(a, b.w, acc[4 * g + 3]);
+    }
+  }
+}
+
+// One row of a 128x32 K-major SWIZZLE_128B operand tile, split into hi / lo TF32 halves.
+__device__ __forceinline__ void write_operand_row(uint8_t* a_hi, uint8_t* a_lo, int row, const float v[32]) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    float4 hi, lo;
+    hi.x = __uint_as_float(__float_as_uint(v[4 * g]) & 0xffffe000u);
+    hi.y = __uint_as_float(__float_as_uint(v[4 * g + 1]) & 0xffffe000u);
+    hi.z = __uint_as_float(__float_as_uint(v[4 * g + 2]) & 0xffffe000u);
+    hi.w = __uint_as_float(__float_as_uint(v[4 * g + 3]) & 0xffffe000u);
+    lo.x = __uint_as_float(__float_as_uint(v[4 * g] - hi.x) & 0xffffe000u);
+    lo.y = __uint_as_float(__float_as_uint(v[4 * g + 1] - hi.y) & 0xffffe000u);
+    lo.z = __uint_as_float(__float_as_uint(v[4 * g + 2] - hi.z) & 0xffffe000u);
+    lo.w = __uint_as_float(__float_as_uint(v[4 * g + 3] - hi.w) & 0xffffe000u);
+    const int off = row * 128 + ((g ^ (row & 7)) << 4);
+    *reinterpret_cast<float4*>(a_hi + off) = hi;
+    *reinterpret_cast<float4*>(a_lo + off) = lo;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// shared memory carve-up (identical for both directions)
+// ------------------------------------------------------------------------------------------------
+struct SmemPlan {
+  int stages, stage_bytes, b_bytes;
+  int off_bufs;   // 3 fp32 chunk buffers (forward) -- the backward recurrence reuses the operand stages
+  int off_L;      // LCAP floats
+  int off_glist;  // 128 int4
+  int off_grow;   // 128 int
+  int off_bars;
+  int total;
+};
+
+__host__ __device__ inline SmemPlan smem_plan(int N, bool forward) {
+  SmemPlan s;
+  s.b_bytes = N * 128;
+  s.stage_bytes = 2 * A_BYTES + 2 * s.b_bytes;
+  const int fixed = (forward ? 3 * A_BYTES : 0) + LCAP * 4 + 128 * 16 + 128 * 4 + 256 + 1024;
+  int stages = (227 * 1024 - fixed) / s.stage_bytes;
+  s.stages = stages > 4 ? 4 : stages;
+  int off = s.stages * s.stage_bytes;
+  s.off_bufs = off;
+  off += forward ? 3 * A_BYTES : 0;
+  s.off_L = off;
+  off += LCAP * 4;
+  s.off_glist = off;
+  off += 128 * 16;
+  s.off_grow = off;
+  off += 128 * 4;
+  s.off_bars = off;
+  off += 256;
+  s.total = off + 1024;  // alignment slack
+  return s;
+}
+
+struct TileRow {
+  int grow;   // global packed row or -1
+  int n;      // nodes of my graph (0: pre tile or padding row)
+  int r0;     // tile row of my graph's first node
+  int lbase;  // float offset of my graph's matrix in the tile's L region
+  int i;      // my index inside the graph
+  int pitch;
+  bool pre;
+};
+
+struct TileArgs {
+  const int4* tile_graphs;     // {g, r0 | row_start, n | nrows, lbase | -1}
+  const int32_t* tile_gstart;  // [tiles + 1]
+  const int32_t* node_off;
+  const int64_t* lap_off;
+  const float* L;              // packed Laplacians (Lint or L_all)
+  int add_identity;
+  int F, Fo, K;
+  int N;                       // MMA N (padded output columns of the mainloop)
+  int nchunks;                 // k-blocks per slice
+};
+
+// Prologue shared by both kernels (worker threads): graph list, row table, L matrices of the tile.
+__device__ __forceinline__ TileRow tile_prologue(const TileArgs& p, int tile, int r, int wt, int4* s_glist, int* s_grow,
+                                                 float* sL) {
+  const int gs = p.tile_gstart[tile], ng = p.tile_gstart[tile + 1] - gs;
+  for (int e = wt; e < ng; e += 128) s_glist[e] = p.tile_graphs[gs + e];
+  worker_barrier();
+  TileRow t;
+  t.grow = -1; t.n = 0; t.r0 = 0; t.lbase = 0; t.i = 0; t.pitch = 1; t.pre = false;
+  for (int e = 0; e < ng; ++e) {
+    const int4 ge = s_glist[e];
+    if (ge.w < 0) {  // pre tile: rows [ge.y, ge.y + ge.z) of graph ge.x
+      t.pre = true;
+      if (r < ge.z) t.grow = p.node_off[ge.x] + ge.y + r;
+    } else if (r >= ge.y && r < ge.y + ge.z) {
+      t.grow = p.node_off[ge.x] + (r - ge.y);
+      t.n = ge.z; t.r0 = ge.y; t.lbase = ge.w; t.i = r - ge.y; t.pitch = ge.z | 1;
+    }
+  }
+  s_grow[r] = t.grow;
+  // per-graph matrices, row pitch n | 1 (odd: the rows read by neighbouring lanes sit in different banks)
+  for (int e = 0; e < ng; ++e) {
+    const int4 ge = s_glist[e];
+    if (ge.w < 0) continue;
+    const int n = ge.z, pitch = n | 1;
+    const float* __restrict__ src = p.L + p.lap_off[ge.x];
+    float* dst = sL + ge.w;
+    for (int idx = wt; idx < n * n; idx += 128) {
+      const int i = idx / n, j = idx - i * n;
+      cp_async4(dst + i * pitch + j, src + idx);
+    }
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  worker_barrier();
+  if (p.add_identity && t.n > 0) sL[t.lbase + t.i * t.pitch + t.i] += 1.f;  // L_all = I + L_int (literal mode)
+  worker_barrier();
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------------
+struct FwdArgs {
+  TileArgs t;
+  const float* X;     // [R,F]
+  float* T;           // [K-1][R][F] saved Chebyshev terms
+  long long tslice;
+  const float* bias;
+  int act;
+  float* Y;           // [R,Fo]
+};
+
+__global__ void __launch_bounds__(192, 1)
+fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, FwdArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const SmemPlan sp = smem_plan(p.t.N, true);
+  float* bufs = reinterpret_cast<float*>(base + sp.off_bufs);
+  float* sL = reinterpret_cast<float*>(base + sp.off_L);
+  int4* s_glist = reinterpret_cast<int4*>(base + sp.off_glist);
+  int* s_grow = reinterpret_cast<int*>(base + sp.off_grow);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + sp.off_bars);
+  uint64_t* full_bar = bars;        // W tiles landed (TMA)
+  uint64_t* split_bar = bars + 4;   // operand rows written by the 128 workers
+  uint64_t* empty_bar = bars + 8;   // MMAs that read the stage retired
+  uint64_t* tmem_full_bar = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int F = p.t.F, Fo = p.t.Fo, K = p.t.K, N = p.t.N, nc = p.t.nchunks;
+  const int num_kb = nc * K;
+  int tmem_cols = 32;
+  while (tmem_cols < N) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < sp.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: W_s[chunk c] as a [N, 32] K-major tile, hi and lo halves =================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % sp.stages, phase = (kb / sp.stages) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = base + stage * sp.stage_bytes + 2 * A_BYTES;
+        const int c = kb / K, s = kb - c * K;
+        mbar_expect_tx(&full_bar[stage], 2 * sp.b_bytes);
+        tma_load_2d(st, &tmBhi, &full_bar[stage], c * CH, s * N);
+        tma_load_2d(st + sp.b_bytes, &tmBlo, &full_bar[stage], c * CH, s * N);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % sp.stages, phase = (kb / sp.stages) & 1;
+        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&split_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(base + stage * sp.stage_bytes);
+        const uint32_t sa_lo = sa + A_BYTES, sb_hi = sa + 2 * A_BYTES, sb_lo = sb_hi + sp.b_bytes;
+#pragma unroll
+        for (int k = 0; k < CH / UMMA_K; ++k) {
+          const uint32_t koff = k * UMMA_K * 4;
+          const uint64_t a_hi = make_desc(sa + koff), a_lo = make_desc(sa_lo + koff);
+          const uint64_t b_hi = make_desc(sb_hi + koff), b_lo = make_desc(sb_lo + koff);
+          umma_tf32(tmem_base, a_lo, b_hi, idesc, (kb | k) != 0);
+          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+          umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    // ================= workers: recurrence + operand production, then epilogue =================
+    const int q = warp & 3;            // TMEM lane quarter of this warp
+    const int r = q * 32 + lane;       // my tile row
+    const int wt = (warp - 2) * 32 + lane;
+    const TileRow me = tile_prologue(p.t, tile, r, wt, s_glist, s_grow, sL);
+    const bool vecX = ((F & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.T) & 15) == 0) && ((p.tslice & 3) == 0);
+    float* xbuf[2] = {bufs, bufs + TM * CH};
+    float* tbuf = bufs + 2 * TM * CH;
+    const float* Lrow = sL + me.lbase + me.i * me.pitch;
+
+    auto emit = [&](int kb, const float v[32]) {
+      const int stage = kb % sp.stages, phase = (kb / sp.stages) & 1;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* st = base + stage * sp.stage_bytes;
+      write_operand_row(st, st + A_BYTES, r, v);
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
+      mbar_arrive(&split_bar[stage]);
+    };
+
+    load_rows_async(xbuf[0], p.X, F, F, 0, s_grow, q, lane, vecX);
+    cp_async_commit();
+    for (int c = 0; c < nc; ++c) {
+      const int cur = c & 1;
+      cp_async_wait_all();
+      worker_barrier();  // T_0 chunk c complete; every worker is done with chunk c-1
+      if (c + 1 < nc) {
+        load_rows_async(xbuf[cur ^ 1], p.X, F, F, c + 1, s_grow, q, lane, vecX);
+        cp_async_commit();
+      }
+      float tm2[32], tm1[32];
+      read_row(xbuf[cur], r, tm1);
+      emit(c * K, tm1);
+      float* src = xbuf[cur];
+      float* dst = tbuf;
+      for (int s = 1; s < K; ++s) {
+        float t[32];
+        if (me.pre) {
+          // the per-graph / row-tiled kernels produced T_s for this graph
+          const float* Ts = p.T + (long long)(s - 1) * p.tslice;
+#pragma unroll
+          for (int u = 0; u < 32; ++u) {
+            const int col = c * CH + u;
+            t[u] = (me.grow >= 0 && col < F) ? Ts[(long long)me.grow * F + col] : 0.f;
+          }
+        } else {
+          lap_times_rows(Lrow, 1, src, me.r0, me.n, t);  // graphconv.py:231
+          if (s >= 2) {
+#pragma unroll
+            for (int u = 0; u < 32; ++u) t[u] = 2.f * t[u] - tm2[u];  // graphconv.py:234
+          }
+          write_row(dst, r, t);
+          __syncwarp();
+          store_rows(dst, p.T + (long long)(s - 1) * p.tslice, F, F, c, s_grow, q, lane, vecX);
+        }
+        emit(c * K + s, t);
+#pragma unroll
+        for (int u = 0; u < 32; ++u) { tm2[u] = tm1[u]; tm1[u] = t[u]; }
+        if (s + 1 < K) {
+          worker_barrier();  // T_s rows of every graph of the tile are in `dst`
+          float* tmp = src; src = dst; dst = tmp;
+        }
+      }
+    }
+    // ---- epilogue: Y = act(acc + bias)   graphconv.py:245-247, :118-123
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    float* stg = reinterpret_cast<float*>(base) + (warp - 2) * (32 * 36);  // operand stages are free now
+    const bool vecY = ((Fo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
+    for (int c0 = 0; c0 < N && c0 < Fo; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        *reinterpret_cast<float4*>(&stg[lane * 36 + 4 * u]) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+      __syncwarp();
+      const int cc = c0 + 4 * (lane & 7);
+      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (p.bias && cc + e < Fo) bv[e] = p.bias[cc + e];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int rr = 4 * i + (lane >> 3);
+        const int grow = s_grow[q * 32 + rr];
+        if (grow < 0 || cc >= Fo) continue;
+        const float4 o4 = *reinterpret_cast<const float4*>(&stg[rr * 36 + 4 * (lane & 7)]);
+        float o[4] = {o4.x + bv[0], o4.y + bv[1], o4.z + bv[2], o4.w + bv[3]};
+        if (p.act == AGCN_ACT_RELU) {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = fmaxf(o[e], 0.f);
+        }
+        float* dstp = p.Y + (long long)grow * Fo + cc;
+        if (vecY && cc + 3 < Fo) {
+          *reinterpret_cast<float4*>(dstp) = make_float4(o[0], o[1], o[2], o[3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (cc + e < Fo) dstp[e] = o[e];
+        }
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward (dX chain)
+// ------------------------------------------------------------------------------------------------
+struct BwdArgs {
+  TileArgs t;          // t.N = padded F (MMA N), t.nchunks = ceil(Fo / 32)
+  const float* dYp;    // [R,Fo]  dY * act'(Y)
+  float* G;            // [K][R][F]: written for pre tiles only (their recurrence runs in the per-graph kernels)
+  long long gslice;
+  float* dX;           // [R,F]
+  int acc_stride;      // TMEM columns between the K accumulators
+};
+
+__global__ void __launch_bounds__(192, 1)
+fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, BwdArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const SmemPlan sp = smem_plan(p.t.N, false);
+  float* sL = reinterpret_cast<float*>(base + sp.off_L);
+  int4* s_glist = reinterpret_cast<int4*>(base + sp.off_glist);
+  int* s_grow = reinterpret_cast<int*>(base + sp.off_grow);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + sp.off_bars);
+  uint64_t* full_bar = bars;
+  uint64_t* split_bar = bars + 4;
+  uint64_t* empty_bar = bars + 8;
+  uint64_t* tmem_full_bar = bars + 12;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x;
+  const int F = p.t.F, Fo = p.t.Fo, K = p.t.K, N = p.t.N, nc = p.t.nchunks;
+  const int num_kb = nc * K;
+  int tmem_cols = 32;
+  while (tmem_cols < K * p.acc_stride) tmem_cols <<= 1;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < sp.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], 128);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer: W_z[:, chunk c] as a [N = F, 32] K-major tile =================
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % sp.stages, phase = (kb / sp.stages) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* st = base + stage * sp.stage_bytes + 2 * A_BYTES;
+        const int z = kb / nc, c = kb - z * nc;
+        mbar_expect_tx(&full_bar[stage], 2 * sp.b_bytes);
+        tma_load_2d(st, &tmBhi, &full_bar[stage], c * CH, z * N);
+        tma_load_2d(st + sp.b_bytes, &tmBlo, &full_bar[stage], c * CH, z * N);
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer: accumulator z at TMEM column z * acc_stride =================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % sp.stages, phase = (kb / sp.stages) & 1;
+        const int z = kb / nc, c = kb - z * nc;
+        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&split_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(base + stage * sp.stage_bytes);
+        const uint32_t sa_lo = sa + A_BYTES, sb_hi = sa + 2 * A_BYTES, sb_lo = sb_hi + sp.b_bytes;
+        const uint32_t d = tmem_base + (uint32_t)(z * p.acc_stride);
+#pragma unroll
+        for (int k = 0; k < CH / UMMA_K; ++k) {
+          const uint32_t koff = k * UMMA_K * 4;
+          const uint64_t a_hi = make_desc(sa + koff), a_lo = make_desc(sa_lo + koff);
+          const uint64_t b_hi = make_desc(sb_hi + koff), b_lo = make_desc(sb_lo + koff);
+          umma_tf32(d, a_lo, b_hi, idesc, (c | k) != 0);
+          umma_tf32(d, a_hi, b_lo, idesc, 1);
+          umma_tf32(d, a_hi, b_hi, idesc, 1);
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const int wt = (warp - 2) * 32 + lane;
+    const TileRow me = tile_prologue(p.t, tile, r, wt, s_glist, s_grow, sL);
+    const bool vecD = ((Fo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dYp) & 15) == 0);
+    // mainloop: my row of dYpre chunk c (one 128-byte line, L1-resident across the K passes) -> hi/lo operand
+    // rows; the row of the next k-block is in flight while this one is split and stored.
+    auto load_row = [&](int kb, float v[32]) {
+      const int c = kb % nc;
+      if (vecD) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const int col = c * CH + 4 * g;
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (me.grow >= 0 && col < Fo) x = __ldg(reinterpret_cast<const float4*>(p.dYp + (long long)me.grow * Fo + col));
+          v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const int col = c * CH + u;
+          v[u] = (me.grow >= 0 && col < Fo) ? __ldg(p.dYp + (long long)me.grow * Fo + col) : 0.f;
+        }
+      }
+    };
+    float nxt[32];
+    load_row(0, nxt);
+    for (int kb = 0; kb < num_kb; ++kb) {
+      float v[32];
+#pragma unroll
+      for (int u = 0; u < 32; ++u) v[u] = nxt[u];
+      if (kb + 1 < num_kb) load_row(kb + 1, nxt);
+      const int stage = kb % sp.stages, phase = (kb / sp.stages) & 1;
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      uint8_t* st = base + stage * sp.stage_bytes;
+      write_operand_row(st, st + A_BYTES, r, v);
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      mbar_arrive(&split_bar[stage]);
+    }
+    // ---- epilogue: reverse recurrence on the accumulators
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    worker_barrier();
+    float* ub[2] = {reinterpret_cast<float*>(base), reinterpret_cast<float*>(base) + TM * CH};  // stages are free now
+    const bool vecX = ((F & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dX) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.G) & 15) == 0) && ((p.gslice & 3) == 0);
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
+    const float* Lcol = sL + me.lbase + me.i;  // column i of my graph's matrix: (L^T U)_i = sum_j L[j][i] U_j
+    const int nfc = (F + CH - 1) / CH;
+    for (int fc = 0; fc < nfc; ++fc) {
+      if (me.pre) {
+        // big graph: hand G_z to the per-graph / row-tiled reverse recurrence
+        for (int z = 0; z < K; ++z) {
+          float g[32];
+          tmem_ld32(lane_base + (uint32_t)(z * p.acc_stride + fc * CH), g);
+          write_row(ub[0], r, g);
+          __syncwarp();
+          store_rows(ub[0], p.G + (long long)z * p.gslice, F, F, fc, s_grow, q, lane, vecX);
+          __syncwarp();
+        }
+        continue;
+      }
+      float u1[32], u2[32];
+      tmem_ld32(lane_base + (uint32_t)((K - 1) * p.acc_stride + fc * CH), u1);  // U_{K-1} = G_{K-1}
+#pragma unroll
+      for (int u = 0; u < 32; ++u) u2[u] = 0.f;
+      int cur = 0;
+      for (int j = K - 2; j >= 0; --j) {
+        write_row(ub[cur], r, u1);
+        worker_barrier();  // U_{j+1} rows of every graph of the tile are visible
+        float acc[32], g[32];
+        lap_times_rows(Lcol, me.pitch, ub[cur], me.r0, me.n, acc);
+        tmem_ld32(lane_base + (uint32_t)(j * p.acc_stride + fc * CH), g);
+        const float cmul = (j + 1 >= 2) ? 2.f : 1.f;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const float o = g[u] + cmul * acc[u] - u2[u];
+          u2[u] = u1[u];
+          u1[u] = o;
+        }
+        cur ^= 1;
+      }
+      // dX = U_0
+      worker_barrier();  // every read of the buffers is done before they are reused for the store / next chunk
+      write_row(ub[cur], r, u1);
+      __syncwarp();
+      store_rows(ub[cur], p.dX, F, F, fc, s_grow, q, lane, vecX);
+      worker_barrier();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
+}
+
+// ------------------------------------------------------------------------------------------------
+// W prep: out_{hi,lo}[(z * N + n) * Kp + k] = split(W[n * sn + k * sk + z * sz])  (zero outside n < Nv, k < Kv)
+// ------------------------------------------------------------------------------------------------
+__global__ void prep_w_kernel(const float* __restrict__ W, long long sn, long long sk, long long sz, int Nv, int Kv,
+                              int N, int Kp, int Z, float* __restrict__ hi, float* __restrict__ lo) {
+  const long long total = (long long)Z * N * Kp;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(e % Kp);
+    const long long rr = e / Kp;
+    const int n = (int)(rr % N), z = (int)(rr / N);
+    float x = 0.f;
+    if (n < Nv && k < Kv) x = W[n * sn + k * sk + z * sz];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    hi[e] = h;
+    lo[e] = __uint_as_float(__float_as_uint(x - h) & 0xffffe000u);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// [rows, cols] fp32 row-major, box = 32 columns x box_rows, 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return AGCN_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)CH, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return AGCN_ERR_CUDA;
+  }
+  return AGCN_OK;
+}
+
+static int pad16(int x) { return (x + 15) & ~15; }
+static int pad32(int x) { return (x + 31) & ~31; }
+
+static TileArgs tile_args(const agcn_plan* plan, const float* L, int add_identity, int F, int Fo, int K) {
+  TileArgs t;
+  t.tile_graphs = reinterpret_cast<const int4*>(plan->d_ft_entries);
+  t.tile_gstart = plan->d_ft_gstart;
+  t.node_off = plan->d_node_off;
+  t.lap_off = plan->d_lap_off;
+  t.L = L;
+  t.add_identity = add_identity;
+  t.F = F; t.Fo = Fo; t.K = K;
+  t.N = 0; t.nchunks = 0;
+  return t;
+}
+
+}  // namespace ft
+
+// ------------------------------------------------------------------------------------------------
+// host API
+// ------------------------------------------------------------------------------------------------
+bool fused_enabled() {
+  // opt-in until the tile kernels beat the per-graph + node-GEMM path they replace
+  static const bool on = getenv("AGCN_ENABLE_FUSED") != nullptr && getenv("AGCN_DISABLE_TCGEN05") == nullptr;
+  return on;
+}
+
+bool fused_fwd_supported(const agcn_plan* plan, int F, int Fo, int K) {
+  return fused_enabled() && plan->ft_tiles > 0 && K >= 2 && Fo >= 1 && Fo <= 128 && F >= 1;
+}
+
+bool fused_bwd_supported(const agcn_plan* plan, int F, int Fo, int K) {
+  if (!fused_enabled() || plan->ft_tiles <= 0 || K < 2 || F > 128) return false;
+  const int N = ft::pad16(F), stride = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  return K * stride <= 512;
+}
+
+size_t fused_w_floats(int Nv, int Kv, int Z) { return 2 * (size_t)Z * ft::pad16(Nv) * ft::pad32(Kv); }
+
+// forward operand: B_s[n, k] = weight[(k*K + s)*Fo + n]  (n < Fo output columns, k < F)
+int fused_fwd_prep(const float* weight, int F, int Fo, int K, float* scratch, cudaStream_t st) {
+  const int N = ft::pad16(Fo), Kp = ft::pad32(F);
+  const long long total = (long long)K * N * Kp;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 1184);
+  ft::prep_w_kernel<<<blocks, 256, 0, st>>>(weight, 1, (long long)K * Fo, Fo, Fo, F, N, Kp, K, scratch, scratch + total);
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+// backward operand: B_z[f, o] = weight[(f*K + z)*Fo + o]  (f < F rows of G_z, o < Fo contraction)
+int fused_bwd_prep(const float* weight, int F, int Fo, int K, float* scratch, cudaStream_t st) {
+  const int N = ft::pad16(F), Kp = ft::pad32(Fo);
+  const long long total = (long long)K * N * Kp;
+  const int blocks = (int)std::min<long long>((total + 255) / 256, 1184);
+  ft::prep_w_kernel<<<blocks, 256, 0, st>>>(weight, (long long)K * Fo, 1, Fo, F, Fo, N, Kp, K, scratch, scratch + total);
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+template <typename Kern>
+static int opt_in_smem(Kern k, int bytes) {
+  static std::mutex mu;
+  static int done_bytes = 0;
+  std::lock_guard<std::mutex> lock(mu);
+  if (bytes > done_bytes) {
+    AGCN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+    done_bytes = bytes;
+  }
+  return AGCN_OK;
+}
+
+int fused_forward(const agcn_plan* plan, const float* X, const float* L, int add_identity, const float* wsplit,
+                  const float* bias, int act, int F, int Fo, int K, float* T, float* Y, cudaStream_t st) {
+  using namespace ft;
+  const int N = pad16(Fo), Kp = pad32(F);
+  const long long half = (long long)K * N * Kp;
+  CUtensorMap mhi, mlo;
+  int rc;
+  if ((rc = make_map(&mhi, wsplit, (uint64_t)K * N, (uint64_t)Kp, (uint32_t)N))) return rc;
+  if ((rc = make_map(&mlo, wsplit + half, (uint64_t)K * N, (uint64_t)Kp, (uint32_t)N))) return rc;
+  FwdArgs a;
+  a.t = tile_args(plan, L, add_identity, F, Fo, K);
+  a.t.N = N;
+  a.t.nchunks = Kp / CH;
+  a.X = X; a.T = T; a.tslice = (long long)plan->R * F;
+  a.bias = bias; a.act = act; a.Y = Y;
+  const SmemPlan sp = smem_plan(N, true);
+  if ((rc = opt_in_smem(fused_fwd_kernel, 227 * 1024))) return rc;
+  fused_fwd_kernel<<<plan->ft_tiles, 192, sp.total, st>>>(mhi, mlo, a);
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+int fused_backward(const agcn_plan* plan, const float* dYp, const float* L, int add_identity, const float* wsplit,
+                   int F, int Fo, int K, float* G, float* dX, cudaStream_t st) {
+  using namespace ft;
+  const int N = pad16(F), Kp = pad32(Fo);
+  const long long half = (long long)K * N * Kp;
+  CUtensorMap mhi, mlo;
+  int rc;
+  if ((rc = make_map(&mhi, wsplit, (uint64_t)K * N, (uint64_t)Kp, (uint32_t)N))) return rc;
+  if ((rc = make_map(&mlo, wsplit + half, (uint64_t)K * N, (uint64_t)Kp, (uint32_t)N))) return rc;
+  BwdArgs a;
+  a.t = tile_args(plan, L, add_identity, F, Fo, K);
+  a.t.N = N;
+  a.t.nchunks = Kp / CH;
+  a.dYp = dYp; a.G = G; a.gslice = (long long)plan->R * F; a.dX = dX;
+  a.acc_stride = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
+  const SmemPlan sp = smem_plan(N, false);
+  if ((rc = opt_in_smem(fused_bwd_kernel, 227 * 1024))) return rc;
+  fused_bwd_kernel<<<plan->ft_tiles, 192, sp.total, st>>>(mhi, mlo, a);
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+}  // namespace agcn

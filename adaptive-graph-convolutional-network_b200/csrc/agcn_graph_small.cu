@@ -774,7 +774,7 @@ static ChunkCfg chunk_cfg(int max_n, int F, int nbuf, int nsq, bool single_chunk
   return c;
 }
 
-int graph_chebyshev_fwd(const GraphArgs& a, cudaStream_t st) {
+int graph_chebyshev_fwd(const GraphArgs& a, cudaStream_t st, int above_n) {
   if (a.K <= 1) return AGCN_OK;
   const agcn_plan* plan = a.plan;
   const bool shortcut = (a.Lall == nullptr);
@@ -784,6 +784,7 @@ int graph_chebyshev_fwd(const GraphArgs& a, cudaStream_t st) {
   for (int b = 0; b < nb; ++b) {
     const Bucket& bk = plan->buckets[b];
     if (bk.max_n > plan->cheb_small_max) continue;  // row-tiled below
+    if (bk.limit <= above_n) continue;              // owned by the fused tile kernel
     ChunkCfg c = chunk_cfg(bk.max_n, a.F, 2, 1, false);
     rc = set_smem(cheb_fwd_kernel, c.smem);
     if (rc) return rc;
@@ -797,7 +798,7 @@ int graph_chebyshev_fwd(const GraphArgs& a, cudaStream_t st) {
   return join_streams(plan, st, nb - 1);
 }
 
-int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st) {
+int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st, int above_n) {
   const agcn_plan* plan = a.plan;
   const bool shortcut = (a.Lall == nullptr);
   const int nb = (int)plan->buckets.size();
@@ -806,6 +807,7 @@ int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st) {
   for (int b = 0; b < nb; ++b) {
     const Bucket& bk = plan->buckets[b];
     if (!need_dL && bk.max_n > plan->cheb_small_max) continue;  // row-tiled below
+    if (bk.limit <= above_n) continue;                          // owned by the fused tile kernel
     ChunkCfg c = chunk_cfg(bk.max_n, a.F, need_dL ? 3 : 2, need_dL ? 2 : 1, need_dL);
     rc = set_smem(recur_bwd_kernel, c.smem);
     if (rc) return rc;

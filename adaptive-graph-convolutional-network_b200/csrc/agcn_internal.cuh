@@ -16,6 +16,11 @@
 // Graphs above this size run their Chebyshev recurrences as row-tiled grouped GEMMs (one launch per step,
 // several CTAs per graph) instead of one CTA per (graph, feature chunk).
 #define AGCN_CHEB_SMALL_MAX 144
+// Fused tile kernels (agcn_fused_tile.cu): graphs up to this size are packed into 128-row tiles and run their
+// Chebyshev recurrences inside the tensor-core kernel; AGCN_FUSE_LCAP floats of shared memory hold the
+// per-graph matrices of one tile (row pitch n | 1; one 96-node graph plus one 32-node graph fit).
+#define AGCN_FUSE_MAX_N 96
+#define AGCN_FUSE_LCAP 10752
 
 namespace agcn {
 
@@ -23,6 +28,7 @@ struct Bucket {
   int start;  // first index into plan->order
   int count;  // graphs in the bucket
   int max_n;  // largest n in the bucket
+  int limit;  // upper size limit of the bucket (every graph of the bucket has n <= limit)
 };
 
 void set_error(const std::string& msg);
@@ -78,6 +84,13 @@ struct agcn_plan {
   int32_t* d_tile_graph = nullptr;
   int32_t* d_tile_row = nullptr;
   int32_t* d_big_tile_start = nullptr;
+  // fused tiles: tile t owns entries ft_gstart[t] .. ft_gstart[t+1]; an entry is {graph, first tile row, n,
+  // float offset of the graph's matrix in the tile's shared-memory L region} for whole small graphs or
+  // {graph, first graph row, rows, -1} for a 128-row range of a graph with n > AGCN_FUSE_MAX_N
+  int ft_tiles = 0;
+  std::vector<int32_t> ft_gstart, ft_entries;
+  int32_t* d_ft_gstart = nullptr;
+  int32_t* d_ft_entries = nullptr;  // int4 per entry, 16-byte aligned
   // side streams so the per-bucket launches of one phase overlap on the device
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
@@ -189,8 +202,9 @@ struct GraphArgs {
 };
 bool literal_shortcut(int variant, int lap_mode);  // L_all == I + Lint, nothing to build
 int graph_build_laplacian(const GraphArgs& a, bool need_W, cudaStream_t st);
-int graph_chebyshev_fwd(const GraphArgs& a, cudaStream_t st);
-int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st);
+// above_n: only the graphs with more than above_n nodes (the fused tile kernels own the others)
+int graph_chebyshev_fwd(const GraphArgs& a, cudaStream_t st, int above_n = 0);
+int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st, int above_n = 0);
 int graph_laplacian_bwd(const GraphArgs& a, cudaStream_t st);
 int reduce_scalar_parts(const float* parts, int B, float* out, cudaStream_t st);
 // graphs with more than AGCN_SMALL_MAX nodes (agcn_graph_large.cu)
@@ -201,6 +215,20 @@ size_t big_work_floats(const agcn_plan* plan, bool full);
 int big_build_laplacian(const GraphArgs& a, bool need_W, float* big_work, cudaStream_t st);
 int big_dL(const GraphArgs& a, const float* U, cudaStream_t st);
 int big_laplacian_bwd(const GraphArgs& a, float* big_work, cudaStream_t st);
+
+// ---------------------------------------------------------------- fused tile kernels (agcn_fused_tile.cu)
+bool fused_fwd_supported(const agcn_plan* plan, int F, int Fo, int K);
+bool fused_bwd_supported(const agcn_plan* plan, int F, int Fo, int K);
+size_t fused_w_floats(int Nv, int Kv, int Z);  // floats of one pre-split parameter operand
+int fused_fwd_prep(const float* weight, int F, int Fo, int K, float* scratch, cudaStream_t st);
+int fused_bwd_prep(const float* weight, int F, int Fo, int K, float* scratch, cudaStream_t st);
+// T_1..T_{K-1} (saved) and Y = act(sum_k T_k W_k + b) for every tile of the plan; L = Lint (add_identity) or L_all
+int fused_forward(const agcn_plan* plan, const float* X, const float* L, int add_identity, const float* wsplit,
+                  const float* bias, int act, int F, int Fo, int K, float* T, float* Y, cudaStream_t st);
+// dX = U_0 of the reverse recurrence over G_z = dYp W_z^T; G receives G_z for the rows of graphs with
+// n > AGCN_FUSE_MAX_N only
+int fused_backward(const agcn_plan* plan, const float* dYp, const float* L, int add_identity, const float* wsplit,
+                   int F, int Fo, int K, float* G, float* dX, cudaStream_t st);
 
 // ---------------------------------------------------------------- helpers
 int fork_streams(const agcn_plan* plan, cudaStream_t main, int n_aux);

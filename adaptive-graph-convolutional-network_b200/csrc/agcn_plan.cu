@@ -84,6 +84,49 @@ __global__ void pack_lap_kernel(const float* __restrict__ padded, float* __restr
   }
 }
 
+
+// Fused tiles (agcn_fused_tile.cu): 128-row ranges of the graphs above AGCN_FUSE_MAX_N, then the small graphs
+// first-fit-decreasing into 128-row tiles under the shared-memory budget of their L matrices.  `order` lists the
+// graphs largest first.  gstart gets tiles + 1 entries.
+static void build_fused_tiles(const std::vector<int32_t>& n, const std::vector<int32_t>& order,
+                              std::vector<int32_t>* gstart, std::vector<int32_t>* entries) {
+  const int B = (int)n.size();
+  gstart->clear();
+  entries->clear();
+  auto push = [&](int g, int a, int b, int c) {
+    entries->push_back(g); entries->push_back(a); entries->push_back(b); entries->push_back(c);
+  };
+  int i = 0;
+  for (; i < B && n[order[i]] > AGCN_FUSE_MAX_N; ++i) {
+    const int g = order[i];
+    for (int r = 0; r < n[g]; r += 128) {
+      gstart->push_back((int32_t)(entries->size() / 4));
+      push(g, r, std::min(128, n[g] - r), -1);
+    }
+  }
+  struct Open { int rows, lused; std::vector<int32_t> e; };
+  std::vector<Open> open;
+  size_t first_open = 0;
+  const int min_n = n[order[B - 1]];
+  for (; i < B; ++i) {
+    const int g = order[i], ng = n[g], need = ng * (ng | 1);
+    size_t t = first_open;
+    for (; t < open.size(); ++t)
+      if (open[t].rows + ng <= 128 && open[t].lused + need <= AGCN_FUSE_LCAP) break;
+    if (t == open.size()) open.push_back(Open{0, 0, {}});
+    Open& o = open[t];
+    o.e.push_back(g); o.e.push_back(o.rows); o.e.push_back(ng); o.e.push_back(o.lused);
+    o.rows += ng;
+    o.lused += need;
+    while (first_open < open.size() && open[first_open].rows + min_n > 128) ++first_open;
+  }
+  for (const Open& o : open) {
+    gstart->push_back((int32_t)(entries->size() / 4));
+    entries->insert(entries->end(), o.e.begin(), o.e.end());
+  }
+  gstart->push_back((int32_t)(entries->size() / 4));
+}
+
 }  // namespace agcn
 
 using namespace agcn;
@@ -140,19 +183,22 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
     p->big_tile_start.push_back(p->large_tiles);
     p->big_tiles = p->large_tiles;
   }
-  static const int limits[] = {AGCN_SMALL_MAX, 64, 32, 16};  // bucket = (limit_next, limit]
+  static const int limits[] = {AGCN_SMALL_MAX, AGCN_FUSE_MAX_N, 32, 16};  // bucket = (limit_next, limit]
   for (int b = 0; b < 4 && pos < B; ++b) {
     const int lo = (b + 1 < 4) ? limits[b + 1] : 0;
     const int start = pos;
     while (pos < B && p->n[p->order[pos]] > lo) ++pos;
-    if (pos > start) p->buckets.push_back(Bucket{start, pos - start, p->n[p->order[start]]});
+    if (pos > start) p->buckets.push_back(Bucket{start, pos - start, p->n[p->order[start]], limits[b]});
   }
+  build_fused_tiles(p->n, p->order, &p->ft_gstart, &p->ft_entries);
+  p->ft_tiles = (int)p->ft_gstart.size() - 1;
   // device block: n[B] node_off[B+1] order[B] tile_graph[T] tile_row[T] (int32) then lap_off[B+1] (int64)
   const size_t T = (size_t)p->large_tiles;
   const size_t NB = p->big_tile_start.size();
-  const size_t n32 = (size_t)B + (B + 1) + B + 2 * T + NB;
+  const size_t n32 = (size_t)B + (B + 1) + B + 2 * T + NB + p->ft_gstart.size();
   const size_t off64 = (n32 * 4 + 15) / 16 * 16;
-  const size_t bytes = off64 + (size_t)(B + 1) * 8;
+  const size_t off_ft = (off64 + (size_t)(B + 1) * 8 + 15) / 16 * 16;  // int4 entries of the fused tiles
+  const size_t bytes = off_ft + p->ft_entries.size() * 4;
   std::vector<char> host(bytes, 0);
   int32_t* h32 = reinterpret_cast<int32_t*>(host.data());
   std::memcpy(h32, p->n.data(), (size_t)B * 4);
@@ -163,7 +209,9 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
     std::memcpy(h32 + 3 * B + 1 + T, p->tile_row.data(), T * 4);
   }
   std::memcpy(h32 + 3 * B + 1 + 2 * T, p->big_tile_start.data(), NB * 4);
+  std::memcpy(h32 + 3 * B + 1 + 2 * T + NB, p->ft_gstart.data(), p->ft_gstart.size() * 4);
   std::memcpy(host.data() + off64, p->lap_off.data(), (size_t)(B + 1) * 8);
+  std::memcpy(host.data() + off_ft, p->ft_entries.data(), p->ft_entries.size() * 4);
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMalloc(&p->d_block, bytes);
   if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_block, host.data(), bytes, cudaMemcpyHostToDevice, st);
@@ -188,8 +236,28 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   p->d_tile_graph = d32 + 3 * B + 1;
   p->d_tile_row = d32 + 3 * B + 1 + T;
   p->d_big_tile_start = d32 + 3 * B + 1 + 2 * T;
+  p->d_ft_gstart = d32 + 3 * B + 1 + 2 * T + NB;
   p->d_lap_off = reinterpret_cast<int64_t*>(reinterpret_cast<char*>(p->d_block) + off64);
+  p->d_ft_entries = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(p->d_block) + off_ft);
   *out = p;
+  return AGCN_OK;
+}
+
+int agcn_fused_tiles_host(const int32_t* n_nodes_host, int32_t B, int32_t* gstart_out, int32_t gstart_cap,
+                          int32_t* entries_out, int32_t entries_cap, int32_t* tiles_out, int32_t* n_entries_out) {
+  AGCN_REQUIRE(n_nodes_host && B >= 1 && tiles_out && n_entries_out, "fused_tiles_host: bad arguments");
+  std::vector<int32_t> n(n_nodes_host, n_nodes_host + B), order(B), gs, en;
+  for (int g = 0; g < B; ++g) AGCN_REQUIRE(n[g] >= 1, "n_nodes[g] must be >= 1");
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n[a] > n[b]; });
+  build_fused_tiles(n, order, &gs, &en);
+  *tiles_out = (int32_t)gs.size() - 1;
+  *n_entries_out = (int32_t)(en.size() / 4);
+  if (gstart_out && entries_out) {
+    AGCN_REQUIRE(gstart_cap >= (int32_t)gs.size() && entries_cap >= (int32_t)en.size(), "fused_tiles_host: buffers too small");
+    std::memcpy(gstart_out, gs.data(), gs.size() * 4);
+    std::memcpy(entries_out, en.data(), en.size() * 4);
+  }
   return AGCN_OK;
 }
 

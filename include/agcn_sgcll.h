@@ -91,6 +91,14 @@ int64_t agcn_plan_total_lap(const agcn_plan* plan);      /* sum n_g^2        */
 const int32_t* agcn_plan_node_off_host(const agcn_plan* plan); /* [B+1] host   */
 const int64_t* agcn_plan_lap_off_host(const agcn_plan* plan);  /* [B+1] host   */
 
+/* Host-only view of the work decomposition of the fused tile kernels (no reference counterpart; exported for
+ * tests and tuning): the graphs of a batch are packed into 128-row tiles.  Tile t owns entries
+ * gstart[t] .. gstart[t+1]; an entry is 4 int32: {graph, first tile row, n_g, offset of the graph's matrix in
+ * the tile's shared-memory Laplacian area} for a whole graph, or {graph, first graph row, rows, -1} for a
+ * 128-row range of a graph too large to share a tile.  Call with NULL buffers to get the counts. */
+int agcn_fused_tiles_host(const int32_t* n_nodes_host, int32_t B, int32_t* gstart_out, int32_t gstart_cap,
+                          int32_t* entries_out, int32_t entries_cap, int32_t* tiles_out, int32_t* n_entries_out);
+
 /* ---- layout conversion (pad_data2sparse / pad_Lap2sparse, graph_topology.py:84-98;
  *      tf.slice at graphconv.py:153-154; tf.pad at graphconv.py:249-251) ------------------ */
 int agcn_pack_nodes(const agcn_plan* plan, const float* d_padded /*[B,Nmax,F]*/, float* d_packed /*[R,F]*/,

@@ -144,3 +144,46 @@ def test_initialisers():
         assert r.vars["beta"].tolist() == [1.0]
     finally:
         gc.DEFAULT_DEVICE[0] = "cuda"
+
+
+def test_fused_tile_packing_invariants():
+    """Work decomposition of the fused tile kernels (agcn_fused_tiles_host, host only): every graph is
+    covered exactly once, tiles hold at most 128 rows and AGCN_FUSE_LCAP floats of Laplacians, graphs
+    above AGCN_FUSE_MAX_N are cut into 128-row ranges."""
+    import ctypes
+    from agcn_b200 import _lib
+    from oracle import sgcll_oracle as O
+    FUSE_MAX_N, LCAP = 96, 10752
+    cases = [np.array([132, 4, 5, 18, 33, 64, 65, 17, 96, 31], np.int32),
+             np.array([1] * 300, np.int32),
+             np.array([1024, 700, 13, 145, 96, 97, 128, 129], np.int32),
+             O.synthetic_molecule_batch(1024, 132, seed=1235)[2].astype(np.int32)]
+    for n in cases:
+        B = len(n)
+        tiles, n_ent = ctypes.c_int32(), ctypes.c_int32()
+        vp = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        _lib.check(_lib.lib().agcn_fused_tiles_host(vp(n), B, None, 0, None, 0, ctypes.byref(tiles), ctypes.byref(n_ent)))
+        gstart = np.zeros(tiles.value + 1, np.int32)
+        ent = np.zeros(n_ent.value * 4, np.int32)
+        _lib.check(_lib.lib().agcn_fused_tiles_host(vp(n), B, vp(gstart), gstart.size, vp(ent), ent.size,
+                                                    ctypes.byref(tiles), ctypes.byref(n_ent)))
+        ent = ent.reshape(-1, 4)
+        assert gstart[0] == 0 and gstart[-1] == n_ent.value and np.all(np.diff(gstart) >= 1)
+        covered = np.zeros(B, np.int64)
+        for t in range(tiles.value):
+            e = ent[gstart[t]:gstart[t + 1]]
+            if e[0, 3] < 0:                                   # row range of a big graph
+                assert len(e) == 1 and n[e[0, 0]] > FUSE_MAX_N
+                assert 1 <= e[0, 2] <= 128 and e[0, 1] % 128 == 0 and e[0, 1] + e[0, 2] <= n[e[0, 0]]
+                covered[e[0, 0]] += e[0, 2]
+            else:
+                rows, lused = 0, 0
+                for g, r0, ng, lbase in e:
+                    assert ng == n[g] <= FUSE_MAX_N and r0 == rows and lbase == lused
+                    rows += ng
+                    lused += ng * (ng | 1)
+                    covered[g] += ng
+                assert rows <= 128 and lused <= LCAP and len(e) <= 128
+        assert np.array_equal(covered, n.astype(np.int64))
+        if B == 1024:   # ToxCast-shape batch: tiles are well filled (R / 128 is the lower bound)
+            assert tiles.value <= int(np.ceil(n.sum() / 128.0 * 1.08)) + 2, (tiles.value, n.sum() / 128.0)
