@@ -231,11 +231,27 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
   }
   ga.Lall = m.shortcut ? nullptr : sv.Lall;
   if (fuse_f) {
-    // graphs above AGCN_FUSE_MAX_N keep their per-graph / row-tiled recurrences; the tile kernel reads their T_k
-    if (plan->max_n > AGCN_FUSE_MAX_N && (rc = graph_chebyshev_fwd(ga, st, AGCN_FUSE_MAX_N))) return rc;
+    const float* Lf = m.shortcut ? d_Lint : sv.Lall;
+    const int ident = m.shortcut ? 1 : 0, n_pre = plan->ft_tiles - plan->ft_small_tiles;
+    if (n_pre > 0) {
+      // graphs above AGCN_FUSE_MAX_N keep their per-graph / row-tiled recurrences (chunk-parallel); their chain
+      // runs on its own stream beside the launch of the small-graph tiles and ends with its own tile launch,
+      // which reads the T_k it produced
+      AGCN_CUDA(cudaEventRecord(plan->ev_big_fork, st));
+      AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_big_fork, 0));
+      if ((rc = graph_chebyshev_fwd(ga, plan->big, AGCN_FUSE_MAX_N))) return rc;
+      AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_side_join, 0));
+      if ((rc = fused_forward(plan, plan->ft_small_tiles, n_pre, d_X, Lf, ident, wk.ftY, d_bias, desc->activation, F, Fo,
+                              K, sv.T, d_Y, plan->big)))
+        return rc;
+      AGCN_CUDA(cudaEventRecord(plan->ev_big_join, plan->big));
+    }
     AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
-    return fused_forward(plan, d_X, m.shortcut ? d_Lint : sv.Lall, m.shortcut ? 1 : 0, wk.ftY, d_bias,
-                         desc->activation, F, Fo, K, sv.T, d_Y, st);
+    if ((rc = fused_forward(plan, 0, plan->ft_small_tiles, d_X, Lf, ident, wk.ftY, d_bias, desc->activation, F, Fo, K,
+                            sv.T, d_Y, st)))
+      return rc;
+    if (n_pre > 0) AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_big_join, 0));
+    return AGCN_OK;
   }
   if ((rc = graph_chebyshev_fwd(ga, st))) return rc;  // graphconv.py:221-236
   if (y_tc || g_tc || fuse_b) AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
@@ -312,10 +328,18 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   if (fuse_b) {
     // G_z = dYpre W_z^T and the reverse recurrence in one kernel; graphs above AGCN_FUSE_MAX_N get their G_z
     // rows in wk.G and finish in the per-graph / row-tiled kernels
-    if ((rc = fused_backward(plan, dYp, m.shortcut ? d_Lint : sv.Lall, m.shortcut ? 1 : 0, sv.ftG, F, Fo, K, wk.G,
-                             d_dX, st)))
-      return rc;
-    if (plan->max_n > AGCN_FUSE_MAX_N && (rc = graph_recurrence_bwd(ga, false, st, AGCN_FUSE_MAX_N))) return rc;
+    const float* Lf = m.shortcut ? d_Lint : sv.Lall;
+    const int ident = m.shortcut ? 1 : 0, n_pre = plan->ft_tiles - plan->ft_small_tiles;
+    if (n_pre > 0) {
+      AGCN_CUDA(cudaEventRecord(plan->ev_big_fork, st));
+      AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_big_fork, 0));
+      if ((rc = fused_backward(plan, plan->ft_small_tiles, n_pre, dYp, Lf, ident, sv.ftG, F, Fo, K, wk.G, d_dX, plan->big)))
+        return rc;
+      if ((rc = graph_recurrence_bwd(ga, false, plan->big, AGCN_FUSE_MAX_N))) return rc;
+      AGCN_CUDA(cudaEventRecord(plan->ev_big_join, plan->big));
+    }
+    if ((rc = fused_backward(plan, 0, plan->ft_small_tiles, dYp, Lf, ident, sv.ftG, F, Fo, K, wk.G, d_dX, st))) return rc;
+    if (n_pre > 0) AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_big_join, 0));
   } else if (K >= 2) {
     if (need_G && (rc = graph_recurrence_bwd(ga, m.need_dL, st))) return rc;
   } else if (m.need_dL) {

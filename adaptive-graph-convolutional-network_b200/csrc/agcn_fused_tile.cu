@@ -71,7 +71,6 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
-__device__ __forceinline__ void worker_barrier() { asm volatile("bar.sync 1, 128;\n" ::: "memory"); }
 
 // shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms of 1024 bytes
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
@@ -130,105 +129,155 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
 }
 
-__device__ __forceinline__ void cp_async4(float* sdst, const float* gsrc) {
-  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+// ---- explicit shared-space accesses (32-bit shared addresses): the operand stages and chunk buffers are carved
+// from one dynamic allocation with integer arithmetic, so plain pointers would compile to generic LD/ST
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
 }
-__device__ __forceinline__ void cp_async16(float* sdst, const float* gsrc) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(smem_u32(sdst)), "l"(gsrc) : "memory");
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ int ldsi32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t sdst, const float* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sdst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async16(uint32_t sdst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sdst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// ---- fp32 chunk buffers: [128 rows][32 floats], 16-byte groups XOR-swizzled by (row & 7) (same pattern as
-// the operand stages, so rows of different graphs read by one warp fall into different banks)
-__device__ __forceinline__ float* chunk_ptr(float* buf, int row, int group) {
-  return buf + row * CH + ((group ^ (row & 7)) << 2);
+// ---- fp32 chunk buffers: [128 rows][32 floats] with a row pitch of 36 floats (144 bytes): rows r and r' read by
+// one warp (different graphs) collide only if r == r' (mod 8), and a row's 16-byte groups sit at immediate
+// offsets from one base register
+constexpr int CPITCH = 144;
+constexpr int CBUF_BYTES = TM * CPITCH;  // 18 KB
+__device__ __forceinline__ uint32_t chunk_addr(uint32_t buf, int row, int group) {
+  return buf + (uint32_t)(row * CPITCH + (group << 4));
 }
 
-// This warp's 32 rows (quarter q) of a 32-column chunk: global [.., ld] rows s_grow[row] -> buf, asynchronously.
-__device__ __forceinline__ void load_rows_async(float* buf, const float* __restrict__ M, int ld, int ncols, int c,
-                                                const int* s_grow, int q, int lane, bool vec) {
+// Worker warp (quarter q, column half h): its 32 rows x 16 columns of chunk c, global rows s_grow[row] -> buf.
+__device__ __forceinline__ void load_rows_async(uint32_t buf, const float* __restrict__ M, int ld, int ncols, int c,
+                                                uint32_t s_grow, int q, int h, int lane, bool vec) {
   if (vec) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = q * 32 + 4 * i + (lane >> 3), grp = lane & 7, col = c * CH + grp * 4;
-      const int grow = s_grow[row];
-      float* d = chunk_ptr(buf, row, grp);
+    for (int i = 0; i < 4; ++i) {
+      const int row = q * 32 + 8 * i + (lane >> 2), grp = 4 * h + (lane & 3), col = c * CH + grp * 4;
+      const int grow = ldsi32(s_grow + 4 * row);
+      const uint32_t d = chunk_addr(buf, row, grp);
       if (grow >= 0 && col < ncols)
         cp_async16(d, M + (int64_t)grow * ld + col);
       else
-        *reinterpret_cast<float4*>(d) = make_float4(0.f, 0.f, 0.f, 0.f);
+        sts128(d, make_float4(0.f, 0.f, 0.f, 0.f));
     }
   } else {
-    for (int i = 0; i < 32; ++i) {
-      const int row = q * 32 + i, col = c * CH + lane;
-      const int grow = s_grow[row];
-      float* d = chunk_ptr(buf, row, lane >> 2) + (lane & 3);
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int row = q * 32 + 2 * i + (lane >> 4), cc = 16 * h + (lane & 15), col = c * CH + cc;
+      const int grow = ldsi32(s_grow + 4 * row);
+      const uint32_t d = chunk_addr(buf, row, cc >> 2) + 4 * (cc & 3);
       if (grow >= 0 && col < ncols)
         cp_async4(d, M + (int64_t)grow * ld + col);
       else
-        *d = 0.f;
+        sts32(d, 0.f);
     }
   }
 }
 
-// This warp's 32 rows of a chunk: buf -> global rows (coalesced).  Callers bracket with __syncwarp.
-__device__ __forceinline__ void store_rows(const float* buf, float* __restrict__ M, int ld, int ncols, int c,
-                                           const int* s_grow, int q, int lane, bool vec) {
+// The same 32 x 16 block, buf -> global rows (coalesced).  Callers bracket with __syncwarp.
+__device__ __forceinline__ void store_rows(uint32_t buf, float* __restrict__ M, int ld, int ncols, int c, uint32_t s_grow,
+                                           int q, int h, int lane, bool vec) {
   if (vec) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int row = q * 32 + 4 * i + (lane >> 3), grp = lane & 7, col = c * CH + grp * 4;
-      const int grow = s_grow[row];
-      if (grow >= 0 && col < ncols)
-        *reinterpret_cast<float4*>(M + (int64_t)grow * ld + col) =
-            *reinterpret_cast<const float4*>(chunk_ptr(const_cast<float*>(buf), row, grp));
+    for (int i = 0; i < 4; ++i) {
+      const int row = q * 32 + 8 * i + (lane >> 2), grp = 4 * h + (lane & 3), col = c * CH + grp * 4;
+      const int grow = ldsi32(s_grow + 4 * row);
+      if (grow >= 0 && col < ncols) *reinterpret_cast<float4*>(M + (int64_t)grow * ld + col) = lds128(chunk_addr(buf, row, grp));
     }
   } else {
-    for (int i = 0; i < 32; ++i) {
-      const int row = q * 32 + i, col = c * CH + lane;
-      const int grow = s_grow[row];
-      if (grow >= 0 && col < ncols) M[(int64_t)grow * ld + col] = *(chunk_ptr(const_cast<float*>(buf), row, lane >> 2) + (lane & 3));
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int row = q * 32 + 2 * i + (lane >> 4), cc = 16 * h + (lane & 15), col = c * CH + cc;
+      const int grow = ldsi32(s_grow + 4 * row);
+      if (grow >= 0 && col < ncols) M[(int64_t)grow * ld + col] = lds32(chunk_addr(buf, row, cc >> 2) + 4 * (cc & 3));
     }
   }
 }
 
-__device__ __forceinline__ void read_row(const float* buf, int row, float v[32]) {
+// my half row (16 columns: groups 4h .. 4h+3)
+__device__ __forceinline__ void read_half(uint32_t buf, int row, int h, float v[16]) {
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
-    const float4 x = *reinterpret_cast<const float4*>(chunk_ptr(const_cast<float*>(buf), row, g));
+  for (int g = 0; g < 4; ++g) {
+    const float4 x = lds128(chunk_addr(buf, row, 4 * h + g));
     v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
   }
 }
-__device__ __forceinline__ void write_row(float* buf, int row, const float v[32]) {
+__device__ __forceinline__ void write_half(uint32_t buf, int row, int h, const float v[16]) {
 #pragma unroll
-  for (int g = 0; g < 8; ++g)
-    *reinterpret_cast<float4*>(chunk_ptr(buf, row, g)) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+  for (int g = 0; g < 4; ++g)
+    sts128(chunk_addr(buf, row, 4 * h + g), make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]));
 }
 
-// acc[:] = sum_j Lrow[j * lstride] * src[r0 + j][:]
-__device__ __forceinline__ void lap_times_rows(const float* __restrict__ Lrow, int lstride, const float* src, int r0, int n,
-                                               float acc[32]) {
+// acc[:] += sum_j L[laddr + j * lstride_bytes] * src[r0 + j][16h .. 16h+15]
+// Four rows per trip with every shared-memory load issued before the first FMA that needs it (2 warps per
+// scheduler cannot hide the LDS latency otherwise).
+__device__ __forceinline__ void fma_row(float a, const float4 b[4], float acc[16]) {
 #pragma unroll
-  for (int i = 0; i < 32; ++i) acc[i] = 0.f;
-  for (int j = 0; j < n; ++j) {
-    const float a = Lrow[j * lstride];
-    const int row = r0 + j;
+  for (int g = 0; g < 4; ++g) {
+    acc[4 * g] = fmaf(a, b[g].x, acc[4 * g]);
+    acc[4 * g + 1] = fmaf(a, b[g].y, acc[4 * g + 1]);
+    acc[4 * g + 2] = fmaf(a, b[g].z, acc[4 * g + 2]);
+    acc[4 * g + 3] = fmaf(a, b[g].w, acc[4 * g + 3]);
+  }
+}
+__device__ __forceinline__ void lap_times_rows(uint32_t laddr, int lstride_bytes, uint32_t src, int r0, int n, int h,
+                                               float acc[16]) {
+  uint32_t ta = src + (uint32_t)(r0 * CPITCH + h * 64);
+  uint32_t la = laddr;
+  int j = 0;
+  for (; j + 4 <= n; j += 4) {
+    float a[4];
+    float4 b[4][4];
 #pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      const float4 b = *reinterpret_cast<const float4*>(chunk_ptr(const_cast<float*>(src), row, g));
-      acc[4 * g] = fmaf(a, b.x, acc[4 * g]);
-      acc[4 * g + 1] = fmaf(a, b.y, acc[4 * g + 1]);
-      acc[4 * g + 2] = fmaf(a, b.z, acc[4 * g + 2]);
-      acc[4 * g + 3] = fmaf(a, b.w, acc[4 * g + 3]);
+    for (int u = 0; u < 4; ++u) {
+      a[u] = lds32(la + (uint32_t)(u * lstride_bytes));
+#pragma unroll
+      for (int g = 0; g < 4; ++g) b[u][g] = lds128(ta + (uint32_t)(u * CPITCH + 16 * g));
     }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) fma_row(a[u], b[u], acc);
+    la += 4 * lstride_bytes;
+    ta += 4 * CPITCH;
+  }
+  for (; j < n; ++j) {
+    const float a = lds32(la);
+    float4 b[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) b[g] = lds128(ta + 16 * g);
+    fma_row(a, b, acc);
+    la += lstride_bytes;
+    ta += CPITCH;
   }
 }
 
-// One row of a 128x32 K-major SWIZZLE_128B operand tile, split into hi / lo TF32 halves.
-__device__ __forceinline__ void write_operand_row(uint8_t* a_hi, uint8_t* a_lo, int row, const float v[32]) {
+// My half of one row of a 128x32 K-major SWIZZLE_128B operand tile, split into hi / lo TF32 halves.
+__device__ __forceinline__ void write_operand_half(uint32_t a_hi, uint32_t a_lo, int row, int h, const float v[16]) {
 #pragma unroll
-  for (int g = 0; g < 8; ++g) {
+  for (int g = 0; g < 4; ++g) {
     float4 hi, lo;
     hi.x = __uint_as_float(__float_as_uint(v[4 * g]) & 0xffffe000u);
     hi.y = __uint_as_float(__float_as_uint(v[4 * g + 1]) & 0xffffe000u);
@@ -238,20 +287,38 @@ __device__ __forceinline__ void write_operand_row(uint8_t* a_hi, uint8_t* a_lo, 
     lo.y = __uint_as_float(__float_as_uint(v[4 * g + 1] - hi.y) & 0xffffe000u);
     lo.z = __uint_as_float(__float_as_uint(v[4 * g + 2] - hi.z) & 0xffffe000u);
     lo.w = __uint_as_float(__float_as_uint(v[4 * g + 3] - hi.w) & 0xffffe000u);
-    const int off = row * 128 + ((g ^ (row & 7)) << 4);
-    *reinterpret_cast<float4*>(a_hi + off) = hi;
-    *reinterpret_cast<float4*>(a_lo + off) = lo;
+    const uint32_t off = (uint32_t)(row * 128 + (((4 * h + g) ^ (row & 7)) << 4));
+    sts128(a_hi + off, hi);
+    sts128(a_lo + off, lo);
   }
+}
+
+// 16 consecutive fp32 accumulator columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t u[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
 }
 
 // ------------------------------------------------------------------------------------------------
 // shared memory carve-up (identical for both directions)
 // ------------------------------------------------------------------------------------------------
+constexpr int WORKERS = 256;  // warps 2..9: two threads per tile row (column halves)
+constexpr int THREADS = 64 + WORKERS;
+
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
 struct SmemPlan {
   int stages, stage_bytes, b_bytes;
   int off_bufs;   // 3 fp32 chunk buffers (forward) -- the backward recurrence reuses the operand stages
   int off_L;      // LCAP floats
-  int off_glist;  // 128 int4
+  int off_glist;  // 128 entries of 2 x int4
   int off_grow;   // 128 int
   int off_bars;
   int total;
@@ -261,16 +328,16 @@ __host__ __device__ inline SmemPlan smem_plan(int N, bool forward) {
   SmemPlan s;
   s.b_bytes = N * 128;
   s.stage_bytes = 2 * A_BYTES + 2 * s.b_bytes;
-  const int fixed = (forward ? 3 * A_BYTES : 0) + LCAP * 4 + 128 * 16 + 128 * 4 + 256 + 1024;
+  const int fixed = (forward ? 3 * CBUF_BYTES : 0) + LCAP * 4 + 128 * 32 + 128 * 4 + 256 + 1024;
   int stages = (227 * 1024 - fixed) / s.stage_bytes;
   s.stages = stages > 4 ? 4 : stages;
   int off = s.stages * s.stage_bytes;
   s.off_bufs = off;
-  off += forward ? 3 * A_BYTES : 0;
+  off += forward ? 3 * CBUF_BYTES : 0;
   s.off_L = off;
   off += LCAP * 4;
   s.off_glist = off;
-  off += 128 * 16;
+  off += 128 * 32;
   s.off_grow = off;
   off += 128 * 4;
   s.off_bars = off;
@@ -290,53 +357,62 @@ struct TileRow {
 };
 
 struct TileArgs {
-  const int4* tile_graphs;     // {g, r0 | row_start, n | nrows, lbase | -1}
+  const int4* tile_graphs;     // 2 x int4 per entry: {g, r0 | row_start, n | nrows, lbase | -1}, {node_off, lap_off lo, hi, 0}
   const int32_t* tile_gstart;  // [tiles + 1]
-  const int32_t* node_off;
-  const int64_t* lap_off;
   const float* L;              // packed Laplacians (Lint or L_all)
   int add_identity;
+  int tile0;                   // first tile of this launch
   int F, Fo, K;
   int N;                       // MMA N (padded output columns of the mainloop)
   int nchunks;                 // k-blocks per slice
 };
 
-// Prologue shared by both kernels (worker threads): graph list, row table, L matrices of the tile.
-__device__ __forceinline__ TileRow tile_prologue(const TileArgs& p, int tile, int r, int wt, int4* s_glist, int* s_grow,
-                                                 float* sL) {
+// Prologue shared by both kernels (worker threads): graph list and row table of the tile; the copies of the
+// per-graph L matrices are left in flight (cp.async): callers wait + worker_sync before the first use.
+__device__ __forceinline__ TileRow tile_prologue(const TileArgs& p, int tile, int r, int h, int wt, uint32_t s_glist,
+                                                 uint32_t s_grow, uint32_t sL, int* ng_out) {
   const int gs = p.tile_gstart[tile], ng = p.tile_gstart[tile + 1] - gs;
-  for (int e = wt; e < ng; e += 128) s_glist[e] = p.tile_graphs[gs + e];
-  worker_barrier();
+  *ng_out = ng;
+  for (int e = wt; e < 2 * ng; e += WORKERS) {
+    const int4 v = __ldg(p.tile_graphs + 2 * gs + e);
+    asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};\n" ::"r"(s_glist + 16 * e), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+  }
+  worker_sync();
   TileRow t;
   t.grow = -1; t.n = 0; t.r0 = 0; t.lbase = 0; t.i = 0; t.pitch = 1; t.pre = false;
   for (int e = 0; e < ng; ++e) {
-    const int4 ge = s_glist[e];
-    if (ge.w < 0) {  // pre tile: rows [ge.y, ge.y + ge.z) of graph ge.x
+    int gx, gy, gz, gw;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];\n" : "=r"(gx), "=r"(gy), "=r"(gz), "=r"(gw) : "r"(s_glist + 32 * e) : "memory");
+    const int noff = ldsi32(s_glist + 32 * e + 16);
+    if (gw < 0) {  // pre tile: rows [gy, gy + gz) of graph gx
       t.pre = true;
-      if (r < ge.z) t.grow = p.node_off[ge.x] + ge.y + r;
-    } else if (r >= ge.y && r < ge.y + ge.z) {
-      t.grow = p.node_off[ge.x] + (r - ge.y);
-      t.n = ge.z; t.r0 = ge.y; t.lbase = ge.w; t.i = r - ge.y; t.pitch = ge.z | 1;
+      if (r < gz) t.grow = noff + gy + r;
+    } else if (r >= gy && r < gy + gz) {
+      t.grow = noff + (r - gy);
+      t.n = gz; t.r0 = gy; t.lbase = gw; t.i = r - gy; t.pitch = gz | 1;
     }
   }
-  s_grow[r] = t.grow;
+  if (h == 0) asm volatile("st.shared.s32 [%0], %1;\n" ::"r"(s_grow + 4 * r), "r"(t.grow) : "memory");
   // per-graph matrices, row pitch n | 1 (odd: the rows read by neighbouring lanes sit in different banks)
   for (int e = 0; e < ng; ++e) {
-    const int4 ge = s_glist[e];
-    if (ge.w < 0) continue;
-    const int n = ge.z, pitch = n | 1;
-    const float* __restrict__ src = p.L + p.lap_off[ge.x];
-    float* dst = sL + ge.w;
-    for (int idx = wt; idx < n * n; idx += 128) {
-      const int i = idx / n, j = idx - i * n;
-      cp_async4(dst + i * pitch + j, src + idx);
+    int gx, gy, gz, gw, lo, hi;
+    asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];\n" : "=r"(gx), "=r"(gy), "=r"(gz), "=r"(gw) : "r"(s_glist + 32 * e) : "memory");
+    if (gw < 0) continue;
+    lo = ldsi32(s_glist + 32 * e + 20);
+    hi = ldsi32(s_glist + 32 * e + 24);
+    const long long loff = (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
+    const int n = gz, pitch = n | 1;
+    const float* __restrict__ src = p.L + loff;
+    const uint32_t dst = sL + 4 * gw;
+    int i = wt / n, j = wt - i * n;  // element wt of the n x n matrix, then steps of 256
+    const int di = WORKERS / n, dj = WORKERS - di * n;
+    for (int idx = wt; idx < n * n; idx += WORKERS) {
+      cp_async4(dst + 4 * (i * pitch + j), src + idx);
+      i += di; j += dj;
+      if (j >= n) { j -= n; ++i; }
     }
   }
   cp_async_commit();
-  cp_async_wait_all();
-  worker_barrier();
-  if (p.add_identity && t.n > 0) sL[t.lbase + t.i * t.pitch + t.i] += 1.f;  // L_all = I + L_int (literal mode)
-  worker_barrier();
   return t;
 }
 
@@ -353,24 +429,23 @@ struct FwdArgs {
   float* Y;           // [R,Fo]
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, FwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(base);
   const SmemPlan sp = smem_plan(p.t.N, true);
-  float* bufs = reinterpret_cast<float*>(base + sp.off_bufs);
-  float* sL = reinterpret_cast<float*>(base + sp.off_L);
-  int4* s_glist = reinterpret_cast<int4*>(base + sp.off_glist);
-  int* s_grow = reinterpret_cast<int*>(base + sp.off_grow);
+  const uint32_t bufs = sbase + sp.off_bufs, sL = sbase + sp.off_L, s_glist = sbase + sp.off_glist,
+                 s_grow = sbase + sp.off_grow;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + sp.off_bars);
   uint64_t* full_bar = bars;        // W tiles landed (TMA)
-  uint64_t* split_bar = bars + 4;   // operand rows written by the 128 workers
+  uint64_t* split_bar = bars + 4;   // operand rows written by the 256 workers
   uint64_t* empty_bar = bars + 8;   // MMAs that read the stage retired
   uint64_t* tmem_full_bar = bars + 12;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
+  const int tile = p.t.tile0 + blockIdx.x;
   const int F = p.t.F, Fo = p.t.Fo, K = p.t.K, N = p.t.N, nc = p.t.nchunks;
   const int num_kb = nc * K;
   int tmem_cols = 32;
@@ -379,7 +454,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < sp.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], 128);
+      mbar_init(&split_bar[s], WORKERS);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -413,7 +488,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
         mbar_wait(&full_bar[stage], phase);
         mbar_wait(&split_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(base + stage * sp.stage_bytes);
+        const uint32_t sa = sbase + stage * sp.stage_bytes;
         const uint32_t sa_lo = sa + A_BYTES, sb_hi = sa + 2 * A_BYTES, sb_lo = sb_hi + sp.b_bytes;
 #pragma unroll
         for (int k = 0; k < CH / UMMA_K; ++k) {
@@ -430,92 +505,98 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
     }
   } else {
     // ================= workers: recurrence + operand production, then epilogue =================
-    const int q = warp & 3;            // TMEM lane quarter of this warp
-    const int r = q * 32 + lane;       // my tile row
+    const int q = warp & 3;             // TMEM lane quarter of this warp
+    const int h = (warp - 2) >> 2;      // column half
+    const int r = q * 32 + lane;        // my tile row
     const int wt = (warp - 2) * 32 + lane;
-    const TileRow me = tile_prologue(p.t, tile, r, wt, s_glist, s_grow, sL);
+    int ng;
+    const TileRow me = tile_prologue(p.t, tile, r, h, wt, s_glist, s_grow, sL, &ng);
+    worker_sync();  // row table visible
     const bool vecX = ((F & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.T) & 15) == 0) && ((p.tslice & 3) == 0);
-    float* xbuf[2] = {bufs, bufs + TM * CH};
-    float* tbuf = bufs + 2 * TM * CH;
-    const float* Lrow = sL + me.lbase + me.i * me.pitch;
+    const uint32_t xbuf[2] = {bufs, bufs + CBUF_BYTES};
+    const uint32_t tbuf = bufs + 2 * CBUF_BYTES;
+    const uint32_t lrow = sL + 4 * (me.lbase + me.i * me.pitch);
 
-    auto emit = [&](int kb, const float v[32]) {
+    auto emit = [&](int kb, const float v[16]) {
       const int stage = kb % sp.stages, phase = (kb / sp.stages) & 1;
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      uint8_t* st = base + stage * sp.stage_bytes;
-      write_operand_row(st, st + A_BYTES, r, v);
+      if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+      __syncwarp();
+      const uint32_t st = sbase + stage * sp.stage_bytes;
+      write_operand_half(st, st + A_BYTES, r, h, v);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
       mbar_arrive(&split_bar[stage]);
     };
 
-    load_rows_async(xbuf[0], p.X, F, F, 0, s_grow, q, lane, vecX);
+    load_rows_async(xbuf[0], p.X, F, F, 0, s_grow, q, h, lane, vecX);
     cp_async_commit();
     for (int c = 0; c < nc; ++c) {
       const int cur = c & 1;
       cp_async_wait_all();
-      worker_barrier();  // T_0 chunk c complete; every worker is done with chunk c-1
+      worker_sync();  // T_0 chunk c (and, first time, the L matrices) complete; chunk c-1 is finished everywhere
       if (c + 1 < nc) {
-        load_rows_async(xbuf[cur ^ 1], p.X, F, F, c + 1, s_grow, q, lane, vecX);
+        load_rows_async(xbuf[cur ^ 1], p.X, F, F, c + 1, s_grow, q, h, lane, vecX);
         cp_async_commit();
       }
-      float tm2[32], tm1[32];
-      read_row(xbuf[cur], r, tm1);
+      float tm2[16], tm1[16];
+      read_half(xbuf[cur], r, h, tm1);
       emit(c * K, tm1);
-      float* src = xbuf[cur];
-      float* dst = tbuf;
+      uint32_t src = xbuf[cur], dst = tbuf;
       for (int s = 1; s < K; ++s) {
-        float t[32];
+        float t[16];
         if (me.pre) {
           // the per-graph / row-tiled kernels produced T_s for this graph
           const float* Ts = p.T + (long long)(s - 1) * p.tslice;
 #pragma unroll
-          for (int u = 0; u < 32; ++u) {
-            const int col = c * CH + u;
-            t[u] = (me.grow >= 0 && col < F) ? Ts[(long long)me.grow * F + col] : 0.f;
+          for (int u = 0; u < 16; ++u) {
+            const int col = c * CH + 16 * h + u;
+            t[u] = (me.grow >= 0 && col < F) ? __ldg(Ts + (long long)me.grow * F + col) : 0.f;
           }
         } else {
-          lap_times_rows(Lrow, 1, src, me.r0, me.n, t);  // graphconv.py:231
+#pragma unroll
+          for (int u = 0; u < 16; ++u) t[u] = p.t.add_identity ? tm1[u] : 0.f;  // L_all = I + L_int (literal mode)
+          lap_times_rows(lrow, 4, src, me.r0, me.n, h, t);  // graphconv.py:231
           if (s >= 2) {
 #pragma unroll
-            for (int u = 0; u < 32; ++u) t[u] = 2.f * t[u] - tm2[u];  // graphconv.py:234
+            for (int u = 0; u < 16; ++u) t[u] = 2.f * t[u] - tm2[u];  // graphconv.py:234
           }
-          write_row(dst, r, t);
+          write_half(dst, r, h, t);
           __syncwarp();
-          store_rows(dst, p.T + (long long)(s - 1) * p.tslice, F, F, c, s_grow, q, lane, vecX);
+          store_rows(dst, p.T + (long long)(s - 1) * p.tslice, F, F, c, s_grow, q, h, lane, vecX);
         }
         emit(c * K + s, t);
 #pragma unroll
-        for (int u = 0; u < 32; ++u) { tm2[u] = tm1[u]; tm1[u] = t[u]; }
+        for (int u = 0; u < 16; ++u) { tm2[u] = tm1[u]; tm1[u] = t[u]; }
         if (s + 1 < K) {
-          worker_barrier();  // T_s rows of every graph of the tile are in `dst`
-          float* tmp = src; src = dst; dst = tmp;
+          worker_sync();  // T_s rows of every graph of the tile are in `dst`
+          const uint32_t tmp = src; src = dst; dst = tmp;
         }
       }
     }
     // ---- epilogue: Y = act(acc + bias)   graphconv.py:245-247, :118-123
-    mbar_wait(tmem_full_bar, 0);
+    if (lane == 0) mbar_wait(tmem_full_bar, 0);
+    __syncwarp();
     tc_fence_after();
-    float* stg = reinterpret_cast<float*>(base) + (warp - 2) * (32 * 36);  // operand stages are free now
+    const uint32_t stg = sbase + (uint32_t)((warp - 2) * (32 * 36 * 4));  // operand stages are free now
     const bool vecY = ((Fo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
-    for (int c0 = 0; c0 < N && c0 < Fo; c0 += 32) {
+    for (int c0 = 32 * h; c0 < N && c0 < Fo; c0 += 64) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
       for (int u = 0; u < 8; ++u)
-        *reinterpret_cast<float4*>(&stg[lane * 36 + 4 * u]) = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+        sts128(stg + 4 * (lane * 36 + 4 * u), make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
       __syncwarp();
       const int cc = c0 + 4 * (lane & 7);
       float bv[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int e = 0; e < 4; ++e)
-        if (p.bias && cc + e < Fo) bv[e] = p.bias[cc + e];
+        if (p.bias && cc + e < Fo) bv[e] = __ldg(p.bias + cc + e);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int rr = 4 * i + (lane >> 3);
-        const int grow = s_grow[q * 32 + rr];
+        const int grow = ldsi32(s_grow + 4 * (q * 32 + rr));
         if (grow < 0 || cc >= Fo) continue;
-        const float4 o4 = *reinterpret_cast<const float4*>(&stg[rr * 36 + 4 * (lane & 7)]);
+        const float4 o4 = lds128(stg + 4 * (rr * 36 + 4 * (lane & 7)));
         float o[4] = {o4.x + bv[0], o4.y + bv[1], o4.z + bv[2], o4.w + bv[3]};
         if (p.act == AGCN_ACT_RELU) {
 #pragma unroll
@@ -550,14 +631,13 @@ struct BwdArgs {
   int acc_stride;      // TMEM columns between the K accumulators
 };
 
-__global__ void __launch_bounds__(192, 1)
+__global__ void __launch_bounds__(THREADS, 1)
 fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, BwdArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(base);
   const SmemPlan sp = smem_plan(p.t.N, false);
-  float* sL = reinterpret_cast<float*>(base + sp.off_L);
-  int4* s_glist = reinterpret_cast<int4*>(base + sp.off_glist);
-  int* s_grow = reinterpret_cast<int*>(base + sp.off_grow);
+  const uint32_t sL = sbase + sp.off_L, s_glist = sbase + sp.off_glist, s_grow = sbase + sp.off_grow;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + sp.off_bars);
   uint64_t* full_bar = bars;
   uint64_t* split_bar = bars + 4;
@@ -566,7 +646,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x;
+  const int tile = p.t.tile0 + blockIdx.x;
   const int F = p.t.F, Fo = p.t.Fo, K = p.t.K, N = p.t.N, nc = p.t.nchunks;
   const int num_kb = nc * K;
   int tmem_cols = 32;
@@ -575,7 +655,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < sp.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], 128);
+      mbar_init(&split_bar[s], WORKERS);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -610,7 +690,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
         mbar_wait(&full_bar[stage], phase);
         mbar_wait(&split_bar[stage], phase);
         tc_fence_after();
-        const uint32_t sa = smem_u32(base + stage * sp.stage_bytes);
+        const uint32_t sa = sbase + stage * sp.stage_bytes;
         const uint32_t sa_lo = sa + A_BYTES, sb_hi = sa + 2 * A_BYTES, sb_lo = sb_hi + sp.b_bytes;
         const uint32_t d = tmem_base + (uint32_t)(z * p.acc_stride);
 #pragma unroll
@@ -628,81 +708,88 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
     }
   } else {
     const int q = warp & 3;
+    const int h = (warp - 2) >> 2;
     const int r = q * 32 + lane;
     const int wt = (warp - 2) * 32 + lane;
-    const TileRow me = tile_prologue(p.t, tile, r, wt, s_glist, s_grow, sL);
+    int ng;
+    const TileRow me = tile_prologue(p.t, tile, r, h, wt, s_glist, s_grow, sL, &ng);
     const bool vecD = ((Fo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dYp) & 15) == 0);
-    // mainloop: my row of dYpre chunk c (one 128-byte line, L1-resident across the K passes) -> hi/lo operand
-    // rows; the row of the next k-block is in flight while this one is split and stored.
-    auto load_row = [&](int kb, float v[32]) {
+    // mainloop: my half row of dYpre chunk c (L1-resident across the K passes) -> hi/lo operand rows; the row of
+    // the next k-block is in flight while this one is split and stored.
+    auto load_row = [&](int kb, float v[16]) {
       const int c = kb % nc;
       if (vecD) {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-          const int col = c * CH + 4 * g;
+        for (int g = 0; g < 4; ++g) {
+          const int col = c * CH + 16 * h + 4 * g;
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
           if (me.grow >= 0 && col < Fo) x = __ldg(reinterpret_cast<const float4*>(p.dYp + (long long)me.grow * Fo + col));
           v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
         }
       } else {
 #pragma unroll
-        for (int u = 0; u < 32; ++u) {
-          const int col = c * CH + u;
+        for (int u = 0; u < 16; ++u) {
+          const int col = c * CH + 16 * h + u;
           v[u] = (me.grow >= 0 && col < Fo) ? __ldg(p.dYp + (long long)me.grow * Fo + col) : 0.f;
         }
       }
     };
-    float nxt[32];
+    float nxt[16];
     load_row(0, nxt);
     for (int kb = 0; kb < num_kb; ++kb) {
-      float v[32];
+      float v[16];
 #pragma unroll
-      for (int u = 0; u < 32; ++u) v[u] = nxt[u];
+      for (int u = 0; u < 16; ++u) v[u] = nxt[u];
       if (kb + 1 < num_kb) load_row(kb + 1, nxt);
       const int stage = kb % sp.stages, phase = (kb / sp.stages) & 1;
-      mbar_wait(&empty_bar[stage], phase ^ 1);
-      uint8_t* st = base + stage * sp.stage_bytes;
-      write_operand_row(st, st + A_BYTES, r, v);
+      if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+      __syncwarp();
+      const uint32_t st = sbase + stage * sp.stage_bytes;
+      write_operand_half(st, st + A_BYTES, r, h, v);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       mbar_arrive(&split_bar[stage]);
     }
     // ---- epilogue: reverse recurrence on the accumulators
-    mbar_wait(tmem_full_bar, 0);
+    cp_async_wait_all();  // the L matrices of the tile (issued in the prologue)
+    if (lane == 0) mbar_wait(tmem_full_bar, 0);
+    __syncwarp();
     tc_fence_after();
-    worker_barrier();
-    float* ub[2] = {reinterpret_cast<float*>(base), reinterpret_cast<float*>(base) + TM * CH};  // stages are free now
+    worker_sync();
+    const uint32_t ub[2] = {sbase, sbase + CBUF_BYTES};  // operand stages are free now
     const bool vecX = ((F & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dX) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.G) & 15) == 0) && ((p.gslice & 3) == 0);
-    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16);
-    const float* Lcol = sL + me.lbase + me.i;  // column i of my graph's matrix: (L^T U)_i = sum_j L[j][i] U_j
+    const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * h);
+    const uint32_t lcol = sL + 4 * (me.lbase + me.i);  // column i of my graph's matrix: (L^T U)_i = sum_j L[j][i] U_j
     const int nfc = (F + CH - 1) / CH;
     for (int fc = 0; fc < nfc; ++fc) {
       if (me.pre) {
         // big graph: hand G_z to the per-graph / row-tiled reverse recurrence
         for (int z = 0; z < K; ++z) {
-          float g[32];
-          tmem_ld32(lane_base + (uint32_t)(z * p.acc_stride + fc * CH), g);
-          write_row(ub[0], r, g);
+          float g[16];
+          tmem_ld16(lane_base + (uint32_t)(z * p.acc_stride + fc * CH), g);
+          write_half(ub[0], r, h, g);
           __syncwarp();
-          store_rows(ub[0], p.G + (long long)z * p.gslice, F, F, fc, s_grow, q, lane, vecX);
+          store_rows(ub[0], p.G + (long long)z * p.gslice, F, F, fc, s_grow, q, h, lane, vecX);
           __syncwarp();
         }
         continue;
       }
-      float u1[32], u2[32];
-      tmem_ld32(lane_base + (uint32_t)((K - 1) * p.acc_stride + fc * CH), u1);  // U_{K-1} = G_{K-1}
+      float u1[16], u2[16];
+      tmem_ld16(lane_base + (uint32_t)((K - 1) * p.acc_stride + fc * CH), u1);  // U_{K-1} = G_{K-1}
 #pragma unroll
-      for (int u = 0; u < 32; ++u) u2[u] = 0.f;
+      for (int u = 0; u < 16; ++u) u2[u] = 0.f;
       int cur = 0;
       for (int j = K - 2; j >= 0; --j) {
-        write_row(ub[cur], r, u1);
-        worker_barrier();  // U_{j+1} rows of every graph of the tile are visible
-        float acc[32], g[32];
-        lap_times_rows(Lcol, me.pitch, ub[cur], me.r0, me.n, acc);
-        tmem_ld32(lane_base + (uint32_t)(j * p.acc_stride + fc * CH), g);
+        write_half(ub[cur], r, h, u1);
+        worker_sync();  // U_{j+1} rows of every graph of the tile are visible
+        float acc[16], g[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc[u] = p.t.add_identity ? u1[u] : 0.f;  // (I + L)^T U = U + L^T U
+        lap_times_rows(lcol, 4 * me.pitch, ub[cur], me.r0, me.n, h, acc);
+        tmem_ld16(lane_base + (uint32_t)(j * p.acc_stride + fc * CH), g);
         const float cmul = (j + 1 >= 2) ? 2.f : 1.f;
 #pragma unroll
-        for (int u = 0; u < 32; ++u) {
+        for (int u = 0; u < 16; ++u) {
           const float o = g[u] + cmul * acc[u] - u2[u];
           u2[u] = u1[u];
           u1[u] = o;
@@ -710,11 +797,11 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
         cur ^= 1;
       }
       // dX = U_0
-      worker_barrier();  // every read of the buffers is done before they are reused for the store / next chunk
-      write_row(ub[cur], r, u1);
+      worker_sync();  // every read of the buffers is done before they are reused for the store / next chunk
+      write_half(ub[cur], r, h, u1);
       __syncwarp();
-      store_rows(ub[cur], p.dX, F, F, fc, s_grow, q, lane, vecX);
-      worker_barrier();
+      store_rows(ub[cur], p.dX, F, F, fc, s_grow, q, h, lane, vecX);
+      worker_sync();
     }
   }
   tc_fence_before();
@@ -785,10 +872,9 @@ static TileArgs tile_args(const agcn_plan* plan, const float* L, int add_identit
   TileArgs t;
   t.tile_graphs = reinterpret_cast<const int4*>(plan->d_ft_entries);
   t.tile_gstart = plan->d_ft_gstart;
-  t.node_off = plan->d_node_off;
-  t.lap_off = plan->d_lap_off;
   t.L = L;
   t.add_identity = add_identity;
+  t.tile0 = 0;
   t.F = F; t.Fo = Fo; t.K = K;
   t.N = 0; t.nchunks = 0;
   return t;
@@ -800,9 +886,8 @@ static TileArgs tile_args(const agcn_plan* plan, const float* L, int add_identit
 // host API
 // ------------------------------------------------------------------------------------------------
 bool fused_enabled() {
-  // opt-in until the tile kernels beat the per-graph + node-GEMM path they replace
-  static const bool on = getenv("AGCN_ENABLE_FUSED") != nullptr && getenv("AGCN_DISABLE_TCGEN05") == nullptr;
-  return on;
+  static const bool off = getenv("AGCN_DISABLE_FUSED") != nullptr || getenv("AGCN_DISABLE_TCGEN05") != nullptr;
+  return !off;
 }
 
 bool fused_fwd_supported(const agcn_plan* plan, int F, int Fo, int K) {
@@ -849,9 +934,11 @@ static int opt_in_smem(Kern k, int bytes) {
   return AGCN_OK;
 }
 
-int fused_forward(const agcn_plan* plan, const float* X, const float* L, int add_identity, const float* wsplit,
-                  const float* bias, int act, int F, int Fo, int K, float* T, float* Y, cudaStream_t st) {
+int fused_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, const float* L, int add_identity,
+                  const float* wsplit, const float* bias, int act, int F, int Fo, int K, float* T, float* Y,
+                  cudaStream_t st) {
   using namespace ft;
+  if (ntiles <= 0) return AGCN_OK;
   const int N = pad16(Fo), Kp = pad32(F);
   const long long half = (long long)K * N * Kp;
   CUtensorMap mhi, mlo;
@@ -862,18 +949,20 @@ int fused_forward(const agcn_plan* plan, const float* X, const float* L, int add
   a.t = tile_args(plan, L, add_identity, F, Fo, K);
   a.t.N = N;
   a.t.nchunks = Kp / CH;
+  a.t.tile0 = tile0;
   a.X = X; a.T = T; a.tslice = (long long)plan->R * F;
   a.bias = bias; a.act = act; a.Y = Y;
   const SmemPlan sp = smem_plan(N, true);
   if ((rc = opt_in_smem(fused_fwd_kernel, 227 * 1024))) return rc;
-  fused_fwd_kernel<<<plan->ft_tiles, 192, sp.total, st>>>(mhi, mlo, a);
+  fused_fwd_kernel<<<ntiles, THREADS, sp.total, st>>>(mhi, mlo, a);
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }
 
-int fused_backward(const agcn_plan* plan, const float* dYp, const float* L, int add_identity, const float* wsplit,
-                   int F, int Fo, int K, float* G, float* dX, cudaStream_t st) {
+int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dYp, const float* L, int add_identity,
+                   const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st) {
   using namespace ft;
+  if (ntiles <= 0) return AGCN_OK;
   const int N = pad16(F), Kp = pad32(Fo);
   const long long half = (long long)K * N * Kp;
   CUtensorMap mhi, mlo;
@@ -884,11 +973,12 @@ int fused_backward(const agcn_plan* plan, const float* dYp, const float* L, int 
   a.t = tile_args(plan, L, add_identity, F, Fo, K);
   a.t.N = N;
   a.t.nchunks = Kp / CH;
+  a.t.tile0 = tile0;
   a.dYp = dYp; a.G = G; a.gslice = (long long)plan->R * F; a.dX = dX;
   a.acc_stride = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
   const SmemPlan sp = smem_plan(N, false);
   if ((rc = opt_in_smem(fused_bwd_kernel, 227 * 1024))) return rc;
-  fused_bwd_kernel<<<plan->ft_tiles, 192, sp.total, st>>>(mhi, mlo, a);
+  fused_bwd_kernel<<<ntiles, THREADS, sp.total, st>>>(mhi, mlo, a);
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }

@@ -18,9 +18,10 @@
 #define AGCN_CHEB_SMALL_MAX 144
 // Fused tile kernels (agcn_fused_tile.cu): graphs up to this size are packed into 128-row tiles and run their
 // Chebyshev recurrences inside the tensor-core kernel; AGCN_FUSE_LCAP floats of shared memory hold the
-// per-graph matrices of one tile (row pitch n | 1; one 96-node graph plus one 32-node graph fit).
-#define AGCN_FUSE_MAX_N 96
-#define AGCN_FUSE_LCAP 10752
+// per-graph matrices of one tile (row pitch n | 1; two 64-node graphs fit).  Larger graphs would make their
+// tile the critical path of the launch: their recurrences run chunk-parallel in the per-graph kernels instead.
+#define AGCN_FUSE_MAX_N 64
+#define AGCN_FUSE_LCAP 8320
 
 namespace agcn {
 
@@ -88,9 +89,10 @@ struct agcn_plan {
   // float offset of the graph's matrix in the tile's shared-memory L region} for whole small graphs or
   // {graph, first graph row, rows, -1} for a 128-row range of a graph with n > AGCN_FUSE_MAX_N
   int ft_tiles = 0;
+  int ft_small_tiles = 0;  // tiles [0, ft_small_tiles) hold whole small graphs, the rest are 128-row ranges of big ones
   std::vector<int32_t> ft_gstart, ft_entries;
   int32_t* d_ft_gstart = nullptr;
-  int32_t* d_ft_entries = nullptr;  // int4 per entry, 16-byte aligned
+  int32_t* d_ft_entries = nullptr;  // 2 x int4 per entry: {g, r0, n, lbase} {node_off, lap_off lo, hi, 0}
   // side streams so the per-bucket launches of one phase overlap on the device
   cudaStream_t aux[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr;
@@ -99,6 +101,10 @@ struct agcn_plan {
   // only depends on dY and overlaps with the dX chain
   cudaStream_t side = nullptr;
   cudaEvent_t ev_side_fork = nullptr, ev_side_join = nullptr;
+  // a stream for the chain of the graphs above AGCN_FUSE_MAX_N (per-graph recurrences + their tile launch), which
+  // runs beside the fused launch of the small-graph tiles
+  cudaStream_t big = nullptr;
+  cudaEvent_t ev_big_fork = nullptr, ev_big_join = nullptr;
 };
 
 namespace agcn {
@@ -223,12 +229,14 @@ size_t fused_w_floats(int Nv, int Kv, int Z);  // floats of one pre-split parame
 int fused_fwd_prep(const float* weight, int F, int Fo, int K, float* scratch, cudaStream_t st);
 int fused_bwd_prep(const float* weight, int F, int Fo, int K, float* scratch, cudaStream_t st);
 // T_1..T_{K-1} (saved) and Y = act(sum_k T_k W_k + b) for every tile of the plan; L = Lint (add_identity) or L_all
-int fused_forward(const agcn_plan* plan, const float* X, const float* L, int add_identity, const float* wsplit,
-                  const float* bias, int act, int F, int Fo, int K, float* T, float* Y, cudaStream_t st);
+// tile0 / ntiles: the tiles of this launch
+int fused_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, const float* L, int add_identity,
+                  const float* wsplit, const float* bias, int act, int F, int Fo, int K, float* T, float* Y,
+                  cudaStream_t st);
 // dX = U_0 of the reverse recurrence over G_z = dYp W_z^T; G receives G_z for the rows of graphs with
 // n > AGCN_FUSE_MAX_N only
-int fused_backward(const agcn_plan* plan, const float* dYp, const float* L, int add_identity, const float* wsplit,
-                   int F, int Fo, int K, float* G, float* dX, cudaStream_t st);
+int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dYp, const float* L, int add_identity,
+                   const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st);
 
 // ---------------------------------------------------------------- helpers
 int fork_streams(const agcn_plan* plan, cudaStream_t main, int n_aux);

@@ -89,7 +89,7 @@ __global__ void pack_lap_kernel(const float* __restrict__ padded, float* __restr
 // first-fit-decreasing into 128-row tiles under the shared-memory budget of their L matrices.  `order` lists the
 // graphs largest first.  gstart gets tiles + 1 entries.
 static void build_fused_tiles(const std::vector<int32_t>& n, const std::vector<int32_t>& order,
-                              std::vector<int32_t>* gstart, std::vector<int32_t>* entries) {
+                              std::vector<int32_t>* gstart, std::vector<int32_t>* entries, int* n_small_tiles) {
   const int B = (int)n.size();
   gstart->clear();
   entries->clear();
@@ -97,13 +97,8 @@ static void build_fused_tiles(const std::vector<int32_t>& n, const std::vector<i
     entries->push_back(g); entries->push_back(a); entries->push_back(b); entries->push_back(c);
   };
   int i = 0;
-  for (; i < B && n[order[i]] > AGCN_FUSE_MAX_N; ++i) {
-    const int g = order[i];
-    for (int r = 0; r < n[g]; r += 128) {
-      gstart->push_back((int32_t)(entries->size() / 4));
-      push(g, r, std::min(128, n[g] - r), -1);
-    }
-  }
+  while (i < B && n[order[i]] > AGCN_FUSE_MAX_N) ++i;  // their 128-row ranges come after the small tiles
+  const int n_big = i;
   struct Open { int rows, lused; std::vector<int32_t> e; };
   std::vector<Open> open;
   size_t first_open = 0;
@@ -123,6 +118,14 @@ static void build_fused_tiles(const std::vector<int32_t>& n, const std::vector<i
   for (const Open& o : open) {
     gstart->push_back((int32_t)(entries->size() / 4));
     entries->insert(entries->end(), o.e.begin(), o.e.end());
+  }
+  if (n_small_tiles) *n_small_tiles = (int)gstart->size();
+  for (int b = 0; b < n_big; ++b) {
+    const int g = order[b];
+    for (int r = 0; r < n[g]; r += 128) {
+      gstart->push_back((int32_t)(entries->size() / 4));
+      push(g, r, std::min(128, n[g] - r), -1);
+    }
   }
   gstart->push_back((int32_t)(entries->size() / 4));
 }
@@ -190,7 +193,7 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
     while (pos < B && p->n[p->order[pos]] > lo) ++pos;
     if (pos > start) p->buckets.push_back(Bucket{start, pos - start, p->n[p->order[start]], limits[b]});
   }
-  build_fused_tiles(p->n, p->order, &p->ft_gstart, &p->ft_entries);
+  build_fused_tiles(p->n, p->order, &p->ft_gstart, &p->ft_entries, &p->ft_small_tiles);
   p->ft_tiles = (int)p->ft_gstart.size() - 1;
   // device block: n[B] node_off[B+1] order[B] tile_graph[T] tile_row[T] (int32) then lap_off[B+1] (int64)
   const size_t T = (size_t)p->large_tiles;
@@ -198,7 +201,7 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   const size_t n32 = (size_t)B + (B + 1) + B + 2 * T + NB + p->ft_gstart.size();
   const size_t off64 = (n32 * 4 + 15) / 16 * 16;
   const size_t off_ft = (off64 + (size_t)(B + 1) * 8 + 15) / 16 * 16;  // int4 entries of the fused tiles
-  const size_t bytes = off_ft + p->ft_entries.size() * 4;
+  const size_t bytes = off_ft + p->ft_entries.size() * 8;  // device entries carry node_off / lap_off of their graph
   std::vector<char> host(bytes, 0);
   int32_t* h32 = reinterpret_cast<int32_t*>(host.data());
   std::memcpy(h32, p->n.data(), (size_t)B * 4);
@@ -211,7 +214,18 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   std::memcpy(h32 + 3 * B + 1 + 2 * T, p->big_tile_start.data(), NB * 4);
   std::memcpy(h32 + 3 * B + 1 + 2 * T + NB, p->ft_gstart.data(), p->ft_gstart.size() * 4);
   std::memcpy(host.data() + off64, p->lap_off.data(), (size_t)(B + 1) * 8);
-  std::memcpy(host.data() + off_ft, p->ft_entries.data(), p->ft_entries.size() * 4);
+  {
+    int32_t* de = reinterpret_cast<int32_t*>(host.data() + off_ft);
+    for (size_t e = 0; e < p->ft_entries.size() / 4; ++e) {
+      const int32_t* src = &p->ft_entries[4 * e];
+      const int64_t lo = p->lap_off[src[0]];
+      de[8 * e + 0] = src[0]; de[8 * e + 1] = src[1]; de[8 * e + 2] = src[2]; de[8 * e + 3] = src[3];
+      de[8 * e + 4] = p->node_off[src[0]];
+      de[8 * e + 5] = (int32_t)(uint32_t)(lo & 0xffffffffll);
+      de[8 * e + 6] = (int32_t)(uint32_t)((uint64_t)lo >> 32);
+      de[8 * e + 7] = 0;
+    }
+  }
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaMalloc(&p->d_block, bytes);
   if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_block, host.data(), bytes, cudaMemcpyHostToDevice, st);
@@ -222,6 +236,9 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->big, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_big_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_big_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_side_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_side_join, cudaEventDisableTiming);
   if (e != cudaSuccess) {
@@ -250,7 +267,7 @@ int agcn_fused_tiles_host(const int32_t* n_nodes_host, int32_t B, int32_t* gstar
   for (int g = 0; g < B; ++g) AGCN_REQUIRE(n[g] >= 1, "n_nodes[g] must be >= 1");
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return n[a] > n[b]; });
-  build_fused_tiles(n, order, &gs, &en);
+  build_fused_tiles(n, order, &gs, &en, nullptr);
   *tiles_out = (int32_t)gs.size() - 1;
   *n_entries_out = (int32_t)(en.size() / 4);
   if (gstart_out && entries_out) {
@@ -269,6 +286,9 @@ int agcn_plan_destroy(agcn_plan* p) {
   }
   if (p->ev_fork) cudaEventDestroy(p->ev_fork);
   if (p->side) cudaStreamDestroy(p->side);
+  if (p->big) cudaStreamDestroy(p->big);
+  if (p->ev_big_fork) cudaEventDestroy(p->ev_big_fork);
+  if (p->ev_big_join) cudaEventDestroy(p->ev_big_join);
   if (p->ev_side_fork) cudaEventDestroy(p->ev_side_fork);
   if (p->ev_side_join) cudaEventDestroy(p->ev_side_join);
   if (p->d_block) cudaFree(p->d_block);

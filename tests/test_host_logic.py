@@ -153,7 +153,7 @@ def test_fused_tile_packing_invariants():
     import ctypes
     from agcn_b200 import _lib
     from oracle import sgcll_oracle as O
-    FUSE_MAX_N, LCAP = 96, 10752
+    FUSE_MAX_N, LCAP = 64, 8320
     cases = [np.array([132, 4, 5, 18, 33, 64, 65, 17, 96, 31], np.int32),
              np.array([1] * 300, np.int32),
              np.array([1024, 700, 13, 145, 96, 97, 128, 129], np.int32),
