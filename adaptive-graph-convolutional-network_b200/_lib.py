@@ -39,6 +39,9 @@ _SIGNATURES = {
     "agcn_plan_node_off_host": (_P, [_P]),
     "agcn_plan_lap_off_host": (_P, [_P]),
     "agcn_fused_tiles_host": (ctypes.c_int, [_P, ctypes.c_int32, _P, ctypes.c_int32, _P, ctypes.c_int32, _P, _P]),
+    "agcn_fused_debug_set": (ctypes.c_int, [_P]),
+    "agcn_fused_profile": (ctypes.c_int, [ctypes.c_int]),
+    "agcn_fused_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "agcn_pack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
     "agcn_unpack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
     "agcn_pack_lap": (ctypes.c_int, [_P, _P, _P, _P]),

@@ -196,7 +196,7 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
   GemmArgs gy = y_gemm_args(desc, R, d_X, sv.T, d_weight, d_bias, d_Y);
   const bool y_tc = !fuse_f && tc_gemm_supported(gy);
   GemmArgs gg = g_gemm_args(desc, R, d_Y /* placeholder with the alignment of dYpre */, d_weight, wk.G);
-  const bool g_tc = (desc->flags & AGCN_SAVE_FOR_BACKWARD) && tc_gemm_supported(gg);
+  const bool g_tc = !fuse_b && (desc->flags & AGCN_SAVE_FOR_BACKWARD) && tc_gemm_supported(gg);
   if (y_tc || g_tc || fuse_f || fuse_b) {
     AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
     AGCN_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_side_fork, 0));
@@ -284,17 +284,21 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   const int R = (int)plan->R;
   const bool has_prev = m.reslap && d_Lprev;
 
-  // dYpre = dY * act'(Y) and per-CTA column sums; dbias = colsum(dYpre) is folded on the side stream
-  const float* dYp = (desc->activation == AGCN_ACT_RELU) ? wk.dYp : d_dY;
-  if ((rc = act_bwd_partials(d_dY, d_Y, wk.dYp, wk.act_part, R, Fo, desc->activation, st))) return rc;
-  // the parameter gradients depend on dYpre only -> side stream, overlapping the dX chain
-  AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
-  AGCN_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_side_fork, 0));
-  if ((rc = act_bwd_reduce(wk.act_part, d_dbias, R, Fo, plan->side))) return rc;
   // d_dX == NULL: the caller does not need the gradient w.r.t. the node features (first layer)
   const bool fuse_b = (desc->flags & AGCN_SAVE_FOR_BACKWARD) && !m.need_dL && d_dX != nullptr &&
                       fused_bwd_supported(plan, F, Fo, K);
   const bool need_G = !fuse_b && (d_dX != nullptr || (m.need_dL && K >= 2));
+  // dYpre = dY * act'(Y) and per-CTA column sums; dbias = colsum(dYpre).  The parameter gradients depend on
+  // dYpre only -> side stream, overlapping the dX chain.  The fused dX kernel applies act' itself, so in that case
+  // (and when the main stream has no use for dYpre at all) the whole dYpre branch lives on the side stream.
+  const float* dYp = (desc->activation == AGCN_ACT_RELU) ? wk.dYp : d_dY;
+  const bool act_on_side = fuse_b || (!need_G && !m.need_dL);
+  if (!act_on_side && (rc = act_bwd_partials(d_dY, d_Y, wk.dYp, wk.act_part, R, Fo, desc->activation, st))) return rc;
+  AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
+  AGCN_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_side_fork, 0));
+  if (act_on_side && (rc = act_bwd_partials(d_dY, d_Y, wk.dYp, wk.act_part, R, Fo, desc->activation, plan->side)))
+    return rc;
+  if ((rc = act_bwd_reduce(wk.act_part, d_dbias, R, Fo, plan->side))) return rc;
   float* dXbuf = d_dX ? d_dX : wk.G;  // scratch target when dX itself is not wanted (K >= 2 only)
   AGCN_REQUIRE(d_dX || !m.full, "backward: d_dX is required with metric_grad = full");
   if (need_G) {  // G_k = dYpre W_k^T   (K == 1: this is dX); W_k^T was split by the forward pass
@@ -333,12 +337,14 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
     if (n_pre > 0) {
       AGCN_CUDA(cudaEventRecord(plan->ev_big_fork, st));
       AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_big_fork, 0));
-      if ((rc = fused_backward(plan, plan->ft_small_tiles, n_pre, dYp, Lf, ident, sv.ftG, F, Fo, K, wk.G, d_dX, plan->big)))
+      if ((rc = fused_backward(plan, plan->ft_small_tiles, n_pre, d_dY, desc->activation == AGCN_ACT_RELU ? d_Y : nullptr, Lf, ident,
+                               sv.ftG, F, Fo, K, wk.G, d_dX, plan->big)))
         return rc;
       if ((rc = graph_recurrence_bwd(ga, false, plan->big, AGCN_FUSE_MAX_N))) return rc;
       AGCN_CUDA(cudaEventRecord(plan->ev_big_join, plan->big));
     }
-    if ((rc = fused_backward(plan, 0, plan->ft_small_tiles, dYp, Lf, ident, sv.ftG, F, Fo, K, wk.G, d_dX, st))) return rc;
+    if ((rc = fused_backward(plan, 0, plan->ft_small_tiles, d_dY, desc->activation == AGCN_ACT_RELU ? d_Y : nullptr, Lf, ident,
+                             sv.ftG, F, Fo, K, wk.G, d_dX, st))) return rc;
     if (n_pre > 0) AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_big_join, 0));
   } else if (K >= 2) {
     if (need_G && (rc = graph_recurrence_bwd(ga, m.need_dL, st))) return rc;
@@ -403,6 +409,19 @@ int agcn_gemm_tn(const float* d_A0, const float* d_A1, const float* d_D, float* 
     return tc_gemm_tn(t, (cudaStream_t)stream);
   }
   return gemm_tn(t, (cudaStream_t)stream);
+}
+
+/* bench.py's roofline: CUDA-event timing of the fused forward kernel on its launching stream */
+int agcn_fused_profile(int enable) {
+  fused_profile_enable(enable);
+  return AGCN_OK;
+}
+int agcn_fused_profile_read(float* ms_sum, int* launches) { return fused_profile_read(ms_sum, launches); }
+
+/* tuning aid: per-tile timeline (nanosecond stamps) of the fused forward kernel; NULL switches it off */
+int agcn_fused_debug_set(void* d_buf) {
+  fused_debug_set(d_buf);
+  return AGCN_OK;
 }
 
 int agcn_sgcll_host_scratch_bytes(const agcn_sgcll_desc* desc, const agcn_plan* plan, size_t* bytes) {

@@ -27,6 +27,8 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "agcn_internal.cuh"
 
@@ -320,6 +322,7 @@ struct SmemPlan {
   int off_L;      // LCAP floats
   int off_glist;  // 128 entries of 2 x int4
   int off_grow;   // 128 int
+  int off_rowinfo;  // 128 int4 {r0, n, lbase, i}
   int off_bars;
   int total;
 };
@@ -328,7 +331,7 @@ __host__ __device__ inline SmemPlan smem_plan(int N, bool forward) {
   SmemPlan s;
   s.b_bytes = N * 128;
   s.stage_bytes = 2 * A_BYTES + 2 * s.b_bytes;
-  const int fixed = (forward ? 3 * CBUF_BYTES : 0) + LCAP * 4 + 128 * 32 + 128 * 4 + 256 + 1024;
+  const int fixed = (forward ? 3 * CBUF_BYTES : 0) + LCAP * 4 + 128 * 32 + 128 * 4 + 128 * 16 + 256 + 1024;
   int stages = (227 * 1024 - fixed) / s.stage_bytes;
   s.stages = stages > 4 ? 4 : stages;
   int off = s.stages * s.stage_bytes;
@@ -340,6 +343,8 @@ __host__ __device__ inline SmemPlan smem_plan(int N, bool forward) {
   off += 128 * 32;
   s.off_grow = off;
   off += 128 * 4;
+  s.off_rowinfo = off;
+  off += 128 * 16;
   s.off_bars = off;
   off += 256;
   s.total = off + 1024;  // alignment slack
@@ -356,7 +361,20 @@ struct TileRow {
   bool pre;
 };
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+// timeline slots per tile (debug builds of a launch: agcn_fused_debug_set)
+constexpr int DBG_SLOTS = 128;
+#define FT_STAMP(slot)                                                        \
+  do {                                                                        \
+    if (p.t.dbg) p.t.dbg[(long long)tile * DBG_SLOTS + (slot)] = gtime();     \
+  } while (0)
+
 struct TileArgs {
+  unsigned long long* dbg;     // optional timeline buffer [tiles][DBG_SLOTS] (nanoseconds), NULL in production
   const int4* tile_graphs;     // 2 x int4 per entry: {g, r0 | row_start, n | nrows, lbase | -1}, {node_off, lap_off lo, hi, 0}
   const int32_t* tile_gstart;  // [tiles + 1]
   const float* L;              // packed Laplacians (Lint or L_all)
@@ -370,7 +388,7 @@ struct TileArgs {
 // Prologue shared by both kernels (worker threads): graph list and row table of the tile; the copies of the
 // per-graph L matrices are left in flight (cp.async): callers wait + worker_sync before the first use.
 __device__ __forceinline__ TileRow tile_prologue(const TileArgs& p, int tile, int r, int h, int wt, uint32_t s_glist,
-                                                 uint32_t s_grow, uint32_t sL, int* ng_out) {
+                                                 uint32_t s_grow, uint32_t s_rowinfo, uint32_t sL, int* ng_out) {
   const int gs = p.tile_gstart[tile], ng = p.tile_gstart[tile + 1] - gs;
   *ng_out = ng;
   for (int e = wt; e < 2 * ng; e += WORKERS) {
@@ -392,7 +410,10 @@ __device__ __forceinline__ TileRow tile_prologue(const TileArgs& p, int tile, in
       t.n = gz; t.r0 = gy; t.lbase = gw; t.i = r - gy; t.pitch = gz | 1;
     }
   }
-  if (h == 0) asm volatile("st.shared.s32 [%0], %1;\n" ::"r"(s_grow + 4 * r), "r"(t.grow) : "memory");
+  if (h == 0) {
+    asm volatile("st.shared.s32 [%0], %1;\n" ::"r"(s_grow + 4 * r), "r"(t.grow) : "memory");
+    asm volatile("st.shared.v4.s32 [%0], {%1,%2,%3,%4};\n" ::"r"(s_rowinfo + 16 * r), "r"(t.r0), "r"(t.n), "r"(t.lbase), "r"(t.i) : "memory");
+  }
   // per-graph matrices, row pitch n | 1 (odd: the rows read by neighbouring lanes sit in different banks)
   for (int e = 0; e < ng; ++e) {
     int gx, gy, gz, gw, lo, hi;
@@ -436,7 +457,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
   const uint32_t sbase = smem_u32(base);
   const SmemPlan sp = smem_plan(p.t.N, true);
   const uint32_t bufs = sbase + sp.off_bufs, sL = sbase + sp.off_L, s_glist = sbase + sp.off_glist,
-                 s_grow = sbase + sp.off_grow;
+                 s_grow = sbase + sp.off_grow, s_rowinfo = sbase + sp.off_rowinfo;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + sp.off_bars);
   uint64_t* full_bar = bars;        // W tiles landed (TMA)
   uint64_t* split_bar = bars + 4;   // operand rows written by the 256 workers
@@ -454,7 +475,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < sp.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], WORKERS);
+      mbar_init(&split_bar[s], WORKERS / 32);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -486,7 +507,9 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
       for (int kb = 0; kb < num_kb; ++kb) {
         const int stage = kb % sp.stages, phase = (kb / sp.stages) & 1;
         mbar_wait(&full_bar[stage], phase);
+        if (kb < 16) FT_STAMP(72 + 3 * kb);
         mbar_wait(&split_bar[stage], phase);
+        if (kb < 16) FT_STAMP(73 + 3 * kb);
         tc_fence_after();
         const uint32_t sa = sbase + stage * sp.stage_bytes;
         const uint32_t sa_lo = sa + A_BYTES, sb_hi = sa + 2 * A_BYTES, sb_lo = sb_hi + sp.b_bytes;
@@ -500,6 +523,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
           umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
         }
         umma_commit(&empty_bar[stage]);
+        if (kb < 16) FT_STAMP(74 + 3 * kb);
       }
       umma_commit(tmem_full_bar);
     }
@@ -510,8 +534,10 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
     const int r = q * 32 + lane;        // my tile row
     const int wt = (warp - 2) * 32 + lane;
     int ng;
-    const TileRow me = tile_prologue(p.t, tile, r, h, wt, s_glist, s_grow, sL, &ng);
+    if (wt == 0) FT_STAMP(0);
+    const TileRow me = tile_prologue(p.t, tile, r, h, wt, s_glist, s_grow, s_rowinfo, sL, &ng);
     worker_sync();  // row table visible
+    if (wt == 0) FT_STAMP(1);
     const bool vecX = ((F & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.T) & 15) == 0) && ((p.tslice & 3) == 0);
     const uint32_t xbuf[2] = {bufs, bufs + CBUF_BYTES};
@@ -525,7 +551,8 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
       const uint32_t st = sbase + stage * sp.stage_bytes;
       write_operand_half(st, st + A_BYTES, r, h, v);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
-      mbar_arrive(&split_bar[stage]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_bar[stage]);  // one arrival per worker warp
     };
 
     load_rows_async(xbuf[0], p.X, F, F, 0, s_grow, q, h, lane, vecX);
@@ -534,13 +561,15 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
       const int cur = c & 1;
       cp_async_wait_all();
       worker_sync();  // T_0 chunk c (and, first time, the L matrices) complete; chunk c-1 is finished everywhere
+      if (wt == 0 && c < 8) FT_STAMP(2 + 8 * c);
       if (c + 1 < nc) {
         load_rows_async(xbuf[cur ^ 1], p.X, F, F, c + 1, s_grow, q, h, lane, vecX);
         cp_async_commit();
       }
-      float tm2[16], tm1[16];
+      float tm2[16], tm1[16];  // my half row of T_{s-2}, T_{s-1}
       read_half(xbuf[cur], r, h, tm1);
       emit(c * K, tm1);
+      if (wt == 0 && c < 8) FT_STAMP(3 + 8 * c);
       uint32_t src = xbuf[cur], dst = tbuf;
       for (int s = 1; s < K; ++s) {
         float t[16];
@@ -552,6 +581,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
             const int col = c * CH + 16 * h + u;
             t[u] = (me.grow >= 0 && col < F) ? __ldg(Ts + (long long)me.grow * F + col) : 0.f;
           }
+          emit(c * K + s, t);
         } else {
 #pragma unroll
           for (int u = 0; u < 16; ++u) t[u] = p.t.add_identity ? tm1[u] : 0.f;  // L_all = I + L_int (literal mode)
@@ -560,11 +590,13 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
 #pragma unroll
             for (int u = 0; u < 16; ++u) t[u] = 2.f * t[u] - tm2[u];  // graphconv.py:234
           }
-          write_half(dst, r, h, t);
+          if (wt == 0 && c < 8 && s < 3) FT_STAMP(2 + 8 * c + 2 * s);
+          emit(c * K + s, t);       // the tensor core gets its operand first ...
+          write_half(dst, r, h, t);  // ... then the next step's input and the copy saved for backward
           __syncwarp();
           store_rows(dst, p.T + (long long)(s - 1) * p.tslice, F, F, c, s_grow, q, h, lane, vecX);
         }
-        emit(c * K + s, t);
+        if (wt == 0 && c < 8 && s < 3) FT_STAMP(3 + 8 * c + 2 * s);
 #pragma unroll
         for (int u = 0; u < 16; ++u) { tm2[u] = tm1[u]; tm1[u] = t[u]; }
         if (s + 1 < K) {
@@ -574,9 +606,11 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
       }
     }
     // ---- epilogue: Y = act(acc + bias)   graphconv.py:245-247, :118-123
+    if (wt == 0) FT_STAMP(66);
     if (lane == 0) mbar_wait(tmem_full_bar, 0);
     __syncwarp();
     tc_fence_after();
+    if (wt == 0) FT_STAMP(67);
     const uint32_t stg = sbase + (uint32_t)((warp - 2) * (32 * 36 * 4));  // operand stages are free now
     const bool vecY = ((Fo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
     for (int c0 = 32 * h; c0 < N && c0 < Fo; c0 += 64) {
@@ -614,6 +648,7 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
       __syncwarp();
     }
   }
+  if (threadIdx.x == 64) FT_STAMP(68);
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem_base, tmem_cols);
@@ -624,7 +659,8 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
 // ------------------------------------------------------------------------------------------------
 struct BwdArgs {
   TileArgs t;          // t.N = padded F (MMA N), t.nchunks = ceil(Fo / 32)
-  const float* dYp;    // [R,Fo]  dY * act'(Y)
+  const float* dYp;    // [R,Fo]  dY
+  const float* Y;      // [R,Fo]  activated output: dYpre = dY * [Y > 0]; NULL: linear activation
   float* G;            // [K][R][F]: written for pre tiles only (their recurrence runs in the per-graph kernels)
   long long gslice;
   float* dX;           // [R,F]
@@ -637,7 +673,8 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(base);
   const SmemPlan sp = smem_plan(p.t.N, false);
-  const uint32_t sL = sbase + sp.off_L, s_glist = sbase + sp.off_glist, s_grow = sbase + sp.off_grow;
+  const uint32_t sL = sbase + sp.off_L, s_glist = sbase + sp.off_glist, s_grow = sbase + sp.off_grow,
+                 s_rowinfo = sbase + sp.off_rowinfo;
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + sp.off_bars);
   uint64_t* full_bar = bars;
   uint64_t* split_bar = bars + 4;
@@ -655,7 +692,7 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
   if (threadIdx.x == 0) {
     for (int s = 0; s < sp.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], WORKERS);
+      mbar_init(&split_bar[s], WORKERS / 32);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -712,8 +749,9 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
     const int r = q * 32 + lane;
     const int wt = (warp - 2) * 32 + lane;
     int ng;
-    const TileRow me = tile_prologue(p.t, tile, r, h, wt, s_glist, s_grow, sL, &ng);
-    const bool vecD = ((Fo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dYp) & 15) == 0);
+    const TileRow me = tile_prologue(p.t, tile, r, h, wt, s_glist, s_grow, s_rowinfo, sL, &ng);
+    const bool vecD = ((Fo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dYp) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
     // mainloop: my half row of dYpre chunk c (L1-resident across the K passes) -> hi/lo operand rows; the row of
     // the next k-block is in flight while this one is split and stored.
     auto load_row = [&](int kb, float v[16]) {
@@ -723,14 +761,26 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
         for (int g = 0; g < 4; ++g) {
           const int col = c * CH + 16 * h + 4 * g;
           float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (me.grow >= 0 && col < Fo) x = __ldg(reinterpret_cast<const float4*>(p.dYp + (long long)me.grow * Fo + col));
+          if (me.grow >= 0 && col < Fo) {
+            x = __ldg(reinterpret_cast<const float4*>(p.dYp + (long long)me.grow * Fo + col));
+            if (p.Y) {  // relu'(0) = 0 (TF's ReluGrad)
+              const float4 y = __ldg(reinterpret_cast<const float4*>(p.Y + (long long)me.grow * Fo + col));
+              x.x = y.x > 0.f ? x.x : 0.f; x.y = y.y > 0.f ? x.y : 0.f;
+              x.z = y.z > 0.f ? x.z : 0.f; x.w = y.w > 0.f ? x.w : 0.f;
+            }
+          }
           v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
         }
       } else {
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const int col = c * CH + 16 * h + u;
-          v[u] = (me.grow >= 0 && col < Fo) ? __ldg(p.dYp + (long long)me.grow * Fo + col) : 0.f;
+          float x = 0.f;
+          if (me.grow >= 0 && col < Fo) {
+            x = __ldg(p.dYp + (long long)me.grow * Fo + col);
+            if (p.Y && !(__ldg(p.Y + (long long)me.grow * Fo + col) > 0.f)) x = 0.f;
+          }
+          v[u] = x;
         }
       }
     };
@@ -747,7 +797,8 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
       const uint32_t st = sbase + stage * sp.stage_bytes;
       write_operand_half(st, st + A_BYTES, r, h, v);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
-      mbar_arrive(&split_bar[stage]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_bar[stage]);
     }
     // ---- epilogue: reverse recurrence on the accumulators
     cp_async_wait_all();  // the L matrices of the tile (issued in the prologue)
@@ -868,8 +919,11 @@ static int make_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t 
 static int pad16(int x) { return (x + 15) & ~15; }
 static int pad32(int x) { return (x + 31) & ~31; }
 
+static unsigned long long* g_dbg = nullptr;
+
 static TileArgs tile_args(const agcn_plan* plan, const float* L, int add_identity, int F, int Fo, int K) {
   TileArgs t;
+  t.dbg = g_dbg;
   t.tile_graphs = reinterpret_cast<const int4*>(plan->d_ft_entries);
   t.tile_gstart = plan->d_ft_gstart;
   t.L = L;
@@ -885,6 +939,42 @@ static TileArgs tile_args(const agcn_plan* plan, const float* L, int add_identit
 // ------------------------------------------------------------------------------------------------
 // host API
 // ------------------------------------------------------------------------------------------------
+void fused_debug_set(void* d_buf) { ft::g_dbg = reinterpret_cast<unsigned long long*>(d_buf); }
+
+// ---- live kernel timing for bench.py's roofline: CUDA events on the launching stream around the main launch
+// (the small-graph tiles) of fused_forward, accumulated until read.  Off in production (and under graph capture).
+namespace {
+struct ProfState {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+  std::mutex mu;
+} g_prof;
+}  // namespace
+
+void fused_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  g_prof.on = on != 0;
+}
+
+int fused_profile_read(float* ms_sum, int* launches) {
+  std::lock_guard<std::mutex> lock(g_prof.mu);
+  float total = 0.f;
+  int n = 0;
+  for (auto& pr : g_prof.pending) {
+    float ms = 0.f;
+    AGCN_CUDA(cudaEventSynchronize(pr.second));
+    AGCN_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
+    total += ms;
+    ++n;
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  g_prof.pending.clear();
+  if (ms_sum) *ms_sum = total;
+  if (launches) *launches = n;
+  return AGCN_OK;
+}
+
 bool fused_enabled() {
   static const bool off = getenv("AGCN_DISABLE_FUSED") != nullptr || getenv("AGCN_DISABLE_TCGEN05") != nullptr;
   return !off;
@@ -954,13 +1044,24 @@ int fused_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, 
   a.bias = bias; a.act = act; a.Y = Y;
   const SmemPlan sp = smem_plan(N, true);
   if ((rc = opt_in_smem(fused_fwd_kernel, 227 * 1024))) return rc;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (g_prof.on && tile0 == 0) {
+    AGCN_CUDA(cudaEventCreate(&e0));
+    AGCN_CUDA(cudaEventCreate(&e1));
+    AGCN_CUDA(cudaEventRecord(e0, st));
+  }
   fused_fwd_kernel<<<ntiles, THREADS, sp.total, st>>>(mhi, mlo, a);
   AGCN_LAUNCH_CHECK();
+  if (e0) {
+    AGCN_CUDA(cudaEventRecord(e1, st));
+    std::lock_guard<std::mutex> lock(g_prof.mu);
+    g_prof.pending.emplace_back(e0, e1);
+  }
   return AGCN_OK;
 }
 
-int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dYp, const float* L, int add_identity,
-                   const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st) {
+int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dYp, const float* Y, const float* L,
+                   int add_identity, const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st) {
   using namespace ft;
   if (ntiles <= 0) return AGCN_OK;
   const int N = pad16(F), Kp = pad32(Fo);
@@ -974,7 +1075,7 @@ int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY
   a.t.N = N;
   a.t.nchunks = Kp / CH;
   a.t.tile0 = tile0;
-  a.dYp = dYp; a.G = G; a.gslice = (long long)plan->R * F; a.dX = dX;
+  a.dYp = dYp; a.Y = Y; a.G = G; a.gslice = (long long)plan->R * F; a.dX = dX;
   a.acc_stride = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
   const SmemPlan sp = smem_plan(N, false);
   if ((rc = opt_in_smem(fused_bwd_kernel, 227 * 1024))) return rc;

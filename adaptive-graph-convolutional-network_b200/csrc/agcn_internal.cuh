@@ -223,6 +223,9 @@ int big_dL(const GraphArgs& a, const float* U, cudaStream_t st);
 int big_laplacian_bwd(const GraphArgs& a, float* big_work, cudaStream_t st);
 
 // ---------------------------------------------------------------- fused tile kernels (agcn_fused_tile.cu)
+void fused_profile_enable(int on);
+int fused_profile_read(float* ms_sum, int* launches);
+void fused_debug_set(void* d_buf);  // timeline buffer [tiles][128] uint64 of the NEXT fused forward launches, or NULL
 bool fused_fwd_supported(const agcn_plan* plan, int F, int Fo, int K);
 bool fused_bwd_supported(const agcn_plan* plan, int F, int Fo, int K);
 size_t fused_w_floats(int Nv, int Kv, int Z);  // floats of one pre-split parameter operand
@@ -233,10 +236,10 @@ int fused_bwd_prep(const float* weight, int F, int Fo, int K, float* scratch, cu
 int fused_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, const float* L, int add_identity,
                   const float* wsplit, const float* bias, int act, int F, int Fo, int K, float* T, float* Y,
                   cudaStream_t st);
-// dX = U_0 of the reverse recurrence over G_z = dYp W_z^T; G receives G_z for the rows of graphs with
-// n > AGCN_FUSE_MAX_N only
-int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dYp, const float* L, int add_identity,
-                   const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st);
+// dX = U_0 of the reverse recurrence over G_z = dYpre W_z^T, dYpre = dY * [Y > 0] (Y == NULL: dYpre = dY);
+// G receives G_z for the rows of graphs with n > AGCN_FUSE_MAX_N only
+int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY, const float* Y, const float* L,
+                   int add_identity, const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st);
 
 // ---------------------------------------------------------------- helpers
 int fork_streams(const agcn_plan* plan, cudaStream_t main, int n_aux);

@@ -38,14 +38,19 @@ class FlatGradBuffer(object):
     """All parameter gradients in one contiguous buffer; every `.grad` is a view into it, so the
     gradient exchange of a step is a single all-reduce (latency-bound: ~0.5 M floats)."""
 
-    def __init__(self, params):
+    def __init__(self, params, direct=()):
+        """direct: parameters whose producers write the gradient straight into the view (the SGC-LL
+        backward overwrites its outputs, include/agcn_sgcll.h), so autograd has nothing to add."""
         self.params = list(params)
         total = sum(p.numel() for p in self.params)
         first = self.params[0]
         self.flat = torch.zeros(total, device=first.device, dtype=first.dtype)
         off = 0
+        direct = set(id(p) for p in direct)
         for p in self.params:
             p.grad = self.flat[off:off + p.numel()].view_as(p)
+            if id(p) in direct:
+                p._agcn_grad_out = p.grad
             off += p.numel()
 
     def zero(self):
@@ -57,3 +62,36 @@ class FlatGradBuffer(object):
 
     def numel(self):
         return int(self.flat.numel())
+
+
+class FlatParamBuffer(object):
+    """All parameters in one contiguous buffer (every parameter keeps its identity and becomes a view
+    into it), paired with a FlatGradBuffer: the optimizer then updates ONE tensor per step instead of
+    one per parameter."""
+
+    def __init__(self, params, grads):
+        self.params = list(params)
+        first = self.params[0]
+        total = sum(p.numel() for p in self.params)
+        assert total == grads.numel()
+        self.flat = torch.empty(total, device=first.device, dtype=first.dtype)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                view = self.flat[off:off + p.numel()].view_as(p)
+                view.copy_(p)
+                p.data = view
+                off += p.numel()
+        self.leaf = self.flat.requires_grad_(True)
+        self.leaf.grad = grads.flat
+
+    def chunks(self, grads, chunk=8192):
+        """The flat buffer as a list of leaf tensors (storage aliases) with `.grad` aliases into the flat
+        gradient: a multi-tensor optimizer then spreads one update over many thread blocks instead of
+        walking a single 0.5 M-element tensor with a handful of them."""
+        out = []
+        for a in range(0, self.flat.numel(), chunk):
+            t = self.flat.data[a:a + chunk].requires_grad_(True)
+            t.grad = grads.flat[a:a + chunk]
+            out.append(t)
+        return out

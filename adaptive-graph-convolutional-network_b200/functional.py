@@ -63,6 +63,9 @@ class _SGCLLFunction(torch.autograd.Function):
             _ptr(alpha), _ptr(beta), _ptr(Y), _ptr(resL), _ptr(resW), _ptr(Lall), _ptr(saved), _ptr(work),
             work.numel(), _stream_ptr()))
         ctx.batch, ctx.cfg, ctx.desc = batch, cfg, desc
+        # parameters registered with FlatGradBuffer(direct=...): backward writes their gradients in place
+        ctx.grad_out = [getattr(t, "_agcn_grad_out", None) if t is not None else None
+                        for t in (M_L, weight, bias, alpha, beta)]
         ctx.set_materialize_grads(False)
         ctx.has_prev = Lprev is not None
         ctx.has_beta = beta is not None
@@ -89,17 +92,23 @@ class _SGCLLFunction(torch.autograd.Function):
         work = _Workspace.get(dev, work_b.value)
         need_dX = ctx.needs_input_grad[0] or cfg["metric_grad"] == "full"
         dX = torch.empty_like(X) if need_dX else None
-        dM = torch.empty_like(M_L)
-        dW = torch.empty_like(weight)
-        db = torch.empty(Fo, device=dev, dtype=torch.float32)
-        dalpha = torch.empty(1, device=dev, dtype=torch.float32)
-        dbeta = torch.zeros(1, device=dev, dtype=torch.float32) if ctx.has_beta else None
+        gM, gW, gb, ga, gbeta = ctx.grad_out
+        dM = gM if gM is not None else torch.empty_like(M_L)
+        dW = gW if gW is not None else torch.empty_like(weight)
+        db = gb if gb is not None else torch.empty(Fo, device=dev, dtype=torch.float32)
+        dalpha = ga if ga is not None else torch.empty(1, device=dev, dtype=torch.float32)
+        dbeta = None
+        if ctx.has_beta:
+            dbeta = gbeta if gbeta is not None else torch.zeros(1, device=dev, dtype=torch.float32)
         dLprev = torch.empty_like(Lprev) if ctx.has_prev else None
         _lib.check(_lib.lib().agcn_sgcll_backward(
             ctypes.byref(desc), batch.handle, _ptr(X), _ptr(Lint), _ptr(Lprev), _ptr(M_L), _ptr(weight), _ptr(alpha),
             _ptr(beta), _ptr(Y), _ptr(dY), _ptr(dLall), _ptr(saved), _ptr(dX), _ptr(dM), _ptr(dW), _ptr(db),
             _ptr(dalpha), _ptr(dbeta), _ptr(dLprev), _ptr(work), work.numel(), _stream_ptr()))
-        return dX, None, dLprev, dM, dW, db, dalpha, dbeta, None, None
+        # gradients written in place are not returned (autograd would add them to themselves)
+        return (dX, None, dLprev, None if gM is not None else dM, None if gW is not None else dW,
+                None if gb is not None else db, None if ga is not None else dalpha,
+                None if gbeta is not None else dbeta, None, None)
 
 
 def sgc_ll_packed(X, Lint, Lprev, params, batch, cfg):

@@ -15,7 +15,7 @@ import torch
 import torch.distributed as dist
 
 from .batch import GraphBatch, PackedLaplacians, PackedNodes
-from .data_parallel import FlatGradBuffer
+from .data_parallel import FlatGradBuffer, FlatParamBuffer
 from .layers import SGC_LL
 from .layers import graphconv as _gc
 
@@ -45,9 +45,13 @@ class SimpleAGCNStep(object):
         self.params = [v for l in self.layers for v in l.vars.values()] + [self.dense_W, self.dense_b, self.head_W,
                                                                            self.head_b]
         # one flat gradient buffer; every .grad is a view into it -> a single all-reduce per step
-        self.grads = FlatGradBuffer(self.params)
+        # the SGC-LL backward writes its parameter gradients straight into the views (no accumulation kernels)
+        self.grads = FlatGradBuffer(self.params, direct=[v for l in self.layers for v in l.vars.values()])
         self.flat_grad = self.grads.flat
-        self.opt = torch.optim.Adam(self.params, lr=learning_rate, betas=(0.9, 0.999), eps=1e-7, fused=True, capturable=True)
+        # ... and one flat parameter tensor: Adam is a single-tensor update
+        self.flat_params = FlatParamBuffer(self.params, self.grads)
+        self.opt = torch.optim.Adam(self.flat_params.chunks(self.grads), lr=learning_rate, betas=(0.9, 0.999), eps=1e-7,
+                                    fused=True, capturable=True)
 
     def _n_nodes_f(self, batch):
         t = getattr(batch, "_n_nodes_float", None)

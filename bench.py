@@ -13,7 +13,9 @@ heads), forward + backward + gradient all-reduce + Adam.  One "step" = one such 
           the timed steps)
   e2e   : graphs/s through the public API from pinned HOST buffers: host->device copy of the
           batch, topology plan, train step, device->host read of the loss, every step
-  roofline : dominant kernel (by live CUDA-event time per launch) against MEASURED_PEAKS.json
+  e2e   : ... the batch crosses PCIe in the reference's zero-padded wire layout and is packed on the device
+          (e2e_packed_host: the same with a host side that already holds the packed ragged layout)
+  roofline : dominant kernel (ft::fused_fwd_kernel, live CUDA-event time per launch) against MEASURED_PEAKS.json
   cpu_baseline / --impl reference : the reference's algorithm as written (oracle port: per-graph
           Python loop with the interpreted O(n^2) metric block, autograd for the rest) on the host
           cores, on a bounded sample of the same workload.
@@ -165,7 +167,7 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     procs = max(1, min(cores, 32))
-    n_graphs = procs * 16
+    n_graphs = args.ref_graphs or B_PER_GPU     # one step = the whole C2 batch (about 2-5 s on 16-32 cores)
     steps = max(1, min(args.steps, 3))
     warmup = max(0, min(args.warmup, 1))
     gps, ms, nbar = cpu_reference_graphs_per_s(n_graphs, steps, warmup, procs)
@@ -207,6 +209,8 @@ def run_ours(args):
     Xpad, Lpad, n_nodes = O.synthetic_molecule_batch(B_PER_GPU, NMAX, seed=1235 + rank)
     Xh = torch.from_numpy(np.concatenate([Xpad[g, :n] for g, n in enumerate(n_nodes)], 0)).pin_memory()
     Lh = torch.from_numpy(np.concatenate([Lpad[g, :n, :n].reshape(-1) for g, n in enumerate(n_nodes)])).pin_memory()
+    # the reference's wire layout (graph_topology.py:84-98): zero-padded [B, Nmax, F] / [B, Nmax, Nmax]
+    Xpad_h, Lpad_h = torch.from_numpy(Xpad).pin_memory(), torch.from_numpy(Lpad).pin_memory()
     onehot, weights = synthetic_labels(B_PER_GPU, N_TASKS, 99 + rank, "cpu")
     onehot_h, weights_h = onehot.pin_memory(), weights.pin_memory()
 
@@ -226,12 +230,23 @@ def run_ours(args):
         return model.step(Xd, Ld, batch, onehot_d, weights_d)
 
     def e2e_step():
+        """The call a user of the reference makes: padded host arrays of one batch in, loss out."""
+        Xp = Xpad_h.to(dev, non_blocking=True)
+        Lp = Lpad_h.to(dev, non_blocking=True)
+        oh = onehot_h.to(dev, non_blocking=True)
+        w = weights_h.to(dev, non_blocking=True)
+        b = agcn_b200.GraphBatch(n_nodes, NMAX, device=dev)
+        X, L = b.pack_nodes(Xp), b.pack_lap(Lp)        # agcn_pack_*: tf.slice of graphconv.py:153-154
+        return float(model.step(X, L, b, oh, w).detach())      # device -> host read of the loss
+
+    def e2e_packed_step():
+        """Same, with the host side already in the packed ragged layout (no padding crosses PCIe)."""
         X = Xh.to(dev, non_blocking=True)
         L = Lh.to(dev, non_blocking=True)
         oh = onehot_h.to(dev, non_blocking=True)
         w = weights_h.to(dev, non_blocking=True)
         b = agcn_b200.GraphBatch(n_nodes, NMAX, device=dev)
-        return float(model.step(X, L, b, oh, w))      # .item(): device -> host read of the loss
+        return float(model.step(X, L, b, oh, w).detach())
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -283,6 +298,15 @@ def run_ours(args):
         ms_step = timed(resident_step, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e = timed(e2e_step, max(3, args.steps // 2), 3)
+    ms_e2e_packed = timed(e2e_packed_step, max(3, args.steps // 2), 3)
+    # the same step with the paper's semantics (normalised Laplacian + differentiable metric): every kernel of
+    # the metric / Laplacian block runs, forward and backward
+    ms_paper = None
+    if not args.no_paper:
+        pm = SimpleAGCNStep(N_FEAT, FILTERS, FINAL, N_TASKS, K_ORDER, B_PER_GPU, device=dev, world_size=world,
+                            laplacian="paper", metric_grad="full")
+        ms_paper = timed(lambda: pm.step(Xd, Ld, batch, onehot_d, weights_d), max(3, args.steps // 2), 3)
+        del pm
 
     # ---- roofline of the dominant kernel class: per-layer kernels timed live with CUDA events
     roof = None
@@ -296,12 +320,14 @@ def run_ours(args):
         if args.skip_cpu:    # quick experiments only: the driver's runs always carry the CPU leg
             gps, procs, sample = None, 0, "skipped (--skip-cpu)"
         else:
-            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "1",
-                                  "--warmup", "0"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
+            out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "3",
+                                  "--warmup", "1"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
                                  env=dict(os.environ, RANK="0", WORLD_SIZE="1"))
             ref = json.loads(out.stdout.strip().splitlines()[-1])
             gps, procs, sample = ref["value"], ref["cpu_baseline"]["cores"], ref["cpu_baseline"]["sample"]
-        h2d = Xh.numel() * 4 + Lh.numel() * 4 + onehot_h.numel() * 4 + weights_h.numel() * 4 + n_nodes.nbytes * 4
+        side = onehot_h.numel() * 4 + weights_h.numel() * 4 + n_nodes.nbytes * 4
+        h2d = Xpad_h.numel() * 4 + Lpad_h.numel() * 4 + side
+        h2d_packed = Xh.numel() * 4 + Lh.numel() * 4 + side
         line = {"metric": "sgc_ll_train_graphs_per_s", "value": value, "unit": "graphs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_step_eager": ms_eager,
                 "higher_is_better": True,
@@ -309,10 +335,17 @@ def run_ours(args):
                 "config": {"workload": WORKLOAD, "global_batch": world * B_PER_GPU, "parallelism": "dp%d" % world, "launch": launch_mode,
                            "semantics": "laplacian=reference_literal, metric_grad=reference",
                            "l2": "flushed between timed steps (256 MB fill)", "mean_nodes": float(n_nodes.mean()),
-                           "parameters": model.n_parameters(), "host_layout_e2e": "packed ragged (pinned)"},
+                           "parameters": model.n_parameters(),
+                           "host_layout_e2e": "reference wire layout: zero-padded [B,132,75] + [B,132,132] (pinned)"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
                         "d2h_bytes_per_step": 4},
+                "e2e_packed_host": {"value": world * B_PER_GPU / (ms_e2e_packed * 1e-3), "unit": "graphs/s",
+                                    "ms_per_step": ms_e2e_packed, "h2d_bytes_per_step": int(h2d_packed),
+                                    "d2h_bytes_per_step": 4},
+                "paper_full_semantics": None if ms_paper is None else {
+                    "value": world * B_PER_GPU / (ms_paper * 1e-3), "unit": "graphs/s", "ms_per_step": ms_paper,
+                    "semantics": "laplacian=paper, metric_grad=full", "launch": "eager"},
                 "gpu_launches": int(round(launches_per_step * args.steps)),
                 "gpu_launches_per_step": launches_per_step,
                 "roofline": roof,
@@ -323,35 +356,57 @@ def run_ours(args):
 
 
 def kernel_roofline(model, batch, Xd, Ld, n_nodes, dev):
-    """Times the SGC-LL layer-2 forward (64 -> 128, the heaviest layer) as one unit with CUDA events
-    and reports its algorithmic bytes / time against the measured HBM copy bandwidth."""
+    """The dominant kernel of the step is ft::fused_fwd_kernel (Chebyshev recurrence + tcgen05 feature transform,
+    one launch per layer; profiles/).  Its launch of layer 3 (128 -> 128, the heaviest) is timed live with CUDA
+    events recorded by the library on the launching stream (agcn_fused_profile), L2 flushed before every launch;
+    algorithmic bytes = 4 (R F + sum n^2 + R Fo) + parameters, the K-1 Chebyshev terms
+    it also saves for backward are reported beside it, not counted."""
+    import ctypes
     import torch
+    from agcn_b200 import _lib
     from agcn_b200.functional import sgc_ll_packed
     peaks = load_peaks()
-    layer = model.layers[1]
+    layer = model.layers[2]
     F, Fo, K = layer.n_atom_feature, layer.nb_filter, layer.K
     X = torch.relu(torch.randn(batch.total_nodes, F, device=dev))
     cfg = layer._cfg('relu')
     p = {k: v.detach() for k, v in layer.vars.items()}
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-    times = []
+    lib = _lib.lib()
+    ms_sum, launches = ctypes.c_float(), ctypes.c_int()
     with torch.no_grad():
         for it in range(13):
             flush.fill_(0.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
+            if it == 3:
+                torch.cuda.synchronize()
+                _lib.check(lib.agcn_fused_profile(1))
             sgc_ll_packed(X, Ld, None, p, batch, cfg)
-            e1.record()
-            torch.cuda.synchronize()
-            if it >= 3:
-                times.append(e0.elapsed_time(e1))
-    ms = sum(times) / len(times)
+        torch.cuda.synchronize()
+        _lib.check(lib.agcn_fused_profile_read(ctypes.byref(ms_sum), ctypes.byref(launches)))
+        _lib.check(lib.agcn_fused_profile(0))
+    if launches.value == 0:
+        return {"bound": "hbm", "kernel": "ft::fused_fwd_kernel", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": None, "traffic": None, "note": "fused path disabled: no launch was timed"}
+    ms = ms_sum.value / launches.value
     ff, fb, bf, bb = layer_algorithmic(n_nodes, F, Fo, K)
+    bf += 4.0 * (K * F * Fo + Fo)
     achieved = bf / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "SGC_LL layer-2 forward (cheb_fwd_kernel + gemm_rows_kernel)",
+    R = float(n_nodes.sum())
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(tpath):
+        t = json.load(open(tpath))
+        traffic, traffic_src = t.get("fused_fwd_kernel_layer3_dram_bytes"), t.get("source")
+    tf32_peak = peaks["bf16_tflops"] / 2.0
+    return {"bound": "hbm", "kernel": "ft::fused_fwd_kernel, layer 3 (F=128 -> Fo=128, K=3), small-graph tiles launch",
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
-            "traffic": None, "peak_source": peaks["source"], "algorithmic_bytes_per_launch": bf,
-            "ms_per_launch": ms, "fp32_tflops_achieved": ff / (ms * 1e-3) / 1e12}
+            "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"],
+            "algorithmic_bytes_per_launch": bf, "saved_for_backward_bytes_per_launch": 4.0 * (K - 1) * R * F,
+            "ms_per_launch": ms, "launches_timed": launches.value,
+            "tensor": {"flops_3xtf32_per_launch": 3.0 * 2.0 * R * K * F * Fo,
+                       "achieved_tflops": 3.0 * 2.0 * R * K * F * Fo / (ms * 1e-3) / 1e12,
+                       "peak_tflops": tf32_peak, "peak_note": "tf32 dense taken as half the measured bf16 peak",
+                       "frac": 3.0 * 2.0 * R * K * F * Fo / (ms * 1e-3) / 1e12 / tf32_peak}}
 
 
 def main():
@@ -361,7 +416,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-graph", action="store_true", help="time eager launches only")
+    ap.add_argument("--no-paper", action="store_true", help="skip the paper-semantics secondary measurement")
     ap.add_argument("--skip-cpu", action="store_true", help="skip the cpu_baseline leg (quick experiments)")
+    ap.add_argument("--ref-graphs", type=int, default=0, help="graphs per step of the reference arm (default: the batch)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

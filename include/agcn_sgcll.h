@@ -99,6 +99,17 @@ const int64_t* agcn_plan_lap_off_host(const agcn_plan* plan);  /* [B+1] host   *
 int agcn_fused_tiles_host(const int32_t* n_nodes_host, int32_t B, int32_t* gstart_out, int32_t gstart_cap,
                           int32_t* entries_out, int32_t entries_cap, int32_t* tiles_out, int32_t* n_entries_out);
 
+/* Measurement aid (no reference counterpart; bench.py's roofline): while enabled, every eager agcn_sgcll_forward on
+ * the fused tile path brackets its main kernel launch with CUDA events on the launching stream;
+ * agcn_fused_profile_read waits for them and returns the summed duration (ms) and the number of launches since
+ * the last read.  Must be off during CUDA graph capture. */
+int agcn_fused_profile(int enable);
+int agcn_fused_profile_read(float* ms_sum, int* launches);
+
+/* Tuning aid (no reference counterpart): d_buf = device buffer of tiles x 128 uint64; the following fused forward
+ * launches record a per-tile timeline of nanosecond stamps into it.  NULL switches the recording off. */
+int agcn_fused_debug_set(void* d_buf);
+
 /* ---- layout conversion (pad_data2sparse / pad_Lap2sparse, graph_topology.py:84-98;
  *      tf.slice at graphconv.py:153-154; tf.pad at graphconv.py:249-251) ------------------ */
 int agcn_pack_nodes(const agcn_plan* plan, const float* d_padded /*[B,Nmax,F]*/, float* d_packed /*[R,F]*/,

@@ -78,3 +78,30 @@ def test_shard_graphs_balance():
         assert work.max() / work.mean() < 1.10                                  # within 10 % of perfect balance
         blocks = [shard_graphs(n, world, r, "count") for r in range(world)]
         assert np.concatenate(blocks).tolist() == list(range(128))
+
+
+def test_flat_param_buffer_single_tensor_adam_matches_per_tensor_adam():
+    """FlatParamBuffer + FlatGradBuffer: one-tensor Adam over the flat views == Adam over the separate
+    parameters; parameters keep their identity and see the update."""
+    from agcn_b200.data_parallel import FlatGradBuffer, FlatParamBuffer
+    torch.manual_seed(0)
+    shapes = [(5, 3), (3,), (1,), (4, 4)]
+    ref = [torch.randn(*s, dtype=torch.float64, requires_grad=True) for s in shapes]
+    ours = [t.detach().clone().requires_grad_(True) for t in ref]
+    grads = FlatGradBuffer(ours, direct=ours[:2])
+    flat = FlatParamBuffer(ours, grads)
+    assert ours[0]._agcn_grad_out.data_ptr() == grads.flat.data_ptr() and not hasattr(ours[2], "_agcn_grad_out")
+    opt_ref = torch.optim.Adam(ref, lr=1e-2, eps=1e-7)
+    opt = torch.optim.Adam([flat.leaf], lr=1e-2, eps=1e-7)
+    for step in range(3):
+        gs = [torch.randn(*s, dtype=torch.float64) for s in shapes]
+        for p, g in zip(ref, gs):
+            p.grad = g.clone()
+        grads.zero()
+        for p, g in zip(ours, gs):
+            p.grad.add_(g)                 # what autograd / the in-place SGC-LL backward do
+        opt_ref.step()
+        opt.step()
+        for a, b in zip(ours, ref):
+            assert torch.allclose(a, b, rtol=1e-12, atol=1e-14)
+            assert a.data_ptr() >= flat.flat.data_ptr()
