@@ -38,6 +38,7 @@ class GraphBatch(object):
         self.node_off = np.concatenate([[0], np.cumsum(n, dtype=np.int64)])
         self.lap_off = np.concatenate([[0], np.cumsum(n.astype(np.int64) ** 2)])
         self._graph_ids = None
+        self._n_dev = None
 
     @property
     def handle(self):
@@ -93,11 +94,20 @@ class GraphBatch(object):
     def node_view(self, packed, g):
         return packed[self.node_off[g]:self.node_off[g + 1]]
 
+    def n_nodes_device(self):
+        """int64 [B] on the device, uploaded from pinned memory (no host synchronisation: a plan per batch
+        must not stall a pipelined training loop)."""
+        if self._n_dev is None:
+            host = torch.from_numpy(self.n_nodes.astype(np.int64)).pin_memory()
+            self._n_dev = host.to(self.device, non_blocking=True)
+            self._n_host_pinned = host      # keep the staging buffer alive until the copy has run
+        return self._n_dev
+
     def graph_ids(self):
         """int64 [R]: graph index of every packed row (for gathers in the callers)."""
         if self._graph_ids is None:
-            ids = np.repeat(np.arange(self.batch_size, dtype=np.int64), self.n_nodes)
-            self._graph_ids = torch.from_numpy(ids).to(self.device)
+            self._graph_ids = torch.repeat_interleave(torch.arange(self.batch_size, device=self.device),
+                                                      self.n_nodes_device(), output_size=self.total_nodes)
         return self._graph_ids
 
 

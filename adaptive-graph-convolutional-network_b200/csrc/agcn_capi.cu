@@ -174,6 +174,7 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
   AGCN_REQUIRE(!(desc->flags & AGCN_OUT_RES_W) || d_resW, "forward: d_resW missing");
   AGCN_REQUIRE(!(desc->flags & AGCN_OUT_L_ALL) || d_Lall, "forward: d_Lall missing");
   cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = plan_use(plan, st))) return rc;
   Saved sv = carve_saved(desc, plan, d_saved);
   Work wk = carve_work(desc, plan, d_work);
   if (wk.bytes > work_bytes) {
@@ -274,6 +275,7 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   const Modes m = modes_of(desc);
   AGCN_REQUIRE(!m.reslap || (d_beta && d_dbeta), "backward: beta / dbeta required for SGC_LL_Reslap");
   cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = plan_use(plan, st))) return rc;
   Saved sv = carve_saved(desc, plan, const_cast<void*>(d_saved));
   Work wk = carve_work(desc, plan, d_work);
   if (wk.bytes > work_bytes) {

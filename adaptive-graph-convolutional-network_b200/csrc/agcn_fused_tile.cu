@@ -555,53 +555,68 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
       if (lane == 0) mbar_arrive(&split_bar[stage]);  // one arrival per worker warp
     };
 
-    load_rows_async(xbuf[0], p.X, F, F, 0, s_grow, q, h, lane, vecX);
-    cp_async_commit();
-    for (int c = 0; c < nc; ++c) {
-      const int cur = c & 1;
-      cp_async_wait_all();
-      worker_sync();  // T_0 chunk c (and, first time, the L matrices) complete; chunk c-1 is finished everywhere
-      if (wt == 0 && c < 8) FT_STAMP(2 + 8 * c);
-      if (c + 1 < nc) {
-        load_rows_async(xbuf[cur ^ 1], p.X, F, F, c + 1, s_grow, q, h, lane, vecX);
-        cp_async_commit();
-      }
-      float tm2[16], tm1[16];  // my half row of T_{s-2}, T_{s-1}
-      read_half(xbuf[cur], r, h, tm1);
-      emit(c * K, tm1);
-      if (wt == 0 && c < 8) FT_STAMP(3 + 8 * c);
-      uint32_t src = xbuf[cur], dst = tbuf;
-      for (int s = 1; s < K; ++s) {
-        float t[16];
-        if (me.pre) {
-          // the per-graph / row-tiled kernels produced T_s for this graph
-          const float* Ts = p.T + (long long)(s - 1) * p.tslice;
+    if (me.pre) {
+      // 128-row range of a big graph: the per-graph / row-tiled kernels produced T_1..T_{K-1}; this tile only feeds
+      // the tensor core.  My half row of k-block kb + 1 is in flight while k-block kb is split and handed over.
+      cp_async_wait_all();  // (nothing of this tile, but keeps the group accounting of the prologue simple)
+      auto load_kb = [&](int kb, float v[16]) {
+        const int c = kb / K, sl = kb - c * K;
+        const float* src = (sl == 0) ? p.X : p.T + (long long)(sl - 1) * p.tslice;
 #pragma unroll
-          for (int u = 0; u < 16; ++u) {
-            const int col = c * CH + 16 * h + u;
-            t[u] = (me.grow >= 0 && col < F) ? __ldg(Ts + (long long)me.grow * F + col) : 0.f;
-          }
-          emit(c * K + s, t);
-        } else {
-#pragma unroll
-          for (int u = 0; u < 16; ++u) t[u] = p.t.add_identity ? tm1[u] : 0.f;  // L_all = I + L_int (literal mode)
-          lap_times_rows(lrow, 4, src, me.r0, me.n, h, t);  // graphconv.py:231
-          if (s >= 2) {
-#pragma unroll
-            for (int u = 0; u < 16; ++u) t[u] = 2.f * t[u] - tm2[u];  // graphconv.py:234
-          }
-          if (wt == 0 && c < 8 && s < 3) FT_STAMP(2 + 8 * c + 2 * s);
-          emit(c * K + s, t);       // the tensor core gets its operand first ...
-          write_half(dst, r, h, t);  // ... then the next step's input and the copy saved for backward
-          __syncwarp();
-          store_rows(dst, p.T + (long long)(s - 1) * p.tslice, F, F, c, s_grow, q, h, lane, vecX);
+        for (int u = 0; u < 16; ++u) {
+          const int col = c * CH + 16 * h + u;
+          v[u] = (me.grow >= 0 && col < F) ? __ldg(src + (long long)me.grow * F + col) : 0.f;
         }
-        if (wt == 0 && c < 8 && s < 3) FT_STAMP(3 + 8 * c + 2 * s);
+      };
+      float nxt[16];
+      load_kb(0, nxt);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        float v[16];
 #pragma unroll
-        for (int u = 0; u < 16; ++u) { tm2[u] = tm1[u]; tm1[u] = t[u]; }
-        if (s + 1 < K) {
-          worker_sync();  // T_s rows of every graph of the tile are in `dst`
-          const uint32_t tmp = src; src = dst; dst = tmp;
+        for (int u = 0; u < 16; ++u) v[u] = nxt[u];
+        if (kb + 1 < num_kb) load_kb(kb + 1, nxt);
+        emit(kb, v);
+      }
+    } else {
+    load_rows_async(xbuf[0], p.X, F, F, 0, s_grow, q, h, lane, vecX);
+      cp_async_commit();
+      for (int c = 0; c < nc; ++c) {
+        const int cur = c & 1;
+        cp_async_wait_all();
+        worker_sync();  // T_0 chunk c (and, first time, the L matrices) complete; chunk c-1 is finished everywhere
+        if (wt == 0 && c < 8) FT_STAMP(2 + 8 * c);
+        if (c + 1 < nc) {
+          load_rows_async(xbuf[cur ^ 1], p.X, F, F, c + 1, s_grow, q, h, lane, vecX);
+          cp_async_commit();
+        }
+        float tm2[16], tm1[16];  // my half row of T_{s-2}, T_{s-1}
+        read_half(xbuf[cur], r, h, tm1);
+        emit(c * K, tm1);
+        if (wt == 0 && c < 8) FT_STAMP(3 + 8 * c);
+        uint32_t src = xbuf[cur], dst = tbuf;
+        for (int s = 1; s < K; ++s) {
+          float t[16];
+          {
+  #pragma unroll
+            for (int u = 0; u < 16; ++u) t[u] = p.t.add_identity ? tm1[u] : 0.f;  // L_all = I + L_int (literal mode)
+            lap_times_rows(lrow, 4, src, me.r0, me.n, h, t);  // graphconv.py:231
+            if (s >= 2) {
+  #pragma unroll
+              for (int u = 0; u < 16; ++u) t[u] = 2.f * t[u] - tm2[u];  // graphconv.py:234
+            }
+            if (wt == 0 && c < 8 && s < 3) FT_STAMP(2 + 8 * c + 2 * s);
+            emit(c * K + s, t);       // the tensor core gets its operand first ...
+            write_half(dst, r, h, t);  // ... then the next step's input and the copy saved for backward
+            __syncwarp();
+            store_rows(dst, p.T + (long long)(s - 1) * p.tslice, F, F, c, s_grow, q, h, lane, vecX);
+          }
+          if (wt == 0 && c < 8 && s < 3) FT_STAMP(3 + 8 * c + 2 * s);
+  #pragma unroll
+          for (int u = 0; u < 16; ++u) { tm2[u] = tm1[u]; tm1[u] = t[u]; }
+          if (s + 1 < K) {
+            worker_sync();  // T_s rows of every graph of the tile are in `dst`
+            const uint32_t tmp = src; src = dst; dst = tmp;
+          }
         }
       }
     }

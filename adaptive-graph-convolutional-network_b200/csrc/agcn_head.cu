@@ -1,0 +1,306 @@
+// The layers that follow the last SGC-LL layer in the reference's networks (basic_AGCN.py:35-47), as ONE
+// loss-and-gradient call on the packed layout:
+//
+//   DenseMol        h_i W_d + b_d, no activation                 models/layers/dense_layer.py:33-50
+//   GraphGatherMol  per-graph sum over the real atoms, tanh      models/layers/graphgather.py:50-78
+//   logits          n_tasks independent [n_feature, 2] heads     models/operators/model_operatos.py:792-864
+//   loss            weighted sigmoid cross-entropy / batch size  models/tf_modules/multitask_classifier.py:41-44,187-209
+//
+// DenseMol is linear, so the gather commutes with it: sum_i (h_i W + b) = (sum_i h_i) W + n_g b.  The dense GEMM
+// then has B rows instead of R = sum n_g.  The n_tasks heads are one [n_feature, 2 n_tasks] matrix.  Every
+// contraction runs on the tcgen05 3xTF32 GEMMs of agcn_tc_gemm.cu; the cross-entropy and its gradient are the
+// epilogue of the logits GEMM, so the [B, 2 n_tasks] logits never reach HBM as logits.
+#include <algorithm>
+
+#include "agcn_internal.cuh"
+
+namespace agcn {
+
+// hsum[g, :] = sum of the rows of graph g          (one warp per graph; every row load of the warp is in flight at
+// once: lanes walk the graph's rows as one contiguous [n_g * F] range, fixed summation order per column)
+__global__ void segment_sum_kernel(const float* __restrict__ H, const int32_t* __restrict__ node_off, int B, int F,
+                                   float* __restrict__ hsum) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= B) return;
+  const int r0 = node_off[g], r1 = node_off[g + 1];
+  if (F % 32 == 0) {
+    // lane owns columns lane, lane + 32, ...: consecutive lanes read consecutive addresses of every row
+    for (int c = lane; c < F; c += 32) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int r = r0;
+      for (; r + 4 <= r1; r += 4) {
+        s0 += __ldg(H + (int64_t)r * F + c);
+        s1 += __ldg(H + (int64_t)(r + 1) * F + c);
+        s2 += __ldg(H + (int64_t)(r + 2) * F + c);
+        s3 += __ldg(H + (int64_t)(r + 3) * F + c);
+      }
+      for (; r < r1; ++r) s0 += __ldg(H + (int64_t)r * F + c);
+      hsum[(int64_t)g * F + c] = (s0 + s1) + (s2 + s3);
+    }
+    return;
+  }
+  for (int c = lane; c < F; c += 32) {
+    float s = 0.f;
+    for (int r = r0; r < r1; ++r) s += H[(int64_t)r * F + c];
+    hsum[(int64_t)g * F + c] = s;
+  }
+}
+
+// mol = tanh(pre + n_g b)   (graphgather.py:77)
+__global__ void gather_tanh_kernel(const float* __restrict__ pre, const float* __restrict__ b,
+                                   const int32_t* __restrict__ n_nodes, int B, int Fm, float* __restrict__ mol) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)B * Fm) return;
+  const int g = (int)(e / Fm), c = (int)(e % Fm);
+  mol[e] = tanhf(pre[e] + (float)n_nodes[g] * b[c]);
+}
+
+// dpre = dmol (1 - mol^2), in place over dmol
+__global__ void tanh_bwd_kernel(const float* __restrict__ mol, float* __restrict__ dmol, int64_t total) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= total) return;
+  const float m = mol[e];
+  dmol[e] = dmol[e] * (1.f - m * m);
+}
+
+// out[c] = sum_r w_r M[r, c]  (w == NULL: plain column sums): 32 columns per CTA, rows over 8 warps, fixed order
+__global__ void __launch_bounds__(256) weighted_colsum_kernel(const float* __restrict__ M, int ld, int rows, int cols,
+                                                              const int32_t* __restrict__ w, float* __restrict__ out) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  float s = 0.f;
+  if (c < cols)
+    for (int r = wid; r < rows; r += 8) s += (w ? (float)w[r] : 1.f) * M[(int64_t)r * ld + c];
+  red[wid][lane] = s;
+  __syncthreads();
+  if (wid == 0 && c < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][lane];
+    out[c] = t;
+  }
+}
+
+// dH[r, :] = dhsum[graph(r), :]      (one warp per graph)
+__global__ void segment_broadcast_kernel(const float* __restrict__ dhsum, const int32_t* __restrict__ node_off, int B,
+                                         int F, float* __restrict__ dH) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (g >= B) return;
+  const int r0 = node_off[g], r1 = node_off[g + 1];
+  for (int c = lane; c < F; c += 32) {
+    const float v = dhsum[(int64_t)g * F + c];
+    for (int r = r0; r < r1; ++r) dH[(int64_t)r * F + c] = v;
+  }
+}
+
+// dst[r, 0:cols] = src[r, 0:cols]  (different row pitches)
+__global__ void copy_pitched_kernel(const float* __restrict__ src, int lds, float* __restrict__ dst, int ldd, int rows,
+                                    int cols) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)rows * cols) return;
+  const int r = (int)(e / cols), c = (int)(e % cols);
+  dst[(int64_t)r * ldd + c] = src[(int64_t)r * lds + c];
+}
+
+__global__ void sum_parts_kernel(const float* __restrict__ parts, int n, float* __restrict__ out) {
+  __shared__ float red[256];
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += parts[i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) out[0] = red[0];
+}
+
+namespace {
+
+// contraction over the rows: tensor cores when the shape allows it (>= 32 rows, TMA-compatible), CUDA cores otherwise
+int tn_any(const GemmTNArgs& t, cudaStream_t st) {
+  if (tc_gemm_tn_supported(t)) return tc_gemm_tn(t, st);
+  return gemm_tn(t, st);
+}
+size_t tn_any_partial(const GemmTNArgs& t) {
+  return std::max(tc_gemm_tn_partial_floats(t), gemm_tn_partial_floats(t.M, t.Kd, t.N, t.S));
+}
+
+inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+inline int pad4(int x) { return (x + 3) & ~3; }
+
+struct HeadWork {
+  float *hsum, *pre, *mol, *dlog, *dmol, *dhsum, *dWh_pad, *loss_part, *tcA, *tcB, *tcC, *tcD, *tn_part;
+  size_t bytes;
+};
+
+HeadWork carve_head(const agcn_plan* plan, int Fh, int Fm, int Nt, void* base) {
+  char* b = reinterpret_cast<char*>(base);
+  size_t off = 0;
+  auto take = [&](size_t floats) {
+    float* r = b ? reinterpret_cast<float*>(b + off) : nullptr;
+    off += al256(floats * sizeof(float));
+    return r;
+  };
+  const size_t B = plan->B;
+  const int Ntp = pad4(Nt);
+  HeadWork w{};
+  w.hsum = take(B * Fh);
+  w.pre = take(B * Fm);
+  w.mol = take(B * Fm);
+  w.dlog = take(B * Ntp);        // d loss / d logits, row pitch Ntp (pad columns stay zero)
+  w.dmol = take(B * Fm);
+  w.dhsum = take(B * Fh);
+  w.dWh_pad = take((size_t)Fm * Ntp);
+  GemmArgs g;
+  g.M = (int)B; g.N = Nt; g.Z = 1;
+  w.loss_part = take((size_t)tc_gemm_loss_parts(g) + 64);
+  w.tcA = take(tc_gemm_scratch_floats(Fm, Fh, 1, 1));   // dense_W            (pre   = hsum dense_W)
+  w.tcB = take(tc_gemm_scratch_floats(Nt, Fm, 1, 1));   // head_W             (logits = mol head_W)
+  w.tcC = take(tc_gemm_scratch_floats(Fm, Nt, 1, 1));   // head_W^T operand   (dmol  = dlog head_W^T)
+  w.tcD = take(tc_gemm_scratch_floats(Fh, Fm, 1, 1));   // dense_W^T operand  (dhsum = dpre dense_W^T)
+  GemmTNArgs t;
+  t.M = (int)B; t.Kd = std::min(Fm, 128); t.N = Ntp; t.S = 1;
+  size_t tn = tn_any_partial(t);
+  t.Kd = Fh; t.N = Fm;
+  tn = std::max(tn, tn_any_partial(t));
+  w.tn_part = take(tn);
+  w.bytes = off;
+  return w;
+}
+
+}  // namespace
+}  // namespace agcn
+
+using namespace agcn;
+
+extern "C" {
+
+int agcn_head_workspace_bytes(const agcn_plan* plan, int32_t Fh, int32_t Fm, int32_t Nt, size_t* bytes) {
+  AGCN_REQUIRE(plan && bytes && Fh >= 1 && Fm >= 1 && Nt >= 1, "head_workspace_bytes: bad arguments");
+  *bytes = carve_head(plan, Fh, Fm, Nt, nullptr).bytes + 256;
+  return AGCN_OK;
+}
+
+int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_dense_W, const float* d_dense_b,
+                        const float* d_head_W, const float* d_head_b, const float* d_targets, const float* d_weights,
+                        float scale, int32_t Fh, int32_t Fm, int32_t Nt, float* d_loss, float* d_dH,
+                        float* d_ddense_W, float* d_ddense_b, float* d_dhead_W, float* d_dhead_b, void* d_work,
+                        size_t work_bytes, void* stream) {
+  AGCN_REQUIRE(plan && d_H && d_dense_W && d_dense_b && d_head_W && d_head_b && d_targets && d_weights && d_loss &&
+                   d_dH && d_ddense_W && d_ddense_b && d_dhead_W && d_dhead_b && d_work,
+               "head_loss_grad: null pointer");
+  // tensor-core shapes: the contraction dims must reach one k-block, operand pitches must be 16-byte multiples
+  AGCN_REQUIRE(Fh >= 32 && Fh % 4 == 0 && Fh <= 128 && Fm >= 32 && Fm % 4 == 0 && Fm <= 256 && Nt >= 32,
+               "head_loss_grad: unsupported sizes (need 32 <= Fh <= 128, 32 <= Fm <= 256, multiples of 4)");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = plan_use(plan, st);
+  if (rc) return rc;
+  HeadWork w = carve_head(plan, Fh, Fm, Nt, d_work);
+  if (w.bytes > work_bytes) {
+    set_error("head_loss_grad: workspace too small");
+    return AGCN_ERR_WORKSPACE;
+  }
+  const int B = plan->B, Ntp = pad4(Nt);
+  const int R = (int)plan->R;
+  (void)R;
+  cudaStream_t side = plan->side;
+
+  // parameter operands (hi / lo split, K-major) on the side stream while the gather runs
+  GemmArgs g_pre, g_log, g_dmol, g_dhs;
+  g_pre.M = B; g_pre.N = Fm; g_pre.Kd = Fh;
+  g_pre.A0 = w.hsum; g_pre.lda0 = Fh;
+  g_pre.B = d_dense_W; g_pre.ldb = Fm;
+  g_pre.C = w.pre; g_pre.ldc = Fm;
+  g_log.M = B; g_log.N = Nt; g_log.Kd = Fm;
+  g_log.A0 = w.mol; g_log.lda0 = Fm;
+  g_log.B = d_head_W; g_log.ldb = Nt;
+  g_log.C = w.dlog; g_log.ldc = Ntp;
+  g_log.bias = d_head_b;
+  g_log.bce_y = d_targets; g_log.bce_w = d_weights; g_log.bce_ld = Nt; g_log.bce_scale = scale;
+  g_log.loss_part = w.loss_part;
+  g_dmol.M = B; g_dmol.N = Fm; g_dmol.Kd = Nt;
+  g_dmol.A0 = w.dlog; g_dmol.lda0 = Ntp;
+  g_dmol.B = d_head_W; g_dmol.ldb = Nt; g_dmol.transB = 1;  // head_W is [Fm, Nt] = [N, Kd]
+  g_dmol.C = w.dmol; g_dmol.ldc = Fm;
+  g_dhs.M = B; g_dhs.N = Fh; g_dhs.Kd = Fm;
+  g_dhs.A0 = w.dmol; g_dhs.lda0 = Fm;
+  g_dhs.B = d_dense_W; g_dhs.ldb = Fm; g_dhs.transB = 1;    // dense_W is [Fh, Fm] = [N, Kd]
+  g_dhs.C = w.dhsum; g_dhs.ldc = Fh;
+  AGCN_REQUIRE(tc_gemm_supported(g_pre) && tc_gemm_supported(g_log) && tc_gemm_supported(g_dmol) &&
+                   tc_gemm_supported(g_dhs),
+               "head_loss_grad: operands are not TMA-compatible (alignment)");
+  AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
+  AGCN_CUDA(cudaStreamWaitEvent(side, plan->ev_side_fork, 0));
+  if ((rc = tc_gemm_split_b(g_pre, w.tcA, side))) return rc;
+  if ((rc = tc_gemm_split_b(g_log, w.tcB, side))) return rc;
+  if ((rc = tc_gemm_split_b(g_dmol, w.tcC, side))) return rc;
+  if ((rc = tc_gemm_split_b(g_dhs, w.tcD, side))) return rc;
+  AGCN_CUDA(cudaMemsetAsync(w.dlog, 0, (size_t)B * Ntp * sizeof(float), side));  // pad columns of dlog
+  AGCN_CUDA(cudaEventRecord(plan->ev_side_join, side));
+
+  // GraphGatherMol + DenseMol (commuted) + tanh
+  segment_sum_kernel<<<(B + 7) / 8, 256, 0, st>>>(d_H, plan->d_node_off, B, Fh, w.hsum);
+  AGCN_LAUNCH_CHECK();
+  AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
+  if ((rc = tc_gemm(g_pre, w.tcA, st))) return rc;
+  {
+    const int64_t total = (int64_t)B * Fm;
+    gather_tanh_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.pre, d_dense_b, plan->d_n, B, Fm, w.mol);
+    AGCN_LAUNCH_CHECK();
+  }
+  // logits + weighted sigmoid cross-entropy: C receives d loss / d logits, the loss its per-warp partial sums
+  if ((rc = tc_gemm(g_log, w.tcB, st))) return rc;
+  sum_parts_kernel<<<1, 256, 0, st>>>(w.loss_part, tc_gemm_loss_parts(g_log), d_loss);
+  AGCN_LAUNCH_CHECK();
+
+  // parameter gradients of the heads on the side stream, beside the chain back to dH
+  AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
+  AGCN_CUDA(cudaStreamWaitEvent(side, plan->ev_side_fork, 0));
+  weighted_colsum_kernel<<<(Nt + 31) / 32, 256, 0, side>>>(w.dlog, Ntp, B, Nt, nullptr, d_dhead_b);
+  AGCN_LAUNCH_CHECK();
+  for (int f0 = 0; f0 < Fm; f0 += 128) {  // dhead_W = mol^T dlog, 128 rows of the result per contraction
+    GemmTNArgs t;
+    t.M = B; t.Kd = std::min(128, Fm - f0); t.N = Ntp; t.S = 1;
+    t.A0 = w.mol + f0; t.lda0 = Fm;
+    t.D = w.dlog; t.ldd = Ntp;
+    t.out = w.dWh_pad + (size_t)f0 * Ntp; t.partial = w.tn_part;
+    if ((rc = tn_any(t, side))) return rc;
+  }
+  {
+    const int64_t total = (int64_t)Fm * Nt;
+    copy_pitched_kernel<<<(unsigned)((total + 255) / 256), 256, 0, side>>>(w.dWh_pad, Ntp, d_dhead_W, Nt, Fm, Nt);
+    AGCN_LAUNCH_CHECK();
+  }
+
+  // main stream: dmol = dlog head_W^T, through tanh, ddense_b, dhsum, dH
+  if ((rc = tc_gemm(g_dmol, w.tcC, st))) return rc;
+  {
+    const int64_t total = (int64_t)B * Fm;
+    tanh_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.mol, w.dmol, total);  // dmol := dpre
+    AGCN_LAUNCH_CHECK();
+  }
+  if ((rc = tc_gemm(g_dhs, w.tcD, st))) return rc;
+  segment_broadcast_kernel<<<(B + 7) / 8, 256, 0, st>>>(w.dhsum, plan->d_node_off, B, Fh, d_dH);
+  AGCN_LAUNCH_CHECK();
+  // dense parameter gradients (need dpre; the dhead_W contraction on the side stream is done with tn_part by now
+  // only if we wait for it, so they follow it on the side stream)
+  AGCN_CUDA(cudaEventRecord(plan->ev_fork, st));
+  AGCN_CUDA(cudaStreamWaitEvent(side, plan->ev_fork, 0));
+  weighted_colsum_kernel<<<(Fm + 31) / 32, 256, 0, side>>>(w.dmol, Fm, B, Fm, plan->d_n, d_ddense_b);
+  AGCN_LAUNCH_CHECK();
+  {
+    GemmTNArgs t;  // ddense_W = hsum^T dpre
+    t.M = B; t.Kd = Fh; t.N = Fm; t.S = 1;
+    t.A0 = w.hsum; t.lda0 = Fh;
+    t.D = w.dmol; t.ldd = Fm;
+    t.out = d_ddense_W; t.partial = w.tn_part;
+    if ((rc = tn_any(t, side))) return rc;
+  }
+  AGCN_CUDA(cudaEventRecord(plan->ev_side_join, side));
+  AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
+  return AGCN_OK;
+}
+
+}  // extern "C"

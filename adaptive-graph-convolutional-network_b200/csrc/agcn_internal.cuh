@@ -105,6 +105,15 @@ struct agcn_plan {
   // runs beside the fused launch of the small-graph tiles
   cudaStream_t big = nullptr;
   cudaEvent_t ev_big_fork = nullptr, ev_big_join = nullptr;
+  // life cycle (agcn_plan.cu): streams / events / staging come from process-wide pools, the device block is
+  // stream-ordered; ev_ready marks the upload of the tables on create_stream
+  cudaEvent_t ev_ready = nullptr;
+  cudaStream_t create_stream = nullptr, last_stream = nullptr;
+  bool ready_done = false;
+  int res_device = -1;
+  void* staging_host = nullptr;
+  size_t staging_bytes = 0;
+  cudaEvent_t staging_done = nullptr;
 };
 
 namespace agcn {
@@ -134,6 +143,7 @@ struct GemmArgs {
   // bce_y / bce_w are laid out like C, loss_part holds tc_gemm_loss_parts() floats
   const float* bce_y = nullptr;
   const float* bce_w = nullptr;
+  int bce_ld = 0;  // row pitch of bce_y / bce_w (0: same as ldc)
   float bce_scale = 1.f;
   float* loss_part = nullptr;
 };
@@ -242,6 +252,7 @@ int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY
                    int add_identity, const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st);
 
 // ---------------------------------------------------------------- helpers
+int plan_use(const agcn_plan* plan, cudaStream_t st);  // call first in every entry point that enqueues work
 int fork_streams(const agcn_plan* plan, cudaStream_t main, int n_aux);
 int join_streams(const agcn_plan* plan, cudaStream_t main, int n_aux);
 

@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <numeric>
 
 #include "agcn_internal.cuh"
@@ -130,6 +131,116 @@ static void build_fused_tiles(const std::vector<int32_t>& n, const std::vector<i
   gstart->push_back((int32_t)(entries->size() / 4));
 }
 
+
+// ------------------------------------------------------------------ pooled plan resources
+// A plan is created for every batch of a training loop, so creating it must not synchronise anything: the side
+// streams / events come from a process-wide pool, the offset tables travel through pooled pinned staging buffers
+// (reused only after the copy that read them has completed) and the device block is stream-ordered
+// (cudaMallocAsync / cudaFreeAsync).
+struct PlanRes {
+  cudaStream_t aux[3] = {nullptr, nullptr, nullptr}, side = nullptr, big = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join[3] = {nullptr, nullptr, nullptr}, ev_side_fork = nullptr, ev_side_join = nullptr,
+              ev_big_fork = nullptr, ev_big_join = nullptr, ev_ready = nullptr;
+  int device = -1;
+};
+struct Staging {
+  void* host = nullptr;
+  size_t bytes = 0;
+  cudaEvent_t done = nullptr;
+  int device = -1;
+};
+static std::mutex g_pool_mu;
+static std::vector<PlanRes> g_res_pool;
+static std::vector<Staging> g_staging_pool;
+
+static cudaError_t acquire_res(PlanRes* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (size_t i = 0; i < g_res_pool.size(); ++i)
+      if (g_res_pool[i].device == dev) {
+        *out = g_res_pool[i];
+        g_res_pool.erase(g_res_pool.begin() + i);
+        return cudaSuccess;
+      }
+  }
+  PlanRes r;
+  r.device = dev;
+  for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
+    e = cudaStreamCreateWithFlags(&r.aux[i], cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_join[i], cudaEventDisableTiming);
+  }
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_side_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_side_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r.big, cudaStreamNonBlocking);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_big_fork, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_big_join, cudaEventDisableTiming);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_ready, cudaEventDisableTiming);
+  *out = r;
+  return e;
+}
+
+static void release_res(const PlanRes& r) {
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  g_res_pool.push_back(r);
+}
+
+static cudaError_t acquire_staging(size_t bytes, Staging* out) {
+  int dev = 0;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  {
+    std::lock_guard<std::mutex> lock(g_pool_mu);
+    for (size_t i = 0; i < g_staging_pool.size(); ++i) {
+      Staging& s = g_staging_pool[i];
+      if (s.device == dev && s.bytes >= bytes && cudaEventQuery(s.done) == cudaSuccess) {
+        *out = s;
+        g_staging_pool.erase(g_staging_pool.begin() + i);
+        return cudaSuccess;
+      }
+    }
+  }
+  Staging s;
+  s.device = dev;
+  s.bytes = std::max<size_t>((bytes + 65535) & ~(size_t)65535, (size_t)1 << 18);
+  e = cudaMallocHost(&s.host, s.bytes);
+  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming);
+  *out = s;
+  return e;
+}
+
+static void release_staging(const Staging& s) {
+  if (!s.host) return;
+  std::lock_guard<std::mutex> lock(g_pool_mu);
+  g_staging_pool.push_back(s);
+}
+
+// Every entry point that enqueues work for a plan: order the stream after the upload of the plan's tables (when it
+// is not the stream the plan was created on) and remember it, so that agcn_plan_destroy releases the device block
+// in the order of the last stream that used it.
+int plan_use(const agcn_plan* plan, cudaStream_t st) {
+  agcn_plan* p = const_cast<agcn_plan*>(plan);
+  if (!p->ready_done && st != p->create_stream) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    AGCN_CUDA(cudaStreamIsCapturing(st, &cs));
+    if (cs == cudaStreamCaptureStatusNone) {  // (a plan used under capture was uploaded long before)
+      const cudaError_t q = cudaEventQuery(p->ev_ready);
+      if (q == cudaSuccess) {
+        p->ready_done = true;
+      } else {
+        (void)cudaGetLastError();  // cudaErrorNotReady is not an error
+        AGCN_CUDA(cudaStreamWaitEvent(st, p->ev_ready, 0));
+      }
+    }
+  }
+  p->last_stream = st;
+  return AGCN_OK;
+}
+
 }  // namespace agcn
 
 using namespace agcn;
@@ -202,8 +313,19 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   const size_t off64 = (n32 * 4 + 15) / 16 * 16;
   const size_t off_ft = (off64 + (size_t)(B + 1) * 8 + 15) / 16 * 16;  // int4 entries of the fused tiles
   const size_t bytes = off_ft + p->ft_entries.size() * 8;  // device entries carry node_off / lap_off of their graph
-  std::vector<char> host(bytes, 0);
-  int32_t* h32 = reinterpret_cast<int32_t*>(host.data());
+  cudaStream_t st = (cudaStream_t)stream;
+  PlanRes res;
+  Staging stg;
+  cudaError_t e = acquire_res(&res);
+  if (e == cudaSuccess) e = acquire_staging(bytes, &stg);
+  if (e != cudaSuccess) {
+    int rc = cuda_fail(e, "agcn_plan_create (resources)", __FILE__, __LINE__);
+    delete p;
+    return rc;
+  }
+  char* host = reinterpret_cast<char*>(stg.host);
+  std::memset(host, 0, bytes);
+  int32_t* h32 = reinterpret_cast<int32_t*>(host);
   std::memcpy(h32, p->n.data(), (size_t)B * 4);
   std::memcpy(h32 + B, p->node_off.data(), (size_t)(B + 1) * 4);
   std::memcpy(h32 + 2 * B + 1, p->order.data(), (size_t)B * 4);
@@ -213,34 +335,30 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   }
   std::memcpy(h32 + 3 * B + 1 + 2 * T, p->big_tile_start.data(), NB * 4);
   std::memcpy(h32 + 3 * B + 1 + 2 * T + NB, p->ft_gstart.data(), p->ft_gstart.size() * 4);
-  std::memcpy(host.data() + off64, p->lap_off.data(), (size_t)(B + 1) * 8);
+  std::memcpy(host + off64, p->lap_off.data(), (size_t)(B + 1) * 8);
   {
-    int32_t* de = reinterpret_cast<int32_t*>(host.data() + off_ft);
-    for (size_t e = 0; e < p->ft_entries.size() / 4; ++e) {
-      const int32_t* src = &p->ft_entries[4 * e];
+    int32_t* de = reinterpret_cast<int32_t*>(host + off_ft);
+    for (size_t en = 0; en < p->ft_entries.size() / 4; ++en) {
+      const int32_t* src = &p->ft_entries[4 * en];
       const int64_t lo = p->lap_off[src[0]];
-      de[8 * e + 0] = src[0]; de[8 * e + 1] = src[1]; de[8 * e + 2] = src[2]; de[8 * e + 3] = src[3];
-      de[8 * e + 4] = p->node_off[src[0]];
-      de[8 * e + 5] = (int32_t)(uint32_t)(lo & 0xffffffffll);
-      de[8 * e + 6] = (int32_t)(uint32_t)((uint64_t)lo >> 32);
-      de[8 * e + 7] = 0;
+      de[8 * en + 0] = src[0]; de[8 * en + 1] = src[1]; de[8 * en + 2] = src[2]; de[8 * en + 3] = src[3];
+      de[8 * en + 4] = p->node_off[src[0]];
+      de[8 * en + 5] = (int32_t)(uint32_t)(lo & 0xffffffffll);
+      de[8 * en + 6] = (int32_t)(uint32_t)((uint64_t)lo >> 32);
+      de[8 * en + 7] = 0;
     }
   }
-  cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMalloc(&p->d_block, bytes);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_block, host.data(), bytes, cudaMemcpyHostToDevice, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  for (int i = 0; i < 3 && e == cudaSuccess; ++i) {
-    e = cudaStreamCreateWithFlags(&p->aux[i], cudaStreamNonBlocking);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_join[i], cudaEventDisableTiming);
-  }
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&p->big, cudaStreamNonBlocking);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_big_fork, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_big_join, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_side_fork, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaEventCreateWithFlags(&p->ev_side_join, cudaEventDisableTiming);
+  for (int i = 0; i < 3; ++i) { p->aux[i] = res.aux[i]; p->ev_join[i] = res.ev_join[i]; }
+  p->ev_fork = res.ev_fork; p->side = res.side; p->ev_side_fork = res.ev_side_fork; p->ev_side_join = res.ev_side_join;
+  p->big = res.big; p->ev_big_fork = res.ev_big_fork; p->ev_big_join = res.ev_big_join; p->ev_ready = res.ev_ready;
+  p->res_device = res.device;
+  p->staging_host = stg.host; p->staging_bytes = stg.bytes; p->staging_done = stg.done;
+  p->create_stream = st;
+  p->last_stream = st;
+  e = cudaMallocAsync(&p->d_block, bytes, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_block, host, bytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaEventRecord(stg.done, st);   // the staging buffer may be reused once this has passed
+  if (e == cudaSuccess) e = cudaEventRecord(p->ev_ready, st);
   if (e != cudaSuccess) {
     int rc = cuda_fail(e, "agcn_plan_create", __FILE__, __LINE__);
     agcn_plan_destroy(p);
@@ -280,18 +398,21 @@ int agcn_fused_tiles_host(const int32_t* n_nodes_host, int32_t B, int32_t* gstar
 
 int agcn_plan_destroy(agcn_plan* p) {
   if (!p) return AGCN_OK;
-  for (int i = 0; i < 3; ++i) {
-    if (p->aux[i]) cudaStreamDestroy(p->aux[i]);
-    if (p->ev_join[i]) cudaEventDestroy(p->ev_join[i]);
+  // stream-ordered: nothing is synchronised; the block is released after the last work queued for this plan
+  if (p->d_block) cudaFreeAsync(p->d_block, p->last_stream);
+  if (p->ev_ready) {
+    PlanRes r;
+    for (int i = 0; i < 3; ++i) { r.aux[i] = p->aux[i]; r.ev_join[i] = p->ev_join[i]; }
+    r.ev_fork = p->ev_fork; r.side = p->side; r.ev_side_fork = p->ev_side_fork; r.ev_side_join = p->ev_side_join;
+    r.big = p->big; r.ev_big_fork = p->ev_big_fork; r.ev_big_join = p->ev_big_join; r.ev_ready = p->ev_ready;
+    r.device = p->res_device;
+    release_res(r);
   }
-  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
-  if (p->side) cudaStreamDestroy(p->side);
-  if (p->big) cudaStreamDestroy(p->big);
-  if (p->ev_big_fork) cudaEventDestroy(p->ev_big_fork);
-  if (p->ev_big_join) cudaEventDestroy(p->ev_big_join);
-  if (p->ev_side_fork) cudaEventDestroy(p->ev_side_fork);
-  if (p->ev_side_join) cudaEventDestroy(p->ev_side_join);
-  if (p->d_block) cudaFree(p->d_block);
+  if (p->staging_host) {
+    Staging sg;
+    sg.host = p->staging_host; sg.bytes = p->staging_bytes; sg.done = p->staging_done; sg.device = p->res_device;
+    release_staging(sg);
+  }
   delete p;
   return AGCN_OK;
 }
@@ -304,6 +425,7 @@ const int64_t* agcn_plan_lap_off_host(const agcn_plan* p) { return p ? p->lap_of
 static int pack_nodes_impl(const agcn_plan* plan, const float* padded, float* packed, int32_t F, void* stream,
                            int to_padded) {
   AGCN_REQUIRE(plan && padded && packed && F >= 1, "null pointer or F < 1");
+  if (int rc = plan_use(plan, (cudaStream_t)stream)) return rc;
   const int64_t rows = (int64_t)plan->B * plan->Nmax;
   const int wpb = 8;
   pack_nodes_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
@@ -321,6 +443,7 @@ int agcn_unpack_nodes(const agcn_plan* plan, const float* d_packed, float* d_pad
 
 static int pack_lap_impl(const agcn_plan* plan, const float* padded, float* packed, void* stream, int to_padded) {
   AGCN_REQUIRE(plan && padded && packed, "null pointer");
+  if (int rc = plan_use(plan, (cudaStream_t)stream)) return rc;
   const int64_t rows = (int64_t)plan->B * plan->Nmax;
   const int wpb = 8;
   pack_lap_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(

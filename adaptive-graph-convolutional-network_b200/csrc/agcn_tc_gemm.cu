@@ -101,6 +101,7 @@ struct Args {
   // fused weighted sigmoid cross-entropy epilogue (multitask head): C receives d loss / d logits
   const float* bce_y;
   const float* bce_w;
+  int bce_ld;        // row pitch of bce_y / bce_w
   float bce_scale;
   float* loss_part;  // [CTAs][4]
 };
@@ -232,11 +233,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
     float loss_acc = 0.f;
     // bias has been added; accumulate / activation / loss epilogue of one element
-    auto finish = [&](float x, float old, long long off) -> float {
+    auto finish = [&](float x, float old, int row, int col) -> float {
       if (p.accumulate) x += old;
       if (p.bce_y) {
         // weighted sigmoid cross-entropy with logits (multitask_classifier.py:41-44): loss and its gradient
-        const float y = p.bce_y[off], w = p.bce_w[off];
+        const long long bo = (long long)row * p.bce_ld + col;
+        const float y = __ldg(p.bce_y + bo), w = __ldg(p.bce_w + bo);
         loss_acc += w * (fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x))));
         return w * (1.f / (1.f + expf(-x)) - y) * p.bce_scale;
       }
@@ -283,14 +285,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (vec_ok && cc + 3 < p.N) {
             float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.accumulate) old = *reinterpret_cast<const float4*>(dst);
-            o.x = finish(o.x, old.x, off); o.y = finish(o.y, old.y, off + 1);
-            o.z = finish(o.z, old.z, off + 2); o.w = finish(o.w, old.w, off + 3);
+            o.x = finish(o.x, old.x, m, cc); o.y = finish(o.y, old.y, m, cc + 1);
+            o.z = finish(o.z, old.z, m, cc + 2); o.w = finish(o.w, old.w, m, cc + 3);
             *reinterpret_cast<float4*>(dst) = o;
           } else {
             const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              if (cc + e < p.N) dst[e] = finish(ov[e], p.accumulate ? dst[e] : 0.f, off + e);
+              if (cc + e < p.N) dst[e] = finish(ov[e], p.accumulate ? dst[e] : 0.f, m, cc + e);
             }
           }
         }
@@ -540,15 +542,16 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
 }
 
 // B prep: out_{hi,lo}[(slice*Npad + n)*Kd + k] = split(src[n*sn + k*sk + slice*ss]),  zero rows for n >= N
+// (Kp = Kd rounded up to 4 is the row pitch: TMA needs 16-byte row strides; the pad columns are zero)
 __global__ void split_b_kernel(const float* __restrict__ src, long long sn, long long sk, long long ss, int N, int Npad,
-                               int Kd, int slices, float* __restrict__ hi, float* __restrict__ lo) {
-  const long long total = (long long)slices * Npad * Kd;
+                               int Kd, int Kp, int slices, float* __restrict__ hi, float* __restrict__ lo) {
+  const long long total = (long long)slices * Npad * Kp;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int k = (int)(e % Kd);
-    const long long r = e / Kd;
+    const int k = (int)(e % Kp);
+    const long long r = e / Kp;
     const int n = (int)(r % Npad), sl = (int)(r / Npad);
     float x = 0.f;
-    if (n < N) x = src[n * sn + k * sk + sl * ss];
+    if (n < N && k < Kd) x = src[n * sn + k * sk + sl * ss];
     const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
     hi[e] = h;
     lo[e] = __uint_as_float(__float_as_uint(x - h) & 0xffffe000u);
@@ -618,11 +621,13 @@ static int make_map3(CUtensorMap* map, const float* ptr, uint64_t slices, uint64
 }  // namespace tc
 
 static int tc_npad(int N) { return N <= 64 ? 64 : (N + 127) / 128 * 128; }
+static int tc_kpitch(int Kd) { return (Kd + 3) & ~3; }
 
 bool tc_gemm_supported(const GemmArgs& a) {
   if (getenv("AGCN_DISABLE_TCGEN05")) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
-  if (a.M < 1 || a.Kd < 32 || a.Kd % 4 != 0) return false;
+  if (a.M < 1 || a.Kd < 32) return false;
+  if (a.S > 1 && a.Kd % 4 != 0) return false;  // stacked slices share one tensor map
   if (a.lda0 % 4 != 0 || !al16(a.A0)) return false;
   if (a.S > 1 && (a.lda1 % 4 != 0 || !al16(a.A1) || a.sliceA1 % a.lda1 != 0)) return false;
   if (a.S > 1 && a.lda1 != a.Kd) return false;  // slices are stacked as one [(S-1)*rows, Kd] matrix
@@ -634,7 +639,7 @@ int tc_gemm_loss_parts(const GemmArgs& a) {
   return 4 * ((a.M + tc::BM - 1) / tc::BM) * a.Z * (Npad / BN);
 }
 
-size_t tc_gemm_scratch_floats(int N, int Kd, int S, int Z) { return 2 * (size_t)Z * S * tc_npad(N) * Kd; }
+size_t tc_gemm_scratch_floats(int N, int Kd, int S, int Z) { return 2 * (size_t)Z * S * tc_npad(N) * tc_kpitch(Kd); }
 
 // Rearranges the parameter operand B to [slice][Npad][Kd] (K-major) and splits it into hi / lo TF32 halves.
 // It depends on the parameters only, so callers run it on a side stream (or once per forward/backward pair).
@@ -642,13 +647,13 @@ int tc_gemm_split_b(const GemmArgs& a, float* scratch, cudaStream_t st) {
   using namespace tc;
   // B element (slice, n, k): row-major [Kd, N] (ldb) or, transposed, [N, Kd]
   const long long sn = a.transB ? a.ldb : 1, sk = a.transB ? 1 : a.ldb, ss = a.sliceB;
-  const int Npad = tc_npad(a.N);
+  const int Npad = tc_npad(a.N), Kp = tc_kpitch(a.Kd);
   const int slices = a.Z * a.S;
   float* Bhi = scratch;
-  float* Blo = scratch + (size_t)slices * Npad * a.Kd;
-  const long long total = (long long)slices * Npad * a.Kd;
+  float* Blo = scratch + (size_t)slices * Npad * Kp;
+  const long long total = (long long)slices * Npad * Kp;
   const int blocks = (int)std::min<long long>((total + 255) / 256, 1184);
-  split_b_kernel<<<blocks, 256, 0, st>>>(a.B, sn, sk, ss, a.N, Npad, a.Kd, slices, Bhi, Blo);
+  split_b_kernel<<<blocks, 256, 0, st>>>(a.B, sn, sk, ss, a.N, Npad, a.Kd, Kp, slices, Bhi, Blo);
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }
@@ -656,10 +661,10 @@ int tc_gemm_split_b(const GemmArgs& a, float* scratch, cudaStream_t st) {
 // scratch holds the hi / lo copies of B written by tc_gemm_split_b (tc_gemm_scratch_floats floats).
 int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
   using namespace tc;
-  const int Npad = tc_npad(a.N);
+  const int Npad = tc_npad(a.N), Kp = tc_kpitch(a.Kd);
   const int slices = a.Z * a.S;
   const float* Bhi = scratch;
-  const float* Blo = scratch + (size_t)slices * Npad * a.Kd;
+  const float* Blo = scratch + (size_t)slices * Npad * Kp;
   CUtensorMap mA0, mA1, mBhi, mBlo;
   int rc;
   if ((rc = make_map(&mA0, a.A0, (uint64_t)a.M, (uint64_t)a.Kd, (uint64_t)a.lda0, BM))) return rc;
@@ -671,8 +676,8 @@ int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
     mA1 = mA0;
   }
   const int BN = Npad <= 64 ? 64 : 128;
-  if ((rc = make_map(&mBhi, Bhi, (uint64_t)slices * Npad, (uint64_t)a.Kd, (uint64_t)a.Kd, BN))) return rc;
-  if ((rc = make_map(&mBlo, Blo, (uint64_t)slices * Npad, (uint64_t)a.Kd, (uint64_t)a.Kd, BN))) return rc;
+  if ((rc = make_map(&mBhi, Bhi, (uint64_t)slices * Npad, (uint64_t)a.Kd, (uint64_t)Kp, BN))) return rc;
+  if ((rc = make_map(&mBlo, Blo, (uint64_t)slices * Npad, (uint64_t)a.Kd, (uint64_t)Kp, BN))) return rc;
   Args p;
   p.M = a.M; p.N = a.N; p.Kd = a.Kd; p.S = a.S;
   p.kb_per_slice = (a.Kd + BK - 1) / BK;
@@ -681,6 +686,7 @@ int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
   p.C = a.C; p.ldc = a.ldc; p.sliceC = a.sliceC;
   p.bias = a.bias; p.act = a.act; p.accumulate = a.accumulate;
   p.bce_y = a.bce_y; p.bce_w = a.bce_w; p.bce_scale = a.bce_scale; p.loss_part = a.loss_part;
+  p.bce_ld = a.bce_ld > 0 ? a.bce_ld : a.ldc;
   dim3 grid((a.M + BM - 1) / BM, a.Z, Npad / BN);
   static std::once_flag once64, once128;
   if (BN == 64) {

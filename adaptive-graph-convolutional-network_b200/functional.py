@@ -117,6 +117,53 @@ def sgc_ll_packed(X, Lint, Lprev, params, batch, cfg):
                                 params.get("beta"), batch, cfg)
 
 
+class _HeadLossFunction(torch.autograd.Function):
+    """DenseMol + GraphGatherMol(tanh) + multitask logits + weighted sigmoid cross-entropy * scale
+    (dense_layer.py:33-50, graphgather.py:50-78, model_operatos.py:792-864, multitask_classifier.py:41-44,187-209)
+    -> scalar loss.  The C call computes the loss AND every gradient; backward hands them out (scaled by the
+    incoming gradient unless `unit_grad` says the loss is differentiated directly)."""
+
+    @staticmethod
+    def forward(ctx, H, dense_W, dense_b, head_W, head_b, targets, weights, batch, scale, unit_grad):
+        H = H.contiguous()
+        R, Fh = H.shape
+        Fm, Nt = head_W.shape
+        dev = H.device
+        assert dense_W.shape == (Fh, Fm) and targets.shape == (batch.batch_size, Nt) and R == batch.total_nodes
+        nbytes = ctypes.c_size_t()
+        _lib.check(_lib.lib().agcn_head_workspace_bytes(batch.handle, Fh, Fm, Nt, ctypes.byref(nbytes)))
+        work = _Workspace.get(dev, nbytes.value)
+        outs = [getattr(t, "_agcn_grad_out", None) for t in (dense_W, dense_b, head_W, head_b)]
+        grads = [o if o is not None else torch.empty_like(t) for o, t in zip(outs, (dense_W, dense_b, head_W, head_b))]
+        loss = torch.empty(1, device=dev, dtype=torch.float32)
+        dH = torch.empty_like(H)
+        _lib.check(_lib.lib().agcn_head_loss_grad(
+            batch.handle, _ptr(H), _ptr(dense_W), _ptr(dense_b), _ptr(head_W), _ptr(head_b), _ptr(targets.contiguous()),
+            _ptr(weights.contiguous()), float(scale), Fh, Fm, Nt, _ptr(loss), _ptr(dH), _ptr(grads[0]), _ptr(grads[1]),
+            _ptr(grads[2]), _ptr(grads[3]), _ptr(work), work.numel(), _stream_ptr()))
+        ctx.unit_grad = unit_grad
+        ctx.in_place = [o is not None for o in outs]
+        ctx.save_for_backward(dH, *grads)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g):
+        dH, *grads = ctx.saved_tensors
+        if not ctx.unit_grad:
+            dH = dH * g
+            grads = [t if ip else t * g for t, ip in zip(grads, ctx.in_place)]
+        # gradients already written into the flat gradient buffer are not returned
+        out = [None if ip else t for t, ip in zip(grads, ctx.in_place)]
+        return (dH, out[0], out[1], out[2], out[3], None, None, None, None, None)
+
+
+def head_loss(H, dense_W, dense_b, head_W, head_b, targets, weights, batch, scale, unit_grad=False):
+    """Scalar loss of the SimpleAGCN head on the packed output of the last SGC-LL layer.
+    unit_grad=True: the caller differentiates this loss directly (d loss / d loss = 1), which skips the
+    rescaling kernels; parameters registered with FlatGradBuffer(direct=...) require it."""
+    return _HeadLossFunction.apply(H, dense_W, dense_b, head_W, head_b, targets, weights, batch, scale, unit_grad)
+
+
 class _UnpackNodes(torch.autograd.Function):
     @staticmethod
     def forward(ctx, packed, batch):

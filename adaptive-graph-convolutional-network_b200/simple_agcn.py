@@ -23,11 +23,14 @@ from .layers import graphconv as _gc
 class SimpleAGCNStep(object):
     def __init__(self, n_feat=75, filters=(64, 128, 128, 64), final_feature_n=256, n_tasks=12, K=3, batch_size=256,
                  learning_rate=2e-3, device="cuda", world_size=1, laplacian="reference_literal",
-                 metric_grad="reference", seed=123):
+                 metric_grad="reference", seed=123, fused_head=True):
         self.device = torch.device(device)
         self.world_size = world_size
         self.global_batch = batch_size * world_size
         self.n_tasks = n_tasks
+        # DenseMol + GraphGatherMol + heads + loss as ONE library call (agcn_head_loss_grad) instead of ~45 torch ops
+        self.fused_head = fused_head and filters[-1] % 4 == 0 and 32 <= filters[-1] <= 128 and \
+            final_feature_n % 4 == 0 and 32 <= final_feature_n <= 256 and 2 * n_tasks >= 32
         torch.manual_seed(seed)  # identical replicas on every rank
         _gc.DEFAULT_DEVICE[0] = str(self.device)
         dims = [n_feat] + list(filters)
@@ -46,7 +49,10 @@ class SimpleAGCNStep(object):
                                                                            self.head_b]
         # one flat gradient buffer; every .grad is a view into it -> a single all-reduce per step
         # the SGC-LL backward writes its parameter gradients straight into the views (no accumulation kernels)
-        self.grads = FlatGradBuffer(self.params, direct=[v for l in self.layers for v in l.vars.values()])
+        direct = [v for l in self.layers for v in l.vars.values()]
+        if self.fused_head:
+            direct += [self.dense_W, self.dense_b, self.head_W, self.head_b]
+        self.grads = FlatGradBuffer(self.params, direct=direct)
         self.flat_grad = self.grads.flat
         # ... and one flat parameter tensor: Adam is a single-tensor update
         self.flat_params = FlatParamBuffer(self.params, self.grads)
@@ -56,7 +62,7 @@ class SimpleAGCNStep(object):
     def _n_nodes_f(self, batch):
         t = getattr(batch, "_n_nodes_float", None)
         if t is None:
-            t = torch.from_numpy(batch.n_nodes.astype(np.float32)).to(self.device)
+            t = batch.n_nodes_device().float()
             batch._n_nodes_float = t
         return t
 
@@ -70,6 +76,10 @@ class SimpleAGCNStep(object):
         for layer in self.layers:
             out, _, _ = layer(x)
             x = dict(x, node_features=out)
+        if self.fused_head:
+            from .functional import head_loss
+            return head_loss(out.data, self.dense_W, self.dense_b, self.head_W, self.head_b, onehot, weights, batch,
+                             1.0 / self.global_batch, unit_grad=True)
         # DenseMol applies no activation (dense_layer.py:42-50), so the per-graph row sum of GraphGatherMol
         # (graphgather.py:68-77) commutes with it: sum_i (h_i W + b) = (sum_i h_i) W + n_g b.  Gathering first
         # shrinks the dense GEMM from R = sum n_g rows to B rows.

@@ -198,12 +198,20 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+
+    def mark(what):   # progress markers on stderr (AGCN_BENCH_VERBOSE=1): where a multi-rank run is
+        if os.environ.get("AGCN_BENCH_VERBOSE"):
+            sys.stderr.write("[bench rank %d] %s\n" % (rank, what))
+            sys.stderr.flush()
+
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py needs a CUDA device; there is no CPU path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        mark("init_process_group")
         dist.init_process_group("nccl", device_id=dev)
+        mark("process group up")
 
     # ---- synthetic C2 batch of this rank (host, pinned, packed ragged layout)
     Xpad, Lpad, n_nodes = O.synthetic_molecule_batch(B_PER_GPU, NMAX, seed=1235 + rank)
@@ -248,6 +256,67 @@ def run_ours(args):
         b = agcn_b200.GraphBatch(n_nodes, NMAX, device=dev)
         return float(model.step(X, L, b, oh, w).detach())
 
+    def timed_e2e_pipelined(steps, warmup):
+        """e2e with the input copy of step i+1 in flight (copy stream, two device buffers) while step i
+        computes, and the loss of step i read after step i+1 has been queued: every timed step still copies
+        its own padded batch from pinned host memory and returns its loss to the host."""
+        copy_stream = torch.cuda.Stream(device=dev)
+        bufs = [(torch.empty_like(Xpad_h, device=dev), torch.empty_like(Lpad_h, device=dev),
+                 torch.empty_like(onehot_h, device=dev), torch.empty_like(weights_h, device=dev)) for _ in range(2)]
+        loss_host = [torch.empty(1).pin_memory() for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]      # copy of slot i landed
+        consumed = [torch.cuda.Event() for _ in range(2)]   # pack kernels of slot i are done reading it
+        main = torch.cuda.current_stream()
+
+        def stage(i):
+            slot = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                for dst, src in zip(bufs[slot], (Xpad_h, Lpad_h, onehot_h, weights_h)):
+                    dst.copy_(src, non_blocking=True)
+                ready[slot].record(copy_stream)
+
+        def run(n_steps):
+            losses, pending = [], None
+            stage(0)
+            for i in range(n_steps):
+                if i + 1 < n_steps:
+                    stage(i + 1)
+                slot = i % 2
+                main.wait_event(ready[slot])
+                Xp, Lp, oh, w = bufs[slot]
+                b = agcn_b200.GraphBatch(n_nodes, NMAX, device=dev)
+                X, L = b.pack_nodes(Xp), b.pack_lap(Lp)
+                loss = model.step(X, L, b, oh, w)          # oh / w are read until the end of the step ...
+                consumed[slot].record(main)                 # ... so the slot is released after it
+                host = loss_host[slot]
+                host.copy_(loss.detach().reshape(1), non_blocking=True)
+                done = torch.cuda.Event()
+                done.record(main)
+                if pending is not None:
+                    pending[1].synchronize()
+                    losses.append(float(pending[0]))
+                pending = (host, done)
+            pending[1].synchronize()
+            losses.append(float(pending[0]))
+            return losses
+
+        for ev in consumed:
+            ev.record(main)
+        run(warmup)
+        barrier()
+        flush.fill_(1.0)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        losses = run(steps)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        assert len(losses) == steps and all(np.isfinite(losses))
+        return float(t) / steps
+
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
@@ -270,7 +339,9 @@ def run_ours(args):
     # eager launches first (also warms every kernel up), then the same step captured in a CUDA graph:
     # a step is ~100 small launches, so replaying the graph removes the host launch path from the timing
     launches0 = _lib.launch_count()
+    mark("eager steps")
     ms_eager = timed(resident_step, args.steps, args.warmup)
+    mark("eager steps done: %.3f ms" % ms_eager)
     launches_per_step = (_lib.launch_count() - launches0) / float(args.steps + args.warmup)
     launch_mode, graph = "eager", None
     if not args.no_graph:
@@ -282,10 +353,12 @@ def run_ours(args):
                     resident_step()
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            mark("graph capture")
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 resident_step()
             launch_mode = "cuda_graph"
+            mark("graph captured")
         except Exception as exc:  # stay on eager launches, say so in the line
             graph, launch_mode = None, "eager (graph capture failed: %s)" % str(exc)[:120]
             torch.cuda.synchronize()
@@ -297,8 +370,12 @@ def run_ours(args):
     else:
         ms_step = timed(resident_step, args.steps, args.warmup)
     clocks = sampler.stop() if rank == 0 else None
-    ms_e2e = timed(e2e_step, max(3, args.steps // 2), 3)
+    mark("timed steps done: %.3f ms (%s)" % (ms_step, launch_mode))
+    ms_e2e_serial = timed(e2e_step, max(3, args.steps // 2), 3)
     ms_e2e_packed = timed(e2e_packed_step, max(3, args.steps // 2), 3)
+    mark("e2e serial / packed done")
+    ms_e2e = timed_e2e_pipelined(max(4, args.steps), 3)
+    mark("e2e pipelined done")
     # the same step with the paper's semantics (normalised Laplacian + differentiable metric): every kernel of
     # the metric / Laplacian block runs, forward and backward
     ms_paper = None
@@ -339,7 +416,12 @@ def run_ours(args):
                            "host_layout_e2e": "reference wire layout: zero-padded [B,132,75] + [B,132,132] (pinned)"},
                 "clocks": clocks,
                 "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": 4},
+                        "d2h_bytes_per_step": 4,
+                        "pipeline": "input copy of step i+1 overlaps step i (copy stream, 2 device slots); loss of step i "
+                                    "read after step i+1 is queued; eager launches"},
+                "e2e_serial": {"value": world * B_PER_GPU / (ms_e2e_serial * 1e-3), "unit": "graphs/s",
+                               "ms_per_step": ms_e2e_serial, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                               "pipeline": "copy, step and loss read strictly one after the other"},
                 "e2e_packed_host": {"value": world * B_PER_GPU / (ms_e2e_packed * 1e-3), "unit": "graphs/s",
                                     "ms_per_step": ms_e2e_packed, "h2d_bytes_per_step": int(h2d_packed),
                                     "d2h_bytes_per_step": 4},
@@ -351,8 +433,16 @@ def run_ours(args):
                 "roofline": roof,
                 "cpu_baseline": {"value": gps, "unit": "graphs/s", "cores": procs, "kind": "port", "sample": sample}}
         print(json.dumps(line))
+    mark("done")
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing NCCL down while CUDA graphs that captured its collectives are alive hangs at
+        # destroy_process_group / interpreter exit (seen on 2 x B200): every rank has finished its collectives
+        # and rank 0 has printed, so leave without the teardown.
+        graph = None
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def kernel_roofline(model, batch, Xd, Ld, n_nodes, dev):

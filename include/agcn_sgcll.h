@@ -82,8 +82,11 @@ uint64_t agcn_launch_count(void);
 /* ---- batch topology (replaces GraphTopologyMol.batch_to_feed_dict's data_slice / lap_slice,
  *      models/tf_modules/graph_topology.py:100-135) ----------------------------------------- */
 /* n_nodes_host[B]: real node count of every graph (host memory, 1 <= n_g <= Nmax).
- * Builds the device-side offset tables and the size-sorted work lists.  Allocates a few KB of
- * device memory (the only allocation in the library); synchronises `stream` before returning. */
+ * Builds the device-side offset tables and the work lists (size-sorted graphs, 128-row tiles).  The tables are
+ * uploaded in stream order on `stream` (stream-ordered allocation, pooled pinned staging, pooled side streams):
+ * nothing is synchronised, so a plan per training batch costs tens of microseconds of host time.  Calls that use
+ * the plan on another stream are ordered after the upload automatically.  agcn_plan_destroy may be called as
+ * soon as the last call using the plan has returned; the device block is released in stream order. */
 int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void* stream, agcn_plan** out);
 int agcn_plan_destroy(agcn_plan* plan);
 int64_t agcn_plan_total_nodes(const agcn_plan* plan);    /* R = sum n_g      */
@@ -161,6 +164,22 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
 size_t agcn_gemm_tn_scratch_bytes(int32_t M, int32_t Kd, int32_t N, int32_t S);
 int agcn_gemm_tn(const float* d_A0, const float* d_A1, const float* d_D, float* d_out, int32_t M, int32_t Kd,
                  int32_t N, int32_t S, void* d_scratch, int32_t use_tensor_cores, void* stream);
+
+/* ---- the layers after the last SGC-LL layer, loss and gradient in one call:
+ *   DenseMol (models/layers/dense_layer.py:33-50, linear) + GraphGatherMol (models/layers/graphgather.py:50-78:
+ *   per-graph sum over the real atoms, tanh) + the n_tasks two-class heads (models/operators/model_operatos.py:
+ *   792-864) as one [Fm, Nt = 2 n_tasks] matrix + weighted sigmoid cross-entropy summed and multiplied by `scale`
+ *   (= 1 / global batch size, models/tf_modules/multitask_classifier.py:41-44,187-209).
+ *   d_H [R,Fh] packed output of the last SGC-LL layer; d_dense_W [Fh,Fm], d_dense_b [Fm]; d_head_W [Fm,Nt],
+ *   d_head_b [Nt]; d_targets / d_weights [B,Nt].
+ *   outputs (overwritten): d_loss [1], d_dH [R,Fh] and the four parameter gradients.
+ *   Needs 32 <= Fh <= 128, 32 <= Fm <= 256 (multiples of 4), Nt >= 32. */
+int agcn_head_workspace_bytes(const agcn_plan* plan, int32_t Fh, int32_t Fm, int32_t Nt, size_t* bytes);
+int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_dense_W, const float* d_dense_b,
+                        const float* d_head_W, const float* d_head_b, const float* d_targets, const float* d_weights,
+                        float scale, int32_t Fh, int32_t Fm, int32_t Nt, float* d_loss, float* d_dH,
+                        float* d_ddense_W, float* d_ddense_b, float* d_dhead_W, float* d_dhead_b, void* d_work,
+                        size_t work_bytes, void* stream);
 
 /* Host-buffer convenience entry (the end-to-end path): padded HOST arrays in the reference's wire
  * layout in, padded HOST output out; host<->device copies are issued on `stream` inside the call.

@@ -281,3 +281,41 @@ def test_big_graph_point_cloud_shape_paper_full():
     orc = oracle_run(X, L, n, p, K, "SGC_LL", "paper", "full", cot_Y=cY)
     cu = cuda_run(X, L, n, p, K, "SGC_LL", "paper", "full", cot_Y=cY)
     print(compare(cu, orc))
+
+
+@pytest.mark.parametrize("Fh,Fm,Nt", [(64, 256, 1234), (32, 64, 40), (128, 132, 50)])
+def test_head_loss_and_gradients_match_torch_fp64(Fh, Fm, Nt):
+    """agcn_head_loss_grad (DenseMol + GraphGatherMol + multitask heads + weighted sigmoid cross-entropy,
+    SURVEY.md section 8f rows 1 and 3) against the same chain written with torch ops in fp64."""
+    import agcn_b200
+    from agcn_b200.functional import head_loss
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(Fh + Nt)
+    n = np.array(SIZES + [7, 1, 20, 19, 44], np.int32)
+    B, R = len(n), int(n.sum())
+    batch = agcn_b200.GraphBatch(n, 132, device=dev)
+    H64 = torch.tensor(np.maximum(rng.standard_normal((R, Fh)), 0) * 0.3, dtype=torch.float64)
+    p64 = [torch.tensor(rng.standard_normal(s) * sc, dtype=torch.float64)
+           for s, sc in (((Fh, Fm), 0.1), ((Fm,), 0.05), ((Fm, Nt), 0.1), ((Nt,), 0.1))]
+    y = torch.tensor((rng.random((B, Nt)) < 0.3).astype(np.float64))
+    w = torch.tensor(rng.random((B, Nt)) + 0.5)
+    scale, up = 1.0 / 37.0, 1.7
+    # reference
+    Hr = H64.clone().requires_grad_(True)
+    pr = [t.clone().requires_grad_(True) for t in p64]
+    ids = torch.tensor(np.repeat(np.arange(B), n))
+    hsum = torch.zeros(B, Fh, dtype=torch.float64).index_add_(0, ids, Hr)
+    mol = torch.tanh(hsum @ pr[0] + torch.tensor(n, dtype=torch.float64)[:, None] * pr[1][None, :])
+    logits = mol @ pr[2] + pr[3]
+    loss_ref = torch.nn.functional.binary_cross_entropy_with_logits(logits, y, weight=w, reduction="sum") * scale
+    (loss_ref * up).backward()
+    # CUDA path
+    Hc = H64.float().to(dev).requires_grad_(True)
+    pc = [t.float().to(dev).requires_grad_(True) for t in p64]
+    loss = head_loss(Hc, pc[0], pc[1], pc[2], pc[3], y.float().to(dev), w.float().to(dev), batch, scale)
+    (loss * up).backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(loss_ref)) <= TOL * abs(float(loss_ref))
+    assert O.rel_err(Hc.grad.cpu(), Hr.grad) <= TOL
+    for a, b, name in zip(pc, pr, ("dense_W", "dense_b", "head_W", "head_b")):
+        assert O.rel_err(a.grad.cpu(), b.grad) <= TOL, name
