@@ -364,7 +364,7 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
       if ((rc = reduce_scalar_parts(wk.dbeta_part, plan->B, d_dbeta, st))) return rc;
     }
   } else {
-    AGCN_CUDA(cudaMemsetAsync(d_dalpha, 0, sizeof(float), st));  // res_L == I >= 0: leaky never sees alpha
+    if ((rc = zero_async(d_dalpha, 1, st))) return rc;  // res_L == I >= 0: leaky never sees alpha
   }
   if (m.full) {
     GemmTNArgs t;  // dM_L = X^T dXW
@@ -381,7 +381,7 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
     if ((rc = node_gemm(g, wk.tcM, st))) return rc;
   } else {
     // tf.py_func has no gradient: M_L receives none (graphconv.py:211)
-    AGCN_CUDA(cudaMemsetAsync(d_dM_L, 0, (size_t)F * F * sizeof(float), st));
+    if ((rc = zero_async(d_dM_L, (size_t)F * F, st))) return rc;
   }
   return AGCN_OK;
 }

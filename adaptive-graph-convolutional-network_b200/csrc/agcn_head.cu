@@ -131,7 +131,7 @@ inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 inline int pad4(int x) { return (x + 3) & ~3; }
 
 struct HeadWork {
-  float *hsum, *pre, *mol, *dlog, *dmol, *dhsum, *dWh_pad, *loss_part, *tcA, *tcB, *tcC, *tcD, *tn_part;
+  float *hsum, *pre, *mol, *dlog, *dmol, *dhsum, *dWh_pad, *loss_part, *tcA, *tcB, *tcC, *tcD, *tn_part, *splitk;
   size_t bytes;
 };
 
@@ -166,6 +166,7 @@ HeadWork carve_head(const agcn_plan* plan, int Fh, int Fm, int Nt, void* base) {
   t.Kd = Fh; t.N = Fm;
   tn = std::max(tn, tn_any_partial(t));
   w.tn_part = take(tn);
+  w.splitk = take((size_t)8 * B * std::max(Fm, Fh));  // split-K partial sums of the two long contractions
   w.bytes = off;
   return w;
 }
@@ -223,11 +224,11 @@ int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_
   g_dmol.M = B; g_dmol.N = Fm; g_dmol.Kd = Nt;
   g_dmol.A0 = w.dlog; g_dmol.lda0 = Ntp;
   g_dmol.B = d_head_W; g_dmol.ldb = Nt; g_dmol.transB = 1;  // head_W is [Fm, Nt] = [N, Kd]
-  g_dmol.C = w.dmol; g_dmol.ldc = Fm;
+  g_dmol.C = w.dmol; g_dmol.ldc = Fm; g_dmol.split_k_partial = w.splitk;
   g_dhs.M = B; g_dhs.N = Fh; g_dhs.Kd = Fm;
   g_dhs.A0 = w.dmol; g_dhs.lda0 = Fm;
   g_dhs.B = d_dense_W; g_dhs.ldb = Fm; g_dhs.transB = 1;    // dense_W is [Fh, Fm] = [N, Kd]
-  g_dhs.C = w.dhsum; g_dhs.ldc = Fh;
+  g_dhs.C = w.dhsum; g_dhs.ldc = Fh; g_dhs.split_k_partial = w.splitk;
   AGCN_REQUIRE(tc_gemm_supported(g_pre) && tc_gemm_supported(g_log) && tc_gemm_supported(g_dmol) &&
                    tc_gemm_supported(g_dhs),
                "head_loss_grad: operands are not TMA-compatible (alignment)");
@@ -237,7 +238,7 @@ int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_
   if ((rc = tc_gemm_split_b(g_log, w.tcB, side))) return rc;
   if ((rc = tc_gemm_split_b(g_dmol, w.tcC, side))) return rc;
   if ((rc = tc_gemm_split_b(g_dhs, w.tcD, side))) return rc;
-  AGCN_CUDA(cudaMemsetAsync(w.dlog, 0, (size_t)B * Ntp * sizeof(float), side));  // pad columns of dlog
+  if ((rc = zero_async(w.dlog, (size_t)B * Ntp, side))) return rc;  // pad columns of dlog
   AGCN_CUDA(cudaEventRecord(plan->ev_side_join, side));
 
   // GraphGatherMol + DenseMol (commuted) + tanh

@@ -146,6 +146,9 @@ struct GemmArgs {
   int bce_ld = 0;  // row pitch of bce_y / bce_w (0: same as ldc)
   float bce_scale = 1.f;
   float* loss_part = nullptr;
+  // tensor-core kernel only: scratch of 8 * M * N floats; when given, long contractions with few output tiles are
+  // split along K (plain outputs only: no bias / activation / accumulate / loss epilogue, ldc == N, Z == 1)
+  float* split_k_partial = nullptr;
 };
 int tc_gemm_loss_parts(const GemmArgs& a);  // number of partial loss sums tc_gemm writes
 int gemm_rows(const GemmArgs& a, cudaStream_t st);
@@ -252,6 +255,7 @@ int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY
                    int add_identity, const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st);
 
 // ---------------------------------------------------------------- helpers
+int zero_async(float* dst, size_t floats, cudaStream_t st);  // zero fill by a kernel (never the copy engine)
 int plan_use(const agcn_plan* plan, cudaStream_t st);  // call first in every entry point that enqueues work
 int fork_streams(const agcn_plan* plan, cudaStream_t main, int n_aux);
 int join_streams(const agcn_plan* plan, cudaStream_t main, int n_aux);

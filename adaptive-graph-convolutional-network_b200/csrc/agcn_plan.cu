@@ -132,6 +132,26 @@ static void build_fused_tiles(const std::vector<int32_t>& n, const std::vector<i
 }
 
 
+// The plan tables reach the device through a kernel that reads the pinned staging buffer over PCIe (unified
+// addressing), not through a copy-engine transfer: a training loop that prefetches the next batch keeps the
+// host-to-device engine busy with a 100 MB copy, and a tiny cudaMemcpyAsync queued behind it would hold back the
+// first kernels of the current step.
+__global__ void upload_tables_kernel(const int4* __restrict__ src, int4* __restrict__ dst, size_t n16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = src[i];
+}
+
+// Same reason for zero fills on the hot path: a kernel, never the copy engine.
+__global__ void zero_fill_kernel(float* __restrict__ dst, size_t n) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) dst[i] = 0.f;
+}
+int zero_async(float* dst, size_t floats, cudaStream_t st) {
+  if (floats == 0) return AGCN_OK;
+  zero_fill_kernel<<<(unsigned)std::min<size_t>((floats + 255) / 256, 592), 256, 0, st>>>(dst, floats);
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
 // ------------------------------------------------------------------ pooled plan resources
 // A plan is created for every batch of a training loop, so creating it must not synchronise anything: the side
 // streams / events come from a process-wide pool, the offset tables travel through pooled pinned staging buffers
@@ -355,8 +375,14 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   p->staging_host = stg.host; p->staging_bytes = stg.bytes; p->staging_done = stg.done;
   p->create_stream = st;
   p->last_stream = st;
-  e = cudaMallocAsync(&p->d_block, bytes, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(p->d_block, host, bytes, cudaMemcpyHostToDevice, st);
+  const size_t n16 = (bytes + 15) / 16;
+  e = cudaMallocAsync(&p->d_block, n16 * 16, st);
+  if (e == cudaSuccess) {
+    upload_tables_kernel<<<(unsigned)std::min<size_t>((n16 + 255) / 256, 64), 256, 0, st>>>(
+        reinterpret_cast<const int4*>(host), reinterpret_cast<int4*>(p->d_block), n16);
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    e = cudaGetLastError();
+  }
   if (e == cudaSuccess) e = cudaEventRecord(stg.done, st);   // the staging buffer may be reused once this has passed
   if (e == cudaSuccess) e = cudaEventRecord(p->ev_ready, st);
   if (e != cudaSuccess) {

@@ -91,6 +91,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 struct Args {
   int M, N, Kd, S;
   int kb_per_slice;   // ceil(Kd / 32)
+  int ksplit;         // split-K: grid.y = Z * ksplit, split ks handles k-blocks [ks * kb_per_split, ...) and writes
+  int kb_per_split;   // its raw partial sums to C + (z * ksplit + ks) * sliceC (the host reduces them)
   int rows_slice1;    // row offset between A1 slices in the stacked 2-D view
   int b_rows_slice;   // rows of one B slice in the stacked [Z*S*Npad, Kd] view (= Npad)
   float* C;
@@ -130,9 +132,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = blockIdx.x * BM;
-  const int z = blockIdx.y;   // output slice
-  const int nb = blockIdx.z;  // 128-column block of wide outputs
-  const int num_kb = p.S * p.kb_per_slice;
+  const int zz = blockIdx.y;
+  const int z = zz / p.ksplit;  // output slice
+  const int nb = blockIdx.z;    // 128-column block of wide outputs
+  const int total_kb = p.S * p.kb_per_slice;
+  const int kb0 = (zz - z * p.ksplit) * p.kb_per_split;            // first k-block of this split
+  const int num_kb = min(p.kb_per_split, total_kb - kb0);           // k-blocks of this split
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SM::STAGES; ++s) {
@@ -160,7 +165,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int stage = kb % SM::STAGES, phase = (kb / SM::STAGES) & 1;
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* st = base + stage * SM::STAGE_BYTES;
-        const int s = kb / p.kb_per_slice, k0 = (kb - s * p.kb_per_slice) * BK;
+        const int s = (kb0 + kb) / p.kb_per_slice, k0 = (kb0 + kb - s * p.kb_per_slice) * BK;
         mbar_expect_tx(&full_bar[stage], A_TILE_BYTES + 2 * SM::B_TILE_BYTES);
         if (s == 0)
           tma_load_2d(st, &tmA0, &full_bar[stage], k0, m0);
@@ -229,7 +234,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     // Each thread owns one accumulator row.  32-column chunks are staged through shared memory (the
     // pipeline stages are free now) so that the global stores are row-contiguous 128-byte segments.
     float* stg = reinterpret_cast<float*>(base) + (warp - 2) * (32 * 36);
-    float* __restrict__ Cz = p.C + (long long)z * p.sliceC;
+    float* __restrict__ Cz = p.C + (long long)zz * p.sliceC;
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
     float loss_acc = 0.f;
     // bias has been added; accumulate / activation / loss epilogue of one element
@@ -620,6 +625,9 @@ static int make_map3(CUtensorMap* map, const float* ptr, uint64_t slices, uint64
 
 }  // namespace tc
 
+__global__ void reduce_chunks_kernel(const float* __restrict__ partial, float* __restrict__ out, long long elems,
+                                     int chunks);
+
 static int tc_npad(int N) { return N <= 64 ? 64 : (N + 127) / 128 * 128; }
 static int tc_kpitch(int Kd) { return (Kd + 3) & ~3; }
 
@@ -681,13 +689,28 @@ int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
   Args p;
   p.M = a.M; p.N = a.N; p.Kd = a.Kd; p.S = a.S;
   p.kb_per_slice = (a.Kd + BK - 1) / BK;
+  const int total_kb = a.S * p.kb_per_slice;
+  // split-K for long contractions with few output tiles (plain outputs only): partial sums + one reduction
+  const int out_tiles = ((a.M + BM - 1) / BM) * a.Z * (Npad / (Npad <= 64 ? 64 : 128));
+  int ksplit = 1;
+  if (a.split_k_partial && !a.bias && a.act == AGCN_ACT_LINEAR && !a.accumulate && !a.bce_y && a.ldc == a.N && a.Z == 1 &&
+      total_kb >= 16 && out_tiles < 74)
+    ksplit = std::min(std::min(8, total_kb / 4), std::max(1, 148 / out_tiles));
+  p.ksplit = ksplit;
+  p.kb_per_split = (total_kb + ksplit - 1) / ksplit;
+  p.ksplit = (total_kb + p.kb_per_split - 1) / p.kb_per_split;
+  ksplit = p.ksplit;
   p.rows_slice1 = rows_slice1;
   p.b_rows_slice = Npad;
   p.C = a.C; p.ldc = a.ldc; p.sliceC = a.sliceC;
+  if (ksplit > 1) {
+    p.C = a.split_k_partial;
+    p.sliceC = (long long)a.M * a.ldc;
+  }
   p.bias = a.bias; p.act = a.act; p.accumulate = a.accumulate;
   p.bce_y = a.bce_y; p.bce_w = a.bce_w; p.bce_scale = a.bce_scale; p.loss_part = a.loss_part;
   p.bce_ld = a.bce_ld > 0 ? a.bce_ld : a.ldc;
-  dim3 grid((a.M + BM - 1) / BM, a.Z, Npad / BN);
+  dim3 grid((a.M + BM - 1) / BM, a.Z * ksplit, Npad / BN);
   static std::once_flag once64, once128;
   if (BN == 64) {
     std::call_once(once64, [] {
@@ -701,6 +724,11 @@ int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
     tc_gemm_kernel<128><<<grid, 192, Smem<128>::TOTAL, st>>>(mA0, mA1, mBhi, mBlo, p);
   }
   AGCN_LAUNCH_CHECK();
+  if (ksplit > 1) {
+    const long long elems = (long long)a.M * a.ldc;
+    reduce_chunks_kernel<<<(unsigned)((elems + 255) / 256), 256, 0, st>>>(a.split_k_partial, a.C, elems, ksplit);
+    AGCN_LAUNCH_CHECK();
+  }
   return AGCN_OK;
 }
 

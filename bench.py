@@ -276,27 +276,37 @@ def run_ours(args):
                     dst.copy_(src, non_blocking=True)
                 ready[slot].record(copy_stream)
 
+        host_ms = {"stage": 0.0, "plan": 0.0, "pack": 0.0, "step": 0.0, "loss_wait": 0.0}
+
         def run(n_steps):
             losses, pending = [], None
             stage(0)
             for i in range(n_steps):
+                t0 = time.perf_counter()
                 if i + 1 < n_steps:
                     stage(i + 1)
                 slot = i % 2
                 main.wait_event(ready[slot])
                 Xp, Lp, oh, w = bufs[slot]
+                t1 = time.perf_counter()
                 b = agcn_b200.GraphBatch(n_nodes, NMAX, device=dev)
+                t2 = time.perf_counter()
                 X, L = b.pack_nodes(Xp), b.pack_lap(Lp)
+                t3 = time.perf_counter()
                 loss = model.step(X, L, b, oh, w)          # oh / w are read until the end of the step ...
                 consumed[slot].record(main)                 # ... so the slot is released after it
                 host = loss_host[slot]
                 host.copy_(loss.detach().reshape(1), non_blocking=True)
                 done = torch.cuda.Event()
                 done.record(main)
+                t4 = time.perf_counter()
                 if pending is not None:
                     pending[1].synchronize()
                     losses.append(float(pending[0]))
                 pending = (host, done)
+                t5 = time.perf_counter()
+                for k, v in zip(("stage", "plan", "pack", "step", "loss_wait"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+                    host_ms[k] += v * 1e3 / n_steps
             pending[1].synchronize()
             losses.append(float(pending[0]))
             return losses
@@ -305,6 +315,8 @@ def run_ours(args):
             ev.record(main)
         run(warmup)
         barrier()
+        for k in host_ms:
+            host_ms[k] = 0.0
         flush.fill_(1.0)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -315,6 +327,7 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         assert len(losses) == steps and all(np.isfinite(losses))
+        mark("e2e pipelined host ms per step (last run + warm-up mix): %s" % {k: round(v, 3) for k, v in host_ms.items()})
         return float(t) / steps
 
     def timed(fn, steps, warmup):
