@@ -1,0 +1,524 @@
+// Chebyshev products of the graphs that do not fit the fused tile kernels (n > cheb_small_max: point clouds,
+// ModelNet40-shape N = 1024, Sydney-shape ragged N, the N <= 4096 sweep), on the tensor cores:
+//
+//     Out = cmul * op(L_g) * In  (+ Add)  (- Sub)  (+ RowScale .* ScaleIn),    op(L) = L (+ I) | L^T (+ I)
+//
+// forward T_k = 2 L T_{k-1} - T_{k-2} (graphconv.py:221-236), its reverse recurrence U_j = G_j + c L^T U_{j+1} - U_{j+2},
+// and the dXW = rowsum(C) xw - C XW product of the metric gradient.  At n = 1024, F = 128 one step is a
+// [1024 x 1024] x [1024 x 128] contraction per graph: dense tensor-core work (north_star item 3).
+//
+// grouped_tc_kernel: one CTA per (graph, 128-row tile, 128-column block of the node matrix).
+//   warps 2-9 : A = L_g[rows, k-block of 32 columns] loaded from global memory (ragged n: rows are not 16-byte
+//               aligned, so no TMA), split into hi / lo TF32 halves and written as a 128 x 32 K-major SWIZZLE_128B
+//               operand (transposed on the fly for L^T); the B tile brought by TMA is split in place;
+//   warp 0    : TMA producer of B = In[k-block of 32 nodes, 128 columns]: row-major node matrix = MN-major operand,
+//               32 x 32 boxes in the 128B-swizzle / 32B-atom layout (as in tc_gemm_tn_kernel);
+//   warp 1    : tcgen05.mma kind::tf32, 3xTF32 (A_lo B_hi + A_hi B_lo + A_hi B_hi) into a TMEM accumulator;
+//   epilogue  : TMEM -> registers -> shared -> coalesced float4 rows with the recurrence terms applied.
+// Rows of In that belong to the next graph (last k-block of a ragged graph) are zeroed during the split, so a
+// non-finite value never crosses a graph boundary.
+//
+// grouped_thin_kernel{,_t}: the 3- or 4-feature first layer of a point cloud (F <= 8) is a stream over L with
+// 2 F flop per element: plain fp32 FMAs, L read once with coalesced rows (columns for L^T).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+#include "agcn_internal.cuh"
+
+namespace agcn {
+namespace bt {
+
+constexpr int TM = 128;
+constexpr int BK = 32;
+constexpr int UMMA_K = 8;
+constexpr int BN = 128;                     // node-matrix columns per CTA
+constexpr int A_BYTES = TM * BK * 4;        // 16 KB: one half (hi or lo) of the A operand of a k-block
+constexpr int B_BYTES = BN * BK * 4;        // 16 KB: four 32 x 32 boxes
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr int STAGES = 3;
+constexpr int WORKERS = 256;
+constexpr int THREADS = 64 + WORKERS;
+constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > SPIN_LIMIT) __trap();  // a protocol bug becomes an error, not a hang
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// A: K-major, SWIZZLE_128B, 8-row atoms of 1024 bytes (same operand format as agcn_fused_tile.cu)
+__device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// B: MN-major TF32, 128B swizzle with 32B atoms (same operand format as tc_gemm_tn_kernel): 32-column groups
+// 4096 bytes apart, groups of 4 contraction rows 512 bytes apart
+__device__ __forceinline__ uint64_t make_desc_mn(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(4096 >> 4) << 16;
+  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)1 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float v[32]) {
+  uint32_t u[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,"
+      "%29,%30,%31}, [%32];\n"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15]), "=r"(u[16]),
+        "=r"(u[17]), "=r"(u[18]), "=r"(u[19]), "=r"(u[20]), "=r"(u[21]), "=r"(u[22]), "=r"(u[23]), "=r"(u[24]),
+        "=r"(u[25]), "=r"(u[26]), "=r"(u[27]), "=r"(u[28]), "=r"(u[29]), "=r"(u[30]), "=r"(u[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void sts32(uint32_t a, float v) {
+  asm volatile("st.shared.f32 [%0], %1;\n" ::"r"(a), "f"(v) : "memory");
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u); }
+
+__global__ void __launch_bounds__(THREADS, 1)
+grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
+  const int g = p.tile_graph[blockIdx.x], m0 = p.tile_row[blockIdx.x];
+  if (m0 & (TM - 1)) return;  // the plan lists 64-row tiles: every even one starts a 128-row tile of this kernel
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(base);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;              // B tile landed (TMA)
+  uint64_t* split_bar = bars + STAGES;    // A written and B split by the 8 worker warps
+  uint64_t* empty_bar = bars + 2 * STAGES;  // MMAs that read the stage retired
+  uint64_t* tmem_full_bar = bars + 3 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = p.n_nodes[g];
+  const long long row0 = p.node_off[g];
+  const float* __restrict__ Lg = p.L + p.lap_off[g];
+  const int F = p.F;
+  const int f0 = blockIdx.y * BN;
+  const int b_boxes = min(BN / 32, (F - f0 + 31) / 32);
+  const int nmma = 32 * b_boxes;
+  const int num_kb = (n + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], WORKERS / 32);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t sb = sbase + stage * STAGE_BYTES + 2 * A_BYTES;
+        mbar_expect_tx(&full_bar[stage], b_boxes * 4096);
+        for (int b = 0; b < b_boxes; ++b)
+          tma_load_2d(sb + b * 4096, &tmIn, &full_bar[stage], f0 + 32 * b, (int)(row0 + (long long)kb * BK));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = f32, A = tf32 K-major, B = tf32 MN-major, N = nmma, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(nmma >> 3) << 17) |
+                             ((uint32_t)(TM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
+        mbar_wait(&split_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa = sbase + stage * STAGE_BYTES, sa_lo = sa + A_BYTES;
+        const uint32_t sb = sa + 2 * A_BYTES, sb_lo = sb + B_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t a_hi = make_desc_k(sa + k * UMMA_K * 4), a_lo = make_desc_k(sa_lo + k * UMMA_K * 4);
+          const uint64_t b_hi = make_desc_mn(sb + k * 1024), b_lo = make_desc_mn(sb_lo + k * 1024);
+          umma_tf32(tmem_base, a_lo, b_hi, idesc, (kb | k) != 0);
+          umma_tf32(tmem_base, a_hi, b_lo, idesc, 1);
+          umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
+        }
+        umma_commit(&empty_bar[stage]);
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else {
+    const int ww = warp - 2;              // worker warp 0..7
+    const int wt = ww * 32 + lane;
+    // ---- A loader: 16 elements per thread and k-block.
+    //   op = L  : warp ww owns tile rows 16 ww .. 16 ww + 15, lane = column of the k-block (rows of L are contiguous)
+    //   op = L^T: warp ww owns items it = 16 ww + u -> (column c = it / 4, 32-row segment it % 4), lane = row of the
+    //             segment (columns of L^T are rows of L: contiguous along the tile rows)
+    auto load_a = [&](int kb, float (&v)[16]) {
+      if (kb >= num_kb) return;
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        int r, c;
+        if (!p.transL) {
+          r = ww * 16 + u; c = lane;
+        } else {
+          const int it = ww * 16 + u;
+          c = it >> 2; r = (it & 3) * 32 + lane;
+        }
+        const int i = m0 + r, j = kb * BK + c;
+        float x = 0.f;
+        if (i < n && j < n) x = p.transL ? __ldg(Lg + (long long)j * n + i) : __ldg(Lg + (long long)i * n + j);
+        v[u] = x;
+      }
+    };
+    auto store_a = [&](uint32_t st, const float (&v)[16]) {
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        int r, c;
+        if (!p.transL) {
+          r = ww * 16 + u; c = lane;
+        } else {
+          const int it = ww * 16 + u;
+          c = it >> 2; r = (it & 3) * 32 + lane;
+        }
+        const uint32_t off = (uint32_t)(r * 128 + ((((c >> 2) ^ (r & 7)) << 4) | ((c & 3) << 2)));
+        const float hi = tf32_hi(v[u]);
+        sts32(st + off, hi);
+        sts32(st + A_BYTES + off, tf32_lo(v[u], hi));
+      }
+    };
+    auto step = [&](int kb, float (&v)[16]) {
+      const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
+      const uint32_t st = sbase + stage * STAGE_BYTES;
+      if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+      __syncwarp();
+      store_a(st, v);
+      load_a(kb + 2, v);                 // two k-blocks ahead: in flight during the split below and the next step
+      mbar_wait(&full_bar[stage], phase);  // every lane: the TMA bytes are read right below
+      const int valid = n - kb * BK;     // contraction rows of this k-block that belong to the graph
+      for (int idx = wt; idx < b_boxes * 256; idx += WORKERS) {
+        const uint32_t a = st + 2 * A_BYTES + 16 * idx;
+        float4 x = lds128(a);
+        if (((idx & 255) >> 3) >= valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 hi, lo;
+        hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
+        lo.x = tf32_lo(x.x, hi.x); lo.y = tf32_lo(x.y, hi.y); lo.z = tf32_lo(x.z, hi.z); lo.w = tf32_lo(x.w, hi.w);
+        sts128(a, hi);
+        sts128(a + B_BYTES, lo);
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&split_bar[stage]);
+    };
+    float va[16], vb[16];
+    load_a(0, va);
+    load_a(1, vb);
+    for (int kb = 0; kb < num_kb; kb += 2) {
+      step(kb, va);
+      if (kb + 1 < num_kb) step(kb + 1, vb);
+    }
+    // ---- epilogue
+    if (lane == 0) mbar_wait(tmem_full_bar, 0);
+    __syncwarp();
+    tc_fence_after();
+    const int q = warp & 3;      // TMEM lane quarter of this warp
+    const int h = ww >> 2;       // column half
+    const uint32_t stg = sbase + (uint32_t)(ww * (32 * 36 * 4));  // the operand stages are free now
+    for (int c0 = 32 * h; c0 < nmma; c0 += 64) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        sts128(stg + 4 * (lane * 36 + 4 * u), make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+      __syncwarp();
+      const int c = f0 + c0 + 4 * (lane & 7);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int rr = 4 * t + (lane >> 3);
+        const int i = m0 + q * 32 + rr;
+        if (i >= n || c >= F) continue;  // F % 4 == 0: a float4 is inside or outside as a whole
+        const float4 a4 = lds128(stg + 4 * (rr * 36 + 4 * (lane & 7)));
+        const long long o = (row0 + i) * F + c;
+        float4 r4 = make_float4(p.cmul * a4.x, p.cmul * a4.y, p.cmul * a4.z, p.cmul * a4.w);
+        if (p.add_identity) {  // (L + I) In = L In + In
+          const float4 x = *reinterpret_cast<const float4*>(p.In + o);
+          r4.x = fmaf(p.cmul, x.x, r4.x); r4.y = fmaf(p.cmul, x.y, r4.y);
+          r4.z = fmaf(p.cmul, x.z, r4.z); r4.w = fmaf(p.cmul, x.w, r4.w);
+        }
+        if (p.Add) {
+          const float4 x = *reinterpret_cast<const float4*>(p.Add + o);
+          r4.x += x.x; r4.y += x.y; r4.z += x.z; r4.w += x.w;
+        }
+        if (p.Sub) {
+          const float4 x = *reinterpret_cast<const float4*>(p.Sub + o);
+          r4.x -= x.x; r4.y -= x.y; r4.z -= x.z; r4.w -= x.w;
+        }
+        if (p.RowScale) {
+          const float sc = p.RowScale[row0 + i];
+          const float4 x = *reinterpret_cast<const float4*>(p.ScaleIn + o);
+          r4.x = fmaf(sc, x.x, r4.x); r4.y = fmaf(sc, x.y, r4.y); r4.z = fmaf(sc, x.z, r4.z); r4.w = fmaf(sc, x.w, r4.w);
+        }
+        *reinterpret_cast<float4*>(p.Out + o) = r4;
+        if (p.Out2) *reinterpret_cast<float4*>(p.Out2 + o) = r4;
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" ::"r"(tmem_base) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
+// F <= 8: stream L once.  One CTA per 64-row tile, 8 warps.
+// ------------------------------------------------------------------------------------------------
+template <int FP>
+__device__ __forceinline__ void thin_epilogue(const GroupedArgs& p, long long row, const float (&acc)[FP]) {
+  const int F = p.F;
+#pragma unroll
+  for (int f = 0; f < FP; ++f) {
+    if (f >= F) break;
+    const long long o = row * F + f;
+    float v = p.cmul * acc[f];
+    if (p.add_identity) v = fmaf(p.cmul, p.In[o], v);
+    if (p.Add) v += p.Add[o];
+    if (p.Sub) v -= p.Sub[o];
+    if (p.RowScale) v = fmaf(p.RowScale[row], p.ScaleIn[o], v);
+    p.Out[o] = v;
+    if (p.Out2) p.Out2[o] = v;
+  }
+}
+
+// op = L: a warp owns 8 rows of the tile, four at a time; lanes stride over the columns (coalesced rows of L)
+template <int FP>
+__global__ void __launch_bounds__(256) grouped_thin_kernel(GroupedArgs p) {
+  const int g = p.tile_graph[blockIdx.x], m0 = p.tile_row[blockIdx.x];
+  const int n = p.n_nodes[g], F = p.F;
+  const long long row0 = p.node_off[g];
+  const float* __restrict__ Lg = p.L + p.lap_off[g];
+  const float* __restrict__ In = p.In + row0 * F;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int pass = 0; pass < 2; ++pass) {
+    const int i0 = m0 + warp * 8 + pass * 4;
+    if (i0 >= n) break;
+    float acc[4][FP];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int f = 0; f < FP; ++f) acc[r][f] = 0.f;
+    const float* lrow[4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) lrow[r] = Lg + (long long)min(i0 + r, n - 1) * n;  // rows past the end repeat the last one
+#pragma unroll 2
+    for (int j = lane; j < n; j += 32) {
+      float l[4], x[FP];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) l[r] = __ldg(lrow[r] + j);
+#pragma unroll
+      for (int f = 0; f < FP; ++f) x[f] = (f < F) ? __ldg(In + (long long)j * F + f) : 0.f;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int f = 0; f < FP; ++f) acc[r][f] = fmaf(l[r], x[f], acc[r][f]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int f = 0; f < FP; ++f)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[r][f] += __shfl_xor_sync(0xffffffffu, acc[r][f], o);
+    if (lane < 4 && i0 + lane < n) {
+      float mine[FP];
+#pragma unroll
+      for (int f = 0; f < FP; ++f) {
+        mine[f] = acc[0][f];
+#pragma unroll
+        for (int r = 1; r < 4; ++r)
+          if (lane == r) mine[f] = acc[r][f];
+      }
+      thin_epilogue<FP>(p, row0 + i0 + lane, mine);
+    }
+  }
+}
+
+// op = L^T: lane = output row of a 32-row segment (coalesced along the rows of L), the 8 warps are
+// 2 segments x 4 interleaved quarters of the contraction, summed through shared memory
+template <int FP>
+__global__ void __launch_bounds__(256) grouped_thin_kernel_t(GroupedArgs p) {
+  __shared__ float red[3][64][FP + 1];
+  const int g = p.tile_graph[blockIdx.x], m0 = p.tile_row[blockIdx.x];
+  const int n = p.n_nodes[g], F = p.F;
+  const long long row0 = p.node_off[g];
+  const float* __restrict__ Lg = p.L + p.lap_off[g];
+  const float* __restrict__ In = p.In + row0 * F;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int seg = warp & 1, jq = warp >> 1;
+  const int il = seg * 32 + lane, i = m0 + il;
+  float acc[FP];
+#pragma unroll
+  for (int f = 0; f < FP; ++f) acc[f] = 0.f;
+  if (i < n) {
+#pragma unroll 4
+    for (int j = jq; j < n; j += 4) {
+      const float l = __ldg(Lg + (long long)j * n + i);
+#pragma unroll
+      for (int f = 0; f < FP; ++f)
+        if (f < F) acc[f] = fmaf(l, __ldg(In + (long long)j * F + f), acc[f]);
+    }
+  }
+  if (jq > 0) {
+#pragma unroll
+    for (int f = 0; f < FP; ++f) red[jq - 1][il][f] = acc[f];
+  }
+  __syncthreads();
+  if (jq == 0 && i < n) {
+#pragma unroll
+    for (int f = 0; f < FP; ++f) acc[f] += red[0][il][f] + red[1][il][f] + red[2][il][f];
+    thin_epilogue<FP>(p, row0 + i, acc);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+}  // namespace bt
+
+bool grouped_tc_supported(const GroupedArgs& g) {
+  static const bool off = getenv("AGCN_DISABLE_BIG_TC") != nullptr || getenv("AGCN_DISABLE_TCGEN05") != nullptr;
+  if (off) return false;
+  auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  if (g.F < 16 || (g.F & 3)) return false;
+  return al16(g.In) && al16(g.Out) && al16(g.Out2) && al16(g.Add) && al16(g.Sub) && al16(g.ScaleIn);
+}
+
+int grouped_tc(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStream_t st) {
+  using namespace bt;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return AGCN_ERR_CUDA;
+  }
+  // In as a [R, F] row-major matrix, boxes of 32 nodes x 32 columns, 128B swizzle with 32B atoms (MN-major TF32 operand)
+  CUtensorMap map;
+  cuuint64_t gdim[2] = {(cuuint64_t)g.F, (cuuint64_t)plan->R};
+  cuuint64_t gstride[1] = {(cuuint64_t)g.F * sizeof(float)};
+  cuuint32_t box[2] = {32, 32};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g.In), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (grouped_tc) failed with code " + std::to_string((int)r));
+    return AGCN_ERR_CUDA;
+  }
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(grouped_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
+  });
+  dim3 grid(tiles, (g.F + BN - 1) / BN);
+  grouped_tc_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(map, g);
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+bool grouped_thin_supported(const GroupedArgs& g) {
+  static const bool off = getenv("AGCN_DISABLE_BIG_THIN") != nullptr;
+  return !off && g.F >= 1 && g.F <= 8;
+}
+
+int grouped_thin(int tiles, const GroupedArgs& g, cudaStream_t st) {
+  using namespace bt;
+  if (g.F <= 4) {
+    if (g.transL)
+      grouped_thin_kernel_t<4><<<tiles, 256, 0, st>>>(g);
+    else
+      grouped_thin_kernel<4><<<tiles, 256, 0, st>>>(g);
+  } else {
+    if (g.transL)
+      grouped_thin_kernel_t<8><<<tiles, 256, 0, st>>>(g);
+    else
+      grouped_thin_kernel<8><<<tiles, 256, 0, st>>>(g);
+  }
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+}  // namespace agcn

@@ -8,25 +8,6 @@
 
 namespace agcn {
 
-struct GroupedArgs {
-  const int32_t* n_nodes;
-  const int32_t* node_off;
-  const int64_t* lap_off;
-  const int32_t* tile_graph;
-  const int32_t* tile_row;
-  const float* L;
-  int add_identity, transL;
-  const float* In;
-  const float* Sub;
-  const float* Add;
-  float* Out;
-  float* Out2;
-  float cmul;
-  int F;
-  const float* RowScale;  // optional: Out += RowScale[row] * ScaleIn[row, c]
-  const float* ScaleIn;
-};
-
 constexpr int GM = 64, GN = 64, GK = 16;
 
 __global__ void __launch_bounds__(256) grouped_lap_gemm_kernel(GroupedArgs p) {
@@ -119,6 +100,22 @@ __global__ void __launch_bounds__(256) grouped_lap_gemm_kernel(GroupedArgs p) {
   }
 }
 
+int grouped_simt(int tiles, const GroupedArgs& g, cudaStream_t st) {
+  dim3 grid(tiles, (g.F + GN - 1) / GN);
+  grouped_lap_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+// One Chebyshev-shaped product over the first `tiles` row tiles of the plan: tensor cores when the shape allows
+// (agcn_big_tc.cu), a streaming kernel for the 3/4-feature first layers of point clouds, else the SIMT kernel above.
+int grouped_launch(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStream_t st) {
+  if (tiles <= 0) return AGCN_OK;
+  if (grouped_thin_supported(g)) return grouped_thin(tiles, g, st);
+  if (grouped_tc_supported(g)) return grouped_tc(plan, tiles, g, st);
+  return grouped_simt(tiles, g, st);
+}
+
 static GroupedArgs base_args(const agcn_plan* plan) {
   GroupedArgs k{};
   k.n_nodes = plan->d_n;
@@ -134,7 +131,6 @@ int large_chebyshev_fwd(const GraphArgs& a, cudaStream_t st) {
   if (plan->large_tiles == 0 || a.K <= 1) return AGCN_OK;
   const bool shortcut = (a.Lall == nullptr);
   const int64_t slice = (int64_t)plan->R * a.F;
-  dim3 grid(plan->large_tiles, (a.F + GN - 1) / GN);
   for (int k = 1; k < a.K; ++k) {
     GroupedArgs g = base_args(plan);
     g.L = shortcut ? a.Lint : a.Lall;
@@ -147,8 +143,7 @@ int large_chebyshev_fwd(const GraphArgs& a, cudaStream_t st) {
     g.Out2 = nullptr;
     g.cmul = (k == 1) ? 1.f : 2.f;
     g.F = a.F;
-    grouped_lap_gemm_kernel<<<grid, 256, 0, st>>>(g);
-    AGCN_LAUNCH_CHECK();
+    if (int rc = grouped_launch(plan, plan->large_tiles, g, st)) return rc;
   }
   return AGCN_OK;
 }
@@ -161,7 +156,6 @@ int large_recurrence_bwd(const GraphArgs& a, float* G, bool big_only, cudaStream
   if (tiles == 0 || a.K <= 1) return AGCN_OK;
   const bool shortcut = (a.Lall == nullptr);
   const int64_t slice = (int64_t)plan->R * a.F;
-  dim3 grid(tiles, (a.F + GN - 1) / GN);
   for (int j = a.K - 2; j >= 0; --j) {
     GroupedArgs g = base_args(plan);
     g.L = shortcut ? a.Lint : a.Lall;
@@ -174,8 +168,7 @@ int large_recurrence_bwd(const GraphArgs& a, float* G, bool big_only, cudaStream
     g.Out2 = (j == 0) ? a.dX : nullptr;
     g.cmul = (j + 1 >= 2) ? 2.f : 1.f;
     g.F = a.F;
-    grouped_lap_gemm_kernel<<<grid, 256, 0, st>>>(g);
-    AGCN_LAUNCH_CHECK();
+    if (int rc = grouped_launch(plan, tiles, g, st)) return rc;
   }
   return AGCN_OK;
 }
@@ -189,10 +182,7 @@ int grouped_rows_gemm(const agcn_plan* plan, int tiles, const float* Lmat, const
   g.In = In; g.Sub = nullptr; g.Add = nullptr;
   g.Out = Out; g.Out2 = nullptr; g.cmul = cmul; g.F = F;
   g.RowScale = row_scale; g.ScaleIn = scale_in;
-  dim3 grid(tiles, (F + GN - 1) / GN);
-  grouped_lap_gemm_kernel<<<grid, 256, 0, st>>>(g);
-  AGCN_LAUNCH_CHECK();
-  return AGCN_OK;
+  return grouped_launch(plan, tiles, g, st);
 }
 
 }  // namespace agcn

@@ -235,6 +235,37 @@ int big_build_laplacian(const GraphArgs& a, bool need_W, float* big_work, cudaSt
 int big_dL(const GraphArgs& a, const float* U, cudaStream_t st);
 int big_laplacian_bwd(const GraphArgs& a, float* big_work, cudaStream_t st);
 
+// ---------------------------------------------------------------- row-tiled products of the graphs above
+// cheb_small_max nodes (agcn_graph_large.cu, agcn_big_tc.cu):
+//     Out = cmul * op(L_g) * In  (+ Add)  (- Sub)  (+ RowScale .* ScaleIn),   op(L) = L (+ I) | L^T (+ I)
+// over (graph, 64-row tile) work items of the plan's tile list.
+struct GroupedArgs {
+  const int32_t* n_nodes;
+  const int32_t* node_off;
+  const int64_t* lap_off;
+  const int32_t* tile_graph;
+  const int32_t* tile_row;
+  const float* L;
+  int add_identity, transL;
+  const float* In;
+  const float* Sub;
+  const float* Add;
+  float* Out;
+  float* Out2;
+  float cmul;
+  int F;
+  const float* RowScale;  // optional: Out += RowScale[row] * ScaleIn[row, c]
+  const float* ScaleIn;
+};
+int grouped_launch(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStream_t st);
+int grouped_simt(int tiles, const GroupedArgs& g, cudaStream_t st);
+// tcgen05 3xTF32 implementation (F % 4 == 0, F >= 16, 16-byte aligned node matrices)
+bool grouped_tc_supported(const GroupedArgs& g);
+int grouped_tc(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStream_t st);
+// streaming implementation for F <= 8 (HBM-bound: the Laplacian is read once, coalesced)
+bool grouped_thin_supported(const GroupedArgs& g);
+int grouped_thin(int tiles, const GroupedArgs& g, cudaStream_t st);
+
 // ---------------------------------------------------------------- fused tile kernels (agcn_fused_tile.cu)
 void fused_profile_enable(int on);
 int fused_profile_read(float* ms_sum, int* launches);

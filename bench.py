@@ -68,6 +68,14 @@ class ClockSampler(object):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def count(self):
+        return len(self.lines)
+
+    def wait_first(self, timeout_s):
+        t_end = time.time() + timeout_s
+        while self.proc is not None and not self.lines and time.time() < t_end:
+            time.sleep(0.02)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -378,11 +386,20 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    if graph is not None:
-        ms_step = timed(graph.replay, args.steps, args.warmup)
-    else:
-        ms_step = timed(resident_step, args.steps, args.warmup)
-    clocks = sampler.stop() if rank == 0 else None
+        sampler.wait_first(2.0)          # nvidia-smi needs ~0.1-0.5 s before its first line
+    step_fn = graph.replay if graph is not None else resident_step
+    ms_step = timed(step_fn, args.steps, args.warmup)
+    # the timed region is a few tens of milliseconds, shorter than nvidia-smi's sampling period: every rank keeps the
+    # SAME step running (untimed, same count on every rank: ms_step is the max over ranks) for ~0.7 s, so the clocks
+    # line describes this load and not an idle GPU
+    for _ in range(int(min(0.7 / (ms_step * 1e-3), 5000))):
+        step_fn()
+    torch.cuda.synchronize()
+    clocks = None
+    if rank == 0:
+        clocks = sampler.stop()
+        clocks["note"] = ("sampled every 100 ms from just before the timed region to the end of ~0.7 s of the same step "
+                          "replayed back to back right after it")
     mark("timed steps done: %.3f ms (%s)" % (ms_step, launch_mode))
     ms_e2e_serial = timed(e2e_step, max(3, args.steps // 2), 3)
     ms_e2e_packed = timed(e2e_packed_step, max(3, args.steps // 2), 3)
