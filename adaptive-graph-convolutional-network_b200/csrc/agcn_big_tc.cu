@@ -461,9 +461,19 @@ static EncodeTiledFn encode_fn() {
 
 }  // namespace bt
 
+// AGCN_BIG_TC=0|1 overrides the default (run both ways when comparing against the SIMT row-tiled kernel)
+#define AGCN_BIG_TC_DEFAULT 0
+static bool big_paths_on() {
+  static const bool on = [] {
+    const char* e = getenv("AGCN_BIG_TC");
+    return e ? atoi(e) != 0 : AGCN_BIG_TC_DEFAULT != 0;
+  }();
+  return on;
+}
+
 bool grouped_tc_supported(const GroupedArgs& g) {
-  static const bool off = getenv("AGCN_DISABLE_BIG_TC") != nullptr || getenv("AGCN_DISABLE_TCGEN05") != nullptr;
-  if (off) return false;
+  static const bool off = getenv("AGCN_DISABLE_TCGEN05") != nullptr;
+  if (off || !big_paths_on()) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (g.F < 16 || (g.F & 3)) return false;
   return al16(g.In) && al16(g.Out) && al16(g.Out2) && al16(g.Add) && al16(g.Sub) && al16(g.ScaleIn);
@@ -500,8 +510,7 @@ int grouped_tc(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStrea
 }
 
 bool grouped_thin_supported(const GroupedArgs& g) {
-  static const bool off = getenv("AGCN_DISABLE_BIG_THIN") != nullptr;
-  return !off && g.F >= 1 && g.F <= 8;
+  return big_paths_on() && g.F >= 1 && g.F <= 8;
 }
 
 int grouped_thin(int tiles, const GroupedArgs& g, cudaStream_t st) {
