@@ -80,6 +80,21 @@ class GraphBatch(object):
         _lib.check(_lib.lib().agcn_pack_lap(self._handle, _ptr(padded), _ptr(out), _stream_ptr()))
         return out
 
+    def pack_lap_csr(self, indptr, indices, values):
+        """Batch CSR (host numpy: indptr [R+1] over the packed rows, column indices inside each graph, fp32 values)
+        -> packed [sum n^2] on the device; the arrays travel through pinned memory."""
+        indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+        indices = np.ascontiguousarray(indices, dtype=np.int32)
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        if indptr.size != self.total_nodes + 1 or indices.size != values.size or int(indptr[-1]) != indices.size:
+            raise ValueError("CSR arrays do not match the batch (indptr needs total_nodes + 1 entries)")
+        dev = [torch.from_numpy(a).pin_memory().to(self.device, non_blocking=True) for a in (indptr, indices, values)]
+        out = torch.empty(self.total_lap, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().agcn_pack_lap_csr(self._handle, _ptr(dev[0]), _ptr(dev[1]), _ptr(dev[2]), _ptr(out),
+                                                    _stream_ptr()))
+        return out
+
     def unpack_lap(self, packed):
         packed = packed.contiguous()
         out = torch.empty(self.batch_size, self.max_atom, self.max_atom, device=packed.device, dtype=torch.float32)

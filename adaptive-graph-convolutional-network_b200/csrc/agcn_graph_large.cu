@@ -186,3 +186,26 @@ int grouped_rows_gemm(const agcn_plan* plan, int tiles, const float* Lmat, const
 }
 
 }  // namespace agcn
+
+// Tuning / debugging aid (include/agcn_sgcll.h): one row-tiled product over every graph above cheb_small_max,
+// impl 0 = dispatcher, 1 = SIMT, 2 = tensor cores, 3 = thin.
+extern "C" int agcn_debug_grouped_product(const agcn_plan* plan, const float* d_L, const float* d_In, float* d_Out,
+                                          int32_t F, int32_t transL, int32_t add_identity, float cmul, int32_t impl,
+                                          void* stream) {
+  using namespace agcn;
+  AGCN_REQUIRE(plan && d_L && d_In && d_Out && F >= 1, "null pointer or F < 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (int rc = plan_use(plan, st)) return rc;
+  GroupedArgs g = base_args(plan);
+  g.L = d_L; g.add_identity = add_identity; g.transL = transL;
+  g.In = d_In; g.Sub = nullptr; g.Add = nullptr; g.Out = d_Out; g.Out2 = nullptr; g.cmul = cmul; g.F = F;
+  const int tiles = plan->large_tiles;
+  if (tiles == 0) return AGCN_OK;
+  switch (impl) {
+    case 1: return grouped_simt(tiles, g, st);
+    case 2: return grouped_tc(plan, tiles, g, st);
+    case 3: return grouped_thin(tiles, g, st);
+    default: return grouped_launch(plan, tiles, g, st);
+  }
+}
+

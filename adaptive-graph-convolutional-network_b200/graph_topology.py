@@ -39,7 +39,8 @@ class GraphTopologyMol(object):
     def batch_to_feed_dict(self, batch, layout='packed'):
         """graph_topology.py:100-135.  layout='padded' reproduces the reference's wire format (lists
         of B padded tensors); layout='packed' (default) builds the native HBM layout directly from
-        the ragged host arrays, so the padding never crosses PCIe."""
+        the ragged host arrays, so the padding never crosses PCIe; layout='csr' ships the Laplacians as the CSR
+        arrays Graph.compute_laplacian produced and expands them on the device (agcn_pack_lap_csr)."""
         graphs = list(batch)
         n_nodes = np.asarray([g.node_features.shape[0] for g in graphs], dtype=np.int32)
         mol_slice = np.stack([np.asarray([n, -1], dtype=np.int32) for n in n_nodes])
@@ -57,7 +58,20 @@ class GraphTopologyMol(object):
             feats = torch.from_numpy(feats).pin_memory().to(self.device, non_blocking=True)
             laps = torch.from_numpy(laps).pin_memory().to(self.device, non_blocking=True)
             node_features, laplacians = PackedNodes(feats, plan), PackedLaplacians(laps, plan)
+        elif layout == 'csr':
+            # Graph.Laplacian is already scipy CSR (graph_structure.py:107): ship its three arrays, expand on the device
+            feats = np.concatenate([np.asarray(g.node_features, np.float32) for g in graphs], 0)
+            mats = [g.Laplacian.tocsr() for g in graphs]
+            for m in mats:
+                m.sum_duplicates()
+            nnz = np.concatenate([[0], np.cumsum([m.nnz for m in mats])]).astype(np.int64)
+            indptr = np.concatenate([m.indptr[:-1].astype(np.int64) + o for m, o in zip(mats, nnz[:-1])] + [nnz[-1:]])
+            indices = np.concatenate([m.indices for m in mats]).astype(np.int32)
+            values = np.concatenate([m.data for m in mats]).astype(np.float32)
+            feats = torch.from_numpy(feats).pin_memory().to(self.device, non_blocking=True)
+            laps = plan.pack_lap_csr(indptr.astype(np.int32), indices, values)
+            node_features, laplacians = PackedNodes(feats, plan), PackedLaplacians(laps, plan)
         else:
-            raise ValueError("layout must be 'packed' or 'padded'")
+            raise ValueError("layout must be 'packed', 'csr' or 'padded'")
         return {'node_features': node_features, 'original_laplacian': laplacians,
                 'data_slice': mol_slice, 'lap_slice': L_slice, '_batch': plan}

@@ -3,3 +3,4 @@ from .basic_layer import Layer
 from .dropout import Dropout
 from .graphconv import SGC_LL, glorot, zeros, truncate_normal
 from .graphconv_reslap import SGC_LL_Reslap
+from .graphpool import GraphPoolMol

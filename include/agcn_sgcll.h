@@ -113,6 +113,14 @@ int agcn_fused_profile_read(float* ms_sum, int* launches);
  * launches record a per-tile timeline of nanosecond stamps into it.  NULL switches the recording off. */
 int agcn_fused_debug_set(void* d_buf);
 
+/* Tuning / debugging aid (no reference counterpart): Out = cmul * op(L_g) In over the rows of every graph with more
+ * than AGCN_CHEB_SMALL_MAX nodes (the row-tiled path; other rows of Out are not written), op = L (+I) or L^T (+I);
+ * impl 0 = the library's own choice, 1 = SIMT kernel, 2 = tcgen05 kernel (F % 4 == 0, F >= 16), 3 = streaming kernel
+ * (F <= 8).  tools/dbg_grouped.py compares the implementations block by block. */
+int agcn_debug_grouped_product(const agcn_plan* plan, const float* d_L /*packed*/, const float* d_In /*[R,F]*/,
+                               float* d_Out /*[R,F]*/, int32_t F, int32_t transL, int32_t add_identity, float cmul,
+                               int32_t impl, void* stream);
+
 /* ---- layout conversion (pad_data2sparse / pad_Lap2sparse, graph_topology.py:84-98;
  *      tf.slice at graphconv.py:153-154; tf.pad at graphconv.py:249-251) ------------------ */
 int agcn_pack_nodes(const agcn_plan* plan, const float* d_padded /*[B,Nmax,F]*/, float* d_packed /*[R,F]*/,
@@ -120,6 +128,21 @@ int agcn_pack_nodes(const agcn_plan* plan, const float* d_padded /*[B,Nmax,F]*/,
 int agcn_unpack_nodes(const agcn_plan* plan, const float* d_packed, float* d_padded, int32_t F, void* stream);
 int agcn_pack_lap(const agcn_plan* plan, const float* d_padded /*[B,Nmax,Nmax]*/, float* d_packed, void* stream);
 int agcn_unpack_lap(const agcn_plan* plan, const float* d_packed, float* d_padded, void* stream);
+/* The same packed matrices from the CSR form Graph.compute_laplacian produces (graph_structure.py:100-107), so the
+ * dense [Nmax,Nmax] padding of pad_Lap2sparse never exists: d_indptr [R+1] row pointers over the packed rows of the
+ * whole batch, d_indices column inside the row's own graph, d_values fp32. */
+int agcn_pack_lap_csr(const agcn_plan* plan, const int32_t* d_indptr, const int32_t* d_indices, const float* d_values,
+                      float* d_packed, void* stream);
+
+/* ---- GraphPoolMol (graphpool.py:55-110) ------------------------
+ * Y[i,:] = max over {j : L[i,j] != 0} of X[j,:] per graph (a row without a non-zero keeps X[i,:]).  d_argmax
+ * (optional, [R,F] int32) receives the packed row that supplied each maximum.  The reference computes this inside
+ * tf.py_func (no gradient); agcn_graph_pool_backward is the arg-max gradient for callers that want one:
+ * dX[argmax[r,f], f] += dY[r,f]. */
+int agcn_graph_pool(const agcn_plan* plan, const float* d_X /*[R,F]*/, const float* d_L /*packed*/, float* d_Y,
+                    int32_t* d_argmax, int32_t F, void* stream);
+int agcn_graph_pool_backward(const agcn_plan* plan, const float* d_dY, const int32_t* d_argmax, float* d_dX, int32_t F,
+                             void* stream);
 
 /* ---- SGC-LL layer ----------------------------------------------------- */
 /* sizes in BYTES of the two scratch areas: `saved` lives from forward to backward, `work` only

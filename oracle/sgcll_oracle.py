@@ -229,6 +229,34 @@ def make_params(F, Fo, K, variant="SGC_LL", seed=0, dtype=torch.float32, perturb
 
 
 # --------------------------------------------------------------------------
+# GraphPoolMol restated (models/layers/graphpool.py:91-105)
+# --------------------------------------------------------------------------
+def graph_pool_literal(x: np.ndarray, L: np.ndarray) -> np.ndarray:
+    """Line-by-line restatement of the ``func`` closure of graphpool.py:91-105: atom i takes the
+    feature-wise maximum over the atoms its Laplacian row marks (non-zero entries); a row without
+    a non-zero entry keeps its own features."""
+    acc_x = []
+    for i, l in enumerate(list(L)):
+        idx = np.nonzero(l)
+        self_neighbor_atoms = x[idx]
+        if len(self_neighbor_atoms) != 0:
+            pooled_x = np.amax(self_neighbor_atoms, axis=0)
+        else:
+            pooled_x = x[i]
+        acc_x.append(pooled_x)
+    return np.vstack(acc_x)
+
+
+def graph_pool(x: torch.Tensor, L: torch.Tensor) -> torch.Tensor:
+    """Vectorised form of the same (differentiable through the arg-max, which the reference is not)."""
+    mask = L != 0
+    big = x.unsqueeze(0).expand(L.shape[0], -1, -1).masked_fill(~mask.unsqueeze(-1), float("-inf"))
+    pooled = big.max(dim=1).values
+    empty = ~mask.any(dim=1)
+    return torch.where(empty.unsqueeze(-1), x, pooled)
+
+
+# --------------------------------------------------------------------------
 # host-side graph preprocessing restated (models/graph_structure.py:75-130)
 # --------------------------------------------------------------------------
 def compute_laplacian_dense(adj_lists) -> np.ndarray:

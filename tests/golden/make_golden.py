@@ -10,6 +10,7 @@ the GPU box; the produced .npz files are committed and travel):
   models/layers/graphconv.py:163-209 and graphconv_reslap.py:136-182 with ``ast``
   at run time -- no reference source is copied into this repository -- compiled
   as a free function and executed on seeded inputs.
+* ``graph_pool.npz``: the same for the ``func`` closure of models/layers/graphpool.py:91-105.
 * ``graph_laplacian.npz``: ``Graph(...).Laplacian`` from the reference's
   models/graph_structure.py, imported as a module from its file.
 
@@ -94,6 +95,30 @@ def main():
     g3 = gs.Graph(np.zeros((3, 2), np.float32), [[1], [0, 2], [1]], 4, 0)
     out["tiny3/has_Lap"] = np.array(g3.has_Lap)
     np.savez_compressed(os.path.join(HERE, "graph_laplacian.npz"), **out)
+
+    # GraphPoolMol: the reference's py_func body (graphpool.py:91-105), executed on seeded inputs
+    func_pool = extract_func(os.path.join(REF, "models/layers/graphpool.py"))
+    out = {}
+    pool_cases = {
+        "mol18_f75": (O.tox21_like_features(rng, 18), gs.MolGraph(np.zeros((18, 3), np.float32), adjs["mol18"]).Laplacian),
+        "isolated5_f4": (rng.standard_normal((5, 4)).astype(np.float32),
+                         gs.MolGraph(np.zeros((5, 3), np.float32), adjs["isolated5"]).Laplacian),
+        "mol132_f64": (np.maximum(rng.standard_normal((132, 64)), 0).astype(np.float32),
+                       gs.MolGraph(np.zeros((132, 3), np.float32), adjs["mol132"]).Laplacian),
+    }
+    for name, (x, lap) in pool_cases.items():
+        Ld = np.asarray(lap.todense()).astype(np.float32)
+        out[name + "/x"], out[name + "/L"] = x, Ld
+        out[name + "/y"] = func_pool(x, Ld)
+    n = 50                                      # dense thresholded point-cloud graph with an all-zero row
+    pts = rng.standard_normal((n, 3)).astype(np.float32)
+    A = (np.linalg.norm(pts[:, None] - pts[None], axis=-1) < 1.2).astype(np.float32)
+    d = 1.0 / np.sqrt(A.sum(1))
+    Ld = (np.eye(n, dtype=np.float32) - d[:, None] * A * d[None, :]).astype(np.float32)
+    Ld[7, :] = 0.0
+    out["cloud50_f3/x"], out["cloud50_f3/L"] = pts, Ld
+    out["cloud50_f3/y"] = func_pool(pts, Ld)
+    np.savez_compressed(os.path.join(HERE, "graph_pool.npz"), **out)
 
     # oracle self-regression (NOT a reference output)
     import torch

@@ -227,7 +227,11 @@ def _dense_laplacians(n_list, Nmax, seed):
 @pytest.mark.parametrize("sizes,F,Fo,K", [([1024, 1024, 1024], 3, 32, 3),          # ModelNet40-shape
                                           ([13, 700, 145, 1024, 64, 144, 333], 4, 26, 3),   # Sydney-shape, ragged
                                           ([2048, 150], 32, 32, 2),              # sweep point
-                                          ([513, 200], 64, 128, 5)])
+                                          ([513, 200], 64, 128, 5),
+                                          ([300, 145, 257, 1000], 256, 32, 3),   # two 128-column blocks, ragged n
+                                          ([161, 450], 96, 48, 4),               # three 32-column boxes
+                                          ([200, 150, 333], 5, 16, 3),           # thin path, F in 5..8
+                                          ([129, 192, 128], 128, 128, 3)])       # tile edges: n = 128 k + 1, 64-row remainder
 def test_large_graphs_row_tiled_path(sizes, F, Fo, K):
     """Graphs that do not fit in shared memory (n > 144) run through the grouped-GEMM path; small and large
     graphs mix freely in one batch."""
@@ -240,6 +244,24 @@ def test_large_graphs_row_tiled_path(sizes, F, Fo, K):
     cu = cuda_run(X, L, n, p, K, "SGC_LL", "reference_literal", "reference", cot_Y=cY, want_res=False)
     errs = compare(cu, orc, skip=("res_L", "res_W", "L_all"))
     print(sizes, errs)
+
+
+@pytest.mark.parametrize("F,Fo,K", [(32, 16, 3), (4, 8, 4)])
+def test_nonsymmetric_laplacian_transpose_paths(F, Fo, K):
+    """The backward recurrence multiplies by L^T: a non-symmetric intrinsic matrix tells L from L^T in every size
+    class (fused tiles, per-graph shared-memory kernels, row-tiled / tensor-core / thin kernels)."""
+    sizes = [150, 70, 20, 300, 129]
+    Nmax = max(sizes)
+    X, _, n = make_batch(sizes, F, Nmax, seed=8)
+    L = _dense_laplacians(sizes, Nmax, seed=2)
+    rng = np.random.default_rng(77)
+    for g, k in enumerate(sizes):
+        L[g, :k, :k] += (rng.standard_normal((k, k)) * 0.02).astype(np.float32)
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=5, dtype=torch.float64)
+    cY = _cot((len(sizes), Nmax, Fo), 21)
+    orc = oracle_run(X, L, n, p, K, "SGC_LL", "reference_literal", "reference", cot_Y=cY)
+    cu = cuda_run(X, L, n, p, K, "SGC_LL", "reference_literal", "reference", cot_Y=cY, want_res=False)
+    print(compare(cu, orc, skip=("res_L", "res_W", "L_all")))
 
 
 @pytest.mark.parametrize("variant,laplacian,metric_grad,with_prev", [

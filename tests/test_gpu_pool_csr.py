@@ -1,0 +1,103 @@
+"""GPU parity of the callers / data formats either side of the SGC-LL path:
+GraphPoolMol against the reference-generated golden vectors and the oracle, CSR Laplacians against the dense
+packing.  Everything goes through the C ABI (agcn_graph_pool, agcn_pack_lap_csr)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import sgcll_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _pad(mats, Nmax, cols=None):
+    out = np.zeros((len(mats), Nmax, cols if cols else Nmax), np.float32)
+    for g, m in enumerate(mats):
+        out[g, :m.shape[0], :m.shape[1]] = m
+    return out
+
+
+def test_graph_pool_matches_reference_golden_bit_exact():
+    import agcn_b200
+    gold = np.load(os.path.join(GOLD, "graph_pool.npz"))
+    names = sorted({k.split("/")[0] for k in gold.files})
+    dev = torch.device("cuda:0")
+    for name in names:            # one graph per call: the feature widths differ
+        x, L, y = gold[name + "/x"], gold[name + "/L"], gold[name + "/y"]
+        n, F = x.shape
+        Nmax = n + 3
+        layer = agcn_b200.GraphPoolMol(1)
+        out = layer({"node_features": [torch.tensor(_pad([x], Nmax, F)[0], device=dev)],
+                     "original_laplacian": [torch.tensor(_pad([L], Nmax)[0], device=dev)],
+                     "data_slice": np.array([[n, -1]], np.int32), "lap_slice": np.array([[n, n]], np.int32)})
+        got = out[0].cpu().numpy()
+        assert np.array_equal(got[:n], y), name
+        assert np.array_equal(got[n:], np.zeros((Nmax - n, F), np.float32)), name   # padded rows stay +0.0
+
+
+@pytest.mark.parametrize("F", [3, 64, 130, 300])
+def test_graph_pool_batch_and_argmax_gradient(F):
+    import agcn_b200
+    from agcn_b200.layers.graphpool import graph_pool_packed
+    rng = np.random.default_rng(F)
+    sizes = [4, 33, 64, 150, 17, 1]
+    dev = torch.device("cuda:0")
+    xs = [rng.standard_normal((n, F)).astype(np.float32) for n in sizes]
+    Ls = []
+    for n in sizes:
+        A = (rng.random((n, n)) < min(0.5, 6.0 / n)).astype(np.float32)
+        A = np.maximum(A, A.T)
+        if n > 2:
+            A[1, :] = 0                       # a row without a marked node
+        Ls.append(A * rng.standard_normal((n, n)).astype(np.float32))
+    batch = agcn_b200.GraphBatch(sizes, max(sizes), device=dev)
+    X = torch.tensor(np.concatenate(xs), device=dev, requires_grad=True)
+    L = torch.tensor(np.concatenate([l.reshape(-1) for l in Ls]), device=dev)
+    Y = graph_pool_packed(X, L, batch, "argmax")
+    cot = torch.tensor(rng.standard_normal((sum(sizes), F)).astype(np.float32), device=dev)
+    (Y * cot).sum().backward()
+    off = 0
+    for x, l in zip(xs, Ls):
+        n = x.shape[0]
+        xt = torch.tensor(x, dtype=torch.float64, requires_grad=True)
+        yo = O.graph_pool(xt, torch.tensor(l, dtype=torch.float64))
+        assert np.array_equal(Y[off:off + n].detach().cpu().numpy(), O.graph_pool_literal(x, l))
+        (yo * cot[off:off + n].cpu().double()).sum().backward()
+        assert O.rel_err(X.grad[off:off + n].cpu(), xt.grad) <= 1e-6   # continuous data: the arg-max is unique
+        off += n
+    # reference semantics: the pooling is a py_func, no gradient flows (graphpool.py:107)
+    X2 = X.detach().clone().requires_grad_(True)
+    Y2 = graph_pool_packed(X2, L, batch, "reference")
+    assert torch.equal(Y2, Y.detach())
+    (Y2.sum() + (X2 * 0).sum()).backward()
+    assert float(X2.grad.abs().max()) == 0.0
+
+
+def test_csr_laplacians_expand_to_the_dense_packing_bit_exact():
+    import agcn_b200
+    rng = np.random.default_rng(5)
+    sizes = [4, 18, 132, 7, 64, 200]
+    graphs = []
+    for n in sizes:
+        feats = O.tox21_like_features(rng, n) if n <= 132 else rng.standard_normal((n, 75)).astype(np.float32)
+        graphs.append(agcn_b200.MolGraph(feats, O.molecule_like_adjacency(rng, n)))
+    topo = agcn_b200.GraphTopologyMol(75, batch_size=len(sizes), max_atom=max(sizes), device="cuda:0")
+    a = topo.batch_to_feed_dict(graphs, layout="packed")
+    b = topo.batch_to_feed_dict(graphs, layout="csr")
+    c = topo.batch_to_feed_dict(graphs, layout="padded")
+    assert torch.equal(a["original_laplacian"].data, b["original_laplacian"].data)
+    assert torch.equal(a["node_features"].data, b["node_features"].data)
+    for g, n in enumerate(sizes):
+        assert torch.equal(b["original_laplacian"][g], c["original_laplacian"][g][:n, :n])
+    # stale memory must not survive: expand into a buffer full of NaN
+    plan = b["_batch"]
+    mats = [g.Laplacian.tocsr() for g in graphs]
+    nnz = np.concatenate([[0], np.cumsum([m.nnz for m in mats])])
+    indptr = np.concatenate([m.indptr[:-1] + o for m, o in zip(mats, nnz[:-1])] + [nnz[-1:]])
+    out = plan.pack_lap_csr(indptr, np.concatenate([m.indices for m in mats]), np.concatenate([m.data for m in mats]))
+    assert torch.equal(out, a["original_laplacian"].data) and bool(torch.isfinite(out).all())
+    with pytest.raises(ValueError):
+        plan.pack_lap_csr(indptr[:-1], np.concatenate([m.indices for m in mats]), np.concatenate([m.data for m in mats]))

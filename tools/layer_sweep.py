@@ -205,6 +205,9 @@ def main():
     ap.add_argument("--iters", type=int, default=7)
     ap.add_argument("--out", default=os.path.join(ROOT, "gpurun_out", "layer_sweep.jsonl"))
     ap.add_argument("--budget-s", type=float, default=240.0, help="stop starting new cases after this many seconds")
+    ap.add_argument("--match", default="", help="only cases whose key 'name F=.. K=.. sem' contains every one of these "
+                                                "comma-separated substrings, e.g. 'N=1024 ,F=128 ,K=3'")
+    ap.add_argument("--tag", default="", help="copied into every line (which build / environment produced it)")
     args = ap.parse_args()
     if not torch.cuda.is_available():
         raise RuntimeError("layer_sweep.py needs a CUDA device; there is no CPU path")
@@ -215,6 +218,9 @@ def main():
     t0 = time.time()
     with open(args.out, "a") as fh:
         for c in cases(set(args.group.split(","))):
+            key = "%s F=%d K=%d %s " % (c["name"] + " ", c["F"], c["K"], c["sem"])
+            if any(m not in key for m in args.match.split(",") if m):
+                continue
             if time.time() - t0 > args.budget_s:
                 print("budget reached, stopping", file=sys.stderr)
                 break
@@ -227,6 +233,8 @@ def main():
                     fh.write(json.dumps(line) + "\n")
                     print(json.dumps(line))
                     break
+            if args.tag:
+                line["tag"] = args.tag
             fh.write(json.dumps(line) + "\n")
             fh.flush()
             print(json.dumps(line))
