@@ -6,9 +6,9 @@ O=gpurun_out
 run() { echo "== $*" ; timeout 170 "$@" ; echo "== rc $?" ; }
 {
 run python tools/dbg_grouped.py
-AGCN_BIG_TC=1 run python -m pytest tests -m gpu -q 2>&1 | tail -40
+run env AGCN_BIG_TC=1 python -m pytest tests -m gpu -q 2>&1 | tail -40
 run python -m pytest tests -m gpu -q 2>&1 | tail -15
-AGCN_BIG_TC=1 AGCN_CHEB_SMALL_MAX=64 run python -m pytest tests -m gpu -q 2>&1 | tail -25
+run env AGCN_BIG_TC=1 AGCN_CHEB_SMALL_MAX=64 python -m pytest tests -m gpu -q 2>&1 | tail -25
 } > $O/parity.log 2>&1
 tail -5 $O/parity.log
 rm -f $O/ab_sweep.jsonl
@@ -20,6 +20,6 @@ AGCN_BIG_TC=1 AGCN_CHEB_SMALL_MAX=64 timeout 100 python tools/layer_sweep.py --g
 wc -l $O/ab_sweep.jsonl
 timeout 200 python bench.py > $O/bench.json 2> $O/bench.err; tail -c 300 $O/bench.json
 AGCN_BIG_TC=1 AGCN_CHEB_SMALL_MAX=64 timeout 100 python bench.py --skip-cpu --no-paper > $O/bench_mid64.json 2> $O/bench_mid64.err
-timeout 150 ncu --set full --clock-control none --import-source on -k regex:grouped_tc -s 6 -c 2 -o $O/ncu_grouped_tc -f \
-  env AGCN_BIG_TC=1 python tools/layer_sweep.py --group c3 --match "F=128 ,literal" --iters 2 --out $O/ncu_sweep.jsonl > $O/ncu.log 2>&1
+AGCN_BIG_TC=1 timeout 150 ncu --set full --clock-control none --import-source on -k regex:grouped_tc -s 6 -c 2 -o $O/ncu_grouped_tc -f \
+  python tools/layer_sweep.py --group c3 --match "F=128 ,literal" --iters 2 --out $O/ncu_sweep.jsonl > $O/ncu.log 2>&1
 ls -la $O | tail -20
