@@ -214,44 +214,60 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
   } else {
     const int ww = warp - 2;              // worker warp 0..7
     const int wt = ww * 32 + lane;
-    // ---- A loader: 16 elements per thread and k-block.
-    //   op = L  : warp ww owns tile rows 16 ww .. 16 ww + 15, lane = column of the k-block (rows of L are contiguous)
-    //   op = L^T: warp ww owns items it = 16 ww + u -> (column c = it / 4, 32-row segment it % 4), lane = row of the
-    //             segment (columns of L^T are rows of L: contiguous along the tile rows)
-    auto load_a = [&](int kb, float (&v)[16]) {
+    // ---- A loader: every thread owns four 16-byte chunks (4 consecutive contraction columns of one operand row) per
+    // k-block, so the split costs one 128-bit shared store per chunk and half.
+    //   op = L  : 8 lanes cover the 32 columns of a row (a float4 each when the graph's rows are 16-byte aligned), a
+    //             warp covers rows 16 ww + 4 t + lane / 8, t = 0..3;
+    //   op = L^T: warp ww owns chunk ww (contraction rows 4 ww .. 4 ww + 3 of the k-block), lane = operand row of the
+    //             32-row segment t: four coalesced scalar loads along a row of L fill the chunk.
+    // Either way the 32 lanes of a store hit 4 x 8 distinct 16-byte slots of the swizzled tile: no bank conflicts.
+    const bool vecL = !p.transL && ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(Lg) & 15) == 0);
+    auto load_a = [&](int kb, float4 (&v)[4]) {
       if (kb >= num_kb) return;
+      const int k0 = kb * BK;
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        int r, c;
+      for (int t = 0; t < 4; ++t) {
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!p.transL) {
-          r = ww * 16 + u; c = lane;
+          const int i = m0 + ww * 16 + 4 * t + (lane >> 3), j = k0 + 4 * (lane & 7);
+          if (i < n && j < n) {
+            const float* src = Lg + (long long)i * n + j;
+            if (vecL) {
+              x = __ldg(reinterpret_cast<const float4*>(src));
+            } else {
+              x.x = __ldg(src);
+              if (j + 1 < n) x.y = __ldg(src + 1);
+              if (j + 2 < n) x.z = __ldg(src + 2);
+              if (j + 3 < n) x.w = __ldg(src + 3);
+            }
+          }
         } else {
-          const int it = ww * 16 + u;
-          c = it >> 2; r = (it & 3) * 32 + lane;
+          const int i = m0 + 32 * t + lane, j = k0 + 4 * ww;
+          if (i < n && j < n) {
+            const float* src = Lg + (long long)j * n + i;
+            x.x = __ldg(src);
+            if (j + 1 < n) x.y = __ldg(src + n);
+            if (j + 2 < n) x.z = __ldg(src + 2 * (long long)n);
+            if (j + 3 < n) x.w = __ldg(src + 3 * (long long)n);
+          }
         }
-        const int i = m0 + r, j = kb * BK + c;
-        float x = 0.f;
-        if (i < n && j < n) x = p.transL ? __ldg(Lg + (long long)j * n + i) : __ldg(Lg + (long long)i * n + j);
-        v[u] = x;
+        v[t] = x;
       }
     };
-    auto store_a = [&](uint32_t st, const float (&v)[16]) {
+    auto store_a = [&](uint32_t st, const float4 (&v)[4]) {
 #pragma unroll
-      for (int u = 0; u < 16; ++u) {
-        int r, c;
-        if (!p.transL) {
-          r = ww * 16 + u; c = lane;
-        } else {
-          const int it = ww * 16 + u;
-          c = it >> 2; r = (it & 3) * 32 + lane;
-        }
-        const uint32_t off = (uint32_t)(r * 128 + ((((c >> 2) ^ (r & 7)) << 4) | ((c & 3) << 2)));
-        const float hi = tf32_hi(v[u]);
-        sts32(st + off, hi);
-        sts32(st + A_BYTES + off, tf32_lo(v[u], hi));
+      for (int t = 0; t < 4; ++t) {
+        const int r = p.transL ? 32 * t + lane : ww * 16 + 4 * t + (lane >> 3);
+        const int chunk = p.transL ? ww : (lane & 7);
+        const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+        float4 hi, lo;
+        hi.x = tf32_hi(v[t].x); hi.y = tf32_hi(v[t].y); hi.z = tf32_hi(v[t].z); hi.w = tf32_hi(v[t].w);
+        lo.x = tf32_lo(v[t].x, hi.x); lo.y = tf32_lo(v[t].y, hi.y); lo.z = tf32_lo(v[t].z, hi.z); lo.w = tf32_lo(v[t].w, hi.w);
+        sts128(st + off, hi);
+        sts128(st + A_BYTES + off, lo);
       }
     };
-    auto step = [&](int kb, float (&v)[16]) {
+    auto step = [&](int kb, float4 (&v)[4]) {
       const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
       const uint32_t st = sbase + stage * STAGE_BYTES;
       if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -274,7 +290,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[stage]);
     };
-    float va[16], vb[16];
+    float4 va[4], vb[4];
     load_a(0, va);
     load_a(1, vb);
     for (int kb = 0; kb < num_kb; kb += 2) {
@@ -461,8 +477,8 @@ static EncodeTiledFn encode_fn() {
 
 }  // namespace bt
 
-// AGCN_BIG_TC=0|1 overrides the default (run both ways when comparing against the SIMT row-tiled kernel)
-#define AGCN_BIG_TC_DEFAULT 0
+// AGCN_BIG_TC=0 sends every row-tiled product back to the SIMT kernel (A/B runs: tools/gpu_check.sh)
+#define AGCN_BIG_TC_DEFAULT 1
 static bool big_paths_on() {
   static const bool on = [] {
     const char* e = getenv("AGCN_BIG_TC");

@@ -21,6 +21,9 @@
 // per-graph matrices of one tile (row pitch n | 1; two 64-node graphs fit).  Larger graphs would make their
 // tile the critical path of the launch: their recurrences run chunk-parallel in the per-graph kernels instead.
 #define AGCN_FUSE_MAX_N 64
+// Batches with at least this many graphs between AGCN_FUSE_MAX_N and AGCN_SMALL_MAX nodes send them through the
+// row-tiled products instead of the per-graph shared-memory recurrence kernels.
+#define AGCN_MID_TILED_MIN 32
 #define AGCN_FUSE_LCAP 8320
 
 namespace agcn {

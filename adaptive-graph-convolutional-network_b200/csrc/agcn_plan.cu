@@ -302,6 +302,14 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   int pos = 0;
   while (pos < B && p->n[p->order[pos]] > AGCN_SMALL_MAX) ++pos;
   p->large_count = pos;
+  // Mid-size graphs (above the fused tiles, up to AGCN_SMALL_MAX): a handful per batch (molecules) run their
+  // recurrences in one per-graph shared-memory kernel; when they are the bulk of the batch (the N = 128 sweep points)
+  // the row-tiled products (tensor cores) are ~2x faster (profiles/r01_m_layer_sweep.jsonl).
+  {
+    int mid = 0;
+    for (int i = pos; i < B && p->n[p->order[i]] > AGCN_FUSE_MAX_N; ++i) ++mid;
+    if (mid >= AGCN_MID_TILED_MIN) p->cheb_small_max = AGCN_FUSE_MAX_N;
+  }
   if (const char* e = getenv("AGCN_CHEB_SMALL_MAX")) p->cheb_small_max = std::min(AGCN_SMALL_MAX, std::max(16, atoi(e)));
   for (int i = 0; i < B && p->n[p->order[i]] > p->cheb_small_max; ++i) {
     const int g = p->order[i];
