@@ -8,7 +8,7 @@
 // [1024 x 1024] x [1024 x 128] contraction per graph: dense tensor-core work (north_star item 3).
 //
 // grouped_tc_kernel: one CTA per (graph, 128-row tile, 128-column block of the node matrix).
-//   warps 2-9 : A = L_g[rows, k-block of 32 columns] loaded from global memory (ragged n: rows are not 16-byte
+//   warps 2-17: A = L_g[rows, k-block of 32 columns] loaded from global memory (ragged n: rows are not 16-byte
 //               aligned, so no TMA), split into hi / lo TF32 halves and written as a 128 x 32 K-major SWIZZLE_128B
 //               operand (transposed on the fly for L^T); the B tile brought by TMA is split in place;
 //   warp 0    : TMA producer of B = In[k-block of 32 nodes, 128 columns]: row-major node matrix = MN-major operand,
@@ -39,7 +39,9 @@ constexpr int A_BYTES = TM * BK * 4;        // 16 KB: one half (hi or lo) of the
 constexpr int B_BYTES = BN * BK * 4;        // 16 KB: four 32 x 32 boxes
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 constexpr int STAGES = 3;
-constexpr int WORKERS = 256;
+constexpr int WORKERS = 512;            // 16 worker warps: the operand split is a latency chain per warp
+constexpr int NW = WORKERS / 32;
+constexpr int CPT = 1024 / WORKERS;     // 16-byte chunks of the A tile (and float4s of a full B tile) per thread and k-block
 constexpr int THREADS = 64 + WORKERS;
 constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
@@ -144,7 +146,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
   const uint32_t sbase = smem_u32(base);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
   uint64_t* full_bar = bars;              // B tile landed (TMA)
-  uint64_t* split_bar = bars + STAGES;    // A written and B split by the 8 worker warps
+  uint64_t* split_bar = bars + STAGES;    // A written and B split by the worker warps
   uint64_t* empty_bar = bars + 2 * STAGES;  // MMAs that read the stage retired
   uint64_t* tmem_full_bar = bars + 3 * STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
@@ -212,24 +214,24 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       umma_commit(tmem_full_bar);
     }
   } else {
-    const int ww = warp - 2;              // worker warp 0..7
+    const int ww = warp - 2;              // worker warp 0..NW-1
     const int wt = ww * 32 + lane;
     // ---- A loader: every thread owns four 16-byte chunks (4 consecutive contraction columns of one operand row) per
     // k-block, so the split costs one 128-bit shared store per chunk and half.
     //   op = L  : 8 lanes cover the 32 columns of a row (a float4 each when the graph's rows are 16-byte aligned), a
-    //             warp covers rows 16 ww + 4 t + lane / 8, t = 0..3;
-    //   op = L^T: warp ww owns chunk ww (contraction rows 4 ww .. 4 ww + 3 of the k-block), lane = operand row of the
-    //             32-row segment t: four coalesced scalar loads along a row of L fill the chunk.
+    //             warp covers rows (128 / NW) ww + 4 t + lane / 8;
+    //   op = L^T: warp ww owns chunk ww % 8 (contraction rows 4 c .. 4 c + 3 of the k-block) of the operand rows
+    //             (ww / 8) * 32 CPT + 32 t + lane: four coalesced scalar loads along a row of L fill the chunk.
     // Either way the 32 lanes of a store hit 4 x 8 distinct 16-byte slots of the swizzled tile: no bank conflicts.
     const bool vecL = !p.transL && ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(Lg) & 15) == 0);
-    auto load_a = [&](int kb, float4 (&v)[4]) {
+    auto load_a = [&](int kb, float4 (&v)[CPT]) {
       if (kb >= num_kb) return;
       const int k0 = kb * BK;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
+      for (int t = 0; t < CPT; ++t) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!p.transL) {
-          const int i = m0 + ww * 16 + 4 * t + (lane >> 3), j = k0 + 4 * (lane & 7);
+          const int i = m0 + ww * (TM / NW) + 4 * t + (lane >> 3), j = k0 + 4 * (lane & 7);
           if (i < n && j < n) {
             const float* src = Lg + (long long)i * n + j;
             if (vecL) {
@@ -242,7 +244,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
             }
           }
         } else {
-          const int i = m0 + 32 * t + lane, j = k0 + 4 * ww;
+          const int i = m0 + (ww >> 3) * (32 * CPT) + 32 * t + lane, j = k0 + 4 * (ww & 7);
           if (i < n && j < n) {
             const float* src = Lg + (long long)j * n + i;
             x.x = __ldg(src);
@@ -254,11 +256,11 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
         v[t] = x;
       }
     };
-    auto store_a = [&](uint32_t st, const float4 (&v)[4]) {
+    auto store_a = [&](uint32_t st, const float4 (&v)[CPT]) {
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int r = p.transL ? 32 * t + lane : ww * 16 + 4 * t + (lane >> 3);
-        const int chunk = p.transL ? ww : (lane & 7);
+      for (int t = 0; t < CPT; ++t) {
+        const int r = p.transL ? (ww >> 3) * (32 * CPT) + 32 * t + lane : ww * (TM / NW) + 4 * t + (lane >> 3);
+        const int chunk = p.transL ? (ww & 7) : (lane & 7);
         const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
         float4 hi, lo;
         hi.x = tf32_hi(v[t].x); hi.y = tf32_hi(v[t].y); hi.z = tf32_hi(v[t].z); hi.w = tf32_hi(v[t].w);
@@ -267,7 +269,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
         sts128(st + A_BYTES + off, lo);
       }
     };
-    auto step = [&](int kb, float4 (&v)[4]) {
+    auto step = [&](int kb, float4 (&v)[CPT]) {
       const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
       const uint32_t st = sbase + stage * STAGE_BYTES;
       if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
@@ -276,13 +278,22 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       load_a(kb + 2, v);                 // two k-blocks ahead: in flight during the split below and the next step
       mbar_wait(&full_bar[stage], phase);  // every lane: the TMA bytes are read right below
       const int valid = n - kb * BK;     // contraction rows of this k-block that belong to the graph
-      for (int idx = wt; idx < b_boxes * 256; idx += WORKERS) {
+      float4 x[CPT];
+#pragma unroll
+      for (int t = 0; t < CPT; ++t) {      // every load first: the chunks are independent
+        const int idx = wt + WORKERS * t;
+        x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (idx < b_boxes * 256 && ((idx & 255) >> 3) < valid) x[t] = lds128(st + 2 * A_BYTES + 16 * idx);
+      }
+#pragma unroll
+      for (int t = 0; t < CPT; ++t) {
+        const int idx = wt + WORKERS * t;
+        if (idx >= b_boxes * 256) continue;
         const uint32_t a = st + 2 * A_BYTES + 16 * idx;
-        float4 x = lds128(a);
-        if (((idx & 255) >> 3) >= valid) x = make_float4(0.f, 0.f, 0.f, 0.f);
         float4 hi, lo;
-        hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
-        lo.x = tf32_lo(x.x, hi.x); lo.y = tf32_lo(x.y, hi.y); lo.z = tf32_lo(x.z, hi.z); lo.w = tf32_lo(x.w, hi.w);
+        hi.x = tf32_hi(x[t].x); hi.y = tf32_hi(x[t].y); hi.z = tf32_hi(x[t].z); hi.w = tf32_hi(x[t].w);
+        lo.x = tf32_lo(x[t].x, hi.x); lo.y = tf32_lo(x[t].y, hi.y); lo.z = tf32_lo(x[t].z, hi.z);
+        lo.w = tf32_lo(x[t].w, hi.w);
         sts128(a, hi);
         sts128(a + B_BYTES, lo);
       }
@@ -290,7 +301,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[stage]);
     };
-    float4 va[4], vb[4];
+    float4 va[CPT], vb[CPT];
     load_a(0, va);
     load_a(1, vb);
     for (int kb = 0; kb < num_kb; kb += 2) {
@@ -302,9 +313,9 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
     __syncwarp();
     tc_fence_after();
     const int q = warp & 3;      // TMEM lane quarter of this warp
-    const int h = ww >> 2;       // column half
+    const int h = ww >> 2;       // 32-column group of this warp (NW / 4 groups)
     const uint32_t stg = sbase + (uint32_t)(ww * (32 * 36 * 4));  // the operand stages are free now
-    for (int c0 = 32 * h; c0 < nmma; c0 += 64) {
+    for (int c0 = 32 * h; c0 < nmma; c0 += 32 * (NW / 4)) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
 #pragma unroll
