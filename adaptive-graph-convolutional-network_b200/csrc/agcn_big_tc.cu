@@ -37,17 +37,13 @@ constexpr int UMMA_K = 8;
 constexpr int BN = 128;                     // node-matrix columns per CTA
 constexpr int A_BYTES = TM * BK * 4;        // 16 KB: one half (hi or lo) of the A operand of a k-block
 constexpr int B_BYTES = BN * BK * 4;        // 16 KB: four 32 x 32 boxes
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // one operand stage: A_hi, A_lo, B_hi, B_lo
-constexpr int STAGES = 2;                   // operand stages (the MMAs of one run while the other is filled)
-constexpr int RAW = 5;                      // landing buffers of the TMA loads of B (fp32, before the split): the
-                                            // loads run this many k-blocks ahead of the tensor core
-constexpr int RAW_OFF = STAGES * STAGE_BYTES;
-constexpr int BAR_OFF = RAW_OFF + RAW * B_BYTES;
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+constexpr int STAGES = 3;
 constexpr int WORKERS = 512;            // 16 worker warps: the operand split is a latency chain per warp
 constexpr int NW = WORKERS / 32;
 constexpr int CPT = 1024 / WORKERS;     // 16-byte chunks of the A tile (and float4s of a full B tile) per thread and k-block
 constexpr int THREADS = 64 + WORKERS;
-constexpr int SMEM_TOTAL = BAR_OFF + 256 + 1024;
+constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -148,13 +144,12 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(base);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + BAR_OFF);
-  uint64_t* raw_full = bars;                      // [RAW]    B tile landed (TMA)
-  uint64_t* raw_empty = bars + RAW;               // [RAW]    every worker warp has read its part of the tile
-  uint64_t* split_bar = bars + 2 * RAW;           // [STAGES] A written and B split by the worker warps
-  uint64_t* empty_bar = bars + 2 * RAW + STAGES;  // [STAGES] MMAs that read the stage retired
-  uint64_t* tmem_full_bar = bars + 2 * RAW + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RAW + 2 * STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;              // B tile landed (TMA)
+  uint64_t* split_bar = bars + STAGES;    // A written and B split by the worker warps
+  uint64_t* empty_bar = bars + 2 * STAGES;  // MMAs that read the stage retired
+  uint64_t* tmem_full_bar = bars + 3 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n = p.n_nodes[g];
@@ -168,12 +163,9 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&split_bar[s], NW);
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], WORKERS / 32);
       mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < RAW; ++s) {
-      mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], NW);
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -190,12 +182,12 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
   if (warp == 0) {
     if (lane == 0) {
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int rs = kb % RAW, rphase = (kb / RAW) & 1;
-        mbar_wait(&raw_empty[rs], rphase ^ 1);
-        const uint32_t sb = sbase + RAW_OFF + rs * B_BYTES;
-        mbar_expect_tx(&raw_full[rs], b_boxes * 4096);
+        const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        const uint32_t sb = sbase + stage * STAGE_BYTES + 2 * A_BYTES;
+        mbar_expect_tx(&full_bar[stage], b_boxes * 4096);
         for (int b = 0; b < b_boxes; ++b)
-          tma_load_2d(sb + b * 4096, &tmIn, &raw_full[rs], f0 + 32 * b, (int)(row0 + (long long)kb * BK));
+          tma_load_2d(sb + b * 4096, &tmIn, &full_bar[stage], f0 + 32 * b, (int)(row0 + (long long)kb * BK));
       }
     }
   } else if (warp == 1) {
@@ -279,28 +271,25 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
     };
     auto step = [&](int kb, float4 (&v)[CPT]) {
       const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
-      const int rs = kb % RAW, rphase = (kb / RAW) & 1;
       const uint32_t st = sbase + stage * STAGE_BYTES;
-      const uint32_t raw = sbase + RAW_OFF + rs * B_BYTES;
-      // everything that does not need the operand stage happens before waiting for it: B out of its landing buffer
-      mbar_wait(&raw_full[rs], rphase);  // every lane: the TMA bytes are read right below
+      if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
+      __syncwarp();
+      store_a(st, v);
+      load_a(kb + 2, v);                 // two k-blocks ahead: in flight during the split below and the next step
+      mbar_wait(&full_bar[stage], phase);  // every lane: the TMA bytes are read right below
       const int valid = n - kb * BK;     // contraction rows of this k-block that belong to the graph
       float4 x[CPT];
 #pragma unroll
-      for (int t = 0; t < CPT; ++t) {
+      for (int t = 0; t < CPT; ++t) {      // every load first: the chunks are independent
         const int idx = wt + WORKERS * t;
         x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < b_boxes * 256 && ((idx & 255) >> 3) < valid) x[t] = lds128(raw + 16 * idx);
+        if (idx < b_boxes * 256 && ((idx & 255) >> 3) < valid) x[t] = lds128(st + 2 * A_BYTES + 16 * idx);
       }
-      if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);  // the MMAs that read this stage have retired
-      __syncwarp();
-      store_a(st, v);
-      load_a(kb + 2, v);                 // two k-blocks ahead: in flight during the next step
 #pragma unroll
       for (int t = 0; t < CPT; ++t) {
         const int idx = wt + WORKERS * t;
         if (idx >= b_boxes * 256) continue;
-        const uint32_t a = st + 2 * A_BYTES + 16 * idx;   // same place in the operand stage: the layout is TMA's
+        const uint32_t a = st + 2 * A_BYTES + 16 * idx;
         float4 hi, lo;
         hi.x = tf32_hi(x[t].x); hi.y = tf32_hi(x[t].y); hi.z = tf32_hi(x[t].z); hi.w = tf32_hi(x[t].w);
         lo.x = tf32_lo(x[t].x, hi.x); lo.y = tf32_lo(x[t].y, hi.y); lo.z = tf32_lo(x[t].z, hi.z);
@@ -310,10 +299,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       }
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&raw_empty[rs]);     // the landing buffer may be overwritten by the next TMA load
-        mbar_arrive(&split_bar[stage]);
-      }
+      if (lane == 0) mbar_arrive(&split_bar[stage]);
     };
     float4 va[CPT], vb[CPT];
     load_a(0, va);
