@@ -224,16 +224,48 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
     //             (ww / 8) * 32 CPT + 32 t + lane: four coalesced scalar loads along a row of L fill the chunk.
     // Either way the 32 lanes of a store hit 4 x 8 distinct 16-byte slots of the swizzled tile: no bank conflicts.
     const bool vecL = !p.transL && ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(Lg) & 15) == 0);
+    // per-thread constants of its CPT chunks: operand row, swizzled byte offset in the tile, global address at k-block 0
+    int arow[CPT];
+    uint32_t aoff[CPT];
+    const float* aptr[CPT];
+#pragma unroll
+    for (int t = 0; t < CPT; ++t) {
+      const int r = p.transL ? (ww >> 3) * (32 * CPT) + 32 * t + lane : ww * (TM / NW) + 4 * t + (lane >> 3);
+      const int chunk = p.transL ? (ww & 7) : (lane & 7);
+      arow[t] = r;
+      aoff[t] = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+      aptr[t] = p.transL ? Lg + (long long)(4 * chunk) * n + (m0 + r) : Lg + (long long)(m0 + r) * n + 4 * chunk;
+    }
+    // interior k-blocks of a tile whose 128 rows all exist need no bounds checks (every k-block of a point cloud with
+    // n % 128 == 0); op = L additionally wants 16-byte aligned rows for the float4 loads
+    const bool fast_rows = (m0 + TM <= n) && (p.transL || vecL);
+    const long long kstep = p.transL ? (long long)BK * n : BK;   // elements between consecutive k-blocks
     auto load_a = [&](int kb, float4 (&v)[CPT]) {
       if (kb >= num_kb) return;
       const int k0 = kb * BK;
+      if (fast_rows && k0 + BK <= n) {
+#pragma unroll
+        for (int t = 0; t < CPT; ++t) {
+          const float* src = aptr[t] + kb * kstep;
+          if (!p.transL) {
+            v[t] = __ldg(reinterpret_cast<const float4*>(src));
+          } else {
+            v[t].x = __ldg(src);
+            v[t].y = __ldg(src + n);
+            v[t].z = __ldg(src + 2 * (long long)n);
+            v[t].w = __ldg(src + 3 * (long long)n);
+          }
+        }
+        return;
+      }
 #pragma unroll
       for (int t = 0; t < CPT; ++t) {
         float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int i = m0 + arow[t];
+        const float* src = aptr[t] + kb * kstep;
         if (!p.transL) {
-          const int i = m0 + ww * (TM / NW) + 4 * t + (lane >> 3), j = k0 + 4 * (lane & 7);
+          const int j = k0 + 4 * (lane & 7);
           if (i < n && j < n) {
-            const float* src = Lg + (long long)i * n + j;
             if (vecL) {
               x = __ldg(reinterpret_cast<const float4*>(src));
             } else {
@@ -244,9 +276,8 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
             }
           }
         } else {
-          const int i = m0 + (ww >> 3) * (32 * CPT) + 32 * t + lane, j = k0 + 4 * (ww & 7);
+          const int j = k0 + 4 * (ww & 7);
           if (i < n && j < n) {
-            const float* src = Lg + (long long)j * n + i;
             x.x = __ldg(src);
             if (j + 1 < n) x.y = __ldg(src + n);
             if (j + 2 < n) x.z = __ldg(src + 2 * (long long)n);
@@ -256,47 +287,42 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
         v[t] = x;
       }
     };
-    auto store_a = [&](uint32_t st, const float4 (&v)[CPT]) {
-#pragma unroll
-      for (int t = 0; t < CPT; ++t) {
-        const int r = p.transL ? (ww >> 3) * (32 * CPT) + 32 * t + lane : ww * (TM / NW) + 4 * t + (lane >> 3);
-        const int chunk = p.transL ? (ww & 7) : (lane & 7);
-        const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
-        float4 hi, lo;
-        hi.x = tf32_hi(v[t].x); hi.y = tf32_hi(v[t].y); hi.z = tf32_hi(v[t].z); hi.w = tf32_hi(v[t].w);
-        lo.x = tf32_lo(v[t].x, hi.x); lo.y = tf32_lo(v[t].y, hi.y); lo.z = tf32_lo(v[t].z, hi.z); lo.w = tf32_lo(v[t].w, hi.w);
-        sts128(st + off, hi);
-        sts128(st + A_BYTES + off, lo);
-      }
+    auto split_store = [&](uint32_t a_hi, uint32_t a_lo, const float4& x) {
+      float4 hi, lo;
+      hi.x = tf32_hi(x.x); hi.y = tf32_hi(x.y); hi.z = tf32_hi(x.z); hi.w = tf32_hi(x.w);
+      lo.x = tf32_lo(x.x, hi.x); lo.y = tf32_lo(x.y, hi.y); lo.z = tf32_lo(x.z, hi.z); lo.w = tf32_lo(x.w, hi.w);
+      sts128(a_hi, hi);
+      sts128(a_lo, lo);
     };
+    // B: float4 number idx = wt + WORKERS t of the landed tile (256 per 32-column box); which of mine exist
+    bool bmine[CPT];
+    int bkrow[CPT];
+#pragma unroll
+    for (int t = 0; t < CPT; ++t) {
+      const int idx = wt + WORKERS * t;
+      bmine[t] = idx < b_boxes * 256;
+      bkrow[t] = (idx & 255) >> 3;   // contraction row of the k-block this float4 belongs to
+    }
     auto step = [&](int kb, float4 (&v)[CPT]) {
       const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
       const uint32_t st = sbase + stage * STAGE_BYTES;
       if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
       __syncwarp();
-      store_a(st, v);
+#pragma unroll
+      for (int t = 0; t < CPT; ++t) split_store(st + aoff[t], st + A_BYTES + aoff[t], v[t]);
       load_a(kb + 2, v);                 // two k-blocks ahead: in flight during the split below and the next step
       mbar_wait(&full_bar[stage], phase);  // every lane: the TMA bytes are read right below
       const int valid = n - kb * BK;     // contraction rows of this k-block that belong to the graph
+      const uint32_t sb = st + 2 * A_BYTES + 16 * wt;
       float4 x[CPT];
 #pragma unroll
       for (int t = 0; t < CPT; ++t) {      // every load first: the chunks are independent
-        const int idx = wt + WORKERS * t;
         x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (idx < b_boxes * 256 && ((idx & 255) >> 3) < valid) x[t] = lds128(st + 2 * A_BYTES + 16 * idx);
+        if (bmine[t] && bkrow[t] < valid) x[t] = lds128(sb + 16 * WORKERS * t);
       }
 #pragma unroll
-      for (int t = 0; t < CPT; ++t) {
-        const int idx = wt + WORKERS * t;
-        if (idx >= b_boxes * 256) continue;
-        const uint32_t a = st + 2 * A_BYTES + 16 * idx;
-        float4 hi, lo;
-        hi.x = tf32_hi(x[t].x); hi.y = tf32_hi(x[t].y); hi.z = tf32_hi(x[t].z); hi.w = tf32_hi(x[t].w);
-        lo.x = tf32_lo(x[t].x, hi.x); lo.y = tf32_lo(x[t].y, hi.y); lo.z = tf32_lo(x[t].z, hi.z);
-        lo.w = tf32_lo(x[t].w, hi.w);
-        sts128(a, hi);
-        sts128(a + B_BYTES, lo);
-      }
+      for (int t = 0; t < CPT; ++t)
+        if (bmine[t]) split_store(sb + 16 * WORKERS * t, sb + 16 * WORKERS * t + B_BYTES, x[t]);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[stage]);
