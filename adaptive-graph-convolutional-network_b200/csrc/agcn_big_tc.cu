@@ -41,6 +41,7 @@ constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 constexpr int STAGES = 3;
 constexpr int WORKERS = 512;            // 16 worker warps: the operand split is a latency chain per warp
 constexpr int NW = WORKERS / 32;
+constexpr int AHEAD = 4;                // k-blocks of L in flight per thread (register prefetch)
 constexpr int CPT = 1024 / WORKERS;     // 16-byte chunks of the A tile (and float4s of a full B tile) per thread and k-block
 constexpr int THREADS = 64 + WORKERS;
 constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
@@ -310,7 +311,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       __syncwarp();
 #pragma unroll
       for (int t = 0; t < CPT; ++t) split_store(st + aoff[t], st + A_BYTES + aoff[t], v[t]);
-      load_a(kb + 2, v);                 // two k-blocks ahead: in flight during the split below and the next step
+      load_a(kb + AHEAD, v);             // AHEAD k-blocks ahead: the L tiles come from HBM, ~2.5 us away under load
       mbar_wait(&full_bar[stage], phase);  // every lane: the TMA bytes are read right below
       const int valid = n - kb * BK;     // contraction rows of this k-block that belong to the graph
       const uint32_t sb = st + 2 * A_BYTES + 16 * wt;
@@ -327,12 +328,16 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[stage]);
     };
-    float4 va[CPT], vb[CPT];
+    float4 va[CPT], vb[CPT], vc[CPT], vd[CPT];   // AHEAD register buffers, one per k-block in flight
     load_a(0, va);
     load_a(1, vb);
-    for (int kb = 0; kb < num_kb; kb += 2) {
+    load_a(2, vc);
+    load_a(3, vd);
+    for (int kb = 0; kb < num_kb; kb += AHEAD) {
       step(kb, va);
       if (kb + 1 < num_kb) step(kb + 1, vb);
+      if (kb + 2 < num_kb) step(kb + 2, vc);
+      if (kb + 3 < num_kb) step(kb + 3, vd);
     }
     // ---- epilogue
     if (lane == 0) mbar_wait(tmem_full_bar, 0);
