@@ -48,6 +48,7 @@ _SIGNATURES = {
     "agcn_unpack_lap": (ctypes.c_int, [_P, _P, _P, _P]),
     "agcn_debug_grouped_product": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                   ctypes.c_float, ctypes.c_int32, _P]),
+    "agcn_debug_grouped_timeline": (ctypes.c_int, [_P]),
     "agcn_pack_lap_csr": (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
     "agcn_graph_pool": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int32, _P]),
     "agcn_graph_pool_backward": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, _P]),

@@ -138,6 +138,17 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
 __device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
 __device__ __forceinline__ float tf32_lo(float x, float hi) { return __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u); }
 
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+  return t;
+}
+// timeline of CTA (0, 0): 8 slots per k-block (first 64) + 3 at 520.. (tools/tc_timeline.py)
+#define BT_STAMP(slot)                                     \
+  do {                                                     \
+    if (dbg_on) p.dbg[(slot)] = gtime();                   \
+  } while (0)
+
 __global__ void __launch_bounds__(THREADS, 1)
 grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
   const int g = p.tile_graph[blockIdx.x], m0 = p.tile_row[blockIdx.x];
@@ -153,6 +164,8 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (threadIdx.x == 0) BT_STAMP(520);
   const int n = p.n_nodes[g];
   const long long row0 = p.node_off[g];
   const float* __restrict__ Lg = p.L + p.lap_off[g];
@@ -185,6 +198,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
         mbar_wait(&empty_bar[stage], phase ^ 1);
+        if (kb < 64) BT_STAMP(8 * kb + 6);
         const uint32_t sb = sbase + stage * STAGE_BYTES + 2 * A_BYTES;
         mbar_expect_tx(&full_bar[stage], b_boxes * 4096);
         for (int b = 0; b < b_boxes; ++b)
@@ -199,6 +213,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       for (int kb = 0; kb < num_kb; ++kb) {
         const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
         mbar_wait(&split_bar[stage], phase);
+        if (kb < 64) BT_STAMP(8 * kb + 4);
         tc_fence_after();
         const uint32_t sa = sbase + stage * STAGE_BYTES, sa_lo = sa + A_BYTES;
         const uint32_t sb = sa + 2 * A_BYTES, sb_lo = sb + B_BYTES;
@@ -211,6 +226,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
           umma_tf32(tmem_base, a_hi, b_hi, idesc, 1);
         }
         umma_commit(&empty_bar[stage]);
+        if (kb < 64) BT_STAMP(8 * kb + 5);
       }
       umma_commit(tmem_full_bar);
     }
@@ -309,10 +325,13 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       const uint32_t st = sbase + stage * STAGE_BYTES;
       if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
       __syncwarp();
+      if (wt == 0 && kb < 64) BT_STAMP(8 * kb);
 #pragma unroll
       for (int t = 0; t < CPT; ++t) split_store(st + aoff[t], st + A_BYTES + aoff[t], v[t]);
-      load_a(kb + AHEAD, v);             // AHEAD k-blocks ahead: the L tiles come from HBM, ~2.5 us away under load
+      load_a(kb + AHEAD, v);             // AHEAD k-blocks ahead of their use
+      if (wt == 0 && kb < 64) BT_STAMP(8 * kb + 1);
       mbar_wait(&full_bar[stage], phase);  // every lane: the TMA bytes are read right below
+      if (wt == 0 && kb < 64) BT_STAMP(8 * kb + 2);
       const int valid = n - kb * BK;     // contraction rows of this k-block that belong to the graph
       const uint32_t sb = st + 2 * A_BYTES + 16 * wt;
       float4 x[CPT];
@@ -327,6 +346,8 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[stage]);
+      if (wt == 0 && kb < 64) BT_STAMP(8 * kb + 3);
+      if (wt == WORKERS - 32 && kb < 64) BT_STAMP(8 * kb + 7);
     };
     float4 va[CPT], vb[CPT], vc[CPT], vd[CPT];   // AHEAD register buffers, one per k-block in flight
     load_a(0, va);
@@ -343,6 +364,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
     if (lane == 0) mbar_wait(tmem_full_bar, 0);
     __syncwarp();
     tc_fence_after();
+    if (wt == 0) BT_STAMP(521);
     const int q = warp & 3;      // TMEM lane quarter of this warp
     const int h = ww >> 2;       // 32-column group of this warp (NW / 4 groups)
     const uint32_t stg = sbase + (uint32_t)(ww * (32 * 36 * 4));  // the operand stages are free now
@@ -388,6 +410,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) BT_STAMP(522);
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" ::"r"(tmem_base) : "memory");
 }
 

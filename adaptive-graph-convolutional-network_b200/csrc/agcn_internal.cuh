@@ -259,6 +259,7 @@ struct GroupedArgs {
   int F;
   const float* RowScale;  // optional: Out += RowScale[row] * ScaleIn[row, c]
   const float* ScaleIn;
+  unsigned long long* dbg;  // tuning aid: timeline of the first CTA of grouped_tc_kernel (NULL in production)
 };
 int grouped_launch(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStream_t st);
 int grouped_simt(int tiles, const GroupedArgs& g, cudaStream_t st);

@@ -121,6 +121,10 @@ int agcn_debug_grouped_product(const agcn_plan* plan, const float* d_L /*packed*
                                float* d_Out /*[R,F]*/, int32_t F, int32_t transL, int32_t add_identity, float cmul,
                                int32_t impl, void* stream);
 
+/* d_buf = device buffer of 1024 uint64 (or NULL): the following agcn_debug_grouped_product calls with impl 2 record a
+ * nanosecond timeline of their first CTA into it (tools/tc_timeline.py). */
+int agcn_debug_grouped_timeline(void* d_buf);
+
 /* ---- layout conversion (pad_data2sparse / pad_Lap2sparse, graph_topology.py:84-98;
  *      tf.slice at graphconv.py:153-154; tf.pad at graphconv.py:249-251) ------------------ */
 int agcn_pack_nodes(const agcn_plan* plan, const float* d_padded /*[B,Nmax,F]*/, float* d_packed /*[R,F]*/,
