@@ -8,7 +8,7 @@
 // [1024 x 1024] x [1024 x 128] contraction per graph: dense tensor-core work (north_star item 3).
 //
 // grouped_tc_kernel: one CTA per (graph, 128-row tile, 128-column block of the node matrix).
-//   warps 2-17: A = L_g[rows, k-block of 32 columns] loaded from global memory (ragged n: rows are not 16-byte
+//   warps 2-17 (two groups of 8, alternating k-blocks): A = L_g[rows, k-block of 32 columns] loaded from global memory (ragged n: rows are not 16-byte
 //               aligned, so no TMA), split into hi / lo TF32 halves and written as a 128 x 32 K-major SWIZZLE_128B
 //               operand (transposed on the fly for L^T); the B tile brought by TMA is split in place;
 //   warp 0    : TMA producer of B = In[k-block of 32 nodes, 128 columns]: row-major node matrix = MN-major operand,
@@ -41,8 +41,11 @@ constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
 constexpr int STAGES = 3;
 constexpr int WORKERS = 512;            // 16 worker warps: the operand split is a latency chain per warp
 constexpr int NW = WORKERS / 32;
-constexpr int AHEAD = 4;                // k-blocks of L in flight per thread (register prefetch)
-constexpr int CPT = 1024 / WORKERS;     // 16-byte chunks of the A tile (and float4s of a full B tile) per thread and k-block
+constexpr int GROUPS = 2;                // worker groups: group g fills the operand stages of k-blocks g, g + 2, ...; a
+                                         // k-block is a chain of dependent waits, two chains in flight hide each other
+constexpr int GW = NW / GROUPS;          // warps per group
+constexpr int GTHREADS = GW * 32;
+constexpr int CPT = 1024 / GTHREADS;     // 16-byte chunks of the A tile (and float4s of a full B tile) per thread and k-block
 constexpr int THREADS = 64 + WORKERS;
 constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
@@ -178,7 +181,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&split_bar[s], WORKERS / 32);
+      mbar_init(&split_bar[s], GW);
       mbar_init(&empty_bar[s], 1);
     }
     mbar_init(tmem_full_bar, 1);
@@ -232,13 +235,14 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
     }
   } else {
     const int ww = warp - 2;              // worker warp 0..NW-1
-    const int wt = ww * 32 + lane;
+    const int group = ww / GW, gw = ww % GW;   // my group and my warp inside it
+    const int gt = gw * 32 + lane;
     // ---- A loader: every thread owns four 16-byte chunks (4 consecutive contraction columns of one operand row) per
     // k-block, so the split costs one 128-bit shared store per chunk and half.
     //   op = L  : 8 lanes cover the 32 columns of a row (a float4 each when the graph's rows are 16-byte aligned), a
-    //             warp covers rows (128 / NW) ww + 4 t + lane / 8;
-    //   op = L^T: warp ww owns chunk ww % 8 (contraction rows 4 c .. 4 c + 3 of the k-block) of the operand rows
-    //             (ww / 8) * 32 CPT + 32 t + lane: four coalesced scalar loads along a row of L fill the chunk.
+    //             warp covers rows (128 / GW) gw + 4 t + lane / 8;
+    //   op = L^T: warp gw owns chunk gw (contraction rows 4 gw .. 4 gw + 3 of the k-block) of the operand rows
+    //             32 t + lane: four coalesced scalar loads along a row of L fill the chunk.
     // Either way the 32 lanes of a store hit 4 x 8 distinct 16-byte slots of the swizzled tile: no bank conflicts.
     const bool vecL = !p.transL && ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(Lg) & 15) == 0);
     // per-thread constants of its CPT chunks: operand row, swizzled byte offset in the tile, global address at k-block 0
@@ -247,8 +251,8 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
     const float* aptr[CPT];
 #pragma unroll
     for (int t = 0; t < CPT; ++t) {
-      const int r = p.transL ? (ww >> 3) * (32 * CPT) + 32 * t + lane : ww * (TM / NW) + 4 * t + (lane >> 3);
-      const int chunk = p.transL ? (ww & 7) : (lane & 7);
+      const int r = p.transL ? 32 * t + lane : gw * (TM / GW) + 4 * t + (lane >> 3);
+      const int chunk = p.transL ? gw : (lane & 7);
       arow[t] = r;
       aoff[t] = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
       aptr[t] = p.transL ? Lg + (long long)(4 * chunk) * n + (m0 + r) : Lg + (long long)(m0 + r) * n + 4 * chunk;
@@ -293,7 +297,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
             }
           }
         } else {
-          const int j = k0 + 4 * (ww & 7);
+          const int j = k0 + 4 * gw;
           if (i < n && j < n) {
             x.x = __ldg(src);
             if (j + 1 < n) x.y = __ldg(src + n);
@@ -311,12 +315,12 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       sts128(a_hi, hi);
       sts128(a_lo, lo);
     };
-    // B: float4 number idx = wt + WORKERS t of the landed tile (256 per 32-column box); which of mine exist
+    // B: float4 number idx = gt + GTHREADS t of the landed tile (256 per 32-column box); which of mine exist
     bool bmine[CPT];
     int bkrow[CPT];
 #pragma unroll
     for (int t = 0; t < CPT; ++t) {
-      const int idx = wt + WORKERS * t;
+      const int idx = gt + GTHREADS * t;
       bmine[t] = idx < b_boxes * 256;
       bkrow[t] = (idx & 255) >> 3;   // contraction row of the k-block this float4 belongs to
     }
@@ -325,46 +329,42 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       const uint32_t st = sbase + stage * STAGE_BYTES;
       if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
       __syncwarp();
-      if (wt == 0 && kb < 64) BT_STAMP(8 * kb);
+      if (gt == 0 && kb < 64) BT_STAMP(8 * kb);
 #pragma unroll
       for (int t = 0; t < CPT; ++t) split_store(st + aoff[t], st + A_BYTES + aoff[t], v[t]);
-      load_a(kb + AHEAD, v);             // AHEAD k-blocks ahead of their use
-      if (wt == 0 && kb < 64) BT_STAMP(8 * kb + 1);
+      load_a(kb + 2 * GROUPS, v);        // two of my k-blocks ahead
+      if (gt == 0 && kb < 64) BT_STAMP(8 * kb + 1);
       mbar_wait(&full_bar[stage], phase);  // every lane: the TMA bytes are read right below
-      if (wt == 0 && kb < 64) BT_STAMP(8 * kb + 2);
+      if (gt == 0 && kb < 64) BT_STAMP(8 * kb + 2);
       const int valid = n - kb * BK;     // contraction rows of this k-block that belong to the graph
-      const uint32_t sb = st + 2 * A_BYTES + 16 * wt;
+      const uint32_t sb = st + 2 * A_BYTES + 16 * gt;
       float4 x[CPT];
 #pragma unroll
       for (int t = 0; t < CPT; ++t) {      // every load first: the chunks are independent
         x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bmine[t] && bkrow[t] < valid) x[t] = lds128(sb + 16 * WORKERS * t);
+        if (bmine[t] && bkrow[t] < valid) x[t] = lds128(sb + 16 * GTHREADS * t);
       }
 #pragma unroll
       for (int t = 0; t < CPT; ++t)
-        if (bmine[t]) split_store(sb + 16 * WORKERS * t, sb + 16 * WORKERS * t + B_BYTES, x[t]);
+        if (bmine[t]) split_store(sb + 16 * GTHREADS * t, sb + 16 * GTHREADS * t + B_BYTES, x[t]);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[stage]);
-      if (wt == 0 && kb < 64) BT_STAMP(8 * kb + 3);
-      if (wt == WORKERS - 32 && kb < 64) BT_STAMP(8 * kb + 7);
+      if (gt == 0 && kb < 64) BT_STAMP(8 * kb + 3);
+      if (gt == GTHREADS - 32 && kb < 64) BT_STAMP(8 * kb + 7);
     };
-    float4 va[CPT], vb[CPT], vc[CPT], vd[CPT];   // AHEAD register buffers, one per k-block in flight
-    load_a(0, va);
-    load_a(1, vb);
-    load_a(2, vc);
-    load_a(3, vd);
-    for (int kb = 0; kb < num_kb; kb += AHEAD) {
+    float4 va[CPT], vb[CPT];   // my next two k-blocks of L, in flight
+    load_a(group, va);
+    load_a(group + GROUPS, vb);
+    for (int kb = group; kb < num_kb; kb += 2 * GROUPS) {
       step(kb, va);
-      if (kb + 1 < num_kb) step(kb + 1, vb);
-      if (kb + 2 < num_kb) step(kb + 2, vc);
-      if (kb + 3 < num_kb) step(kb + 3, vd);
+      if (kb + GROUPS < num_kb) step(kb + GROUPS, vb);
     }
     // ---- epilogue
     if (lane == 0) mbar_wait(tmem_full_bar, 0);
     __syncwarp();
     tc_fence_after();
-    if (wt == 0) BT_STAMP(521);
+    if (ww == 0 && lane == 0) BT_STAMP(521);
     const int q = warp & 3;      // TMEM lane quarter of this warp
     const int h = ww >> 2;       // 32-column group of this warp (NW / 4 groups)
     const uint32_t stg = sbase + (uint32_t)(ww * (32 * 36 * 4));  // the operand stages are free now
