@@ -8,12 +8,11 @@
 // [1024 x 1024] x [1024 x 128] contraction per graph: dense tensor-core work (north_star item 3).
 //
 // grouped_tc_kernel: one CTA per (graph, 128-row tile, 128-column block of the node matrix).
-//   warps 2-17 (two groups of 8, alternating k-blocks): A = L_g[rows, k-block of 32 columns] loaded from global memory (ragged n: rows are not 16-byte
+//   warps 2-17: A = L_g[rows, k-block of 32 columns] loaded from global memory (ragged n: rows are not 16-byte
 //               aligned, so no TMA), split into hi / lo TF32 halves and written as a 128 x 32 K-major SWIZZLE_128B
 //               operand (transposed on the fly for L^T); the B tile brought by TMA is split in place;
 //   warp 0    : TMA producer of B = In[k-block of 32 nodes, 128 columns]: row-major node matrix = MN-major operand,
-//               32 x 32 boxes in the 128B-swizzle / 32B-atom layout (as in tc_gemm_tn_kernel), into a ring of landing
-//               buffers that runs ahead of the operand stages;
+//               32 x 32 boxes in the 128B-swizzle / 32B-atom layout (as in tc_gemm_tn_kernel);
 //   warp 1    : tcgen05.mma kind::tf32, 3xTF32 (A_lo B_hi + A_hi B_lo + A_hi B_hi) into a TMEM accumulator;
 //   epilogue  : TMEM -> registers -> shared -> coalesced float4 rows with the recurrence terms applied.
 // Rows of In that belong to the next graph (last k-block of a ragged graph) are zeroed during the split, so a
@@ -39,23 +38,13 @@ constexpr int BN = 128;                     // node-matrix columns per CTA
 constexpr int A_BYTES = TM * BK * 4;        // 16 KB: one half (hi or lo) of the A operand of a k-block
 constexpr int B_BYTES = BN * BK * 4;        // 16 KB: four 32 x 32 boxes
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-constexpr int STAGES = 2;                   // operand stages (A_hi, A_lo, B_hi, B_lo): one per worker group, the MMAs of
-                                            // one run while the other is filled
-constexpr int RAW = 6;                      // landing buffers of the TMA loads of B (fp32, before the split), three per
-                                            // worker group: a load is issued as soon as a landing buffer is free, not
-                                            // when an operand stage is (the 1.5 us from issue to landing were on the
-                                            // critical path, tools/tc_timeline.py)
-constexpr int RAW_OFF = STAGES * STAGE_BYTES;
-constexpr int BAR_OFF = RAW_OFF + RAW * B_BYTES;
+constexpr int STAGES = 3;
 constexpr int WORKERS = 512;            // 16 worker warps: the operand split is a latency chain per warp
 constexpr int NW = WORKERS / 32;
-constexpr int GROUPS = 2;                // worker groups: group g fills the operand stages of k-blocks g, g + 2, ...; a
-                                         // k-block is a chain of dependent waits, two chains in flight hide each other
-constexpr int GW = NW / GROUPS;          // warps per group
-constexpr int GTHREADS = GW * 32;
-constexpr int CPT = 1024 / GTHREADS;     // 16-byte chunks of the A tile (and float4s of a full B tile) per thread and k-block
+constexpr int AHEAD = 4;                // k-blocks of L in flight per thread (register prefetch)
+constexpr int CPT = 1024 / WORKERS;     // 16-byte chunks of the A tile (and float4s of a full B tile) per thread and k-block
 constexpr int THREADS = 64 + WORKERS;
-constexpr int SMEM_TOTAL = BAR_OFF + 256 + 1024;
+constexpr int SMEM_TOTAL = STAGES * STAGE_BYTES + 256 + 1024;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -167,13 +156,12 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   const uint32_t sbase = smem_u32(base);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(base + BAR_OFF);
-  uint64_t* raw_full = bars;                      // [RAW]    B tile landed (TMA)
-  uint64_t* raw_empty = bars + RAW;               // [RAW]    the worker group of the k-block has read the tile
-  uint64_t* split_bar = bars + 2 * RAW;           // [STAGES] A written and B split by the worker group
-  uint64_t* empty_bar = bars + 2 * RAW + STAGES;  // [STAGES] MMAs that read the stage retired
-  uint64_t* tmem_full_bar = bars + 2 * RAW + 2 * STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * RAW + 2 * STAGES + 1);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + STAGES * STAGE_BYTES);
+  uint64_t* full_bar = bars;              // B tile landed (TMA)
+  uint64_t* split_bar = bars + STAGES;    // A written and B split by the worker warps
+  uint64_t* empty_bar = bars + 2 * STAGES;  // MMAs that read the stage retired
+  uint64_t* tmem_full_bar = bars + 3 * STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * STAGES + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const bool dbg_on = p.dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
@@ -189,12 +177,9 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&split_bar[s], GW);
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&split_bar[s], WORKERS / 32);
       mbar_init(&empty_bar[s], 1);
-    }
-    for (int s = 0; s < RAW; ++s) {
-      mbar_init(&raw_full[s], 1);
-      mbar_init(&raw_empty[s], GW);
     }
     mbar_init(tmem_full_bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -211,13 +196,13 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
   if (warp == 0) {
     if (lane == 0) {
       for (int kb = 0; kb < num_kb; ++kb) {
-        const int rs = kb % RAW, rphase = (kb / RAW) & 1;
-        mbar_wait(&raw_empty[rs], rphase ^ 1);
+        const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
+        mbar_wait(&empty_bar[stage], phase ^ 1);
         if (kb < 64) BT_STAMP(8 * kb + 6);
-        const uint32_t sb = sbase + RAW_OFF + rs * B_BYTES;
-        mbar_expect_tx(&raw_full[rs], b_boxes * 4096);
+        const uint32_t sb = sbase + stage * STAGE_BYTES + 2 * A_BYTES;
+        mbar_expect_tx(&full_bar[stage], b_boxes * 4096);
         for (int b = 0; b < b_boxes; ++b)
-          tma_load_2d(sb + b * 4096, &tmIn, &raw_full[rs], f0 + 32 * b, (int)(row0 + (long long)kb * BK));
+          tma_load_2d(sb + b * 4096, &tmIn, &full_bar[stage], f0 + 32 * b, (int)(row0 + (long long)kb * BK));
       }
     }
   } else if (warp == 1) {
@@ -247,14 +232,13 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
     }
   } else {
     const int ww = warp - 2;              // worker warp 0..NW-1
-    const int group = ww / GW, gw = ww % GW;   // my group and my warp inside it
-    const int gt = gw * 32 + lane;
+    const int wt = ww * 32 + lane;
     // ---- A loader: every thread owns four 16-byte chunks (4 consecutive contraction columns of one operand row) per
     // k-block, so the split costs one 128-bit shared store per chunk and half.
     //   op = L  : 8 lanes cover the 32 columns of a row (a float4 each when the graph's rows are 16-byte aligned), a
-    //             warp covers rows (128 / GW) gw + 4 t + lane / 8;
-    //   op = L^T: warp gw owns chunk gw (contraction rows 4 gw .. 4 gw + 3 of the k-block) of the operand rows
-    //             32 t + lane: four coalesced scalar loads along a row of L fill the chunk.
+    //             warp covers rows (128 / NW) ww + 4 t + lane / 8;
+    //   op = L^T: warp ww owns chunk ww % 8 (contraction rows 4 c .. 4 c + 3 of the k-block) of the operand rows
+    //             (ww / 8) * 32 CPT + 32 t + lane: four coalesced scalar loads along a row of L fill the chunk.
     // Either way the 32 lanes of a store hit 4 x 8 distinct 16-byte slots of the swizzled tile: no bank conflicts.
     const bool vecL = !p.transL && ((n & 3) == 0) && ((reinterpret_cast<uintptr_t>(Lg) & 15) == 0);
     // per-thread constants of its CPT chunks: operand row, swizzled byte offset in the tile, global address at k-block 0
@@ -263,8 +247,8 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
     const float* aptr[CPT];
 #pragma unroll
     for (int t = 0; t < CPT; ++t) {
-      const int r = p.transL ? 32 * t + lane : gw * (TM / GW) + 4 * t + (lane >> 3);
-      const int chunk = p.transL ? gw : (lane & 7);
+      const int r = p.transL ? (ww >> 3) * (32 * CPT) + 32 * t + lane : ww * (TM / NW) + 4 * t + (lane >> 3);
+      const int chunk = p.transL ? (ww & 7) : (lane & 7);
       arow[t] = r;
       aoff[t] = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
       aptr[t] = p.transL ? Lg + (long long)(4 * chunk) * n + (m0 + r) : Lg + (long long)(m0 + r) * n + 4 * chunk;
@@ -309,7 +293,7 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
             }
           }
         } else {
-          const int j = k0 + 4 * gw;
+          const int j = k0 + 4 * (ww & 7);
           if (i < n && j < n) {
             x.x = __ldg(src);
             if (j + 1 < n) x.y = __ldg(src + n);
@@ -327,63 +311,60 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
       sts128(a_hi, hi);
       sts128(a_lo, lo);
     };
-    // B: float4 number idx = gt + GTHREADS t of the landed tile (256 per 32-column box); which of mine exist
+    // B: float4 number idx = wt + WORKERS t of the landed tile (256 per 32-column box); which of mine exist
     bool bmine[CPT];
     int bkrow[CPT];
 #pragma unroll
     for (int t = 0; t < CPT; ++t) {
-      const int idx = gt + GTHREADS * t;
+      const int idx = wt + WORKERS * t;
       bmine[t] = idx < b_boxes * 256;
       bkrow[t] = (idx & 255) >> 3;   // contraction row of the k-block this float4 belongs to
     }
     auto step = [&](int kb, float4 (&v)[CPT]) {
       const int stage = kb % STAGES, phase = (kb / STAGES) & 1;
-      const int rs = kb % RAW, rphase = (kb / RAW) & 1;
       const uint32_t st = sbase + stage * STAGE_BYTES;
-      const uint32_t raw = sbase + RAW_OFF + rs * B_BYTES + 16 * gt;
-      // B out of its landing buffer first: nothing here needs the operand stage
-      mbar_wait(&raw_full[rs], rphase);  // every lane: the TMA bytes are read right below
-      if (gt == 0 && kb < 64) BT_STAMP(8 * kb + 2);
-      const int valid = n - kb * BK;     // contraction rows of this k-block that belong to the graph
-      float4 x[CPT];
-#pragma unroll
-      for (int t = 0; t < CPT; ++t) {
-        x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bmine[t] && bkrow[t] < valid) x[t] = lds128(raw + 16 * GTHREADS * t);
-      }
-      __syncwarp();                      // every lane's reads of the landing buffer have been performed
-      if (lane == 0) {
-        mbar_arrive(&raw_empty[rs]);     // ... so the next TMA load may overwrite it
-        mbar_wait(&empty_bar[stage], phase ^ 1);  // the MMAs that read this operand stage have retired
-      }
+      if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
       __syncwarp();
-      if (gt == 0 && kb < 64) BT_STAMP(8 * kb);
+      if (wt == 0 && kb < 64) BT_STAMP(8 * kb);
 #pragma unroll
       for (int t = 0; t < CPT; ++t) split_store(st + aoff[t], st + A_BYTES + aoff[t], v[t]);
-      load_a(kb + 2 * GROUPS, v);        // two of my k-blocks ahead
-      if (gt == 0 && kb < 64) BT_STAMP(8 * kb + 1);
-      const uint32_t sb = st + 2 * A_BYTES + 16 * gt;   // same place in the operand stage: the layout is TMA's
+      load_a(kb + AHEAD, v);             // AHEAD k-blocks ahead of their use
+      if (wt == 0 && kb < 64) BT_STAMP(8 * kb + 1);
+      mbar_wait(&full_bar[stage], phase);  // every lane: the TMA bytes are read right below
+      if (wt == 0 && kb < 64) BT_STAMP(8 * kb + 2);
+      const int valid = n - kb * BK;     // contraction rows of this k-block that belong to the graph
+      const uint32_t sb = st + 2 * A_BYTES + 16 * wt;
+      float4 x[CPT];
+#pragma unroll
+      for (int t = 0; t < CPT; ++t) {      // every load first: the chunks are independent
+        x[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bmine[t] && bkrow[t] < valid) x[t] = lds128(sb + 16 * WORKERS * t);
+      }
 #pragma unroll
       for (int t = 0; t < CPT; ++t)
-        if (bmine[t]) split_store(sb + 16 * GTHREADS * t, sb + 16 * GTHREADS * t + B_BYTES, x[t]);
+        if (bmine[t]) split_store(sb + 16 * WORKERS * t, sb + 16 * WORKERS * t + B_BYTES, x[t]);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[stage]);
-      if (gt == 0 && kb < 64) BT_STAMP(8 * kb + 3);
-      if (gt == GTHREADS - 32 && kb < 64) BT_STAMP(8 * kb + 7);
+      if (wt == 0 && kb < 64) BT_STAMP(8 * kb + 3);
+      if (wt == WORKERS - 32 && kb < 64) BT_STAMP(8 * kb + 7);
     };
-    float4 va[CPT], vb[CPT];   // my next two k-blocks of L, in flight
-    load_a(group, va);
-    load_a(group + GROUPS, vb);
-    for (int kb = group; kb < num_kb; kb += 2 * GROUPS) {
+    float4 va[CPT], vb[CPT], vc[CPT], vd[CPT];   // AHEAD register buffers, one per k-block in flight
+    load_a(0, va);
+    load_a(1, vb);
+    load_a(2, vc);
+    load_a(3, vd);
+    for (int kb = 0; kb < num_kb; kb += AHEAD) {
       step(kb, va);
-      if (kb + GROUPS < num_kb) step(kb + GROUPS, vb);
+      if (kb + 1 < num_kb) step(kb + 1, vb);
+      if (kb + 2 < num_kb) step(kb + 2, vc);
+      if (kb + 3 < num_kb) step(kb + 3, vd);
     }
     // ---- epilogue
     if (lane == 0) mbar_wait(tmem_full_bar, 0);
     __syncwarp();
     tc_fence_after();
-    if (ww == 0 && lane == 0) BT_STAMP(521);
+    if (wt == 0) BT_STAMP(521);
     const int q = warp & 3;      // TMEM lane quarter of this warp
     const int h = ww >> 2;       // 32-column group of this warp (NW / 4 groups)
     const uint32_t stg = sbase + (uint32_t)(ww * (32 * 36 * 4));  // the operand stages are free now

@@ -53,7 +53,7 @@ def main():
     kbs = min(64, (args.n + 31) // 32)
     print("kernel %.1f us (events); CTA 0: accumulator ready at %.2f us, done at %.2f us" %
           (e0.elapsed_time(e1) * 1e3, (t[521] - t0) / 1e3, (t[522] - t0) / 1e3))
-    print("times in us from the start of CTA 0; w0 = first, w15 = last warp of the worker group that fills the k-block")
+    print("times in us from the start of CTA 0; w0 = first, w15 = last worker warp")
     print(" kb | tma issue | w0 stage free  A split done  B landed  arrive | w15 arrive | mma start  mma issued | k-block period")
     prev = None
     for kb in range(kbs):
