@@ -12,6 +12,24 @@ import torch
 from .batch import GraphBatch, PackedLaplacians, PackedNodes
 
 
+def batch_csr(laplacians):
+    """Per-graph scipy sparse Laplacians (Graph.Laplacian, graph_structure.py:100-107) -> one CSR over the packed rows
+    of the batch: ``indptr`` [R + 1] int32, ``indices`` int32 (column inside the row's own graph), ``values`` fp32.
+    Duplicate entries are summed first, so every (row, column) appears once (agcn_pack_lap_csr scatters, not adds)."""
+    mats = []
+    for m in laplacians:
+        m = m.tocsr().copy()
+        m.sum_duplicates()
+        mats.append(m)
+    nnz = np.concatenate([[0], np.cumsum([m.nnz for m in mats])]).astype(np.int64)
+    if nnz[-1] >= 2 ** 31:
+        raise ValueError("batch CSR has more than 2^31 - 1 stored entries")
+    indptr = np.concatenate([m.indptr[:-1].astype(np.int64) + o for m, o in zip(mats, nnz[:-1])] + [nnz[-1:]])
+    indices = np.concatenate([m.indices for m in mats]).astype(np.int32)
+    values = np.concatenate([m.data for m in mats]).astype(np.float32)
+    return indptr.astype(np.int32), indices, values
+
+
 class GraphTopologyMol(object):
     def __init__(self, n_feat, batch_size=50, max_atom=128, name='topology_mol', max_deg=10, min_deg=0,
                  device='cuda'):
@@ -61,15 +79,9 @@ class GraphTopologyMol(object):
         elif layout == 'csr':
             # Graph.Laplacian is already scipy CSR (graph_structure.py:107): ship its three arrays, expand on the device
             feats = np.concatenate([np.asarray(g.node_features, np.float32) for g in graphs], 0)
-            mats = [g.Laplacian.tocsr() for g in graphs]
-            for m in mats:
-                m.sum_duplicates()
-            nnz = np.concatenate([[0], np.cumsum([m.nnz for m in mats])]).astype(np.int64)
-            indptr = np.concatenate([m.indptr[:-1].astype(np.int64) + o for m, o in zip(mats, nnz[:-1])] + [nnz[-1:]])
-            indices = np.concatenate([m.indices for m in mats]).astype(np.int32)
-            values = np.concatenate([m.data for m in mats]).astype(np.float32)
+            indptr, indices, values = batch_csr([g.Laplacian for g in graphs])
             feats = torch.from_numpy(feats).pin_memory().to(self.device, non_blocking=True)
-            laps = plan.pack_lap_csr(indptr.astype(np.int32), indices, values)
+            laps = plan.pack_lap_csr(indptr, indices, values)
             node_features, laplacians = PackedNodes(feats, plan), PackedLaplacians(laps, plan)
         else:
             raise ValueError("layout must be 'packed', 'csr' or 'padded'")

@@ -187,3 +187,31 @@ def test_fused_tile_packing_invariants():
         assert np.array_equal(covered, n.astype(np.int64))
         if B == 1024:   # ToxCast-shape batch: tiles are well filled (R / 128 is the lower bound)
             assert tiles.value <= int(np.ceil(n.sum() / 128.0 * 1.08)) + 2, (tiles.value, n.sum() / 128.0)
+
+
+def test_batch_csr_matches_the_dense_laplacians():
+    """Host side of the CSR input path: the batch CSR scattered by hand reproduces the
+    dense per-graph matrices; duplicate stored entries are summed like scipy's todense()."""
+    import scipy.sparse as sp
+    import agcn_b200
+    from agcn_b200.graph_topology import batch_csr
+    from oracle import sgcll_oracle as O
+    rng = np.random.default_rng(3)
+    graphs = [agcn_b200.MolGraph(np.zeros((n, 2), np.float32), O.molecule_like_adjacency(rng, n)) for n in (4, 9, 31)]
+    mats = [g.Laplacian for g in graphs]
+    dup = sp.coo_matrix((np.array([1.0, 2.0, 0.5], np.float32), (np.array([0, 0, 2]), np.array([1, 1, 0]))), shape=(3, 3))
+    mats.append(dup)
+    indptr, indices, values = batch_csr(mats)
+    assert indptr.dtype == np.int32 and indices.dtype == np.int32 and values.dtype == np.float32
+    assert indptr[0] == 0 and indptr[-1] == len(indices) == len(values)
+    row = 0
+    for m in mats:
+        n = m.shape[0]
+        dense = np.zeros((n, n), np.float32)
+        for i in range(n):
+            cols = indices[indptr[row]:indptr[row + 1]]
+            assert len(set(cols.tolist())) == len(cols)          # one entry per (row, column)
+            dense[i, cols] = values[indptr[row]:indptr[row + 1]]
+            row += 1
+        assert np.array_equal(dense, np.asarray(m.todense(), np.float32))
+    assert row == len(indptr) - 1

@@ -1,5 +1,13 @@
-import sys, ctypes
-sys.path.insert(0, '/root/repo')
+"""Probe of the MN-major tcgen05 contraction (agcn_gemm_tn): identity-like operands make a wrong shared-memory layout
+visible as a permutation of the output.  Needs a GPU.
+
+    python tools/dbg_tn.py
+"""
+import ctypes
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, numpy as np
 import agcn_b200
 from agcn_b200 import _lib
