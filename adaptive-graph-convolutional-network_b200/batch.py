@@ -53,13 +53,23 @@ class GraphBatch(object):
             pass
 
     # ---- layout conversion (graph_topology.py:84-98 <-> packed) -------------------------------
+    def _device_readable(self, padded):
+        """The pack kernels read their input with plain loads, and only the real rows of it: a PINNED host tensor
+        (page-locked memory is mapped into the device's address space) can be passed as it is -- the kernel then pulls
+        exactly the n_g rows of every graph across PCIe and the zero padding of the wire layout never moves."""
+        padded = padded.contiguous().float()
+        if not padded.is_cuda and not padded.is_pinned():
+            raise ValueError("host tensors must be pinned (tensor.pin_memory()) to be read by the device")
+        return padded
+
     def pack_nodes(self, padded):
-        """[B, max_atom, F] -> [R, F] (rows >= n_g dropped)."""
+        """[B, max_atom, F] (device, or pinned host: zero-copy) -> [R, F] (rows >= n_g dropped)."""
         B, N, F = padded.shape
         assert B == self.batch_size and N == self.max_atom
-        padded = padded.contiguous().float()
-        out = torch.empty(self.total_nodes, F, device=padded.device, dtype=torch.float32)
-        _lib.check(_lib.lib().agcn_pack_nodes(self._handle, _ptr(padded), _ptr(out), F, _stream_ptr()))
+        padded = self._device_readable(padded)
+        out = torch.empty(self.total_nodes, F, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().agcn_pack_nodes(self._handle, _ptr(padded), _ptr(out), F, _stream_ptr()))
         return out
 
     def unpack_nodes(self, packed):
@@ -72,12 +82,13 @@ class GraphBatch(object):
         return out
 
     def pack_lap(self, padded):
-        """[B, max_atom, max_atom] -> packed [sum n^2]."""
+        """[B, max_atom, max_atom] (device, or pinned host: zero-copy) -> packed [sum n^2]."""
         B, N, N2 = padded.shape
         assert B == self.batch_size and N == self.max_atom and N2 == N
-        padded = padded.contiguous().float()
-        out = torch.empty(self.total_lap, device=padded.device, dtype=torch.float32)
-        _lib.check(_lib.lib().agcn_pack_lap(self._handle, _ptr(padded), _ptr(out), _stream_ptr()))
+        padded = self._device_readable(padded)
+        out = torch.empty(self.total_lap, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().agcn_pack_lap(self._handle, _ptr(padded), _ptr(out), _stream_ptr()))
         return out
 
     def pack_lap_csr(self, indptr, indices, values):
