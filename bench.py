@@ -11,10 +11,14 @@ heads), forward + backward + gradient all-reduce + Adam.  One "step" = one such 
 
   value : graphs/s with the batch resident in HBM (CUDA events, max over ranks, L2 flushed between
           the timed steps)
-  e2e   : graphs/s through the public API from pinned HOST buffers: host->device copy of the
-          batch, topology plan, train step, device->host read of the loss, every step
-  e2e   : ... the batch crosses PCIe in the reference's zero-padded wire layout and is packed on the device
-          (e2e_packed_host: the same with a host side that already holds the packed ragged layout)
+  e2e   : graphs/s through the public API from pinned HOST buffers in the reference's zero-padded wire layout:
+          host->device transfer of the batch, topology plan, train step, device->host read of the loss, every step.
+          Two ways of taking the same host buffers in are timed and the faster one is the headline (the other
+          stays in the line): `e2e_copy_engine` stages the padded arrays through the copy engine (122 MB per step,
+          PCIe-bound) and packs on the device; `e2e_zero_copy_host` lets the pack kernels read the pinned arrays in
+          place, so only the real rows cross PCIe (1 GPU only this round; used only if its packed tensors are
+          bit-identical to the copy path's in the same run).  `e2e_packed_host`: a host side that already holds the
+          packed ragged layout; `e2e_serial`: no overlap at all.
   roofline : dominant kernel (ft::fused_fwd_kernel, live CUDA-event time per launch) against MEASURED_PEAKS.json
   cpu_baseline / --impl reference : the reference's algorithm as written (oracle port: per-graph
           Python loop with the interpreted O(n^2) metric block, autograd for the rest) on the host
@@ -508,12 +512,25 @@ def run_ours(args):
                         torch.equal(bz.pack_lap(Lpad_h), bz.pack_lap(Lpad_h.to(dev))))
                 zero_copy = {"value": B_PER_GPU / (ms_zc * 1e-3), "unit": "graphs/s", "ms_per_step": ms_zc,
                              "h2d_bytes_per_step": int(h2d_packed), "host_layout_bytes": int(h2d), "d2h_bytes_per_step": 4,
+                             "h2d_note": "bytes of the real rows the kernels read over PCIe (sector granularity adds a "
+                                         "little); the padded host arrays are host_layout_bytes",
                              "packed_bit_exact_vs_copy_path": bool(same),
                              "pipeline": "host buffers in the reference's padded wire layout (pinned); the pack kernels read "
                                          "them in place over PCIe (only the real rows), packing of step i+1 on a side "
                                          "stream under step i; eager launches"}
             except Exception as exc:      # reported, never fatal
                 zero_copy = {"value": None, "error": str(exc)[:200]}
+        e2e_copy = {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": 4,
+                    "pipeline": "input copy of step i+1 overlaps step i (copy stream, 2 device slots); loss of step i "
+                                "read after step i+1 is queued; eager launches"}
+        # the headline is the faster of the two ways of taking the SAME pinned host buffers (reference wire layout) in:
+        # staged through the copy engine, or read in place by the pack kernels (only when that path produced bit-exact
+        # packed tensors in this very run)
+        e2e_best = e2e_copy
+        if zero_copy and zero_copy.get("value") and zero_copy.get("packed_bit_exact_vs_copy_path") and \
+                zero_copy["value"] > e2e_value:
+            e2e_best = dict(zero_copy)
         line = {"metric": "sgc_ll_train_graphs_per_s", "value": value, "unit": "graphs/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "ms_per_step_eager": ms_eager,
                 "higher_is_better": True,
@@ -524,10 +541,8 @@ def run_ours(args):
                            "parameters": model.n_parameters(),
                            "host_layout_e2e": "reference wire layout: zero-padded [B,132,75] + [B,132,132] (pinned)"},
                 "clocks": clocks,
-                "e2e": {"value": e2e_value, "unit": "graphs/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
-                        "d2h_bytes_per_step": 4,
-                        "pipeline": "input copy of step i+1 overlaps step i (copy stream, 2 device slots); loss of step i "
-                                    "read after step i+1 is queued; eager launches"},
+                "e2e": e2e_best,
+                "e2e_copy_engine": e2e_copy,
                 "e2e_serial": {"value": world * B_PER_GPU / (ms_e2e_serial * 1e-3), "unit": "graphs/s",
                                "ms_per_step": ms_e2e_serial, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                                "pipeline": "copy, step and loss read strictly one after the other"},

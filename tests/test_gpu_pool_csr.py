@@ -101,3 +101,28 @@ def test_csr_laplacians_expand_to_the_dense_packing_bit_exact():
     assert torch.equal(out, a["original_laplacian"].data) and bool(torch.isfinite(out).all())
     with pytest.raises(ValueError):
         plan.pack_lap_csr(indptr[:-1], np.concatenate([m.indices for m in mats]), np.concatenate([m.data for m in mats]))
+
+
+def test_pack_reads_pinned_host_buffers_in_place():
+    """The padded wire layout (graph_topology.py:84-98) can stay in pinned host memory: the pack kernels read it in
+    place (only the real rows cross PCIe) and produce the same packed tensors, bit for bit, as from a device copy;
+    pageable host memory is refused."""
+    import agcn_b200
+    rng = np.random.default_rng(11)
+    sizes = [4, 132, 17, 64, 9]
+    B, N, F = len(sizes), 132, 75
+    X = rng.standard_normal((B, N, F)).astype(np.float32)
+    L = rng.standard_normal((B, N, N)).astype(np.float32)
+    dev = torch.device("cuda:0")
+    batch = agcn_b200.GraphBatch(sizes, N, device=dev)
+    Xh, Lh = torch.from_numpy(X).pin_memory(), torch.from_numpy(L).pin_memory()
+    Xa, La = batch.pack_nodes(Xh), batch.pack_lap(Lh)
+    Xb, Lb = batch.pack_nodes(Xh.to(dev)), batch.pack_lap(Lh.to(dev))
+    assert Xa.is_cuda and La.is_cuda
+    assert torch.equal(Xa, Xb) and torch.equal(La, Lb)
+    off = 0
+    for g, n in enumerate(sizes):
+        assert np.array_equal(Xa[off:off + n].cpu().numpy(), X[g, :n])
+        off += n
+    with pytest.raises(ValueError):
+        batch.pack_nodes(torch.from_numpy(X))
