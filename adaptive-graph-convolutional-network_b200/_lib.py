@@ -14,6 +14,8 @@ VARIANT = {"SGC_LL": 0, "SGC_LL_Reslap": 1}
 LAPLACIAN = {"reference_literal": 0, "paper": 1}
 METRIC_GRAD = {"reference": 0, "full": 1}
 ACT = {"linear": 0, "relu": 1}
+LOSS = {"sigmoid_ce": 0, "softmax_ce": 1}
+NOTIFY_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p)
 OUT_RES_L, OUT_RES_W, OUT_L_ALL, SAVE_FOR_BACKWARD = 1, 2, 4, 8
 
 
@@ -42,6 +44,8 @@ _SIGNATURES = {
     "agcn_fused_debug_set": (ctypes.c_int, [_P]),
     "agcn_fused_profile": (ctypes.c_int, [ctypes.c_int]),
     "agcn_fused_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
+    "agcn_profile_enable": (ctypes.c_int, [ctypes.c_int]),
+    "agcn_profile_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "agcn_pack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
     "agcn_unpack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
     "agcn_pack_lap": (ctypes.c_int, [_P, _P, _P, _P]),
@@ -63,6 +67,14 @@ _SIGNATURES = {
                                                   ctypes.POINTER(ctypes.c_size_t)]),
     "agcn_head_loss_grad": (ctypes.c_int, [_P] * 8 + [ctypes.c_float, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32] +
                             [_P] * 7 + [ctypes.c_size_t, _P]),
+    "agcn_head_loss_grad_ex": (ctypes.c_int, [_P] * 8 + [ctypes.c_float, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                     ctypes.c_int32] + [_P] * 7 + [ctypes.c_size_t, _P]),
+    "agcn_stack_create": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P,
+                                         ctypes.POINTER(_P)]),
+    "agcn_stack_destroy": (ctypes.c_int, [_P]),
+    "agcn_stack_workspace_bytes": (ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_size_t)]),
+    "agcn_stack_loss_grad": (ctypes.c_int, [_P] * 6 + [ctypes.c_float] + [_P] * 4 + [ctypes.c_size_t, _P, _P, _P]),
+    "agcn_adam_step": (ctypes.c_int, [_P] * 5 + [ctypes.c_int64] + [ctypes.c_float] * 4 + [_P]),
     "agcn_sgcll_host_scratch_bytes": (ctypes.c_int, [ctypes.POINTER(Desc), _P, ctypes.POINTER(ctypes.c_size_t)]),
     "agcn_sgcll_forward_host": (ctypes.c_int, [ctypes.POINTER(Desc), _P] + [_P] * 8 + [ctypes.c_size_t, _P]),
 }
@@ -93,3 +105,18 @@ def check(rc):
 
 def launch_count():
     return int(lib().agcn_launch_count())
+
+
+def profile_enable(on):
+    check(lib().agcn_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """{kernel name: (launches, milliseconds)} of the launches recorded since the last read (waits for them)."""
+    buf = ctypes.create_string_buffer(1 << 16)
+    check(lib().agcn_profile_read(buf, len(buf), None))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, n, ms = line.split("\t")
+        out[name] = (int(n), float(ms))
+    return out

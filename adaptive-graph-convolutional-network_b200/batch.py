@@ -12,8 +12,9 @@ import torch
 from . import _lib
 
 
-def _stream_ptr():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+def _stream_ptr(device=None):
+    """Current stream OF `device` (not of whatever device happens to be current)."""
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
 def _ptr(t):
@@ -32,13 +33,14 @@ class GraphBatch(object):
         self._handle = ctypes.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().agcn_plan_create(n.ctypes.data_as(ctypes.c_void_p), self.batch_size, self.max_atom,
-                                                   _stream_ptr(), ctypes.byref(self._handle)))
+                                                   _stream_ptr(self.device), ctypes.byref(self._handle)))
         self.total_nodes = int(_lib.lib().agcn_plan_total_nodes(self._handle))
         self.total_lap = int(_lib.lib().agcn_plan_total_lap(self._handle))
         self.node_off = np.concatenate([[0], np.cumsum(n, dtype=np.int64)])
         self.lap_off = np.concatenate([[0], np.cumsum(n.astype(np.int64) ** 2)])
         self._graph_ids = None
         self._n_dev = None
+        self._host_reads = []   # (event, pinned host tensor) of zero-copy pack kernels still in flight
 
     @property
     def handle(self):
@@ -62,6 +64,17 @@ class GraphBatch(object):
             raise ValueError("host tensors must be pinned (tensor.pin_memory()) to be read by the device")
         return padded
 
+    def _hold_host(self, host):
+        """A pack kernel is reading `host` (pinned) asynchronously: keep the tensor alive until an event recorded
+        behind the kernel has passed, so a temporary (``x.pin_memory()``) cannot be recycled by torch's pinned
+        allocator under the kernel.  The CALLER must still not overwrite the buffer before the stream gets there."""
+        if host.is_cuda:
+            return
+        self._host_reads = [(e, t) for e, t in self._host_reads if not e.query()]
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(self.device))
+        self._host_reads.append((ev, host))
+
     def pack_nodes(self, padded):
         """[B, max_atom, F] (device, or pinned host: zero-copy) -> [R, F] (rows >= n_g dropped)."""
         B, N, F = padded.shape
@@ -69,7 +82,8 @@ class GraphBatch(object):
         padded = self._device_readable(padded)
         out = torch.empty(self.total_nodes, F, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().agcn_pack_nodes(self._handle, _ptr(padded), _ptr(out), F, _stream_ptr()))
+            _lib.check(_lib.lib().agcn_pack_nodes(self._handle, _ptr(padded), _ptr(out), F, _stream_ptr(self.device)))
+            self._hold_host(padded)
         return out
 
     def unpack_nodes(self, packed):
@@ -78,7 +92,8 @@ class GraphBatch(object):
         assert R == self.total_nodes
         packed = packed.contiguous()
         out = torch.empty(self.batch_size, self.max_atom, F, device=packed.device, dtype=torch.float32)
-        _lib.check(_lib.lib().agcn_unpack_nodes(self._handle, _ptr(packed), _ptr(out), F, _stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().agcn_unpack_nodes(self._handle, _ptr(packed), _ptr(out), F, _stream_ptr(self.device)))
         return out
 
     def pack_lap(self, padded):
@@ -88,7 +103,8 @@ class GraphBatch(object):
         padded = self._device_readable(padded)
         out = torch.empty(self.total_lap, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
-            _lib.check(_lib.lib().agcn_pack_lap(self._handle, _ptr(padded), _ptr(out), _stream_ptr()))
+            _lib.check(_lib.lib().agcn_pack_lap(self._handle, _ptr(padded), _ptr(out), _stream_ptr(self.device)))
+            self._hold_host(padded)
         return out
 
     def pack_lap_csr(self, indptr, indices, values):
@@ -103,13 +119,14 @@ class GraphBatch(object):
         out = torch.empty(self.total_lap, device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().agcn_pack_lap_csr(self._handle, _ptr(dev[0]), _ptr(dev[1]), _ptr(dev[2]), _ptr(out),
-                                                    _stream_ptr()))
+                                                    _stream_ptr(self.device)))
         return out
 
     def unpack_lap(self, packed):
         packed = packed.contiguous()
         out = torch.empty(self.batch_size, self.max_atom, self.max_atom, device=packed.device, dtype=torch.float32)
-        _lib.check(_lib.lib().agcn_unpack_lap(self._handle, _ptr(packed), _ptr(out), _stream_ptr()))
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().agcn_unpack_lap(self._handle, _ptr(packed), _ptr(out), _stream_ptr(self.device)))
         return out
 
     def lap_view(self, packed, g):

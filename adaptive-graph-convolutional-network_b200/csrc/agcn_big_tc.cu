@@ -585,7 +585,10 @@ int grouped_tc(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStrea
     cudaFuncSetAttribute(grouped_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
   });
   dim3 grid(tiles, (g.F + BN - 1) / BN);
-  grouped_tc_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(map, g);
+  {
+    ProfScope prof("bt::grouped_tc_kernel", st);
+    grouped_tc_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(map, g);
+  }
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }
@@ -598,14 +601,26 @@ int grouped_thin(int tiles, const GroupedArgs& g, cudaStream_t st) {
   using namespace bt;
   if (g.F <= 4) {
     if (g.transL)
-      grouped_thin_kernel_t<4><<<tiles, 256, 0, st>>>(g);
+      {
+        ProfScope prof("bt::grouped_thin_kernel", st);
+        grouped_thin_kernel_t<4><<<tiles, 256, 0, st>>>(g);
+      }
     else
-      grouped_thin_kernel<4><<<tiles, 256, 0, st>>>(g);
+      {
+        ProfScope prof("bt::grouped_thin_kernel", st);
+        grouped_thin_kernel<4><<<tiles, 256, 0, st>>>(g);
+      }
   } else {
     if (g.transL)
-      grouped_thin_kernel_t<8><<<tiles, 256, 0, st>>>(g);
+      {
+        ProfScope prof("bt::grouped_thin_kernel", st);
+        grouped_thin_kernel_t<8><<<tiles, 256, 0, st>>>(g);
+      }
     else
-      grouped_thin_kernel<8><<<tiles, 256, 0, st>>>(g);
+      {
+        ProfScope prof("bt::grouped_thin_kernel", st);
+        grouped_thin_kernel<8><<<tiles, 256, 0, st>>>(g);
+      }
   }
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;

@@ -470,10 +470,31 @@ int agcn_sgcll_forward_host(const agcn_sgcll_desc* desc, const agcn_plan* plan, 
   float* dY = (float*)take((size_t)plan->R * desc->Fo * 4);
   void* dsaved = take(saved);
   void* dwork = take(work);
-  AGCN_CUDA(cudaMemcpyAsync(dXpad, h_X_padded, B * N * desc->F * 4, cudaMemcpyHostToDevice, st));
-  AGCN_CUDA(cudaMemcpyAsync(dLpad, h_L_padded, B * N * N * 4, cudaMemcpyHostToDevice, st));
-  if ((rc = agcn_pack_nodes(plan, dXpad, dX, desc->F, st))) return rc;
-  if ((rc = agcn_pack_lap(plan, dLpad, dL, st))) return rc;
+  // Page-locked host arrays are mapped into the device's address space: the pack kernels then read them in place
+  // and only the n_g real rows of every graph cross PCIe (the zero padding of the wire layout, 98 % of a
+  // molecule batch, never moves).  Pageable arrays are staged through the copy engine.
+  auto device_view = [](const float* h) -> const float* {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, h) != cudaSuccess) {
+      (void)cudaGetLastError();
+      return nullptr;
+    }
+    if ((at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged) && at.devicePointer)
+      return reinterpret_cast<const float*>(at.devicePointer);
+    return nullptr;
+  };
+  const float* xsrc = device_view(h_X_padded);
+  const float* lsrc = device_view(h_L_padded);
+  if (!xsrc) {
+    AGCN_CUDA(cudaMemcpyAsync(dXpad, h_X_padded, B * N * desc->F * 4, cudaMemcpyHostToDevice, st));
+    xsrc = dXpad;
+  }
+  if (!lsrc) {
+    AGCN_CUDA(cudaMemcpyAsync(dLpad, h_L_padded, B * N * N * 4, cudaMemcpyHostToDevice, st));
+    lsrc = dLpad;
+  }
+  if ((rc = agcn_pack_nodes(plan, xsrc, dX, desc->F, st))) return rc;
+  if ((rc = agcn_pack_lap(plan, lsrc, dL, st))) return rc;
   if ((rc = agcn_sgcll_forward(desc, plan, dX, dL, nullptr, d_M_L, d_weight, d_bias, d_alpha, nullptr, dY, nullptr,
                                nullptr, nullptr, dsaved, dwork, work, st)))
     return rc;

@@ -956,40 +956,6 @@ static TileArgs tile_args(const agcn_plan* plan, const float* L, int add_identit
 // ------------------------------------------------------------------------------------------------
 void fused_debug_set(void* d_buf) { ft::g_dbg = reinterpret_cast<unsigned long long*>(d_buf); }
 
-// ---- live kernel timing for bench.py's roofline: CUDA events on the launching stream around the main launch
-// (the small-graph tiles) of fused_forward, accumulated until read.  Off in production (and under graph capture).
-namespace {
-struct ProfState {
-  bool on = false;
-  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
-  std::mutex mu;
-} g_prof;
-}  // namespace
-
-void fused_profile_enable(int on) {
-  std::lock_guard<std::mutex> lock(g_prof.mu);
-  g_prof.on = on != 0;
-}
-
-int fused_profile_read(float* ms_sum, int* launches) {
-  std::lock_guard<std::mutex> lock(g_prof.mu);
-  float total = 0.f;
-  int n = 0;
-  for (auto& pr : g_prof.pending) {
-    float ms = 0.f;
-    AGCN_CUDA(cudaEventSynchronize(pr.second));
-    AGCN_CUDA(cudaEventElapsedTime(&ms, pr.first, pr.second));
-    total += ms;
-    ++n;
-    cudaEventDestroy(pr.first);
-    cudaEventDestroy(pr.second);
-  }
-  g_prof.pending.clear();
-  if (ms_sum) *ms_sum = total;
-  if (launches) *launches = n;
-  return AGCN_OK;
-}
-
 bool fused_enabled() {
   static const bool off = getenv("AGCN_DISABLE_FUSED") != nullptr || getenv("AGCN_DISABLE_TCGEN05") != nullptr;
   return !off;
@@ -1059,19 +1025,11 @@ int fused_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, 
   a.bias = bias; a.act = act; a.Y = Y;
   const SmemPlan sp = smem_plan(N, true);
   if ((rc = opt_in_smem(fused_fwd_kernel, 227 * 1024))) return rc;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (g_prof.on && tile0 == 0) {
-    AGCN_CUDA(cudaEventCreate(&e0));
-    AGCN_CUDA(cudaEventCreate(&e1));
-    AGCN_CUDA(cudaEventRecord(e0, st));
+  {
+    ProfScope prof(tile0 == 0 ? "ft::fused_fwd_kernel" : "ft::fused_fwd_kernel(pre tiles)", st);
+    fused_fwd_kernel<<<ntiles, THREADS, sp.total, st>>>(mhi, mlo, a);
   }
-  fused_fwd_kernel<<<ntiles, THREADS, sp.total, st>>>(mhi, mlo, a);
   AGCN_LAUNCH_CHECK();
-  if (e0) {
-    AGCN_CUDA(cudaEventRecord(e1, st));
-    std::lock_guard<std::mutex> lock(g_prof.mu);
-    g_prof.pending.emplace_back(e0, e1);
-  }
   return AGCN_OK;
 }
 
@@ -1094,7 +1052,10 @@ int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY
   a.acc_stride = N <= 32 ? 32 : (N <= 64 ? 64 : 128);
   const SmemPlan sp = smem_plan(N, false);
   if ((rc = opt_in_smem(fused_bwd_kernel, 227 * 1024))) return rc;
-  fused_bwd_kernel<<<ntiles, THREADS, sp.total, st>>>(mhi, mlo, a);
+  {
+    ProfScope prof(tile0 == 0 ? "ft::fused_bwd_kernel" : "ft::fused_bwd_kernel(pre tiles)", st);
+    fused_bwd_kernel<<<ntiles, THREADS, sp.total, st>>>(mhi, mlo, a);
+  }
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }

@@ -505,7 +505,10 @@ int big_build_laplacian(const GraphArgs& a, bool need_W, float* big_work, cudaSt
     k.pp = pp; k.F = a.F; k.XW = a.XW; k.dist = a.dist; k.resW = a.resW;
     k.rowpart = paper ? w.rowpart : nullptr; k.ncb = w.ncb;
     dim3 grid(tiles, w.ncb);
-    big_pair_kernel<PAIR_SIM><<<grid, 256, 0, st>>>(k);
+    {
+      ProfScope prof("big_pair_kernel<SIM>", st);
+      big_pair_kernel<PAIR_SIM><<<grid, 256, 0, st>>>(k);
+    }
     AGCN_LAUNCH_CHECK();
     if (paper) {
       big_dis_kernel<<<tiles, PT, 0, st>>>(pp, w.rowpart, w.ncb, a.dis);
@@ -520,14 +523,20 @@ int big_build_laplacian(const GraphArgs& a, bool need_W, float* big_work, cudaSt
   s.dist = a.dist; s.dis = a.dis; s.Lint = a.Lint; s.Lprev = reslap ? a.Lprev : nullptr;
   s.alpha = a.alpha; s.beta = a.beta; s.stats = stats;
   s.resL = a.resL; s.Lall = a.Lall; s.Lall2 = a.Lall_out; s.tilepart = w.tilepart;
-  big_sweep_kernel<SW_NORM><<<tiles, 256, 0, st>>>(s);
+  {
+    ProfScope prof("big_sweep_kernel", st);
+    big_sweep_kernel<SW_NORM><<<tiles, 256, 0, st>>>(s);
+  }
   AGCN_LAUNCH_CHECK();
   StatArgs q{};
   q.pp = pp; q.variant = a.variant; q.reslap = reslap ? 1 : 0; q.has_prev = (reslap && a.Lprev) ? 1 : 0;
   q.tilepart = w.tilepart; q.stats = stats; q.gstat = w.gstat;
   big_stats_kernel<ST_FWD><<<plan->large_count, 32, 0, st>>>(q);
   AGCN_LAUNCH_CHECK();
-  big_sweep_kernel<SW_FINAL><<<tiles, 256, 0, st>>>(s);
+  {
+    ProfScope prof("big_sweep_kernel", st);
+    big_sweep_kernel<SW_FINAL><<<tiles, 256, 0, st>>>(s);
+  }
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }
@@ -542,7 +551,10 @@ int big_dL(const GraphArgs& a, const float* U, cudaStream_t st) {
   k.S = a.K - 1; k.U = U; k.X = a.X; k.T = a.T; k.slice = (int64_t)plan->R * a.F;
   k.dL_in = a.dLall_in; k.dL = a.dL;
   dim3 grid(plan->big_tiles, (plan->max_n + PT - 1) / PT);
-  big_pair_kernel<PAIR_DL><<<grid, 256, 0, st>>>(k);
+  {
+    ProfScope prof("big_pair_kernel<DL>", st);
+    big_pair_kernel<PAIR_DL><<<grid, 256, 0, st>>>(k);
+  }
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }
@@ -569,12 +581,18 @@ int big_laplacian_bwd(const GraphArgs& a, float* big_work, cudaStream_t st) {
   q.tilepart = w.tilepart; q.stats = a.stats; q.gstat = w.gstat;
   q.dalpha_part = a.dalpha_part; q.dbeta_part = a.dbeta_part;
   if (reslap) {
-    big_sweep_kernel<SW_B1><<<tiles, 256, 0, st>>>(s);
+    {
+      ProfScope prof("big_sweep_kernel", st);
+      big_sweep_kernel<SW_B1><<<tiles, 256, 0, st>>>(s);
+    }
     AGCN_LAUNCH_CHECK();
     big_stats_kernel<ST_B1><<<plan->large_count, 32, 0, st>>>(q);
     AGCN_LAUNCH_CHECK();
   }
-  big_sweep_kernel<SW_B2><<<tiles, 256, 0, st>>>(s);
+  {
+    ProfScope prof("big_sweep_kernel", st);
+    big_sweep_kernel<SW_B2><<<tiles, 256, 0, st>>>(s);
+  }
   AGCN_LAUNCH_CHECK();
   big_stats_kernel<ST_B2><<<plan->large_count, 32, 0, st>>>(q);
   AGCN_LAUNCH_CHECK();
@@ -582,9 +600,15 @@ int big_laplacian_bwd(const GraphArgs& a, float* big_work, cudaStream_t st) {
   TransArgs t{};
   t.pp = pp; t.dist = a.dist; t.dis = a.dis; t.stats = a.stats; t.gstat = w.gstat; t.gu = a.dL;
   t.dd = w.dd; t.C = w.C; t.rs = w.rs;
-  big_trans_kernel<TR_DD><<<tiles, 256, 0, st>>>(t);
+  {
+    ProfScope prof("big_trans_kernel", st);
+    big_trans_kernel<TR_DD><<<tiles, 256, 0, st>>>(t);
+  }
   AGCN_LAUNCH_CHECK();
-  big_trans_kernel<TR_C><<<tiles, 256, 0, st>>>(t);
+  {
+    ProfScope prof("big_trans_kernel", st);
+    big_trans_kernel<TR_C><<<tiles, 256, 0, st>>>(t);
+  }
   AGCN_LAUNCH_CHECK();
   // dXW_i = rowsum(C)_i xw_i - (C XW)_i
   return grouped_rows_gemm(plan, tiles, w.C, a.XW, -1.f, w.rs, a.XW, a.dXW, a.F, st);

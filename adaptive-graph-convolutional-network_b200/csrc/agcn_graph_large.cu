@@ -102,7 +102,10 @@ __global__ void __launch_bounds__(256) grouped_lap_gemm_kernel(GroupedArgs p) {
 
 int grouped_simt(int tiles, const GroupedArgs& g, cudaStream_t st) {
   dim3 grid(tiles, (g.F + GN - 1) / GN);
-  grouped_lap_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  {
+    ProfScope prof("grouped_lap_gemm_kernel", st);
+    grouped_lap_gemm_kernel<<<grid, 256, 0, st>>>(g);
+  }
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }

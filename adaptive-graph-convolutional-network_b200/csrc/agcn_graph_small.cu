@@ -791,7 +791,10 @@ int graph_chebyshev_fwd(const GraphArgs& a, cudaStream_t st, int above_n) {
     ChebArgs k{plan_ptrs(plan), bk.start, c.chunks, c.FC, a.F, a.K, a.X, shortcut ? a.Lint : a.Lall, shortcut ? 1 : 0,
                a.T, (int64_t)plan->R * a.F};
     cudaStream_t s = (b == 0) ? st : plan->aux[(b - 1) % 3];
-    cheb_fwd_kernel<<<bk.count * c.chunks, c.threads, c.smem, s>>>(k);
+    {
+      ProfScope prof("cheb_fwd_kernel", s);
+      cheb_fwd_kernel<<<bk.count * c.chunks, c.threads, c.smem, s>>>(k);
+    }
     AGCN_LAUNCH_CHECK();
   }
   if ((rc = large_chebyshev_fwd(a, st))) return rc;  // graphs that do not fit in shared memory
@@ -814,7 +817,10 @@ int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st, int 
     RecurArgs k{plan_ptrs(plan), bk.start, c.chunks, c.FC, a.F, a.K, shortcut ? a.Lint : a.Lall, shortcut ? 1 : 0,
                 a.G, (int64_t)plan->R * a.F, a.dX, need_dL ? 1 : 0, a.X, a.T, (int64_t)plan->R * a.F, a.dLall_in, a.dL};
     cudaStream_t s = (b == 0) ? st : plan->aux[(b - 1) % 3];
-    recur_bwd_kernel<<<bk.count * c.chunks, c.threads, c.smem, s>>>(k);
+    {
+      ProfScope prof("recur_bwd_kernel", s);
+      recur_bwd_kernel<<<bk.count * c.chunks, c.threads, c.smem, s>>>(k);
+    }
     AGCN_LAUNCH_CHECK();
   }
   // row-tiled reverse recurrence: every graph above AGCN_CHEB_SMALL_MAX, or, when dL is needed, only those
@@ -842,7 +848,10 @@ int graph_build_laplacian(const GraphArgs& a, bool need_W, cudaStream_t st) {
                 a.alpha, a.beta, a.Lall, a.Lall_out, a.resL, a.resW, a.dist, a.dis, a.stats};
     cudaStream_t s = (b == 0) ? st : plan->aux[(b - 1) % 3];
     const int threads = (bk.max_n <= 32) ? 128 : (bk.max_n <= 64 ? 256 : 512);
-    build_lap_kernel<<<bk.count, threads, smem, s>>>(k);
+    {
+      ProfScope prof("build_lap_kernel", s);
+      build_lap_kernel<<<bk.count, threads, smem, s>>>(k);
+    }
     AGCN_LAUNCH_CHECK();
   }
   if ((rc = big_build_laplacian(a, need_W, a.big_work, st))) return rc;
@@ -868,7 +877,10 @@ int graph_laplacian_bwd(const GraphArgs& a, cudaStream_t st) {
                  a.alpha, a.beta, a.dist, a.dis, a.stats, a.dL, a.dLprev, a.dXW, a.dalpha_part, a.dbeta_part};
     cudaStream_t s = (b == 0) ? st : plan->aux[(b - 1) % 3];
     const int threads = (bk.max_n <= 32) ? 128 : (bk.max_n <= 64 ? 256 : 512);
-    lap_bwd_kernel<<<bk.count, threads, smem, s>>>(k);
+    {
+      ProfScope prof("lap_bwd_kernel", s);
+      lap_bwd_kernel<<<bk.count, threads, smem, s>>>(k);
+    }
     AGCN_LAUNCH_CHECK();
   }
   if ((rc = big_laplacian_bwd(a, a.big_work, st))) return rc;

@@ -103,6 +103,37 @@ __global__ void copy_pitched_kernel(const float* __restrict__ src, int lds, floa
   dst[(int64_t)r * ldd + c] = src[(int64_t)r * lds + c];
 }
 
+// Single-task multi-class head (SingletaskGraphClassifier: models/tf_modules/singletask_classifier.py:124-151 with
+// get_loss_fn('softmax_cross_entropy'), multitask_classifier.py:45-48): one warp per sample,
+//   loss_b = w_b * sum_c y_c (logsumexp(x) - x_c),   d loss / d x_c = w_b (softmax_c * sum y - y_c) * scale
+// `logits` [B, ld] is overwritten by the gradient; part[b] receives loss_b * scale.
+__global__ void softmax_ce_kernel(float* __restrict__ logits, int ld, const float* __restrict__ y, const float* __restrict__ w,
+                                  int B, int C, float scale, float* __restrict__ part) {
+  const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (b >= B) return;
+  float* x = logits + (int64_t)b * ld;
+  const float* yb = y + (int64_t)b * C;
+  float mx = -INFINITY;
+  for (int c = lane; c < C; c += 32) mx = fmaxf(mx, x[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float se = 0.f, sy = 0.f, sxy = 0.f;
+  for (int c = lane; c < C; c += 32) {
+    se += expf(x[c] - mx);
+    sy += yb[c];
+    sxy += yb[c] * x[c];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    se += __shfl_xor_sync(0xffffffffu, se, o);
+    sy += __shfl_xor_sync(0xffffffffu, sy, o);
+    sxy += __shfl_xor_sync(0xffffffffu, sxy, o);
+  }
+  const float lse = mx + logf(se), wb = w[b];
+  for (int c = lane; c < C; c += 32) x[c] = wb * (expf(x[c] - lse) * sy - yb[c]) * scale;
+  if (lane == 0) part[b] = wb * (lse * sy - sxy) * scale;
+}
+
 __global__ void sum_parts_kernel(const float* __restrict__ parts, int n, float* __restrict__ out) {
   __shared__ float red[256];
   float s = 0.f;
@@ -155,7 +186,7 @@ HeadWork carve_head(const agcn_plan* plan, int Fh, int Fm, int Nt, void* base) {
   w.dWh_pad = take((size_t)Fm * Ntp);
   GemmArgs g;
   g.M = (int)B; g.N = Nt; g.Z = 1;
-  w.loss_part = take((size_t)tc_gemm_loss_parts(g) + 64);
+  w.loss_part = take(std::max((size_t)tc_gemm_loss_parts(g), B) + 64);
   w.tcA = take(tc_gemm_scratch_floats(Fm, Fh, 1, 1));   // dense_W            (pre   = hsum dense_W)
   w.tcB = take(tc_gemm_scratch_floats(Nt, Fm, 1, 1));   // head_W             (logits = mol head_W)
   w.tcC = take(tc_gemm_scratch_floats(Fm, Nt, 1, 1));   // head_W^T operand   (dmol  = dlog head_W^T)
@@ -189,12 +220,25 @@ int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_
                         float scale, int32_t Fh, int32_t Fm, int32_t Nt, float* d_loss, float* d_dH,
                         float* d_ddense_W, float* d_ddense_b, float* d_dhead_W, float* d_dhead_b, void* d_work,
                         size_t work_bytes, void* stream) {
+  return agcn_head_loss_grad_ex(plan, d_H, d_dense_W, d_dense_b, d_head_W, d_head_b, d_targets, d_weights, scale,
+                                AGCN_LOSS_SIGMOID_CE, Fh, Fm, Nt, d_loss, d_dH, d_ddense_W, d_ddense_b, d_dhead_W,
+                                d_dhead_b, d_work, work_bytes, stream);
+}
+
+int agcn_head_loss_grad_ex(const agcn_plan* plan, const float* d_H, const float* d_dense_W, const float* d_dense_b,
+                           const float* d_head_W, const float* d_head_b, const float* d_targets, const float* d_weights,
+                           float scale, int32_t loss_kind, int32_t Fh, int32_t Fm, int32_t Nt, float* d_loss,
+                           float* d_dH, float* d_ddense_W, float* d_ddense_b, float* d_dhead_W, float* d_dhead_b,
+                           void* d_work, size_t work_bytes, void* stream) {
   AGCN_REQUIRE(plan && d_H && d_dense_W && d_dense_b && d_head_W && d_head_b && d_targets && d_weights && d_loss &&
                    d_dH && d_ddense_W && d_ddense_b && d_dhead_W && d_dhead_b && d_work,
                "head_loss_grad: null pointer");
-  // tensor-core shapes: the contraction dims must reach one k-block, operand pitches must be 16-byte multiples
-  AGCN_REQUIRE(Fh >= 32 && Fh % 4 == 0 && Fh <= 128 && Fm >= 32 && Fm % 4 == 0 && Fm <= 256 && Nt >= 32,
-               "head_loss_grad: unsupported sizes (need 32 <= Fh <= 128, 32 <= Fm <= 256, multiples of 4)");
+  AGCN_REQUIRE(loss_kind == AGCN_LOSS_SIGMOID_CE || loss_kind == AGCN_LOSS_SOFTMAX_CE, "head_loss_grad: unknown loss_kind");
+  // the logits GEMM carries the cross-entropy epilogue on the tensor cores: its contraction (Fm) must reach one
+  // k-block with 16-byte operand pitches; every other contraction falls back to the CUDA-core kernels when its
+  // shape is not TMA-compatible (e.g. 12 tasks: Nt = 24)
+  AGCN_REQUIRE(Fh >= 1 && Fm >= 32 && Fm % 4 == 0 && Nt >= 1,
+               "head_loss_grad: unsupported sizes (need Fm >= 32 and a multiple of 4)");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = plan_use(plan, st);
   if (rc) return rc;
@@ -219,8 +263,11 @@ int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_
   g_log.B = d_head_W; g_log.ldb = Nt;
   g_log.C = w.dlog; g_log.ldc = Ntp;
   g_log.bias = d_head_b;
-  g_log.bce_y = d_targets; g_log.bce_w = d_weights; g_log.bce_ld = Nt; g_log.bce_scale = scale;
-  g_log.loss_part = w.loss_part;
+  const bool sigmoid = loss_kind == AGCN_LOSS_SIGMOID_CE;
+  if (sigmoid) {
+    g_log.bce_y = d_targets; g_log.bce_w = d_weights; g_log.bce_ld = Nt; g_log.bce_scale = scale;
+    g_log.loss_part = w.loss_part;
+  }
   g_dmol.M = B; g_dmol.N = Fm; g_dmol.Kd = Nt;
   g_dmol.A0 = w.dlog; g_dmol.lda0 = Ntp;
   g_dmol.B = d_head_W; g_dmol.ldb = Nt; g_dmol.transB = 1;  // head_W is [Fm, Nt] = [N, Kd]
@@ -229,15 +276,15 @@ int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_
   g_dhs.A0 = w.dmol; g_dhs.lda0 = Fm;
   g_dhs.B = d_dense_W; g_dhs.ldb = Fm; g_dhs.transB = 1;    // dense_W is [Fh, Fm] = [N, Kd]
   g_dhs.C = w.dhsum; g_dhs.ldc = Fh; g_dhs.split_k_partial = w.splitk;
-  AGCN_REQUIRE(tc_gemm_supported(g_pre) && tc_gemm_supported(g_log) && tc_gemm_supported(g_dmol) &&
-                   tc_gemm_supported(g_dhs),
-               "head_loss_grad: operands are not TMA-compatible (alignment)");
+  AGCN_REQUIRE(tc_gemm_supported(g_log), "head_loss_grad: operands are not TMA-compatible (alignment)");
+  const bool tc_pre = tc_gemm_supported(g_pre), tc_dmol = tc_gemm_supported(g_dmol), tc_dhs = tc_gemm_supported(g_dhs);
+  auto gemm_any = [&](const GemmArgs& g, const float* scratch, bool tc) { return tc ? tc_gemm(g, scratch, st) : gemm_rows(g, st); };
   AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
   AGCN_CUDA(cudaStreamWaitEvent(side, plan->ev_side_fork, 0));
-  if ((rc = tc_gemm_split_b(g_pre, w.tcA, side))) return rc;
+  if (tc_pre && (rc = tc_gemm_split_b(g_pre, w.tcA, side))) return rc;
   if ((rc = tc_gemm_split_b(g_log, w.tcB, side))) return rc;
-  if ((rc = tc_gemm_split_b(g_dmol, w.tcC, side))) return rc;
-  if ((rc = tc_gemm_split_b(g_dhs, w.tcD, side))) return rc;
+  if (tc_dmol && (rc = tc_gemm_split_b(g_dmol, w.tcC, side))) return rc;
+  if (tc_dhs && (rc = tc_gemm_split_b(g_dhs, w.tcD, side))) return rc;
   if ((rc = zero_async(w.dlog, (size_t)B * Ntp, side))) return rc;  // pad columns of dlog
   AGCN_CUDA(cudaEventRecord(plan->ev_side_join, side));
 
@@ -245,7 +292,7 @@ int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_
   segment_sum_kernel<<<(B + 7) / 8, 256, 0, st>>>(d_H, plan->d_node_off, B, Fh, w.hsum);
   AGCN_LAUNCH_CHECK();
   AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
-  if ((rc = tc_gemm(g_pre, w.tcA, st))) return rc;
+  if ((rc = gemm_any(g_pre, w.tcA, tc_pre))) return rc;
   {
     const int64_t total = (int64_t)B * Fm;
     gather_tanh_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.pre, d_dense_b, plan->d_n, B, Fm, w.mol);
@@ -253,7 +300,13 @@ int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_
   }
   // logits + weighted sigmoid cross-entropy: C receives d loss / d logits, the loss its per-warp partial sums
   if ((rc = tc_gemm(g_log, w.tcB, st))) return rc;
-  sum_parts_kernel<<<1, 256, 0, st>>>(w.loss_part, tc_gemm_loss_parts(g_log), d_loss);
+  int n_parts = tc_gemm_loss_parts(g_log);
+  if (!sigmoid) {  // the GEMM wrote the logits; softmax cross-entropy and its gradient row by row
+    softmax_ce_kernel<<<(B + 7) / 8, 256, 0, st>>>(w.dlog, Ntp, d_targets, d_weights, B, Nt, scale, w.loss_part);
+    AGCN_LAUNCH_CHECK();
+    n_parts = B;
+  }
+  sum_parts_kernel<<<1, 256, 0, st>>>(w.loss_part, n_parts, d_loss);
   AGCN_LAUNCH_CHECK();
 
   // parameter gradients of the heads on the side stream, beside the chain back to dH
@@ -276,13 +329,13 @@ int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_
   }
 
   // main stream: dmol = dlog head_W^T, through tanh, ddense_b, dhsum, dH
-  if ((rc = tc_gemm(g_dmol, w.tcC, st))) return rc;
+  if ((rc = gemm_any(g_dmol, w.tcC, tc_dmol))) return rc;
   {
     const int64_t total = (int64_t)B * Fm;
     tanh_bwd_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(w.mol, w.dmol, total);  // dmol := dpre
     AGCN_LAUNCH_CHECK();
   }
-  if ((rc = tc_gemm(g_dhs, w.tcD, st))) return rc;
+  if ((rc = gemm_any(g_dhs, w.tcD, tc_dhs))) return rc;
   segment_broadcast_kernel<<<(B + 7) / 8, 256, 0, st>>>(w.dhsum, plan->d_node_off, B, Fh, d_dH);
   AGCN_LAUNCH_CHECK();
   // dense parameter gradients (need dpre; the dhead_W contraction on the side stream is done with tn_part by now

@@ -289,6 +289,22 @@ int fused_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, 
 int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY, const float* Y, const float* L,
                    int add_identity, const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st);
 
+// ---------------------------------------------------------------- live per-kernel timing (agcn_profile.cu)
+// RAII bracket around ONE kernel launch in a host wrapper; records only while agcn_profile_enable(1) is in effect and
+// the stream is not capturing.
+class ProfScope {
+ public:
+  ProfScope(const char* name, cudaStream_t st);
+  ~ProfScope();
+  ProfScope(const ProfScope&) = delete;
+  ProfScope& operator=(const ProfScope&) = delete;
+
+ private:
+  const char* name_;
+  cudaStream_t st_;
+  cudaEvent_t e0_;
+};
+
 // ---------------------------------------------------------------- helpers
 int zero_async(float* dst, size_t floats, cudaStream_t st);  // zero fill by a kernel (never the copy engine)
 int plan_use(const agcn_plan* plan, cudaStream_t st);  // call first in every entry point that enqueues work

@@ -130,14 +130,26 @@ int gemm_rows(const GemmArgs& a, cudaStream_t st) {
   dim3 grid((a.M + BM - 1) / BM, (a.N + BN - 1) / BN, a.Z);
   if (vec) {
     if (a.transB)
-      gemm_rows_kernel<true, true><<<grid, 256, 0, st>>>(a);
+      {
+        ProfScope prof("gemm_rows_kernel", st);
+        gemm_rows_kernel<true, true><<<grid, 256, 0, st>>>(a);
+      }
     else
-      gemm_rows_kernel<true, false><<<grid, 256, 0, st>>>(a);
+      {
+        ProfScope prof("gemm_rows_kernel", st);
+        gemm_rows_kernel<true, false><<<grid, 256, 0, st>>>(a);
+      }
   } else {
     if (a.transB)
-      gemm_rows_kernel<false, true><<<grid, 256, 0, st>>>(a);
+      {
+        ProfScope prof("gemm_rows_kernel", st);
+        gemm_rows_kernel<false, true><<<grid, 256, 0, st>>>(a);
+      }
     else
-      gemm_rows_kernel<false, false><<<grid, 256, 0, st>>>(a);
+      {
+        ProfScope prof("gemm_rows_kernel", st);
+        gemm_rows_kernel<false, false><<<grid, 256, 0, st>>>(a);
+      }
   }
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;

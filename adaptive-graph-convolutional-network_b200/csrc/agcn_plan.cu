@@ -217,11 +217,16 @@ static cudaError_t acquire_staging(size_t bytes, Staging* out) {
     std::lock_guard<std::mutex> lock(g_pool_mu);
     for (size_t i = 0; i < g_staging_pool.size(); ++i) {
       Staging& s = g_staging_pool[i];
-      if (s.device == dev && s.bytes >= bytes && cudaEventQuery(s.done) == cudaSuccess) {
+      if (s.device != dev || s.bytes < bytes) continue;
+      const cudaError_t q = cudaEventQuery(s.done);
+      if (q == cudaSuccess) {
         *out = s;
         g_staging_pool.erase(g_staging_pool.begin() + i);
         return cudaSuccess;
       }
+      // still being read by the upload of a plan that was destroyed early: cudaErrorNotReady is not an error and
+      // must not stay in the runtime's last-error slot (the next AGCN_LAUNCH_CHECK would report it)
+      (void)cudaGetLastError();
     }
   }
   Staging s;

@@ -1,0 +1,111 @@
+// Live per-kernel timing for bench.py's roofline table: while enabled, the host wrappers of the main kernels bracket
+// their launch with CUDA events on the launching stream (ProfScope); agcn_profile_read waits for them and returns
+// launches and summed milliseconds per kernel name.  Off in production and never active under stream capture.
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "agcn_internal.cuh"
+
+namespace agcn {
+
+std::atomic<int> g_prof_on{0};
+
+namespace {
+struct ProfRec {
+  const char* name;
+  cudaEvent_t e0, e1;
+};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof_recs;
+}  // namespace
+
+ProfScope::ProfScope(const char* name, cudaStream_t st) : name_(name), st_(st), e0_(nullptr) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+    (void)cudaGetLastError();
+    return;
+  }
+  if (cudaEventCreate(&e0_) != cudaSuccess) {
+    e0_ = nullptr;
+    return;
+  }
+  cudaEventRecord(e0_, st);
+}
+
+ProfScope::~ProfScope() {
+  if (!e0_) return;
+  cudaEvent_t e1 = nullptr;
+  if (cudaEventCreate(&e1) != cudaSuccess) {
+    cudaEventDestroy(e0_);
+    return;
+  }
+  cudaEventRecord(e1, st_);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof_recs.push_back(ProfRec{name_, e0_, e1});
+}
+
+void prof_enable(int on) { g_prof_on.store(on ? 1 : 0); }
+
+// Drains the pending records.  only != NULL: sum of the records of that kernel name (the others are dropped).
+int prof_drain(const char* only, float* ms_sum, int* launches, std::string* table) {
+  std::vector<ProfRec> recs;
+  {
+    std::lock_guard<std::mutex> lock(g_prof_mu);
+    recs.swap(g_prof_recs);
+  }
+  std::map<std::string, std::pair<int, double>> agg;
+  float total = 0.f;
+  int n = 0;
+  for (ProfRec& r : recs) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(r.e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.e0, r.e1);
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+    if (e != cudaSuccess) return cuda_fail(e, "profile read", __FILE__, __LINE__);
+    auto& a = agg[r.name];
+    a.first += 1;
+    a.second += ms;
+    if (only && std::string(only) == r.name) {
+      total += ms;
+      ++n;
+    }
+  }
+  if (ms_sum) *ms_sum = total;
+  if (launches) *launches = n;
+  if (table) {
+    table->clear();
+    for (auto& kv : agg) *table += kv.first + "\t" + std::to_string(kv.second.first) + "\t" + std::to_string(kv.second.second) + "\n";
+  }
+  return AGCN_OK;
+}
+
+void fused_profile_enable(int on) { prof_enable(on); }
+int fused_profile_read(float* ms_sum, int* launches) { return prof_drain("ft::fused_fwd_kernel", ms_sum, launches, nullptr); }
+
+}  // namespace agcn
+
+extern "C" {
+
+int agcn_profile_enable(int enable) {
+  agcn::prof_enable(enable);
+  return AGCN_OK;
+}
+
+int agcn_profile_read(char* buf, size_t cap, size_t* needed) {
+  std::string table;
+  int rc = agcn::prof_drain(nullptr, nullptr, nullptr, &table);
+  if (rc) return rc;
+  if (needed) *needed = table.size() + 1;
+  if (buf && cap) {
+    const size_t n = table.size() < cap - 1 ? table.size() : cap - 1;
+    table.copy(buf, n);
+    buf[n] = 0;
+  }
+  return AGCN_OK;
+}
+
+}  // extern "C"

@@ -716,12 +716,18 @@ int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
     std::call_once(once64, [] {
       cudaFuncSetAttribute(tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64>::TOTAL);
     });
-    tc_gemm_kernel<64><<<grid, 192, Smem<64>::TOTAL, st>>>(mA0, mA1, mBhi, mBlo, p);
+    {
+      ProfScope prof("tc::tc_gemm_kernel", st);
+      tc_gemm_kernel<64><<<grid, 192, Smem<64>::TOTAL, st>>>(mA0, mA1, mBhi, mBlo, p);
+    }
   } else {
     std::call_once(once128, [] {
       cudaFuncSetAttribute(tc_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<128>::TOTAL);
     });
-    tc_gemm_kernel<128><<<grid, 192, Smem<128>::TOTAL, st>>>(mA0, mA1, mBhi, mBlo, p);
+    {
+      ProfScope prof("tc::tc_gemm_kernel", st);
+      tc_gemm_kernel<128><<<grid, 192, Smem<128>::TOTAL, st>>>(mA0, mA1, mBhi, mBlo, p);
+    }
   }
   AGCN_LAUNCH_CHECK();
   if (ksplit > 1) {
@@ -795,12 +801,18 @@ int tc_gemm_tn(const GemmTNArgs& a, cudaStream_t st) {
     std::call_once(once64, [] {
       cudaFuncSetAttribute(tc_gemm_tn_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemTn<64>::TOTAL);
     });
-    tc_gemm_tn_kernel<64><<<grid, 192, SmemTn<64>::TOTAL, st>>>(mA0, mA1, mD, p);
+    {
+      ProfScope prof("tc::tc_gemm_tn_kernel", st);
+      tc_gemm_tn_kernel<64><<<grid, 192, SmemTn<64>::TOTAL, st>>>(mA0, mA1, mD, p);
+    }
   } else {
     std::call_once(once128, [] {
       cudaFuncSetAttribute(tc_gemm_tn_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemTn<128>::TOTAL);
     });
-    tc_gemm_tn_kernel<128><<<grid, 192, SmemTn<128>::TOTAL, st>>>(mA0, mA1, mD, p);
+    {
+      ProfScope prof("tc::tc_gemm_tn_kernel", st);
+      tc_gemm_tn_kernel<128><<<grid, 192, SmemTn<128>::TOTAL, st>>>(mA0, mA1, mD, p);
+    }
   }
   AGCN_LAUNCH_CHECK();
   const long long elems = (long long)a.Kd * a.S * a.N;

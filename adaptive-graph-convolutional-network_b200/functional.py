@@ -8,15 +8,17 @@ from .batch import GraphBatch, _ptr, _stream_ptr
 
 
 class _Workspace(object):
-    """Grow-only scratch buffer per device (the `work` area of agcn_sgcll_forward/backward)."""
+    """Grow-only scratch buffer per (device, stream) (the `work` area of agcn_sgcll_forward/backward): calls on
+    one stream are ordered, so they can share it; calls on different streams must not."""
     _bufs = {}
 
     @classmethod
     def get(cls, device, nbytes):
-        buf = cls._bufs.get(device)
+        key = (device, torch.cuda.current_stream(device).cuda_stream)
+        buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
             buf = torch.empty(int(nbytes * 1.25) + 1024, dtype=torch.uint8, device=device)
-            cls._bufs[device] = buf
+            cls._bufs[key] = buf
         return buf
 
 
@@ -58,10 +60,11 @@ class _SGCLLFunction(torch.autograd.Function):
         resL = torch.empty(batch.total_lap, device=dev, dtype=torch.float32) if want_resL else None
         resW = torch.empty(batch.total_lap, device=dev, dtype=torch.float32) if want_resW else None
         Lall = torch.empty(batch.total_lap, device=dev, dtype=torch.float32) if reslap else None
-        _lib.check(_lib.lib().agcn_sgcll_forward(
-            ctypes.byref(desc), batch.handle, _ptr(X), _ptr(Lint), _ptr(Lprev), _ptr(M_L), _ptr(weight), _ptr(bias),
-            _ptr(alpha), _ptr(beta), _ptr(Y), _ptr(resL), _ptr(resW), _ptr(Lall), _ptr(saved), _ptr(work),
-            work.numel(), _stream_ptr()))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().agcn_sgcll_forward(
+                ctypes.byref(desc), batch.handle, _ptr(X), _ptr(Lint), _ptr(Lprev), _ptr(M_L), _ptr(weight), _ptr(bias),
+                _ptr(alpha), _ptr(beta), _ptr(Y), _ptr(resL), _ptr(resW), _ptr(Lall), _ptr(saved), _ptr(work),
+                work.numel(), _stream_ptr(dev)))
         ctx.batch, ctx.cfg, ctx.desc = batch, cfg, desc
         # parameters registered with FlatGradBuffer(direct=...): backward writes their gradients in place
         ctx.grad_out = [getattr(t, "_agcn_grad_out", None) if t is not None else None
@@ -101,10 +104,11 @@ class _SGCLLFunction(torch.autograd.Function):
         if ctx.has_beta:
             dbeta = gbeta if gbeta is not None else torch.zeros(1, device=dev, dtype=torch.float32)
         dLprev = torch.empty_like(Lprev) if ctx.has_prev else None
-        _lib.check(_lib.lib().agcn_sgcll_backward(
-            ctypes.byref(desc), batch.handle, _ptr(X), _ptr(Lint), _ptr(Lprev), _ptr(M_L), _ptr(weight), _ptr(alpha),
-            _ptr(beta), _ptr(Y), _ptr(dY), _ptr(dLall), _ptr(saved), _ptr(dX), _ptr(dM), _ptr(dW), _ptr(db),
-            _ptr(dalpha), _ptr(dbeta), _ptr(dLprev), _ptr(work), work.numel(), _stream_ptr()))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().agcn_sgcll_backward(
+                ctypes.byref(desc), batch.handle, _ptr(X), _ptr(Lint), _ptr(Lprev), _ptr(M_L), _ptr(weight), _ptr(alpha),
+                _ptr(beta), _ptr(Y), _ptr(dY), _ptr(dLall), _ptr(saved), _ptr(dX), _ptr(dM), _ptr(dW), _ptr(db),
+                _ptr(dalpha), _ptr(dbeta), _ptr(dLprev), _ptr(work), work.numel(), _stream_ptr(dev)))
         # gradients written in place are not returned (autograd would add them to themselves)
         return (dX, None, dLprev, None if gM is not None else dM, None if gW is not None else dW,
                 None if gb is not None else db, None if ga is not None else dalpha,
@@ -124,12 +128,13 @@ class _HeadLossFunction(torch.autograd.Function):
     incoming gradient unless `unit_grad` says the loss is differentiated directly)."""
 
     @staticmethod
-    def forward(ctx, H, dense_W, dense_b, head_W, head_b, targets, weights, batch, scale, unit_grad):
+    def forward(ctx, H, dense_W, dense_b, head_W, head_b, targets, weights, batch, scale, unit_grad, loss_kind):
         H = H.contiguous()
         R, Fh = H.shape
         Fm, Nt = head_W.shape
         dev = H.device
         assert dense_W.shape == (Fh, Fm) and targets.shape == (batch.batch_size, Nt) and R == batch.total_nodes
+        assert weights.numel() == (batch.batch_size * Nt if loss_kind == "sigmoid_ce" else batch.batch_size)
         nbytes = ctypes.c_size_t()
         _lib.check(_lib.lib().agcn_head_workspace_bytes(batch.handle, Fh, Fm, Nt, ctypes.byref(nbytes)))
         work = _Workspace.get(dev, nbytes.value)
@@ -137,10 +142,13 @@ class _HeadLossFunction(torch.autograd.Function):
         grads = [o if o is not None else torch.empty_like(t) for o, t in zip(outs, (dense_W, dense_b, head_W, head_b))]
         loss = torch.empty(1, device=dev, dtype=torch.float32)
         dH = torch.empty_like(H)
-        _lib.check(_lib.lib().agcn_head_loss_grad(
-            batch.handle, _ptr(H), _ptr(dense_W), _ptr(dense_b), _ptr(head_W), _ptr(head_b), _ptr(targets.contiguous()),
-            _ptr(weights.contiguous()), float(scale), Fh, Fm, Nt, _ptr(loss), _ptr(dH), _ptr(grads[0]), _ptr(grads[1]),
-            _ptr(grads[2]), _ptr(grads[3]), _ptr(work), work.numel(), _stream_ptr()))
+        with torch.cuda.device(dev):
+            _lib.check(_lib.lib().agcn_head_loss_grad_ex(
+                batch.handle, _ptr(H), _ptr(dense_W), _ptr(dense_b), _ptr(head_W), _ptr(head_b),
+                _ptr(targets.contiguous()), _ptr(weights.contiguous()), float(scale), _lib.LOSS[loss_kind], Fh, Fm, Nt,
+                _ptr(loss), _ptr(dH),
+                _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]), _ptr(grads[3]), _ptr(work), work.numel(),
+                _stream_ptr(dev)))
         ctx.unit_grad = unit_grad
         ctx.in_place = [o is not None for o in outs]
         ctx.save_for_backward(dH, *grads)
@@ -154,14 +162,17 @@ class _HeadLossFunction(torch.autograd.Function):
             grads = [t if ip else t * g for t, ip in zip(grads, ctx.in_place)]
         # gradients already written into the flat gradient buffer are not returned
         out = [None if ip else t for t, ip in zip(grads, ctx.in_place)]
-        return (dH, out[0], out[1], out[2], out[3], None, None, None, None, None)
+        return (dH, out[0], out[1], out[2], out[3], None, None, None, None, None, None)
 
 
-def head_loss(H, dense_W, dense_b, head_W, head_b, targets, weights, batch, scale, unit_grad=False):
+def head_loss(H, dense_W, dense_b, head_W, head_b, targets, weights, batch, scale, unit_grad=False,
+              loss_kind="sigmoid_ce"):
     """Scalar loss of the SimpleAGCN head on the packed output of the last SGC-LL layer.
-    unit_grad=True: the caller differentiates this loss directly (d loss / d loss = 1), which skips the
-    rescaling kernels; parameters registered with FlatGradBuffer(direct=...) require it."""
-    return _HeadLossFunction.apply(H, dense_W, dense_b, head_W, head_b, targets, weights, batch, scale, unit_grad)
+    loss_kind "sigmoid_ce": multitask two-class heads, weights [B, Nt]; "softmax_ce": one n_classes head,
+    weights [B].  unit_grad=True: the caller differentiates this loss directly (d loss / d loss = 1), which skips
+    the rescaling kernels; parameters registered with FlatGradBuffer(direct=...) require it."""
+    return _HeadLossFunction.apply(H, dense_W, dense_b, head_W, head_b, targets, weights, batch, scale, unit_grad,
+                                   loss_kind)
 
 
 class _UnpackNodes(torch.autograd.Function):
@@ -191,4 +202,8 @@ def unpack_nodes(packed, batch):
 
 
 def pack_nodes(padded, batch):
+    if not padded.is_cuda:
+        # pinned host input (zero-copy read by the pack kernel): an input placeholder, never differentiated --
+        # routing it through autograd would hand a CUDA gradient to a CPU tensor
+        return batch.pack_nodes(padded)
     return _PackNodes.apply(padded, batch)

@@ -78,8 +78,15 @@ class SGC_LL(Layer):
         self.metric_grad = kwargs.pop('metric_grad', None)
         super(SGC_LL, self).__init__(**kwargs)
         self.dropout = dropout
-        self.activation_name = activation if isinstance(activation, str) or activation is None else None
-        self.activation = activations.get(activation)
+        self.activation = activations.get(activation)           # callables pass through (activations.py:15-53)
+        # the kernel epilogue fuses relu / linear; every other activation (by name or as a callable) is applied
+        # by the host on the kernel's linear output (graphconv.py:120)
+        if self.activation is activations.relu:
+            self.activation_name = 'relu'
+        elif self.activation is activations.linear:
+            self.activation_name = 'linear'
+        else:
+            self.activation_name = None
         self.batch_size = batch_size
         self.nb_filter = output_dim
         self.n_atom_feature = input_dim
@@ -153,6 +160,13 @@ class SGC_LL(Layer):
         return {"F": self.n_atom_feature, "Fo": self.nb_filter, "K": self.K, "variant": self.variant,
                 "laplacian": lap, "metric_grad": mg, "activation": fused_act}
 
+    def _fused_activation(self):
+        """(fused?, activation the kernel applies).  Not fused: the kernel runs linear and _finish applies
+        self.activation, whatever it is (a registry name or a caller's own callable)."""
+        if self.activation_name in ('relu', 'linear'):
+            return True, self.activation_name
+        return False, 'linear'
+
     def _finish(self, Y, fused):
         if not fused:
             Y = self.activation(Y)                      # graphconv.py:120
@@ -167,8 +181,7 @@ class SGC_LL(Layer):
         batch = self._resolve_batch(x, node_features)
         X = self._packed_nodes(node_features, batch)
         Lint = self._packed_laps(x['original_laplacian'], batch, x, '_packed_laplacian')
-        fused = self.activation_name in ('relu', 'linear', None)
-        fused_act = 'relu' if self.activation_name == 'relu' else 'linear'
+        fused, fused_act = self._fused_activation()
         cfg = self._cfg(fused_act)
         Y, _, _, _ = sgc_ll_packed(X, Lint, None, self.vars, batch, cfg)
         Y = self._finish(Y, fused)

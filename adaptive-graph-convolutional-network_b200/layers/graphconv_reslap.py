@@ -32,8 +32,7 @@ class SGC_LL_Reslap(SGC_LL):
         Lprev = None
         if self.early_laps is not None and len(self.early_laps) > 0:     # graphconv_reslap.py:188
             Lprev = self._packed_laps(self.early_laps, batch)
-        fused = self.activation_name in ('relu', 'linear', None)
-        fused_act = 'relu' if self.activation_name == 'relu' else 'linear'
+        fused, fused_act = self._fused_activation()
         cfg = self._cfg(fused_act)
         Y, _, _, Lall = sgc_ll_packed(X, Lint, Lprev, self.vars, batch, cfg)
         Y = self._finish(Y, fused)

@@ -25,8 +25,9 @@ class _GraphPool(torch.autograd.Function):
         assert R == batch.total_nodes and L.numel() == batch.total_lap and X.is_cuda
         Y = torch.empty_like(X)
         arg = torch.empty(R, F, dtype=torch.int32, device=X.device) if with_grad else None
-        _lib.check(_lib.lib().agcn_graph_pool(batch.handle, _ptr(X), _ptr(L.contiguous()), _ptr(Y), _ptr(arg), F,
-                                              _stream_ptr()))
+        with torch.cuda.device(X.device):
+            _lib.check(_lib.lib().agcn_graph_pool(batch.handle, _ptr(X), _ptr(L.contiguous()), _ptr(Y), _ptr(arg), F,
+                                                  _stream_ptr(X.device)))
         ctx.batch, ctx.F, ctx.with_grad = batch, F, with_grad
         if with_grad:
             ctx.save_for_backward(arg)
@@ -38,8 +39,9 @@ class _GraphPool(torch.autograd.Function):
             return None, None, None, None      # tf.py_func has no gradient (graphpool.py:107)
         arg, = ctx.saved_tensors
         dX = torch.empty_like(dY)
-        _lib.check(_lib.lib().agcn_graph_pool_backward(ctx.batch.handle, _ptr(dY.contiguous()), _ptr(arg), _ptr(dX),
-                                                       ctx.F, _stream_ptr()))
+        with torch.cuda.device(dY.device):
+            _lib.check(_lib.lib().agcn_graph_pool_backward(ctx.batch.handle, _ptr(dY.contiguous()), _ptr(arg), _ptr(dX),
+                                                           ctx.F, _stream_ptr(dY.device)))
         return dX, None, None, None
 
 

@@ -1,20 +1,28 @@
-"""SimpleAGCN-shaped training step used to MEASURE the SGC-LL hot path (bench.py).
+"""SimpleAGCN-shaped training step used to MEASURE the SGC-LL hot path (bench.py) and to test it end to end.
 
 The reference assembles the same stack in models/networks/basic_AGCN.py:35-47: four SGC_LL layers
-(l_n_filters = [64, 128, 128, 64], utils/hyper_parameters.py:14), DenseMol, GraphGatherMol(tanh),
-then MultitaskGraphClassifier's per-task 2-class logits with weighted sigmoid cross-entropy divided
-by the batch size (models/tf_modules/multitask_classifier.py:41-44,187-209) and Adam
-(:233-237).  Only the SGC_LL layers are this repository's product; the dense / gather / head / Adam
-pieces are plain torch ops here (SURVEY.md section 8f lists them as the next rows to fuse).
+(l_n_filters = [64, 128, 128, 64], utils/hyper_parameters.py:14), DenseMol, GraphGatherMol(tanh), then either
+MultitaskGraphClassifier's per-task 2-class logits with weighted sigmoid cross-entropy divided by the batch size
+(models/tf_modules/multitask_classifier.py:41-44,187-209) or SingletaskGraphClassifier's n_classes logits with
+softmax cross-entropy (models/tf_modules/singletask_classifier.py:124-151), and tf.train.AdamOptimizer
+(multitask_classifier.py:233-237).  The reference executes one step as a single ``sess.run``; the counterpart
+here is ONE library call, ``agcn_stack_loss_grad`` (engine="stack", the default and the path bench.py times),
+which chains the same C entry points the layer classes use.  engine="autograd" runs the same step through the
+layer classes and torch.autograd (the drop-in path of models/layers); tests pin both against the oracle and
+against each other.
 
-Data parallel: every rank holds a replica and its own shard of graphs; one all-reduce of a flat
-gradient buffer per step.  The loss is normalised by the GLOBAL batch size.
+Data parallel: every rank holds a replica and its own shard of graphs; the flat gradient buffer is all-reduced
+ -- in buckets issued while the earlier layers are still running backward when
+``overlap_allreduce`` is set.  The loss is normalised by the GLOBAL batch size.
 """
+import ctypes
+
 import numpy as np
 import torch
 import torch.distributed as dist
 
-from .batch import GraphBatch, PackedLaplacians, PackedNodes
+from . import _lib
+from .batch import GraphBatch, PackedLaplacians, PackedNodes, _ptr, _stream_ptr
 from .data_parallel import FlatGradBuffer, FlatParamBuffer
 from .layers import SGC_LL
 from .layers import graphconv as _gc
@@ -23,14 +31,26 @@ from .layers import graphconv as _gc
 class SimpleAGCNStep(object):
     def __init__(self, n_feat=75, filters=(64, 128, 128, 64), final_feature_n=256, n_tasks=12, K=3, batch_size=256,
                  learning_rate=2e-3, device="cuda", world_size=1, laplacian="reference_literal",
-                 metric_grad="reference", seed=123, fused_head=True):
+                 metric_grad="reference", seed=123, loss="sigmoid_ce", engine="stack", overlap_allreduce=False,
+                 beta1=0.9, beta2=0.999, epsilon=1e-8):
+        """loss="sigmoid_ce": n_tasks two-class heads (Nt = 2 n_tasks logits);  loss="softmax_ce": one head with
+        n_tasks classes (Nt = n_tasks logits)."""
+        if engine not in ("stack", "autograd"):
+            raise ValueError("engine must be 'stack' or 'autograd'")
+        if loss not in _lib.LOSS:
+            raise ValueError("loss must be one of %s" % sorted(_lib.LOSS))
         self.device = torch.device(device)
         self.world_size = world_size
         self.global_batch = batch_size * world_size
         self.n_tasks = n_tasks
-        # DenseMol + GraphGatherMol + heads + loss as ONE library call (agcn_head_loss_grad) instead of ~45 torch ops
-        self.fused_head = fused_head and filters[-1] % 4 == 0 and 32 <= filters[-1] <= 128 and \
-            final_feature_n % 4 == 0 and 32 <= final_feature_n <= 256 and 2 * n_tasks >= 32
+        self.loss_kind = loss
+        self.engine = engine
+        self.overlap_allreduce = overlap_allreduce and world_size > 1
+        self.lr, self.beta1, self.beta2, self.epsilon = learning_rate, beta1, beta2, epsilon
+        self.Nt = 2 * n_tasks if loss == "sigmoid_ce" else n_tasks
+        self.Fm = final_feature_n
+        if final_feature_n < 32 or final_feature_n % 4:
+            raise ValueError("final_feature_n must be >= 32 and a multiple of 4 (agcn_head_loss_grad)")
         torch.manual_seed(seed)  # identical replicas on every rank
         _gc.DEFAULT_DEVICE[0] = str(self.device)
         dims = [n_feat] + list(filters)
@@ -42,69 +62,142 @@ class SimpleAGCNStep(object):
         self.dense_W = ((torch.rand(filters[-1], final_feature_n) * 2 - 1) * lim).to(self.device).requires_grad_(True)
         self.dense_b = torch.zeros(final_feature_n, device=self.device, requires_grad=True)
         # n_tasks independent [n_feature, 2] logits heads == one [n_feature, 2 * n_tasks] matrix
-        self.head_W = torch.nn.init.trunc_normal_(torch.empty(final_feature_n, 2 * n_tasks), std=0.01, a=-0.02,
+        self.head_W = torch.nn.init.trunc_normal_(torch.empty(final_feature_n, self.Nt), std=0.01, a=-0.02,
                                                   b=0.02).to(self.device).requires_grad_(True)
-        self.head_b = torch.zeros(2 * n_tasks, device=self.device, requires_grad=True)
+        self.head_b = torch.zeros(self.Nt, device=self.device, requires_grad=True)
         self.params = [v for l in self.layers for v in l.vars.values()] + [self.dense_W, self.dense_b, self.head_W,
                                                                            self.head_b]
-        # one flat gradient buffer; every .grad is a view into it -> a single all-reduce per step
-        # the SGC-LL backward writes its parameter gradients straight into the views (no accumulation kernels)
-        direct = [v for l in self.layers for v in l.vars.values()]
-        if self.fused_head:
-            direct += [self.dense_W, self.dense_b, self.head_W, self.head_b]
-        self.grads = FlatGradBuffer(self.params, direct=direct)
+        # one flat gradient buffer and one flat parameter buffer; every parameter / .grad is a view into them, and every
+        # producer (SGC-LL backward, head) OVERWRITES its gradients in place: nothing to zero, nothing to accumulate
+        self.grads = FlatGradBuffer(self.params, direct=self.params)
         self.flat_grad = self.grads.flat
-        # ... and one flat parameter tensor: Adam is a single-tensor update
         self.flat_params = FlatParamBuffer(self.params, self.grads)
-        self.opt = torch.optim.Adam(self.flat_params.chunks(self.grads), lr=learning_rate, betas=(0.9, 0.999), eps=1e-7,
-                                    fused=True, capturable=True)
+        self.adam_m = torch.zeros_like(self.flat_grad)
+        self.adam_v = torch.zeros_like(self.flat_grad)
+        self.adam_step = torch.zeros(1, dtype=torch.int32, device=self.device)
+        # offsets of every tensor in the flat buffers (the layout agcn_stack_create takes)
+        offs, off = [], 0
+        self._stage_slices = []
+        for l in self.layers:
+            start = off
+            per = {}
+            for name, v in l.vars.items():
+                per[name] = off
+                off += v.numel()
+            offs += [per["weight"], per["bias"], per["M_L"], per["alpha"], -1]
+            self._stage_slices.append((start, off))
+        start = off
+        for t in (self.dense_W, self.dense_b, self.head_W, self.head_b):
+            offs.append(off)
+            off += t.numel()
+        self._stage_slices.append((start, off))      # stage n_layers = dense + head
+        assert off == self.flat_grad.numel()
+        self._stack = ctypes.c_void_p()
+        descs = (_lib.Desc * len(self.layers))()
+        for i, l in enumerate(self.layers):
+            lap, mg = l._semantics()
+            descs[i] = _lib.Desc(l.n_atom_feature, l.nb_filter, l.K, _lib.VARIANT["SGC_LL"], _lib.LAPLACIAN[lap],
+                                 _lib.METRIC_GRAD[mg], _lib.ACT["relu"], _lib.SAVE_FOR_BACKWARD)
+        offs_c = (ctypes.c_int64 * len(offs))(*offs)
+        _lib.check(_lib.lib().agcn_stack_create(descs, len(self.layers), self.Fm, self.Nt, _lib.LOSS[loss], offs_c,
+                                                ctypes.byref(self._stack)))
+        self._arena = None
+        self._loss = torch.zeros(1, device=self.device, dtype=torch.float32)
+        self._pending = []
+        self._notify = _lib.NOTIFY_FN(self._on_stage)     # keep the ctypes thunk alive
 
-    def _n_nodes_f(self, batch):
-        t = getattr(batch, "_n_nodes_float", None)
-        if t is None:
-            t = batch.n_nodes_device().float()
-            batch._n_nodes_float = t
-        return t
+    def __del__(self):
+        try:
+            if self._stack:
+                _lib.lib().agcn_stack_destroy(self._stack)
+                self._stack = ctypes.c_void_p()
+        except Exception:
+            pass
 
     def n_parameters(self):
         return int(self.flat_grad.numel())
 
-    def forward_loss(self, X, Lint, batch, onehot, weights):
-        """X [R, F] packed, Lint packed, onehot [B, 2*T] float, weights [B, 2*T] float -> scalar loss."""
+    # ---- gradient exchange ----------------------------------------------------------------------------------
+    def _on_stage(self, _user, stage, _stream):
+        """agcn_stack_notify_fn: the gradients of `stage` are enqueued -> start the all-reduce of that bucket on
+        NCCL's stream while the earlier layers run backward."""
+        a, b = self._stage_slices[stage]
+        self._pending.append(dist.all_reduce(self.flat_grad[a:b], async_op=True))
+
+    def _all_reduce(self):
+        if self.world_size <= 1:
+            return
+        if self.overlap_allreduce and self.engine == "stack":
+            for w in self._pending:
+                w.wait()                        # stream-level wait: Adam is ordered after every bucket
+            self._pending = []
+        else:
+            self.grads.all_reduce()
+
+    # ---- engines --------------------------------------------------------------------------------------------
+    def _loss_grad_stack(self, X, Lint, batch, targets, weights):
+        nbytes = ctypes.c_size_t()
+        lib = _lib.lib()
+        _lib.check(lib.agcn_stack_workspace_bytes(self._stack, batch.handle, ctypes.byref(nbytes)))
+        if self._arena is None or self._arena.numel() < nbytes.value:
+            self._arena = torch.empty(int(nbytes.value * 1.25) + 4096, dtype=torch.uint8, device=self.device)
+        notify = ctypes.cast(self._notify, ctypes.c_void_p) if self.overlap_allreduce else None
+        with torch.cuda.device(self.device):
+            _lib.check(lib.agcn_stack_loss_grad(
+                self._stack, batch.handle, _ptr(X), _ptr(Lint), _ptr(targets), _ptr(weights),
+                1.0 / self.global_batch, _ptr(self.flat_params.flat), _ptr(self.flat_grad), _ptr(self._loss),
+                _ptr(self._arena), self._arena.numel(), notify, None, _stream_ptr(self.device)))
+        return self._loss
+
+    def forward_loss(self, X, Lint, batch, targets, weights):
+        """The drop-in path: layer classes + torch.autograd.  X [R, F] packed, Lint packed, targets [B, Nt] float,
+        weights [B, Nt] (sigmoid_ce) or [B] (softmax_ce) -> scalar loss."""
+        from .functional import head_loss
         x = {'node_features': PackedNodes(X, batch), 'original_laplacian': PackedLaplacians(Lint, batch),
              'data_slice': None, 'lap_slice': None, '_batch': batch}
         for layer in self.layers:
             out, _, _ = layer(x)
             x = dict(x, node_features=out)
-        if self.fused_head:
-            from .functional import head_loss
-            return head_loss(out.data, self.dense_W, self.dense_b, self.head_W, self.head_b, onehot, weights, batch,
-                             1.0 / self.global_batch, unit_grad=True)
-        # DenseMol applies no activation (dense_layer.py:42-50), so the per-graph row sum of GraphGatherMol
-        # (graphgather.py:68-77) commutes with it: sum_i (h_i W + b) = (sum_i h_i) W + n_g b.  Gathering first
-        # shrinks the dense GEMM from R = sum n_g rows to B rows.
-        hsum = torch.zeros(batch.batch_size, out.data.shape[1], device=out.data.device).index_add_(
-            0, batch.graph_ids(), out.data)
-        mol = torch.addmm(self._n_nodes_f(batch)[:, None] * self.dense_b[None, :], hsum, self.dense_W)
-        mol = torch.tanh(mol)                                                  # GraphGatherMol
-        logits = torch.addmm(self.head_b, mol, self.head_W)
-        loss = torch.nn.functional.binary_cross_entropy_with_logits(logits, onehot, weight=weights, reduction='sum')
-        return loss / self.global_batch
+        return head_loss(out.data, self.dense_W, self.dense_b, self.head_W, self.head_b, targets, weights, batch,
+                         1.0 / self.global_batch, unit_grad=True, loss_kind=self.loss_kind)
 
-    def step(self, X, Lint, batch, onehot, weights):
-        """One training step: forward, backward, gradient all-reduce, Adam.  Returns the loss tensor."""
-        self.grads.zero()
-        loss = self.forward_loss(X, Lint, batch, onehot, weights)
+    def loss_and_grads(self, X, Lint, batch, targets, weights):
+        """Loss (1-element tensor) with every gradient written into the flat gradient buffer (not yet reduced)."""
+        X, Lint = X.contiguous(), Lint.contiguous()
+        targets, weights = targets.contiguous(), weights.contiguous()
+        assert X.shape[0] == batch.total_nodes and Lint.numel() == batch.total_lap
+        assert targets.shape == (batch.batch_size, self.Nt)
+        if self.engine == "stack":
+            return self._loss_grad_stack(X, Lint, batch, targets, weights)
+        loss = self.forward_loss(X, Lint, batch, targets, weights)
         loss.backward()
-        if self.world_size > 1:
-            self.grads.all_reduce()
-        self.opt.step()
+        return loss.detach().reshape(1)
+
+    def apply_adam(self):
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().agcn_adam_step(
+                _ptr(self.flat_params.flat), _ptr(self.flat_grad), _ptr(self.adam_m), _ptr(self.adam_v),
+                _ptr(self.adam_step), self.flat_grad.numel(), self.lr, self.beta1, self.beta2, self.epsilon,
+                _stream_ptr(self.device)))
+
+    def step(self, X, Lint, batch, targets, weights):
+        """One training step: forward, backward, gradient all-reduce, Adam.  Returns the loss (1-element tensor,
+        valid until the next step)."""
+        loss = self.loss_and_grads(X, Lint, batch, targets, weights)
+        self._all_reduce()
+        self.apply_adam()
         return loss
 
 
-def synthetic_labels(B, n_tasks, seed, device):
-    """Bernoulli(0.1) labels as one-hot float targets [B, 2T], weights 1."""
+def synthetic_labels(B, n_tasks, seed, device, loss="sigmoid_ce"):
+    """sigmoid_ce: Bernoulli(0.1) labels as one-hot float targets [B, 2T], weights [B, 2T] = 1.
+    softmax_ce: uniform class labels as one-hot [B, T], per-sample weights [B] = 1."""
     rng = np.random.default_rng(seed)
+    if loss == "softmax_ce":
+        y = rng.integers(0, n_tasks, B)
+        onehot = np.zeros((B, n_tasks), np.float32)
+        onehot[np.arange(B), y] = 1.0
+        return torch.from_numpy(onehot).to(device), torch.ones(B, dtype=torch.float32).to(device)
     y = (rng.random((B, n_tasks)) < 0.1)
     onehot = np.zeros((B, n_tasks, 2), np.float32)
     onehot[..., 0] = ~y

@@ -109,6 +109,13 @@ int agcn_fused_tiles_host(const int32_t* n_nodes_host, int32_t B, int32_t* gstar
 int agcn_fused_profile(int enable);
 int agcn_fused_profile_read(float* ms_sum, int* launches);
 
+/* The same for every main kernel of the library (bench.py's per-kernel roofline table): while enabled (and the stream
+ * is not capturing) the host wrappers bracket each launch with CUDA events on its stream.  agcn_profile_read waits
+ * for them, clears the records and writes one line per kernel, "name<TAB>launches<TAB>milliseconds\n", into buf
+ * (NUL-terminated, truncated to cap); *needed receives the size the whole table takes. */
+int agcn_profile_enable(int enable);
+int agcn_profile_read(char* buf, size_t cap, size_t* needed);
+
 /* Tuning aid (no reference counterpart): d_buf = device buffer of tiles x 128 uint64; the following fused forward
  * launches record a per-tile timeline of nanosecond stamps into it.  NULL switches the recording off. */
 int agcn_fused_debug_set(void* d_buf);
@@ -200,7 +207,16 @@ int agcn_gemm_tn(const float* d_A0, const float* d_A1, const float* d_D, float* 
  *   d_H [R,Fh] packed output of the last SGC-LL layer; d_dense_W [Fh,Fm], d_dense_b [Fm]; d_head_W [Fm,Nt],
  *   d_head_b [Nt]; d_targets / d_weights [B,Nt].
  *   outputs (overwritten): d_loss [1], d_dH [R,Fh] and the four parameter gradients.
- *   Needs 32 <= Fh <= 128, 32 <= Fm <= 256 (multiples of 4), Nt >= 32. */
+ *   Needs Fm >= 32 and a multiple of 4 (the logits contraction runs on the tensor cores with the loss as its
+ *   epilogue); the other contractions fall back to CUDA-core kernels when their shape is not TMA-compatible.
+ *
+ *   agcn_head_loss_grad_ex adds `loss_kind`: AGCN_LOSS_SIGMOID_CE (the multitask head above) or
+ *   AGCN_LOSS_SOFTMAX_CE = the single-task multi-class head of SingletaskGraphClassifier
+ *   (models/tf_modules/singletask_classifier.py:124-151, get_loss_fn('softmax_cross_entropy') of
+ *   multitask_classifier.py:45-48): Nt = n_classes, d_targets [B,Nt] one-hot, d_weights [B] per-sample weights,
+ *   loss = scale * sum_b w_b (logsumexp(x_b) - <y_b, x_b>). */
+#define AGCN_LOSS_SIGMOID_CE 0
+#define AGCN_LOSS_SOFTMAX_CE 1
 int agcn_head_workspace_bytes(const agcn_plan* plan, int32_t Fh, int32_t Fm, int32_t Nt, size_t* bytes);
 int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_dense_W, const float* d_dense_b,
                         const float* d_head_W, const float* d_head_b, const float* d_targets, const float* d_weights,
@@ -208,8 +224,45 @@ int agcn_head_loss_grad(const agcn_plan* plan, const float* d_H, const float* d_
                         float* d_ddense_W, float* d_ddense_b, float* d_dhead_W, float* d_dhead_b, void* d_work,
                         size_t work_bytes, void* stream);
 
+int agcn_head_loss_grad_ex(const agcn_plan* plan, const float* d_H, const float* d_dense_W, const float* d_dense_b,
+                           const float* d_head_W, const float* d_head_b, const float* d_targets, const float* d_weights,
+                           float scale, int32_t loss_kind, int32_t Fh, int32_t Fm, int32_t Nt, float* d_loss,
+                           float* d_dH, float* d_ddense_W, float* d_ddense_b, float* d_dhead_W, float* d_dhead_b,
+                           void* d_work, size_t work_bytes, void* stream);
+
+/* ---- one training step's loss and gradients as ONE call: the counterpart of `sess.run([train_op, loss, ...])`
+ *      (models/tf_modules/multitask_classifier.py:255-264), which executes the whole graph of
+ *      models/networks/basic_AGCN.py:35-47 inside the TensorFlow runtime.  A stack = n_layers SGC_LL layers (relu or
+ *      linear activation, any semantics modes) + DenseMol + GraphGatherMol + logits + loss; the call chains
+ *      agcn_sgcll_forward / agcn_head_loss_grad_ex / agcn_sgcll_backward over one arena.
+ *   param_offsets: element offsets into the flat parameter buffer (and, identically, the flat gradient buffer):
+ *      5 per layer {weight [F*K,Fo], bias [Fo], M_L [F,F], alpha [1], -1}, then dense_W [Fh,Fm], dense_b [Fm],
+ *      head_W [Fm,Nt], head_b [Nt].
+ *   notify (optional): called on the host right after the gradients of a stage have been ENQUEUED on `stream`
+ *      (stage n_layers = head + dense, then n_layers-1 .. 0 = that SGC_LL layer), so a data-parallel caller can start
+ *      the all-reduce of a gradient bucket while the earlier layers are still running backward. */
+typedef struct agcn_stack agcn_stack;
+typedef void (*agcn_stack_notify_fn)(void* user, int32_t stage, void* stream);
+int agcn_stack_create(const agcn_sgcll_desc* layer_descs, int32_t n_layers, int32_t Fm, int32_t Nt, int32_t loss_kind,
+                      const int64_t* param_offsets, agcn_stack** out);
+int agcn_stack_destroy(agcn_stack* stack);
+int agcn_stack_workspace_bytes(const agcn_stack* stack, const agcn_plan* plan, size_t* bytes);
+int agcn_stack_loss_grad(const agcn_stack* stack, const agcn_plan* plan, const float* d_X, const float* d_Lint,
+                         const float* d_targets, const float* d_weights, float scale, const float* d_params,
+                         float* d_grads, float* d_loss, void* d_work, size_t work_bytes, agcn_stack_notify_fn notify,
+                         void* notify_user, void* stream);
+
+/* tf.train.AdamOptimizer's update (multitask_classifier.py:233-237) over a flat parameter buffer:
+ *   t = *d_step + 1;  lr_t = lr sqrt(1 - beta2^t) / (1 - beta1^t);  m = beta1 m + (1 - beta1) g;
+ *   v = beta2 v + (1 - beta2) g^2;  p -= lr_t m / (sqrt(v) + eps);  *d_step = t.
+ * The step counter lives on the device so that a captured CUDA graph of the step replays correctly. */
+int agcn_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int32_t* d_step, int64_t n, float lr,
+                   float beta1, float beta2, float eps, void* stream);
+
 /* Host-buffer convenience entry (the end-to-end path): padded HOST arrays in the reference's wire
  * layout in, padded HOST output out; host<->device copies are issued on `stream` inside the call.
+ * Page-locked inputs (cudaMallocHost / cudaHostRegister / torch pin_memory) are read in place by the pack kernels
+ * (only the real rows cross PCIe); pageable inputs are staged through the copy engine.
  * d_scratch must hold agcn_sgcll_host_scratch_bytes() bytes of device memory. */
 int agcn_sgcll_host_scratch_bytes(const agcn_sgcll_desc* desc, const agcn_plan* plan, size_t* bytes);
 int agcn_sgcll_forward_host(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* h_X_padded,

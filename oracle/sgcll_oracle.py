@@ -146,7 +146,7 @@ def residual_laplacian(W: torch.Tensor, laplacian: str) -> torch.Tensor:
 # one graph through one SGC-LL layer
 # --------------------------------------------------------------------------
 def sgc_ll_graph(x, L_int, params, K, variant="SGC_LL", laplacian="reference_literal",
-                 metric_grad="reference", L_prev=None):
+                 metric_grad="reference", L_prev=None, compute_similarity=True):
     """x [n,F], L_int [n,n], params dict(weight[F*K,Fo], bias[Fo], M_L[F,F],
     alpha[1] (, beta[1])) -> (y [n,Fo] pre-activation, res_L, res_W, L_all).
 
@@ -156,11 +156,16 @@ def sgc_ll_graph(x, L_int, params, K, variant="SGC_LL", laplacian="reference_lit
     n, F = x.shape
     M_L, alpha = params["M_L"], params["alpha"]
     xm, Mm = (x, M_L) if metric_grad == "full" else (x.detach(), M_L.detach())
-    x_w = xm @ Mm                                           # :164
-    res_W = similarity(x_w)
-    res_L = residual_laplacian(res_W, laplacian)
+    if compute_similarity or laplacian != "reference_literal":
+        x_w = xm @ Mm                                       # :164
+        res_W = similarity(x_w)
+    else:
+        # callers that only need y / gradients in literal mode: res_L == I whatever W is (:198-200), so the
+        # O(n^2 F) similarity (returned, never used downstream) is skipped; res_W comes back as None
+        res_W = None
+    res_L = residual_laplacian(res_W if res_W is not None else torch.zeros(n, n, dtype=x.dtype), laplacian)
     if metric_grad != "full":                               # py_func: no gradient (:211)
-        res_W, res_L = res_W.detach(), res_L.detach()
+        res_W, res_L = (None if res_W is None else res_W.detach()), res_L.detach()
     if variant == "SGC_LL":
         res_L = leaky(clip_by_average_norm(res_L, 1.0), alpha)     # :212-213
         L_all = res_L + L_int                                      # :216
@@ -185,7 +190,7 @@ def sgc_ll_graph(x, L_int, params, K, variant="SGC_LL", laplacian="reference_lit
 
 
 def sgc_ll_batch(X, L, n_nodes, params, K, variant="SGC_LL", laplacian="reference_literal",
-                 metric_grad="reference", L_prev=None, activation="relu"):
+                 metric_grad="reference", L_prev=None, activation="relu", compute_similarity=True):
     """Whole padded batch.  X [B,Nmax,F], L [B,Nmax,Nmax], n_nodes [B];
     L_prev: list of B [n,n] tensors or None.  Returns (Y [B,Nmax,Fo] activated,
     zero rows >= n (graphconv.py:249-251 pads AFTER the bias), lists res_L,
@@ -196,7 +201,7 @@ def sgc_ll_batch(X, L, n_nodes, params, K, variant="SGC_LL", laplacian="referenc
     for g in range(B):
         n = int(n_nodes[g])
         y, rl, rw, la = sgc_ll_graph(X[g, :n], L[g, :n, :n], params, K, variant, laplacian, metric_grad,
-                                     None if L_prev is None else L_prev[g])
+                                     None if L_prev is None else L_prev[g], compute_similarity)
         if activation == "relu":
             y = torch.relu(y)
         elif activation not in (None, "linear"):

@@ -305,12 +305,70 @@ def test_big_graph_point_cloud_shape_paper_full():
     print(compare(cu, orc))
 
 
-@pytest.mark.parametrize("Fh,Fm,Nt", [(64, 256, 1234), (32, 64, 40), (128, 132, 50)])
-def test_head_loss_and_gradients_match_torch_fp64(Fh, Fm, Nt):
-    """agcn_head_loss_grad (DenseMol + GraphGatherMol + multitask heads + weighted sigmoid cross-entropy,
-    SURVEY.md section 8f rows 1 and 3) against the same chain written with torch ops in fp64."""
+@pytest.mark.parametrize("laplacian,metric_grad", [("reference_literal", "reference"), ("paper", "reference"),
+                                                   ("paper", "full")])
+@pytest.mark.parametrize("K", [1, 3])
+@pytest.mark.parametrize("sizes,F,Fo", [([132, 4, 5, 18, 33, 64, 65, 17, 96, 31], 75, 64),     # molecules: fused tiles
+                                        ([300, 20, 145, 513], 16, 24)])                       # big graphs
+def test_first_layer_backward_without_input_gradient(laplacian, metric_grad, K, sizes, F, Fo):
+    """d_dX == NULL (the first layer of every training step: atom features have no gradient): the fused backward is
+    off, the whole dYpre branch runs on the side stream and, in paper mode, dX is scratch aliasing G_0.  The
+    parameter gradients must not change."""
+    Nmax = max(sizes)
+    X, L, n = make_batch(sizes, F, Nmax, seed=K + F, kind="tox" if F == 75 else "normal")
+    if F != 75:
+        X *= 0.6
+        L = _dense_laplacians(sizes, Nmax, seed=4)
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=3 + K, dtype=torch.float64)
+    cY = _cot((len(sizes), Nmax, Fo), 17)
+    orc = oracle_run(X, L, n, p, K, "SGC_LL", laplacian, metric_grad, cot_Y=cY)
+    if metric_grad == "full":
+        # the library needs d_dX with a differentiable metric (the gradient reaches M_L through X M_L); the autograd
+        # bridge allocates it even when X itself needs none
+        cu = cuda_run(X, L, n, p, K, "SGC_LL", laplacian, metric_grad, cot_Y=cY, want_res=False, x_grad=False)
+    else:
+        cu = cuda_run(X, L, n, p, K, "SGC_LL", laplacian, metric_grad, cot_Y=cY, want_res=False, x_grad=False)
+    assert "dX" not in cu
+    errs = compare(cu, orc, skip=("res_L", "res_W", "L_all", "dX"))
+    for k in ("dweight", "dbias", "dM_L", "dalpha"):
+        assert k in errs, k
+    print(laplacian, metric_grad, K, errs)
+
+
+@pytest.mark.parametrize("sizes,F,Fo,K,laplacian,metric_grad", [
+    ([1024, 1024, 700], 128, 128, 3, "reference_literal", "reference"),   # the shape grouped_tc_kernel is profiled on
+    ([1024, 300], 128, 128, 3, "paper", "full"),
+    ([4096, 50], 32, 32, 3, "reference_literal", "reference"),            # largest sweep size
+    ([132, 20, 64, 9, 100, 31], 256, 256, 3, "reference_literal", "reference"),   # F = Fo = 256 on molecules
+    ([132, 20, 64, 9, 100, 31], 256, 256, 2, "paper", "full"),
+    ([600, 130], 256, 256, 3, "reference_literal", "reference")])          # F = Fo = 256 on big graphs
+def test_named_baseline_shapes(sizes, F, Fo, K, laplacian, metric_grad):
+    """Shapes BASELINE.json names that no other case reaches: N = 1024 with F = 128, N = 4096, F = Fo = 256
+    (the widths the fused tile kernels hand to the split path)."""
+    Nmax = max(sizes)
+    X, _, n = make_batch(sizes, F, Nmax, seed=F + K)
+    X *= 0.3
+    L = _dense_laplacians(sizes, Nmax, seed=K + 1)
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=F + 2, dtype=torch.float64)
+    cY = _cot((len(sizes), Nmax, Fo), 23)
+    literal = laplacian == "reference_literal"
+    orc = oracle_run(X, L, n, p, K, "SGC_LL", laplacian, metric_grad, cot_Y=cY, compute_similarity=not literal)
+    cu = cuda_run(X, L, n, p, K, "SGC_LL", laplacian, metric_grad, cot_Y=cY, want_res=False)
+    errs = compare(cu, orc, skip=("res_L", "res_W", "L_all"))
+    print(sizes, F, Fo, K, laplacian, errs)
+
+
+@pytest.mark.parametrize("Fh,Fm,Nt,kind", [(64, 256, 1234, "sigmoid_ce"), (32, 64, 40, "sigmoid_ce"),
+                                           (128, 132, 50, "sigmoid_ce"), (64, 256, 24, "sigmoid_ce"),
+                                           (64, 256, 40, "softmax_ce"), (64, 128, 26, "softmax_ce"),
+                                           (256, 64, 6, "softmax_ce")])
+def test_head_loss_and_gradients_match_oracle(Fh, Fm, Nt, kind):
+    """agcn_head_loss_grad_ex (DenseMol + GraphGatherMol + logits + loss) against
+    oracle/network_oracle.py in fp64: the multitask sigmoid heads (incl. Tox21's 12 tasks = 24 logits, below one
+    tensor-core k-block) and the single-task softmax head of the point-cloud networks."""
     import agcn_b200
     from agcn_b200.functional import head_loss
+    from oracle import network_oracle as NO
     dev = torch.device("cuda:0")
     rng = np.random.default_rng(Fh + Nt)
     n = np.array(SIZES + [7, 1, 20, 19, 44], np.int32)
@@ -319,22 +377,27 @@ def test_head_loss_and_gradients_match_torch_fp64(Fh, Fm, Nt):
     H64 = torch.tensor(np.maximum(rng.standard_normal((R, Fh)), 0) * 0.3, dtype=torch.float64)
     p64 = [torch.tensor(rng.standard_normal(s) * sc, dtype=torch.float64)
            for s, sc in (((Fh, Fm), 0.1), ((Fm,), 0.05), ((Fm, Nt), 0.1), ((Nt,), 0.1))]
-    y = torch.tensor((rng.random((B, Nt)) < 0.3).astype(np.float64))
-    w = torch.tensor(rng.random((B, Nt)) + 0.5)
     scale, up = 1.0 / 37.0, 1.7
-    # reference
     Hr = H64.clone().requires_grad_(True)
     pr = [t.clone().requires_grad_(True) for t in p64]
-    ids = torch.tensor(np.repeat(np.arange(B), n))
-    hsum = torch.zeros(B, Fh, dtype=torch.float64).index_add_(0, ids, Hr)
-    mol = torch.tanh(hsum @ pr[0] + torch.tensor(n, dtype=torch.float64)[:, None] * pr[1][None, :])
-    logits = mol @ pr[2] + pr[3]
-    loss_ref = torch.nn.functional.binary_cross_entropy_with_logits(logits, y, weight=w, reduction="sum") * scale
+    off = np.concatenate([[0], np.cumsum(n)])
+    H_list = [Hr[off[g]:off[g + 1]] for g in range(B)]
+    if kind == "sigmoid_ce":
+        y = torch.tensor((rng.random((B, Nt)) < 0.3).astype(np.float64))
+        w = torch.tensor(rng.random((B, Nt)) + 0.5)
+        loss_ref = NO.head_loss(H_list, pr[0], pr[1], pr[2], pr[3], y, w, scale)
+    else:
+        y = torch.zeros(B, Nt, dtype=torch.float64)
+        y[torch.arange(B), torch.tensor(rng.integers(0, Nt, B))] = 1.0
+        w = torch.tensor(rng.random(B) + 0.5)
+        mol = torch.tanh(torch.stack([(h @ pr[0] + pr[1]).sum(0) for h in H_list]))
+        logits = mol @ pr[2] + pr[3]
+        loss_ref = ((torch.logsumexp(logits, 1) - (logits * y).sum(1)) * w).sum() * scale
     (loss_ref * up).backward()
-    # CUDA path
     Hc = H64.float().to(dev).requires_grad_(True)
     pc = [t.float().to(dev).requires_grad_(True) for t in p64]
-    loss = head_loss(Hc, pc[0], pc[1], pc[2], pc[3], y.float().to(dev), w.float().to(dev), batch, scale)
+    loss = head_loss(Hc, pc[0], pc[1], pc[2], pc[3], y.float().to(dev), w.float().to(dev), batch, scale,
+                     loss_kind=kind)
     (loss * up).backward()
     torch.cuda.synchronize()
     assert abs(float(loss) - float(loss_ref)) <= TOL * abs(float(loss_ref))

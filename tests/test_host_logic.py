@@ -215,3 +215,78 @@ def test_batch_csr_matches_the_dense_laplacians():
             row += 1
         assert np.array_equal(dense, np.asarray(m.todense(), np.float32))
     assert row == len(indptr) - 1
+
+
+def test_callable_activation_is_applied_not_dropped():
+    """activations.get passes callables through (activations.py:15-53) and the layer calls them (graphconv.py:120):
+    a caller's own function must not silently become 'linear'."""
+    from agcn_b200.layers import SGC_LL
+    from agcn_b200.operators import activations
+    calls = []
+
+    def mine(x):
+        calls.append(1)
+        return x * 2
+
+    layer = SGC_LL(8, 8, 4, activation=mine)
+    assert layer.activation is mine and layer._fused_activation() == (False, 'linear')
+    assert layer._finish(torch.ones(2, 2), False).tolist() == [[2.0, 2.0], [2.0, 2.0]] and calls
+    assert SGC_LL(8, 8, 4, activation=activations.tanh)._fused_activation() == (False, 'linear')
+    assert SGC_LL(8, 8, 4, activation='tanh')._fused_activation() == (False, 'linear')
+    assert SGC_LL(8, 8, 4, activation=activations.relu)._fused_activation() == (True, 'relu')
+    assert SGC_LL(8, 8, 4, activation='relu')._fused_activation() == (True, 'relu')
+    assert SGC_LL(8, 8, 4, activation=None)._fused_activation() == (True, 'linear')
+    assert SGC_LL(8, 8, 4, activation='linear')._fused_activation() == (True, 'linear')
+
+
+def test_product_side_generator_matches_the_oracle_copy():
+    """bench.py draws its inputs from agcn_b200.synthetic (the product harness never imports oracle/); the molecule
+    batch must be the one the oracle-side generator of the tests produces."""
+    from agcn_b200 import synthetic
+    from oracle import sgcll_oracle as O
+    X1, L1, n1 = synthetic.molecule_batch(24, 132, seed=1235)
+    X2, L2, n2 = O.synthetic_molecule_batch(24, 132, seed=1235)
+    assert np.array_equal(n1, n2) and np.array_equal(X1, X2)
+    assert np.abs(L1 - L2).max() <= 1e-6
+
+
+def test_point_cloud_adjacency_rules_restated_literally():
+    """adjacency_mean_rule / adjacency_cutoff_rule against a literal double loop of meshloader.py:264-285 and
+    pointcloudloader.py:240-263."""
+    from agcn_b200 import synthetic
+    rng = np.random.default_rng(0)
+    for n, F in ((13, 3), (37, 4), (9, 4)):
+        P = rng.standard_normal((n, F)).astype(np.float32)
+        dist = [np.linalg.norm(P[i] - P[j]) for i in range(n) for j in range(i + 1)]
+        for rule, d_lim in (("mean", np.mean(dist)), ("cut", np.sort(dist)[-int(n * 0.1)])):
+            A = np.zeros((n, n), bool)
+            for i in range(n):
+                for j in range(i + 1, n):
+                    if np.linalg.norm(P[i] - P[j]) < d_lim:
+                        A[i, j] = A[j, i] = True
+            got = synthetic.adjacency_mean_rule(P) if rule == "mean" else synthetic.adjacency_cutoff_rule(P)
+            assert np.array_equal(got, A), (n, F, rule)
+    # and the dense Laplacian helper against the Graph class (graph_structure.py:85-130)
+    from agcn_b200 import Graph
+    A = synthetic.adjacency_mean_rule(rng.standard_normal((20, 3)).astype(np.float32))
+    adj = [list(np.nonzero(r)[0]) for r in A]
+    ref = np.asarray(Graph(np.zeros((20, 3), np.float32), adj, 20, 0).Laplacian.todense())
+    assert np.abs(synthetic.laplacian_from_dense_adjacency(A) - ref).max() <= 1e-12
+
+
+def test_network_oracle_head_and_adam():
+    from oracle import network_oracle as NO
+    g = torch.Generator().manual_seed(0)
+    H = [torch.randn(n, 8, generator=g, dtype=torch.float64) for n in (3, 5)]
+    dW, db = torch.randn(8, 6, generator=g, dtype=torch.float64), torch.randn(6, generator=g, dtype=torch.float64)
+    hW, hb = torch.randn(6, 4, generator=g, dtype=torch.float64), torch.randn(4, generator=g, dtype=torch.float64)
+    t = torch.tensor([[1., 0, 0, 1], [0, 1, 1, 0]], dtype=torch.float64)
+    w = torch.ones(2, 4, dtype=torch.float64)
+    loss = NO.head_loss(H, dW, db, hW, hb, t, w, 0.5)
+    mol = torch.tanh(torch.stack([(h @ dW).sum(0) + h.shape[0] * db for h in H]))     # gather commutes with the dense layer
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(mol @ hW + hb, t, reduction="sum") * 0.5
+    assert abs(float(loss - ref)) < 1e-12
+    # tf Adam: first step moves every parameter by ~lr * sign(g)
+    p, m, v = NO.adam_tf(torch.zeros(3, dtype=torch.float64), torch.tensor([1., -2., 0.5], dtype=torch.float64),
+                         torch.zeros(3, dtype=torch.float64), torch.zeros(3, dtype=torch.float64), 1, lr=0.1)
+    assert torch.allclose(p, torch.tensor([-0.1, 0.1, -0.1], dtype=torch.float64), atol=1e-6)

@@ -36,17 +36,20 @@ def random_prev_laps(n_nodes, seed=0):
 
 
 def oracle_run(X, L, n_nodes, params64, K, variant, laplacian, metric_grad, Lprev=None, activation="relu",
-               cot_Y=None, cot_L=None):
-    """fp64 oracle forward (+ backward when cotangents are given)."""
+               cot_Y=None, cot_L=None, compute_similarity=True):
+    """fp64 oracle forward (+ backward when cotangents are given).  compute_similarity=False (literal mode only)
+    skips the O(n^2 F) similarity tensor for graphs of thousands of nodes; res_W is then absent."""
     Xt = torch.tensor(X, dtype=torch.float64, requires_grad=True)
     Lt = torch.tensor(L, dtype=torch.float64)
     p = {k: v.clone().double().requires_grad_(True) for k, v in params64.items()}
     Lp = None
     if Lprev is not None:
         Lp = [torch.tensor(l, dtype=torch.float64, requires_grad=True) for l in Lprev]
-    Y, RL, RW, LA = O.sgc_ll_batch(Xt, Lt, n_nodes, p, K, variant, laplacian, metric_grad, Lp, activation)
-    res = {"Y": Y.detach(), "res_L": [t.detach() for t in RL], "res_W": [t.detach() for t in RW],
-           "L_all": [t.detach() for t in LA]}
+    Y, RL, RW, LA = O.sgc_ll_batch(Xt, Lt, n_nodes, p, K, variant, laplacian, metric_grad, Lp, activation,
+                                   compute_similarity)
+    res = {"Y": Y.detach(), "res_L": [t.detach() for t in RL], "L_all": [t.detach() for t in LA]}
+    if all(t is not None for t in RW):
+        res["res_W"] = [t.detach() for t in RW]
     if cot_Y is not None:
         loss = (Y * torch.tensor(cot_Y, dtype=torch.float64)).sum()
         if cot_L is not None:
@@ -62,15 +65,16 @@ def oracle_run(X, L, n_nodes, params64, K, variant, laplacian, metric_grad, Lpre
 
 
 def cuda_run(X, L, n_nodes, params64, K, variant, laplacian, metric_grad, Lprev=None, activation="relu",
-             cot_Y=None, cot_L=None, want_res=True):
-    """The same through agcn_b200's autograd bridge -> C ABI -> CUDA kernels (fp32)."""
+             cot_Y=None, cot_L=None, want_res=True, x_grad=True):
+    """The same through agcn_b200's autograd bridge -> C ABI -> CUDA kernels (fp32).  x_grad=False: the node
+    features need no gradient (first layer of a network): the backward call gets d_dX == NULL."""
     import agcn_b200
     from agcn_b200.functional import sgc_ll_packed
 
     dev = torch.device("cuda:0")
     B, Nmax, F = X.shape
     batch = agcn_b200.GraphBatch(n_nodes, Nmax, device=dev)
-    Xp = batch.pack_nodes(torch.tensor(X, device=dev)).requires_grad_(True)
+    Xp = batch.pack_nodes(torch.tensor(X, device=dev)).requires_grad_(x_grad)
     Lp = batch.pack_lap(torch.tensor(L, device=dev))
     p = {k: v.float().to(dev).requires_grad_(True) for k, v in params64.items()}
     Lprev_p = None
@@ -93,7 +97,8 @@ def cuda_run(X, L, n_nodes, params64, K, variant, laplacian, metric_grad, Lprev=
             cL = torch.cat([torch.tensor(c, device=dev).reshape(-1) for c in cot_L])
             loss = loss + (Lall * cL).sum()
         loss.backward()
-        res["dX"] = batch.unpack_nodes(Xp.grad).cpu()
+        if x_grad:
+            res["dX"] = batch.unpack_nodes(Xp.grad).cpu()
         for k, v in p.items():
             res["d" + k] = v.grad.cpu() if v.grad is not None else torch.zeros_like(v).cpu()
         if Lprev_p is not None:
