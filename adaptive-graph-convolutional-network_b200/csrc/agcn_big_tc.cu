@@ -135,8 +135,8 @@ __device__ __forceinline__ float4 lds128(uint32_t a) {
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];\n" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a) : "memory");
   return v;
 }
-__device__ __forceinline__ float tf32_hi(float x) { return __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
-__device__ __forceinline__ float tf32_lo(float x, float hi) { return __uint_as_float(__float_as_uint(x - hi) & 0xffffe000u); }
+__device__ __forceinline__ float tf32_hi(float x) { return tf32_rn(x); }
+__device__ __forceinline__ float tf32_lo(float x, float hi) { return tf32_rn(x - hi); }
 
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;

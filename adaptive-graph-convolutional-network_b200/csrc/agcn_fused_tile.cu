@@ -281,14 +281,14 @@ __device__ __forceinline__ void write_operand_half(uint32_t a_hi, uint32_t a_lo,
 #pragma unroll
   for (int g = 0; g < 4; ++g) {
     float4 hi, lo;
-    hi.x = __uint_as_float(__float_as_uint(v[4 * g]) & 0xffffe000u);
-    hi.y = __uint_as_float(__float_as_uint(v[4 * g + 1]) & 0xffffe000u);
-    hi.z = __uint_as_float(__float_as_uint(v[4 * g + 2]) & 0xffffe000u);
-    hi.w = __uint_as_float(__float_as_uint(v[4 * g + 3]) & 0xffffe000u);
-    lo.x = __uint_as_float(__float_as_uint(v[4 * g] - hi.x) & 0xffffe000u);
-    lo.y = __uint_as_float(__float_as_uint(v[4 * g + 1] - hi.y) & 0xffffe000u);
-    lo.z = __uint_as_float(__float_as_uint(v[4 * g + 2] - hi.z) & 0xffffe000u);
-    lo.w = __uint_as_float(__float_as_uint(v[4 * g + 3] - hi.w) & 0xffffe000u);
+    hi.x = tf32_rn(v[4 * g]);
+    hi.y = tf32_rn(v[4 * g + 1]);
+    hi.z = tf32_rn(v[4 * g + 2]);
+    hi.w = tf32_rn(v[4 * g + 3]);
+    lo.x = tf32_rn(v[4 * g] - hi.x);
+    lo.y = tf32_rn(v[4 * g + 1] - hi.y);
+    lo.z = tf32_rn(v[4 * g + 2] - hi.z);
+    lo.w = tf32_rn(v[4 * g + 3] - hi.w);
     const uint32_t off = (uint32_t)(row * 128 + (((4 * h + g) ^ (row & 7)) << 4));
     sts128(a_hi + off, hi);
     sts128(a_lo + off, lo);
@@ -887,9 +887,9 @@ __global__ void prep_w_kernel(const float* __restrict__ W, long long sn, long lo
     const int n = (int)(rr % N), z = (int)(rr / N);
     float x = 0.f;
     if (n < Nv && k < Kv) x = W[n * sn + k * sk + z * sz];
-    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    const float h = tf32_rn(x);
     hi[e] = h;
-    lo[e] = __uint_as_float(__float_as_uint(x - h) & 0xffffe000u);
+    lo[e] = tf32_rn(x - h);
   }
 }
 

@@ -28,6 +28,18 @@
 
 namespace agcn {
 
+// 3xTF32 operand split: x = hi + lo (+ a remainder below 2^-23 |x|), both halves exact TF32 values.  ROUND-TO-NEAREST
+// (cvt.rna) on both halves: truncation drops up to 3 * 2^-23 |x| and always in the same direction, a bias that
+// accumulates linearly over a contraction; rounding leaves at most 2^-23 |x|, zero-mean (measured on the 4-layer
+// network gradients: 2-3e-4 relative error with truncation against 3e-5 for plain fp32 arithmetic).
+#ifdef __CUDACC__
+__device__ __forceinline__ float tf32_rn(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+#endif
+
 struct Bucket {
   int start;  // first index into plan->order
   int count;  // graphs in the bucket

@@ -214,14 +214,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         const int idx = t + 128 * i;
         const float4 v = a[idx];
         float4 hi, lo;
-        hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-        hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-        hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-        hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-        lo.x = __uint_as_float(__float_as_uint(v.x - hi.x) & 0xffffe000u);
-        lo.y = __uint_as_float(__float_as_uint(v.y - hi.y) & 0xffffe000u);
-        lo.z = __uint_as_float(__float_as_uint(v.z - hi.z) & 0xffffe000u);
-        lo.w = __uint_as_float(__float_as_uint(v.w - hi.w) & 0xffffe000u);
+        hi.x = tf32_rn(v.x);
+        hi.y = tf32_rn(v.y);
+        hi.z = tf32_rn(v.z);
+        hi.w = tf32_rn(v.w);
+        lo.x = tf32_rn(v.x - hi.x);
+        lo.y = tf32_rn(v.y - hi.y);
+        lo.z = tf32_rn(v.z - hi.z);
+        lo.w = tf32_rn(v.w - hi.w);
         a[idx] = hi;
         alo[idx] = lo;
       }
@@ -461,14 +461,14 @@ tc_gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constan
         for (int idx = t; idx < n16; idx += 128) {
           const float4 v = hi_p[idx];
           float4 hi, lo;
-          hi.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
-          hi.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
-          hi.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
-          hi.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
-          lo.x = __uint_as_float(__float_as_uint(v.x - hi.x) & 0xffffe000u);
-          lo.y = __uint_as_float(__float_as_uint(v.y - hi.y) & 0xffffe000u);
-          lo.z = __uint_as_float(__float_as_uint(v.z - hi.z) & 0xffffe000u);
-          lo.w = __uint_as_float(__float_as_uint(v.w - hi.w) & 0xffffe000u);
+          hi.x = tf32_rn(v.x);
+          hi.y = tf32_rn(v.y);
+          hi.z = tf32_rn(v.z);
+          hi.w = tf32_rn(v.w);
+          lo.x = tf32_rn(v.x - hi.x);
+          lo.y = tf32_rn(v.y - hi.y);
+          lo.z = tf32_rn(v.z - hi.z);
+          lo.w = tf32_rn(v.w - hi.w);
           hi_p[idx] = hi;
           lo_p[idx] = lo;
         }
@@ -557,9 +557,9 @@ __global__ void split_b_kernel(const float* __restrict__ src, long long sn, long
     const int n = (int)(r % Npad), sl = (int)(r / Npad);
     float x = 0.f;
     if (n < N && k < Kd) x = src[n * sn + k * sk + sl * ss];
-    const float h = __uint_as_float(__float_as_uint(x) & 0xffffe000u);
+    const float h = tf32_rn(x);
     hi[e] = h;
-    lo[e] = __uint_as_float(__float_as_uint(x - h) & 0xffffe000u);
+    lo[e] = tf32_rn(x - h);
   }
 }
 
