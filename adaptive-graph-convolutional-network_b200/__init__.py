@@ -11,7 +11,7 @@ from .graph_structure import Graph, MolGraph
 from .graph_topology import GraphTopologyMol
 from . import layers
 from . import operators
-from .layers import SGC_LL, SGC_LL_Reslap, GraphPoolMol
+from .layers import SGC_LL, SGC_LL_Reslap, GraphPoolMol, BlockEnd, DenseBlockEnd, MLP
 
 __all__ = ["Graph", "MolGraph", "GraphTopologyMol", "GraphBatch", "PackedNodes", "PackedLaplacians", "layers",
-           "operators", "SGC_LL", "SGC_LL_Reslap", "GraphPoolMol"]
+           "operators", "SGC_LL", "SGC_LL_Reslap", "GraphPoolMol", "BlockEnd", "DenseBlockEnd", "MLP"]

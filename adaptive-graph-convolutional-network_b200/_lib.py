@@ -46,6 +46,7 @@ _SIGNATURES = {
     "agcn_fused_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "agcn_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "agcn_profile_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    "agcn_probe_fp32_fma": (ctypes.c_int, [_P, ctypes.c_int32, _P]),
     "agcn_pack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
     "agcn_unpack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
     "agcn_pack_lap": (ctypes.c_int, [_P, _P, _P, _P]),
@@ -63,6 +64,11 @@ _SIGNATURES = {
     "agcn_gemm_tn_scratch_bytes": (ctypes.c_size_t, [ctypes.c_int32] * 4),
     "agcn_gemm_tn": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                     _P, ctypes.c_int32, _P]),
+    "agcn_node_gemm_scratch_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32]),
+    "agcn_node_gemm": (ctypes.c_int, [_P, ctypes.c_int32, _P, ctypes.c_int32, ctypes.c_int32, _P, ctypes.c_int32,
+                                      ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P, ctypes.c_int32,
+                                      ctypes.c_int32, _P, _P]),
+    "agcn_dropout": (ctypes.c_int, [_P, _P, ctypes.c_int64, ctypes.c_float, ctypes.c_uint64, _P]),
     "agcn_head_workspace_bytes": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                   ctypes.POINTER(ctypes.c_size_t)]),
     "agcn_head_loss_grad": (ctypes.c_int, [_P] * 8 + [ctypes.c_float, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32] +

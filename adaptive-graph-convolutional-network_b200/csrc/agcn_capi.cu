@@ -413,6 +413,26 @@ int agcn_gemm_tn(const float* d_A0, const float* d_A1, const float* d_D, float* 
   return gemm_tn(t, (cudaStream_t)stream);
 }
 
+/* Node-level linear map over the packed rows, the building block of the layers around SGC-LL that are plain
+ * per-graph matmuls in the reference (BlockEnd blockend.py:67-86, DenseBlockEnd densenet_block.py:98-131, MLP
+ * MLP.py:69-83, DenseMol dense_layer.py:33-50): because the rows of all graphs are stored back to back, "for every
+ * graph: x_g W" is ONE [R, Kd] x [Kd, N] product. */
+size_t agcn_node_gemm_scratch_bytes(int32_t N, int32_t Kd) { return 4 * tc_gemm_scratch_floats(N, Kd, 1, 1) + 256; }
+
+int agcn_node_gemm(const float* d_A, int32_t lda, const float* d_B, int32_t ldb, int32_t transB, float* d_C, int32_t ldc,
+                   int32_t M, int32_t N, int32_t Kd, const float* d_bias, const float* d_scale, int32_t accumulate,
+                   int32_t activation, void* d_scratch, void* stream) {
+  AGCN_REQUIRE(d_A && d_B && d_C && d_scratch && M >= 1 && N >= 1 && Kd >= 1, "node_gemm: bad arguments");
+  AGCN_REQUIRE(activation == AGCN_ACT_LINEAR || activation == AGCN_ACT_RELU, "node_gemm: unknown activation");
+  GemmArgs g;
+  g.M = M; g.N = N; g.Kd = Kd;
+  g.A0 = d_A; g.lda0 = lda;
+  g.B = d_B; g.ldb = ldb; g.transB = transB;
+  g.C = d_C; g.ldc = ldc;
+  g.bias = d_bias; g.scale = d_scale; g.accumulate = accumulate; g.act = activation;
+  return node_gemm(g, reinterpret_cast<float*>(d_scratch), (cudaStream_t)stream);
+}
+
 /* bench.py's roofline: CUDA-event timing of the fused forward kernel on its launching stream */
 int agcn_fused_profile(int enable) {
   fused_profile_enable(enable);

@@ -186,7 +186,7 @@ __global__ void big_dis_kernel(BigPtrs pp, const float* __restrict__ rowpart, in
   const int nb = (n + PT - 1) / PT;
   float d = 0.f;
   for (int c = 0; c < nb; ++c) d += rowpart[row * ncb + c];
-  dis[row] = (d > 0.f) ? 1.0f / sqrtf(d) : 0.f;
+  dis[row] = (d > AGCN_DEGREE_FLOOR) ? 1.0f / sqrtf(d) : 0.f;
 }
 
 // ------------------------------------------------------------------------------------------------

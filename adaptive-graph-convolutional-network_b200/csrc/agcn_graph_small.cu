@@ -440,7 +440,7 @@ __global__ void build_lap_kernel(BuildArgs p) {
       float d = 0.f;
       if (j < n)
         for (int i = 0; i < n; ++i) d += sM[i * pl + j];
-      const float v = (d > 0.f) ? 1.0f / sqrtf(d) : 0.f;
+      const float v = (d > AGCN_DEGREE_FLOOR) ? 1.0f / sqrtf(d) : 0.f;
       sdis[j] = v;
       if (j < n && p.dis) p.dis[row0 + j] = v;
     }

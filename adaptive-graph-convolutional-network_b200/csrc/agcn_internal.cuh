@@ -25,6 +25,11 @@
 // row-tiled products instead of the per-graph shared-memory recurrence kernels.
 #define AGCN_MID_TILED_MIN 32
 #define AGCN_FUSE_LCAP 8320
+// Paper-mode degree floor: a node whose similarity column sum d = sum_i exp(-dist_ij) is below 2^-80 (every other node
+// farther than ~55 in the learned metric) counts as isolated, d^-1/2 := 0.  The reference adds a denormal epsilon
+// (graphconv.py:196, 1.4e-45, zero under FTZ: SURVEY Q8) and then evaluates d^-1/2 ~ 1e22 on sums of denormals; the
+// floor keeps d^-1/2 <= 1.1e12 and its derivative (-1/2 d^-3/2) finite in fp32.  The oracle uses the same floor.
+#define AGCN_DEGREE_FLOOR 8.271806125530277e-25f
 
 namespace agcn {
 
@@ -152,6 +157,7 @@ struct GemmArgs {
   int ldc = 0;
   int64_t sliceC = 0;
   const float* bias = nullptr;
+  const float* scale = nullptr;  // optional device scalar: the product is multiplied by scale[0] before bias / accumulate
   int act = AGCN_ACT_LINEAR;
   int accumulate = 0;  // C += result
   // tensor-core kernel only: fused weighted sigmoid cross-entropy epilogue (C = d loss / d logits, see agcn_head.cu);

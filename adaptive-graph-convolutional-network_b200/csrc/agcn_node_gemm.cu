@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(256) gemm_rows_kernel(GemmArgs p) {
       const int c = n0 + tx * 4 + t;
       if (c >= p.N) continue;
       float v = acc[q][t];
+      if (p.scale) v *= __ldg(p.scale);
       if (p.bias) v += p.bias[c];
       if (p.accumulate) v += C[(int64_t)m * p.ldc + c];
       if (p.act == AGCN_ACT_RELU) v = fmaxf(v, 0.f);

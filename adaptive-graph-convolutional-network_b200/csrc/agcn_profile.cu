@@ -83,6 +83,19 @@ int prof_drain(const char* only, float* ms_sum, int* launches, std::string* tabl
   return AGCN_OK;
 }
 
+// fp32 FMA peak probe: 8 independent FMA chains per thread, `iters` trips, 2 flop per FMA
+__global__ void __launch_bounds__(256) fma_probe_kernel(float* __restrict__ sink, int iters) {
+  float a0 = threadIdx.x * 1e-3f, a1 = a0 + 1.f, a2 = a0 + 2.f, a3 = a0 + 3.f, a4 = a0 + 4.f, a5 = a0 + 5.f, a6 = a0 + 6.f,
+        a7 = a0 + 7.f;
+  const float b = 1.000001f, c = 1e-7f;
+#pragma unroll 4
+  for (int i = 0; i < iters; ++i) {
+    a0 = fmaf(a0, b, c); a1 = fmaf(a1, b, c); a2 = fmaf(a2, b, c); a3 = fmaf(a3, b, c);
+    a4 = fmaf(a4, b, c); a5 = fmaf(a5, b, c); a6 = fmaf(a6, b, c); a7 = fmaf(a7, b, c);
+  }
+  sink[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
 void fused_profile_enable(int on) { prof_enable(on); }
 int fused_profile_read(float* ms_sum, int* launches) { return prof_drain("ft::fused_fwd_kernel", ms_sum, launches, nullptr); }
 
@@ -92,6 +105,13 @@ extern "C" {
 
 int agcn_profile_enable(int enable) {
   agcn::prof_enable(enable);
+  return AGCN_OK;
+}
+
+int agcn_probe_fp32_fma(float* d_sink, int32_t iters, void* stream) {
+  AGCN_REQUIRE(d_sink && iters >= 1, "probe_fp32_fma: bad arguments");
+  agcn::fma_probe_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_sink, iters);
+  AGCN_LAUNCH_CHECK();
   return AGCN_OK;
 }
 

@@ -99,6 +99,7 @@ struct Args {
   int ldc;
   long long sliceC;
   const float* bias;
+  const float* scale;  // optional device scalar multiplying the product
   int act, accumulate;
   // fused weighted sigmoid cross-entropy epilogue (multitask head): C receives d loss / d logits
   const float* bce_y;
@@ -271,6 +272,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
                         __uint_as_float(v[4 * u + 3]));
       __syncwarp();
       const int cc = nb * BN + c0 + 4 * (lane & 7);  // first of this lane's 4 output columns
+      const float sc = p.scale ? __ldg(p.scale) : 1.f;
       float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
       if (p.bias) {
         if (cc + 0 < p.N) bv.x = p.bias[cc + 0];
@@ -286,7 +288,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (m < p.M && cc < p.N) {
           const long long off = (long long)m * p.ldc + cc;
           float* dst = Cz + off;
-          o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
+          o.x = o.x * sc + bv.x; o.y = o.y * sc + bv.y; o.z = o.z * sc + bv.z; o.w = o.w * sc + bv.w;
           if (vec_ok && cc + 3 < p.N) {
             float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.accumulate) old = *reinterpret_cast<const float4*>(dst);
@@ -693,7 +695,7 @@ int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
   // split-K for long contractions with few output tiles (plain outputs only): partial sums + one reduction
   const int out_tiles = ((a.M + BM - 1) / BM) * a.Z * (Npad / (Npad <= 64 ? 64 : 128));
   int ksplit = 1;
-  if (a.split_k_partial && !a.bias && a.act == AGCN_ACT_LINEAR && !a.accumulate && !a.bce_y && a.ldc == a.N && a.Z == 1 &&
+  if (a.split_k_partial && !a.bias && !a.scale && a.act == AGCN_ACT_LINEAR && !a.accumulate && !a.bce_y && a.ldc == a.N && a.Z == 1 &&
       total_kb >= 16 && out_tiles < 74)
     ksplit = std::min(std::min(8, total_kb / 4), std::max(1, 148 / out_tiles));
   p.ksplit = ksplit;
@@ -707,7 +709,7 @@ int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
     p.C = a.split_k_partial;
     p.sliceC = (long long)a.M * a.ldc;
   }
-  p.bias = a.bias; p.act = a.act; p.accumulate = a.accumulate;
+  p.bias = a.bias; p.scale = a.scale; p.act = a.act; p.accumulate = a.accumulate;
   p.bce_y = a.bce_y; p.bce_w = a.bce_w; p.bce_scale = a.bce_scale; p.loss_part = a.loss_part;
   p.bce_ld = a.bce_ld > 0 ? a.bce_ld : a.ldc;
   dim3 grid((a.M + BM - 1) / BM, a.Z * ksplit, Npad / BN);

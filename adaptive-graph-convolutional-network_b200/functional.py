@@ -207,3 +207,65 @@ def pack_nodes(padded, batch):
         # routing it through autograd would hand a CUDA gradient to a CPU tensor
         return batch.pack_nodes(padded)
     return _PackNodes.apply(padded, batch)
+
+
+class _NodeLinear(torch.autograd.Function):
+    """C = act(scale * A W + bias + add) over the packed rows (agcn_node_gemm): the per-graph matmuls of BlockEnd
+    (blockend.py:67-86), DenseBlockEnd (densenet_block.py:98-131), MLP (MLP.py:69-83) for the whole batch at once."""
+
+    @staticmethod
+    def forward(ctx, A, W, bias, scale, add, act):
+        A = A.contiguous()
+        W = W.contiguous()
+        M, Kd = A.shape
+        N = W.shape[1]
+        assert W.shape[0] == Kd and A.is_cuda and A.dtype == torch.float32
+        dev = A.device
+        lib = _lib.lib()
+        C = torch.empty(M, N, device=dev, dtype=torch.float32)
+        if add is not None:
+            C.copy_(add)
+        scratch = _Workspace.get(dev, lib.agcn_node_gemm_scratch_bytes(max(N, Kd), max(N, Kd)))
+        with torch.cuda.device(dev):
+            _lib.check(lib.agcn_node_gemm(_ptr(A), Kd, _ptr(W), N, 0, _ptr(C), N, M, N, Kd, _ptr(bias), _ptr(scale),
+                                          1 if add is not None else 0, _lib.ACT[act], _ptr(scratch), _stream_ptr(dev)))
+        ctx.act = act
+        ctx.has = (bias is not None, scale is not None, add is not None)
+        ctx.save_for_backward(A, W, scale, C)
+        return C
+
+    @staticmethod
+    def backward(ctx, dC):
+        A, W, scale, C = ctx.saved_tensors
+        has_bias, has_scale, has_add = ctx.has
+        dev = A.device
+        lib = _lib.lib()
+        M, Kd = A.shape
+        N = W.shape[1]
+        dpre = (dC * (C > 0)) if ctx.act == "relu" else dC
+        dpre = dpre.contiguous()
+        dA = dW = dbias = dscale = None
+        scratch = _Workspace.get(dev, lib.agcn_node_gemm_scratch_bytes(max(N, Kd), max(N, Kd)))
+        with torch.cuda.device(dev):
+            if ctx.needs_input_grad[0]:
+                dA = torch.empty_like(A)          # dA = scale * dpre W^T
+                _lib.check(lib.agcn_node_gemm(_ptr(dpre), N, _ptr(W), N, 1, _ptr(dA), Kd, M, Kd, N, None, _ptr(scale), 0,
+                                              _lib.ACT["linear"], _ptr(scratch), _stream_ptr(dev)))
+            if ctx.needs_input_grad[1] or (has_scale and ctx.needs_input_grad[3]):
+                dWu = torch.empty_like(W)         # A^T dpre (contraction over the rows)
+                tn = torch.empty(lib.agcn_gemm_tn_scratch_bytes(M, Kd, N, 1), dtype=torch.uint8, device=dev)
+                use_tc = 1 if (Kd <= 128 and Kd % 4 == 0 and N % 4 == 0 and M >= 32) else 0
+                _lib.check(lib.agcn_gemm_tn(_ptr(A), None, _ptr(dpre), _ptr(dWu), M, Kd, N, 1, _ptr(tn), use_tc,
+                                            _stream_ptr(dev)))
+                if has_scale and ctx.needs_input_grad[3]:
+                    dscale = (dWu * W).sum().reshape(scale.shape)       # <dpre, A W>
+                dW = dWu * scale if has_scale else dWu
+        if has_bias and ctx.needs_input_grad[2]:
+            dbias = dpre.sum(0)
+        dadd = dpre if (has_add and ctx.needs_input_grad[4]) else None
+        return dA, dW, dbias, dscale, dadd, None
+
+
+def node_linear(A, W, bias=None, scale=None, add=None, activation="linear"):
+    """[R, Fin] x [Fin, Fout] over all packed rows: act(scale * A W + bias + add).  activation in {linear, relu}."""
+    return _NodeLinear.apply(A, W, bias, scale, add, activation)

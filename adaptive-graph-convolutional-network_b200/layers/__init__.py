@@ -4,3 +4,6 @@ from .dropout import Dropout
 from .graphconv import SGC_LL, glorot, zeros, truncate_normal
 from .graphconv_reslap import SGC_LL_Reslap
 from .graphpool import GraphPoolMol
+from .blockend import BlockEnd
+from .densenet_block import DenseBlockEnd
+from .MLP import MLP

@@ -200,7 +200,7 @@ def _cpu_literal_worker(args):
         loss = loss + torch.nn.functional.binary_cross_entropy_with_logits(logits, torch.zeros_like(logits),
                                                                            reduction='sum')
     loss.backward()
-    return float(loss)
+    return float(loss.detach())
 
 
 def cpu_literal(cfg, n_graphs, steps, warmup, procs):

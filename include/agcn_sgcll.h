@@ -115,6 +115,10 @@ int agcn_fused_profile_read(float* ms_sum, int* launches);
  * (NUL-terminated, truncated to cap); *needed receives the size the whole table takes. */
 int agcn_profile_enable(int enable);
 int agcn_profile_read(char* buf, size_t cap, size_t* needed);
+/* fp32-FMA peak probe for the roofline denominators (SURVEY.md section 8d asks for a measured fp32 peak next to the
+ * recorded bf16 one): 148 x 8 CTAs of 256 threads, 8 independent FMA chains of `iters` trips per thread, i.e.
+ * 148 * 8 * 256 * 8 * 2 * iters FLOP; d_sink needs 148 * 8 * 256 floats.  The caller times it with CUDA events. */
+int agcn_probe_fp32_fma(float* d_sink, int32_t iters, void* stream);
 
 /* Tuning aid (no reference counterpart): d_buf = device buffer of tiles x 128 uint64; the following fused forward
  * launches record a per-tile timeline of nanosecond stamps into it.  NULL switches the recording off. */
@@ -198,6 +202,22 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
 size_t agcn_gemm_tn_scratch_bytes(int32_t M, int32_t Kd, int32_t N, int32_t S);
 int agcn_gemm_tn(const float* d_A0, const float* d_A1, const float* d_D, float* d_out, int32_t M, int32_t Kd,
                  int32_t N, int32_t S, void* d_scratch, int32_t use_tensor_cores, void* stream);
+
+/* Node-level linear map over the packed rows:  C (+)= act(scale * A op(B) + bias),  A [M,Kd] (row pitch lda),
+ * op(B) = B [Kd,N] or, transB, B^T with B [N,Kd]; d_scale = optional DEVICE scalar (a learned beta), d_bias [N] optional.
+ * The per-graph matmuls of BlockEnd (models/layers/blockend.py:67-86), DenseBlockEnd (densenet_block.py:98-131), MLP
+ * (MLP.py:69-83) and DenseMol (dense_layer.py:33-50) are this product over all R rows at once; tcgen05 3xTF32 when the
+ * operands are TMA-compatible (Kd >= 32, 16-byte pitches), CUDA cores otherwise.  Scratch:
+ * agcn_node_gemm_scratch_bytes(N, Kd) bytes. */
+size_t agcn_node_gemm_scratch_bytes(int32_t N, int32_t Kd);
+int agcn_node_gemm(const float* d_A, int32_t lda, const float* d_B, int32_t ldb, int32_t transB, float* d_C, int32_t ldc,
+                   int32_t M, int32_t N, int32_t Kd, const float* d_bias, const float* d_scale, int32_t accumulate,
+                   int32_t activation, void* d_scratch, void* stream);
+
+/* Dropout of the layer output in the train phase (models/layers/dropout.py:27-41 -> tf.nn.dropout(x, 1 - p, seed);
+ * graphconv.py:121-122): y[i] = keep_i ? x[i] / (1 - p) : 0 with keep_i from a counter-based Philox4x32-10 stream
+ * keyed by (seed, i).  Nothing is stored: the same call on dY with the same seed is the gradient.  d_Y may alias d_X. */
+int agcn_dropout(const float* d_X, float* d_Y, int64_t n, float p, uint64_t seed, void* stream);
 
 /* ---- the layers after the last SGC-LL layer, loss and gradient in one call:
  *   DenseMol (models/layers/dense_layer.py:33-50, linear) + GraphGatherMol (models/layers/graphgather.py:50-78:

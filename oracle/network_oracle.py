@@ -42,19 +42,37 @@ def head_loss(H_list, dense_W, dense_b, head_W, head_b, targets, weights, scale)
     return costs.sum() * scale                           # :203-208 (scale = 1 / batch_size)
 
 
-def simple_agcn_loss(X, L, n_nodes, layer_params, head_params, targets, weights, global_batch, K,
-                     laplacian="reference_literal", metric_grad="reference"):
-    """basic_AGCN.py:35-47 over a padded batch: X [B,Nmax,F], L [B,Nmax,Nmax] tensors, n_nodes [B].
-    layer_params: list of dicts (weight, bias, M_L, alpha); head_params: dict dense_W, dense_b, head_W, head_b."""
-    H = []
+def simple_agcn_features(X, L, n_nodes, layer_params, K, laplacian="reference_literal", metric_grad="reference",
+                         relu_masks=None):
+    """The SGC_LL stack of basic_AGCN.py:35-45 over a padded batch -> list of B [n_g, Fo] outputs of the last layer.
+
+    relu_masks (optional): per layer a bool tensor [R, Fo_l] over the packed rows (graph after graph) saying which
+    outputs the implementation under test found positive.  The gradient of a ReLU network is discontinuous where a
+    pre-activation crosses zero: a value within rounding error of 0 can land on either side in two correct
+    implementations, and that single flip moves a weight gradient by ~1/sqrt(R) of its size.  With the masks given,
+    relu(y) is evaluated as y * mask, so both sides differentiate the SAME piecewise-linear branch (the forward
+    values differ by the rounding error of those near-zero entries only)."""
+    H, row = [], 0
     skip = laplacian == "reference_literal"
     for g in range(X.shape[0]):
         n = int(n_nodes[g])
         x, Lg = X[g, :n], L[g, :n, :n]
-        for p in layer_params:
+        for l, p in enumerate(layer_params):
             y, _, _, _ = O.sgc_ll_graph(x, Lg, p, K, "SGC_LL", laplacian, metric_grad, compute_similarity=not skip)
-            x = torch.relu(y)                            # graphconv.py:118-123
+            if relu_masks is None:
+                x = torch.relu(y)                        # graphconv.py:118-123
+            else:
+                x = y * relu_masks[l][row:row + n].to(y.dtype)
         H.append(x)
+        row += n
+    return H
+
+
+def simple_agcn_loss(X, L, n_nodes, layer_params, head_params, targets, weights, global_batch, K,
+                     laplacian="reference_literal", metric_grad="reference", relu_masks=None):
+    """basic_AGCN.py:35-47 over a padded batch: X [B,Nmax,F], L [B,Nmax,Nmax] tensors, n_nodes [B].
+    layer_params: list of dicts (weight, bias, M_L, alpha); head_params: dict dense_W, dense_b, head_W, head_b."""
+    H = simple_agcn_features(X, L, n_nodes, layer_params, K, laplacian, metric_grad, relu_masks)
     return head_loss(H, head_params["dense_W"], head_params["dense_b"], head_params["head_W"], head_params["head_b"],
                      targets, weights, 1.0 / global_batch)
 

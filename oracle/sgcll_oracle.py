@@ -36,6 +36,7 @@ import numpy as np
 import torch
 
 EPS_F32 = float(np.spacing(np.array(0, np.float32)))  # 1.4e-45, graphconv.py:196
+DEGREE_FLOOR = 2.0 ** -80                               # see residual_laplacian
 
 
 # --------------------------------------------------------------------------
@@ -135,9 +136,12 @@ def residual_laplacian(W: torch.Tensor, laplacian: str) -> torch.Tensor:
         raise ValueError(laplacian)
     d = W.sum(dim=0)                                       # :195 (column sums)
     # :196-197.  eps = 1.4e-45 is a denormal (0 under FTZ): the guard is written
-    # out: d == 0 -> d^-1/2 := 0.  Such a row of W is all zero, so
-    # the row of L is the identity row either way.
-    pos = d > 0
+    # out: d <= DEGREE_FLOOR = 2^-80 -> d^-1/2 := 0, i.e. a node farther
+    # than ~55 from every other node in the learned metric is isolated and its row
+    # of L is the identity row.  (The reference evaluates 1/sqrt(d + 1.4e-45) ~ 1e22
+    # on sums of float32 denormals there; the floor keeps every term and its
+    # derivative finite in fp32.)
+    pos = d > DEGREE_FLOOR
     dis = torch.where(pos, 1.0 / torch.sqrt(torch.where(pos, d, torch.ones_like(d))), torch.zeros_like(d))
     return I - (dis[:, None] * W) * dis[None, :]
 

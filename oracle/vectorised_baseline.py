@@ -48,7 +48,7 @@ def sgc_ll_bucket(X, L, mask, p, K, laplacian, metric_grad):
         dist = torch.where(pos, torch.sqrt(torch.where(pos, d2, torch.ones_like(d2))), torch.zeros_like(d2))
         W = torch.exp(-dist) * m2 * (1 - torch.eye(N, dtype=X.dtype))
         d = W.sum(1)
-        ok = d > 0
+        ok = d > 2.0 ** -80
         dis = torch.where(ok, 1.0 / torch.sqrt(torch.where(ok, d, torch.ones_like(d))), torch.zeros_like(d))
         res_L = eye - dis[:, :, None] * W * dis[:, None, :]
         if metric_grad != "full":

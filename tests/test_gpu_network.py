@@ -99,28 +99,39 @@ def test_simple_agcn_step_matches_oracle_network(name, B, n_tasks, loss_kind, la
     _perturb(model, 5)
     with torch.no_grad():
         model.dense_W.mul_(dense_scale)
+        if lap == "paper":
+            # Glorot weights grow the activations ~4x per layer (|H_3| ~ 50 |X|): pairwise distances of ~100 put
+            # exp(-dist) into fp32 denormals, where neither the reference (float32 numpy) nor any fp32 implementation
+            # has significant digits left.  A smaller feature transform keeps the learned metric in range.
+            for l in model.layers:
+                l.vars["weight"].mul_(0.3)
     layer_p, head_p = _oracle_params(model)
     p_before = model.flat_params.flat.detach().clone()
+
+    # ---- which outputs the CUDA path finds positive, layer by layer (see NO.simple_agcn_features: the oracle then
+    # differentiates the same piecewise-linear branch; forward values are still compared through the loss)
+    masks = []
+    with torch.no_grad():
+        from agcn_b200.batch import PackedLaplacians, PackedNodes
+        xin = {'node_features': PackedNodes(Xd, batch), 'original_laplacian': PackedLaplacians(Ld, batch),
+               'data_slice': None, 'lap_slice': None, '_batch': batch}
+        for layer in model.layers:
+            out, _, _ = layer(xin)
+            masks.append((out.data > 0).cpu())
+            xin = dict(xin, node_features=out)
 
     # ---- oracle: loss and gradients in fp64
     w_o = w.double().cpu()
     tg_o = tg.double().cpu()
+    X64, L64 = torch.tensor(X, dtype=torch.float64), torch.tensor(L, dtype=torch.float64)
     if loss_kind == "softmax_ce":
-        H = []
-        for g in range(B):
-            x = torch.tensor(X[g, :n[g]], dtype=torch.float64)
-            Lg = torch.tensor(L[g, :n[g], :n[g]], dtype=torch.float64)
-            for p in layer_p:
-                y, _, _, _ = O.sgc_ll_graph(x, Lg, p, 3, "SGC_LL", lap, mg, compute_similarity=False)
-                x = torch.relu(y)
-            H.append(x)
+        H = NO.simple_agcn_features(X64, L64, n, layer_p, 3, lap, mg, masks)
         mol = torch.tanh(torch.stack([(h @ head_p["dense_W"] + head_p["dense_b"]).sum(0) for h in H]))
         logits = mol @ head_p["head_W"] + head_p["head_b"]
         ce = torch.logsumexp(logits, 1) - (logits * tg_o).sum(1)
         loss_o = (ce * w_o).sum() / B
     else:
-        loss_o = NO.simple_agcn_loss(torch.tensor(X, dtype=torch.float64), torch.tensor(L, dtype=torch.float64), n,
-                                     layer_p, head_p, tg_o, w_o, B, 3, lap, mg)
+        loss_o = NO.simple_agcn_loss(X64, L64, n, layer_p, head_p, tg_o, w_o, B, 3, lap, mg, masks)
     loss_o.backward()
     grads_o = _flat_oracle_grad(layer_p, head_p)
 
@@ -140,7 +151,7 @@ def test_simple_agcn_step_matches_oracle_network(name, B, n_tasks, loss_kind, la
         lp32 = [{k: v.detach().float().requires_grad_(True) for k, v in p.items()} for p in layer_p]
         hp32 = {k: v.detach().float().requires_grad_(True) for k, v in head_p.items()}
         NO.simple_agcn_loss(torch.tensor(X), torch.tensor(L), n, lp32, hp32, tg_o.float(), w_o.float(), B, 3, lap,
-                            mg).backward()
+                            mg, masks).backward()
         e32 = [O.rel_err(a, b) for a, b in zip(_flat_oracle_grad(lp32, hp32), grads_o) if float(b.abs().max()) > 0]
         print("fp32 CPU oracle vs fp64: max %.1e; CUDA vs fp64: max %.1e" % (max(e32), max(worst.values())))
         assert max(worst.values()) <= 12 * max(max(e32), 1e-5)
