@@ -15,6 +15,7 @@ LAPLACIAN = {"reference_literal": 0, "paper": 1}
 METRIC_GRAD = {"reference": 0, "full": 1}
 ACT = {"linear": 0, "relu": 1}
 LOSS = {"sigmoid_ce": 0, "softmax_ce": 1}
+ADJ_RULE = {"mean_distance": 0, "cutoff": 1}
 NOTIFY_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p)
 OUT_RES_L, OUT_RES_W, OUT_L_ALL, SAVE_FOR_BACKWARD = 1, 2, 4, 8
 
@@ -55,6 +56,9 @@ _SIGNATURES = {
                                                   ctypes.c_float, ctypes.c_int32, _P]),
     "agcn_debug_grouped_timeline": (ctypes.c_int, [_P]),
     "agcn_pack_lap_csr": (ctypes.c_int, [_P, _P, _P, _P, _P, _P]),
+    "agcn_point_laplacian_workspace_bytes": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_size_t)]),
+    "agcn_point_laplacian": (ctypes.c_int, [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_float, _P, _P,
+                                            ctypes.c_size_t, _P]),
     "agcn_graph_pool": (ctypes.c_int, [_P, _P, _P, _P, _P, ctypes.c_int32, _P]),
     "agcn_graph_pool_backward": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, _P]),
     "agcn_sgcll_workspace_bytes": (ctypes.c_int, [ctypes.POINTER(Desc), _P, ctypes.POINTER(ctypes.c_size_t),

@@ -122,6 +122,23 @@ class GraphBatch(object):
                                                     _stream_ptr(self.device)))
         return out
 
+    def point_laplacians(self, points, rule="mean_distance", sparse_ratio=0.1):
+        """Packed intrinsic Laplacians of point-cloud graphs built on the device (agcn_point_laplacian): the threshold
+        adjacency of meshloader.py:264-285 ("mean_distance") or pointcloudloader.py:240-263 ("cutoff"), then
+        Graph.compute_laplacian.  points: packed [R, F] coordinates (device), F <= 8."""
+        points = points.contiguous().float()
+        R, F = points.shape
+        assert R == self.total_nodes and points.is_cuda
+        nbytes = ctypes.c_size_t()
+        _lib.check(_lib.lib().agcn_point_laplacian_workspace_bytes(self._handle, ctypes.byref(nbytes)))
+        work = torch.empty(nbytes.value, dtype=torch.uint8, device=self.device)
+        out = torch.empty(self.total_lap, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().agcn_point_laplacian(self._handle, _ptr(points), F, _lib.ADJ_RULE[rule],
+                                                       float(sparse_ratio), _ptr(out), _ptr(work), work.numel(),
+                                                       _stream_ptr(self.device)))
+        return out
+
     def unpack_lap(self, packed):
         packed = packed.contiguous()
         out = torch.empty(self.batch_size, self.max_atom, self.max_atom, device=packed.device, dtype=torch.float32)

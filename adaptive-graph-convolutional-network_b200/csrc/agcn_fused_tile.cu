@@ -626,6 +626,10 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
     __syncwarp();
     tc_fence_after();
     if (wt == 0) FT_STAMP(67);
+    // Every worker's operand rows were consumed before tmem_full_bar fired (operand write -> split_bar -> MMA ->
+    // commit), so the stages are free; the named barrier states that ordering between the workers explicitly
+    // (compute-sanitizer racecheck does not follow the tcgen05.commit edge and reports the reuse otherwise).
+    worker_sync();
     const uint32_t stg = sbase + (uint32_t)((warp - 2) * (32 * 36 * 4));  // operand stages are free now
     const bool vecY = ((Fo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
     for (int c0 = 32 * h; c0 < N && c0 < Fo; c0 += 64) {

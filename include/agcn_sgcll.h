@@ -149,6 +149,20 @@ int agcn_unpack_lap(const agcn_plan* plan, const float* d_packed, float* d_padde
 int agcn_pack_lap_csr(const agcn_plan* plan, const int32_t* d_indptr, const int32_t* d_indices, const float* d_values,
                       float* d_packed, void* stream);
 
+/* ---- graph construction for point clouds on the device: the threshold adjacency of the
+ * reference's loaders, then Graph.compute_laplacian (models/graph_structure.py:85-130), for a whole packed batch.
+ *   AGCN_ADJ_MEAN_DISTANCE  utils/data_loader/meshloader.py:264-285: i ~ j iff d_ij < mean distance over the pairs j <= i
+ *   AGCN_ADJ_CUTOFF         utils/data_loader/pointcloudloader.py:240-263: d_lim = the int(n * sparse_ratio)-th largest
+ *                           distance (np.sort(all_dist)[-cut_off_idx]; index -0 = the smallest = 0: no edges)
+ * d_points [R, F] packed coordinates (1 <= F <= 8; the distance uses all F columns, like the reference), d_L packed
+ * float32 Laplacians out (what batch_to_feed_dict would feed as 'original_laplacian').  The n x n distance matrix is
+ * never stored: every sweep recomputes it from the coordinates. */
+#define AGCN_ADJ_MEAN_DISTANCE 0
+#define AGCN_ADJ_CUTOFF 1
+int agcn_point_laplacian_workspace_bytes(const agcn_plan* plan, size_t* bytes);
+int agcn_point_laplacian(const agcn_plan* plan, const float* d_points, int32_t F, int32_t rule, float sparse_ratio,
+                         float* d_L, void* d_work, size_t work_bytes, void* stream);
+
 /* ---- GraphPoolMol (graphpool.py:55-110) ------------------------
  * Y[i,:] = max over {j : L[i,j] != 0} of X[j,:] per graph (a row without a non-zero keeps X[i,:]).  d_argmax
  * (optional, [R,F] int32) receives the packed row that supplied each maximum.  The reference computes this inside

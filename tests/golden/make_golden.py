@@ -42,6 +42,47 @@ def extract_func(path):
     raise RuntimeError("func not found in " + path)
 
 
+def extract_method(path, name):
+    """A (static) method of a class in a reference file as a free function, pulled out with ast at run time."""
+    tree = ast.parse(open(path).read())
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            node.decorator_list = []
+            mod = ast.Module(body=[node], type_ignores=[])
+            ns = {"np": np}
+            exec(compile(mod, path, "exec"), ns)
+            return ns[name]
+    raise RuntimeError(name + " not found in " + path)
+
+
+def point_graphs():
+    """point_graph.npz: the reference's own graph construction for point clouds, executed here --
+    get_adjacency of utils/data_loader/meshloader.py:264-285 (mean-distance rule, ModelNet40) and of
+    utils/data_loader/pointcloudloader.py:240-263 (cut-off rule, Sydney), then Graph(...).Laplacian of
+    models/graph_structure.py:85-130."""
+    adj_mean = extract_method(os.path.join(REF, "utils/data_loader/meshloader.py"), "get_adjacency")
+    adj_cut = extract_method(os.path.join(REF, "utils/data_loader/pointcloudloader.py"), "get_adjacency")
+    spec = importlib.util.spec_from_file_location("ref_graph_structure", os.path.join(REF, "models/graph_structure.py"))
+    gs = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gs)
+    rng = np.random.default_rng(20261018)
+    out = {}
+    cases = [("mean13", 13, 3, adj_mean), ("mean50", 50, 3, adj_mean), ("mean64", 64, 3, adj_mean),
+             ("mean200", 200, 3, adj_mean), ("cut9", 9, 4, adj_cut), ("cut13", 13, 4, adj_cut),
+             ("cut50", 50, 4, adj_cut), ("cut200", 200, 4, adj_cut)]
+    for name, n, F, fn in cases:
+        P = rng.standard_normal((n, F)).astype(np.float32) * rng.uniform(0.5, 2.0, F).astype(np.float32)
+        if F == 4:
+            P[:, 3] = rng.integers(0, 256, n) / 255.0
+        adj_list, adj_matrix = fn(P)
+        g = gs.Graph(P, adj_list, max_deg=n, min_deg=0)
+        out[name + "/P"] = P
+        out[name + "/A"] = (adj_matrix + adj_matrix.T).astype(np.uint8)      # the reference fills the upper triangle
+        out[name + "/L"] = np.asarray(g.Laplacian.todense())
+        print(name, "edges", int(adj_matrix.sum()), "of", n * (n - 1) // 2)
+    np.savez_compressed(os.path.join(HERE, "point_graph.npz"), **out)
+
+
 def main():
     from oracle import sgcll_oracle as O
 
@@ -139,4 +180,8 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "point_graphs":
+        point_graphs()
+    else:
+        main()
+        point_graphs()

@@ -167,6 +167,5 @@ def test_dropout_mask_statistics_determinism_and_gradient():
     L = torch.zeros(3, 20, 20, device=dev)
     layer = SGC_LL(32, 16, 3, K=2, dropout=0.5)
     out, _, _ = layer(_x(batch, dev, node_features=X, original_laplacian=L, lap_slice=None))
-    base, _, _ = SGC_LL.call(layer.__class__(32, 16, 3, K=2), _x(batch, dev, node_features=X, original_laplacian=L, lap_slice=None))
     frac = float((out.data == 0).float().mean())
     assert 0.4 < frac < 0.95

@@ -312,3 +312,18 @@ def test_network_oracle_head_and_adam():
     p, m, v = NO.adam_tf(torch.zeros(3, dtype=torch.float64), torch.tensor([1., -2., 0.5], dtype=torch.float64),
                          torch.zeros(3, dtype=torch.float64), torch.zeros(3, dtype=torch.float64), 1, lr=0.1)
     assert torch.allclose(p, torch.tensor([-0.1, 0.1, -0.1], dtype=torch.float64), atol=1e-6)
+
+
+def test_host_point_graph_construction_matches_reference_goldens():
+    """agcn_b200.synthetic's vectorised adjacency rules + dense Laplacian against the outputs of the reference's own
+    loaders and Graph class (tests/golden/point_graph.npz, generated by executing the reference)."""
+    from agcn_b200 import synthetic
+    gold = np.load(os.path.join(GOLD, "point_graph.npz"))
+    names = sorted({k.split("/")[0] for k in gold.files})
+    assert len(names) == 8
+    for nm in names:
+        P, A, L = gold[nm + "/P"], gold[nm + "/A"].astype(bool), gold[nm + "/L"]
+        got = synthetic.adjacency_mean_rule(P) if nm.startswith("mean") else synthetic.adjacency_cutoff_rule(P)
+        assert np.array_equal(got, A), nm
+        assert np.abs(synthetic.laplacian_from_dense_adjacency(got) - L).max() <= 1e-12, nm
+    assert not gold["cut9/A"].any()                       # int(9 * 0.1) == 0 -> threshold 0 -> no edge at all
