@@ -86,8 +86,8 @@ __global__ void pack_lap_kernel(const float* __restrict__ padded, float* __restr
 }
 
 
-// Fused tiles (agcn_fused_tile.cu): 128-row ranges of the graphs above AGCN_FUSE_MAX_N, then the small graphs
-// first-fit-decreasing into 128-row tiles under the shared-memory budget of their L matrices.  `order` lists the
+// Fused tiles (agcn_fused_tile.cu): 128-row ranges of the graphs above AGCN_FUSE_MAX_N, then every other graph
+// first-fit-decreasing into 128-row tiles (entry field 3 = running sum of n * (n | 1), >= 0: a whole graph).  `order` lists the
 // graphs largest first.  gstart gets tiles + 1 entries.
 static void build_fused_tiles(const std::vector<int32_t>& n, const std::vector<int32_t>& order,
                               std::vector<int32_t>* gstart, std::vector<int32_t>* entries, int* n_small_tiles) {
@@ -108,7 +108,7 @@ static void build_fused_tiles(const std::vector<int32_t>& n, const std::vector<i
     const int g = order[i], ng = n[g], need = ng * (ng | 1);
     size_t t = first_open;
     for (; t < open.size(); ++t)
-      if (open[t].rows + ng <= 128 && open[t].lused + need <= AGCN_FUSE_LCAP) break;
+      if (open[t].rows + ng <= 128) break;
     if (t == open.size()) open.push_back(Open{0, 0, {}});
     Open& o = open[t];
     o.e.push_back(g); o.e.push_back(o.rows); o.e.push_back(ng); o.e.push_back(o.lused);
