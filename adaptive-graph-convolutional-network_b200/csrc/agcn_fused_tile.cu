@@ -55,7 +55,7 @@ constexpr int THREADS = 64 + WORKERS;
 constexpr int SLOTS = 2;
 constexpr uint32_t SPIN_LIMIT = 1u << 26;
 // tensor memory columns
-constexpr int TM_LT_HI = 0, TM_LT_LO = 128, TM_REC = 256 /* + 32 * slot */, TM_OUT = 320;
+constexpr int TM_LT_HI = 0, TM_LT_LO = 128, TM_REC = 256 /* + 64 * slot: [hh + lh | hl] */, TM_OUT = 384;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
@@ -175,10 +175,12 @@ __device__ __forceinline__ void write_rows_operand(uint32_t a_hi, uint32_t a_lo,
   }
 }
 // The same 16 values (times `scale`, a power of two) as my column `row` of the chunk x rows operand: 4 k-blocks of
-// [32 features][32 tile rows] (K-major, SWIZZLE_128B); feature f of tile row r sits in k-block r / 32, row f, element
-// r % 32.  The 32 lanes of a warp (consecutive tile rows) fill one 128-byte row: no bank conflicts.
+// [64][32 tile rows] (K-major, SWIZZLE_128B) whose rows 0..31 are the hi halves of the chunk's 32 features and rows
+// 32..63 the lo halves, so that ONE N = 64 product with Lt_hi yields [Lt_hi v_hi | Lt_hi v_lo]; feature f of tile row
+// r sits in k-block r / 32, row f (+ 32), element r % 32.  The 32 lanes of a warp (consecutive tile rows) fill one
+// 128-byte row: no bank conflicts.
 __device__ __forceinline__ void write_cols_operand(uint32_t b_hi, uint32_t b_lo, int row, int h, const float v[16], float scale) {
-  const uint32_t kb = (uint32_t)(row >> 5) * 4096u, e = (uint32_t)(row & 31);
+  const uint32_t kb = (uint32_t)(row >> 5) * 8192u, e = (uint32_t)(row & 31);
 #pragma unroll
   for (int u = 0; u < 16; ++u) {
     const int f = 16 * h + u;
@@ -323,15 +325,20 @@ fused_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_consta
       // D = f32, A = B = tf32, both K-major
       const uint32_t idesc_x = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       const uint32_t idesc_r = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(CH >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      const uint32_t idesc_r2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)((2 * CH) >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       int use[SLOTS] = {0, 0};
+      int tcount = 0;
       bool first = true;
       auto item = [&](int cc, int s, int slot, bool recur) {
         const int u = use[slot]++;
+        const int t = tcount++;
         mbar_wait(&full_bar[slot], (uint32_t)(u & 1));
+        if (t < 14) FT_STAMP(72 + 3 * t);
         mbar_wait(&ops_bar[slot], (uint32_t)(u & 1));
+        if (t < 14) FT_STAMP(73 + 3 * t);
         tc_fence_after();
         const uint32_t sa = sbase + slot * sp.slot_bytes, sa_lo = sa + A_BYTES;
-        const uint32_t sr = sa + 2 * A_BYTES, sr_lo = sr + R_BYTES;
+        const uint32_t sr = sa + 2 * A_BYTES;
         const uint32_t sw = sr + 2 * R_BYTES, sw_lo = sw + sp.w_bytes;
         // transform: Out += V_s[:, chunk] B_s[chunk, :]
 #pragma unroll
@@ -344,20 +351,22 @@ fused_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_consta
           umma_ss(tmem_base + TM_OUT, a_hi, b_hi, idesc_x, 1);
         }
         first = false;
-        // recurrence: Rec[slot] = Lt (c V_s[:, chunk]), the tile's block-diagonal Lt from tensor memory
+        // recurrence: Rec[slot] = Lt (c V_s[:, chunk]), the tile's block-diagonal Lt from tensor memory.  A product with
+        // the A operand in tensor memory costs its A fetch (128 x 8 elements) whatever N is, so the two products that
+        // share Lt_hi are ONE N = 64 instruction over the operand's [v_hi | v_lo] rows: columns 0..31 of the
+        // accumulator collect Lt_hi v_hi + Lt_lo v_hi, columns 32..63 Lt_hi v_lo; the workers add the two halves.
         if (recur) {
-          const uint32_t d = tmem_base + TM_REC + 32 * slot;
+          const uint32_t d = tmem_base + TM_REC + 64 * slot;
 #pragma unroll 4
           for (int k = 0; k < TM / UMMA_K; ++k) {
-            const uint32_t boff = (uint32_t)(k >> 2) * 4096u + (uint32_t)(k & 3) * (UMMA_K * 4);
-            const uint64_t b_hi = make_desc(sr + boff), b_lo = make_desc(sr_lo + boff);
+            const uint64_t b = make_desc(sr + (uint32_t)(k >> 2) * 8192u + (uint32_t)(k & 3) * (UMMA_K * 4));
             const uint32_t a_hi = tmem_base + TM_LT_HI + k * UMMA_K, a_lo = tmem_base + TM_LT_LO + k * UMMA_K;
-            umma_ts(d, a_lo, b_hi, idesc_r, k != 0);
-            umma_ts(d, a_hi, b_lo, idesc_r, 1);
-            umma_ts(d, a_hi, b_hi, idesc_r, 1);
+            umma_ts(d, a_hi, b, idesc_r2, k != 0);
+            umma_ts(d, a_lo, b, idesc_r, 1);
           }
         }
         umma_commit(&done_bar[slot]);
+        if (t < 14) FT_STAMP(74 + 3 * t);
       };
       if (zloop) {
         for (int z = 0; z < K; ++z) {
@@ -404,10 +413,44 @@ fused_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_consta
         me.lap = (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
       }
     }
-    // ---- Lt -> tensor memory: my row of the block-diagonal matrix, my half (h = 0: hi, 1: lo)
+    // ---- Lt -> tensor memory.  The tile's matrices are first staged in shared memory (the rows / cols operand area of
+    // slot 0, 64 KB, idle now; the parameter tiles that TMA is already bringing sit behind it) with coalesced
+    // asynchronous copies, row pitch n | 1 (odd: rows and columns are both conflict-free to read; a 128-node graph
+    // fills the area exactly with pitch 128 and rotates row i by i elements instead);
+    // then every thread builds its row of the block-diagonal matrix -- row i of L, or column i for Lt = L^T -- and
+    // stores its half (h = 0: hi, 1: lo) with tcgen05.st.  Reading L row by row straight from global memory costs
+    // 16 .. 46 us per tile in a cold first wave (profiles/r02_a_tile_v2_timeline_ts_n32.txt).
     if (!pre && K > 1) {
-      const float* __restrict__ Lg = p.L + me.lap;
+      int my_base = 0;
+      {
+        int acc = 0;
+        for (int e = 0; e < ng; ++e) {
+          int gx, gy, gz, gw;
+          asm volatile("ld.shared.v4.s32 {%0,%1,%2,%3}, [%4];\n" : "=r"(gx), "=r"(gy), "=r"(gz), "=r"(gw) : "r"(s_glist + 32 * e) : "memory");
+          const int lo = ldsi32(s_glist + 32 * e + 20), hi = ldsi32(s_glist + 32 * e + 24);
+          const long long loff = (long long)(((unsigned long long)(unsigned)hi << 32) | (unsigned)lo);
+          const int n = gz, pitch = (n == TM) ? TM : (n | 1);
+          if (r >= gy && r < gy + gz) my_base = acc;
+          const float* __restrict__ src = p.L + loff;
+          const uint32_t dst = sbase + 4u * (uint32_t)acc;
+          int i = wt / n, j = wt - i * n;  // element wt of the n x n matrix, then steps of 256
+          const int di = WORKERS / n, dj = WORKERS - di * n;
+          for (int idx = wt; idx < n * n; idx += WORKERS) {
+            const int jj = (n == TM) ? ((i + j) & (TM - 1)) : j;
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(dst + 4u * (uint32_t)(i * pitch + jj)), "l"(src + idx) : "memory");
+            i += di; j += dj;
+            if (j >= n) { j -= n; ++i; }
+          }
+          acc += n * pitch;
+          (void)gx; (void)gw;
+        }
+      }
+      asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+      worker_sync();
       const uint32_t lt = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(h ? TM_LT_LO : TM_LT_HI);
+      const bool rot = me.n == TM;
+      const int pitch = rot ? TM : (me.n | 1);
+      const uint32_t mine0 = sbase + 4u * (uint32_t)my_base;
 #pragma unroll 1
       for (int jb = 0; jb < 4; ++jb) {
         float v[32];
@@ -417,7 +460,10 @@ fused_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_consta
           const int j = j0 + jj;
           float x = 0.f;
           if (me.n > 0 && j >= 0 && j < me.n) {
-            x = p.transL ? __ldg(Lg + (long long)j * me.n + me.i) : __ldg(Lg + (long long)me.i * me.n + j);
+            // element (row, col) = (i, j) of L, or (j, i) for the transpose
+            const int er = p.transL ? j : me.i, ec = p.transL ? me.i : j;
+            const int ecs = rot ? ((er + ec) & (TM - 1)) : ec;
+            asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(x) : "r"(mine0 + 4u * (uint32_t)(er * pitch + ecs)) : "memory");
             if (p.add_identity && j == me.i) x += 1.f;
           }
           const float hi = tf32_rn(x);
@@ -426,6 +472,7 @@ fused_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_consta
         tmem_st32(lt + 32 * jb, v);
       }
       tmem_st_wait();
+      worker_sync();   // the staging area is about to become operand slot 0
     }
     if (wt == 0) FT_STAMP(1);
 
@@ -534,14 +581,18 @@ fused_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_consta
     };
 
     int use[SLOTS] = {0, 0};
+    int tcount = 0;
     // one hand-off: V_s[:, chunk cc] -> rows operand (transform) and, when another step follows, cols operand
     auto item = [&](int cc, int s, int slot, const float* pre0) {
       const int u = use[slot]++;
+      const int t = tcount++;
+      if (wt == 0 && t < 14) FT_STAMP(8 + 4 * t);
       if (u > 0) {
         if (lane == 0) mbar_wait(&done_bar[slot], (uint32_t)((u - 1) & 1));
         __syncwarp();
         tc_fence_after();
       }
+      if (wt == 0 && t < 14) FT_STAMP(9 + 4 * t);
       float v[16];
       if (s == 0) {
 #pragma unroll
@@ -549,7 +600,14 @@ fused_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_consta
       } else if (pre) {
         load_saved(cc, s, v);
       } else {
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TM_REC + 32 * slot + 16 * h), v);
+        {
+          float v2[16];
+          const uint32_t rec = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(TM_REC + 64 * slot + 16 * h);
+          tmem_ld16(rec, v);
+          tmem_ld16(rec + 32, v2);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[e] += v2[e];
+        }
         if (s >= 2) {
           float w[16];
           if (s == 2) load_in(cc, w); else load_saved(cc, s - 2, w);
@@ -558,13 +616,15 @@ fused_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_consta
         }
         if (p.forward || s + 2 < K) store_saved(cc, s, v);   // forward: saved for dweight; backward: V_{s+2} needs it
       }
+      if (wt == 0 && t < 14) FT_STAMP(10 + 4 * t);
       const uint32_t st = sbase + slot * sp.slot_bytes;
       write_rows_operand(st, st + A_BYTES, r, h, v);
-      if (!pre && s + 1 < K) write_cols_operand(st + 2 * A_BYTES, st + 2 * A_BYTES + R_BYTES, r, h, v, s == 0 ? 1.f : 2.f);
+      if (!pre && s + 1 < K) write_cols_operand(st + 2 * A_BYTES, st + 2 * A_BYTES + 4096, r, h, v, s == 0 ? 1.f : 2.f);
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&ops_bar[slot]);
+      if (wt == 0 && t < 14) FT_STAMP(11 + 4 * t);
     };
 
     if (zloop) {
@@ -596,7 +656,6 @@ fused_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_consta
           if (s == K - 1)   // the next group's inputs travel while this group's last step is handed over
             for (int ci = 0; ci < SLOTS && g0 + SLOTS + ci < nc; ++ci) load_in(g0 + SLOTS + ci, nxt[ci]);
           for (int ci = 0; ci < SLOTS && g0 + ci < nc; ++ci) item(g0 + ci, s, ci, cur[ci]);
-          if (wt == 0 && g0 == 0 && s < 8) FT_STAMP(2 + s);
         }
       }
       if (wt == 0) FT_STAMP(66);
