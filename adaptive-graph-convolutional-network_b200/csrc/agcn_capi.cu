@@ -100,7 +100,7 @@ Saved carve_saved(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
 }
 
 struct Work {
-  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tcY, *tcM, *big, *ftY, *ftS;
+  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tcY, *tcM, *big, *ftY;
   size_t bytes;
 };
 
@@ -131,7 +131,6 @@ Work carve_work(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
   w.tcM = c.take(tc_gemm_scratch_floats(d->F, d->F, 1, 1));
   w.big = c.take(big_work_floats(p, m.full));  // sweeps of the graphs with n > AGCN_SMALL_MAX
   w.ftY = c.take(fused_w_floats(d->Fo, d->F, d->K));  // pre-split W_k of the fused forward kernel
-  w.ftS = c.take((size_t)(d->K > 3 ? d->K - 3 : 0) * p->R * d->Fo);  // fused backward, K >= 4: V_s for the recurrence
   w.bytes = c.off;
   return w;
 }
@@ -341,13 +340,13 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
       AGCN_CUDA(cudaEventRecord(plan->ev_big_fork, st));
       AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_big_fork, 0));
       if ((rc = fused_backward(plan, plan->ft_small_tiles, n_pre, d_dY, desc->activation == AGCN_ACT_RELU ? d_Y : nullptr, Lf, ident,
-                               sv.ftG, F, Fo, K, wk.G, d_dX, wk.ftS, plan->big)))
+                               sv.ftG, F, Fo, K, wk.G, d_dX, plan->big)))
         return rc;
       if ((rc = graph_recurrence_bwd(ga, false, plan->big, AGCN_FUSE_MAX_N))) return rc;
       AGCN_CUDA(cudaEventRecord(plan->ev_big_join, plan->big));
     }
     if ((rc = fused_backward(plan, 0, plan->ft_small_tiles, d_dY, desc->activation == AGCN_ACT_RELU ? d_Y : nullptr, Lf, ident,
-                             sv.ftG, F, Fo, K, wk.G, d_dX, wk.ftS, st))) return rc;
+                             sv.ftG, F, Fo, K, wk.G, d_dX, st))) return rc;
     if (n_pre > 0) AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_big_join, 0));
   } else if (K >= 2) {
     if (need_G && (rc = graph_recurrence_bwd(ga, m.need_dL, st))) return rc;

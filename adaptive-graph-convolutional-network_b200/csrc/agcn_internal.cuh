@@ -16,10 +16,12 @@
 // Graphs above this size run their Chebyshev recurrences as row-tiled grouped GEMMs (one launch per step,
 // several CTAs per graph) instead of one CTA per (graph, feature chunk).
 #define AGCN_CHEB_SMALL_MAX 144
-// Fused tile kernel (agcn_fused_tile.cu): graphs up to this size (one MMA tile of 128 rows) are packed into 128-row
-// tiles and run their Chebyshev recurrences on the tensor cores inside the tile kernel, with the tile's
-// block-diagonal Laplacian resident in tensor memory.
-#define AGCN_FUSE_MAX_N 128
+// Fused tile kernels (agcn_fused_tile.cu): graphs up to this size are packed into 128-row tiles and run their
+// Chebyshev recurrences inside the tensor-core kernel; AGCN_FUSE_LCAP floats of shared memory hold the
+// per-graph matrices of one tile (row pitch n | 1; two 64-node graphs fit).  Larger graphs would make their
+// tile the critical path of the launch: their recurrences run chunk-parallel in the per-graph kernels instead.
+#define AGCN_FUSE_MAX_N 64
+#define AGCN_FUSE_LCAP 8320
 // Batches with at least this many graphs between AGCN_FUSE_MAX_N and AGCN_SMALL_MAX nodes send them through the
 // row-tiled products instead of the per-graph shared-memory recurrence kernels.
 #define AGCN_MID_TILED_MIN 32
@@ -303,10 +305,8 @@ int fused_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, 
                   cudaStream_t st);
 // dX = U_0 of the reverse recurrence over G_z = dYpre W_z^T, dYpre = dY * [Y > 0] (Y == NULL: dYpre = dY);
 // G receives G_z for the rows of graphs with n > AGCN_FUSE_MAX_N only
-// scratch: (K - 3) x [R, Fo] floats when K >= 4 (the three-term recurrence re-reads V_{s-2}), unused otherwise
 int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY, const float* Y, const float* L,
-                   int add_identity, const float* wsplit, int F, int Fo, int K, float* G, float* dX, float* scratch,
-                   cudaStream_t st);
+                   int add_identity, const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st);
 
 // ---------------------------------------------------------------- live per-kernel timing (agcn_profile.cu)
 // RAII bracket around ONE kernel launch in a host wrapper; records only while agcn_profile_enable(1) is in effect and

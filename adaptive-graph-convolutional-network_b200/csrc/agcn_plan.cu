@@ -86,8 +86,59 @@ __global__ void pack_lap_kernel(const float* __restrict__ padded, float* __restr
 }
 
 
-// Fused tiles (agcn_fused_tile.cu): 128-row ranges of the graphs above AGCN_FUSE_MAX_N, then every other graph
-// first-fit-decreasing into 128-row tiles (entry field 3 = running sum of n * (n | 1), >= 0: a whole graph).  `order` lists the
+// Padded -> packed over the REAL rows only (the direction every training step takes): a persistent grid of at most
+// PACK_CTAS CTAs of 1024 threads walks the R packed rows, one warp per row, the row's graph found by binary search in
+// node_off.  When the padded array is a pinned host buffer read in place over PCIe, the kernel lives for the PCIe
+// transfer time (0.2 ms for a ToxCast batch) beside the previous training step, whose tile kernels need a whole SM
+// each (222 KB of shared memory, ~60 k registers): a pack CTA on EVERY SM keeps them from being scheduled anywhere
+// (measured: +0.15 ms per step), so the pack grid stays on a few SMs -- 24 x 32 warps keep ~80 KB in flight, enough to
+// saturate PCIe -- and leaves the other ~124 to the step (its 153 tiles need two waves on 148 SMs anyway).
+__device__ __forceinline__ int graph_of_row(const int32_t* __restrict__ node_off, int B, int r) {
+  int lo = 0, hi = B;   // node_off[lo] <= r < node_off[hi]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (node_off[mid] <= r) lo = mid; else hi = mid;
+  }
+  return lo;
+}
+
+constexpr int PACK_CTAS = 24;
+__global__ void __launch_bounds__(1024) pack_rows_kernel(const float* __restrict__ padded, float* __restrict__ packed,
+                                                        const int32_t* __restrict__ n_nodes,
+                                                        const int32_t* __restrict__ node_off,
+                                                        const int64_t* __restrict__ lap_off, int B, int Nmax, int F,
+                                                        int R, int lap) {
+  const int lane = threadIdx.x & 31;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  for (int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < R; r += warps) {
+    const int g = graph_of_row(node_off, B, r);
+    const int i = r - node_off[g];
+    const float* __restrict__ src;
+    float* __restrict__ dst;
+    int len;
+    if (lap) {
+      const int n = n_nodes[g];
+      src = padded + ((int64_t)g * Nmax + i) * Nmax;
+      dst = packed + lap_off[g] + (int64_t)i * n;
+      len = n;
+    } else {
+      src = padded + ((int64_t)g * Nmax + i) * F;
+      dst = packed + (int64_t)r * F;
+      len = F;
+    }
+    if (((len & 3) == 0) && (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0)) {
+      for (int c = lane; c < (len >> 2); c += 32)
+        reinterpret_cast<float4*>(dst)[c] = __ldg(reinterpret_cast<const float4*>(src) + c);
+    } else {
+      for (int c = lane; c < len; c += 32) dst[c] = __ldg(src + c);
+    }
+  }
+}
+
+static unsigned pack_grid(int64_t R) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((R + 31) / 32, PACK_CTAS)); }
+
+// Fused tiles (agcn_fused_tile.cu): 128-row ranges of the graphs above AGCN_FUSE_MAX_N, then the small graphs
+// first-fit-decreasing into 128-row tiles under the shared-memory budget of their L matrices.  `order` lists the
 // graphs largest first.  gstart gets tiles + 1 entries.
 static void build_fused_tiles(const std::vector<int32_t>& n, const std::vector<int32_t>& order,
                               std::vector<int32_t>* gstart, std::vector<int32_t>* entries, int* n_small_tiles) {
@@ -108,7 +159,7 @@ static void build_fused_tiles(const std::vector<int32_t>& n, const std::vector<i
     const int g = order[i], ng = n[g], need = ng * (ng | 1);
     size_t t = first_open;
     for (; t < open.size(); ++t)
-      if (open[t].rows + ng <= 128) break;
+      if (open[t].rows + ng <= 128 && open[t].lused + need <= AGCN_FUSE_LCAP) break;
     if (t == open.size()) open.push_back(Open{0, 0, {}});
     Open& o = open[t];
     o.e.push_back(g); o.e.push_back(o.rows); o.e.push_back(ng); o.e.push_back(o.lused);
@@ -465,6 +516,13 @@ static int pack_nodes_impl(const agcn_plan* plan, const float* padded, float* pa
                            int to_padded) {
   AGCN_REQUIRE(plan && padded && packed && F >= 1, "null pointer or F < 1");
   if (int rc = plan_use(plan, (cudaStream_t)stream)) return rc;
+  if (!to_padded) {
+    pack_rows_kernel<<<pack_grid(plan->R), 1024, 0, (cudaStream_t)stream>>>(padded, packed, plan->d_n, plan->d_node_off,
+                                                                           plan->d_lap_off, plan->B, plan->Nmax, F,
+                                                                           (int)plan->R, 0);
+    AGCN_LAUNCH_CHECK();
+    return AGCN_OK;
+  }
   const int64_t rows = (int64_t)plan->B * plan->Nmax;
   const int wpb = 8;
   pack_nodes_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(
@@ -483,6 +541,13 @@ int agcn_unpack_nodes(const agcn_plan* plan, const float* d_packed, float* d_pad
 static int pack_lap_impl(const agcn_plan* plan, const float* padded, float* packed, void* stream, int to_padded) {
   AGCN_REQUIRE(plan && padded && packed, "null pointer");
   if (int rc = plan_use(plan, (cudaStream_t)stream)) return rc;
+  if (!to_padded) {
+    pack_rows_kernel<<<pack_grid(plan->R), 1024, 0, (cudaStream_t)stream>>>(padded, packed, plan->d_n, plan->d_node_off,
+                                                                           plan->d_lap_off, plan->B, plan->Nmax, 0,
+                                                                           (int)plan->R, 1);
+    AGCN_LAUNCH_CHECK();
+    return AGCN_OK;
+  }
   const int64_t rows = (int64_t)plan->B * plan->Nmax;
   const int wpb = 8;
   pack_lap_kernel<<<(unsigned)((rows + wpb - 1) / wpb), wpb * 32, 0, (cudaStream_t)stream>>>(

@@ -170,12 +170,12 @@ def test_initialisers():
 
 def test_fused_tile_packing_invariants():
     """Work decomposition of the fused tile kernels (agcn_fused_tiles_host, host only): every graph is
-    covered exactly once, tiles hold at most 128 rows of whole graphs, graphs above AGCN_FUSE_MAX_N (one MMA tile)
-    are cut into 128-row ranges."""
+    covered exactly once, tiles hold at most 128 rows and AGCN_FUSE_LCAP floats of Laplacians, graphs
+    above AGCN_FUSE_MAX_N are cut into 128-row ranges."""
     import ctypes
     from agcn_b200 import _lib
     from oracle import sgcll_oracle as O
-    FUSE_MAX_N = 128
+    FUSE_MAX_N, LCAP = 64, 8320
     cases = [np.array([132, 4, 5, 18, 33, 64, 65, 17, 96, 31], np.int32),
              np.array([1] * 300, np.int32),
              np.array([1024, 700, 13, 145, 96, 97, 128, 129], np.int32),
@@ -205,7 +205,7 @@ def test_fused_tile_packing_invariants():
                     rows += ng
                     lused += ng * (ng | 1)
                     covered[g] += ng
-                assert rows <= 128 and len(e) <= 128
+                assert rows <= 128 and lused <= LCAP and len(e) <= 128
         assert np.array_equal(covered, n.astype(np.int64))
         if B == 1024:   # ToxCast-shape batch: tiles are well filled (R / 128 is the lower bound)
             assert tiles.value <= int(np.ceil(n.sum() / 128.0 * 1.08)) + 2, (tiles.value, n.sum() / 128.0)

@@ -41,13 +41,17 @@ order = used[np.argsort(-dur)]
 for name, t in (("slowest", order[0]), ("median", order[len(order) // 2]), ("fastest", order[-1]), ("tile0", used[0]),
                 ("last", used[-1])):
     r = d[t]
-    us = lambda k: (r[k] - r[0]) / 1e3 if r[k] > 0 else float("nan")
     print("== %s tile %d: start %.1f end %.1f (dur %.1f)" % (name, t, rel(r[0]), rel(r[68]), (r[68] - r[0]) / 1e3))
-    print("   Lt in tensor memory +%.2f" % us(1))
-    print("   worker hand-offs (enter, slot free, value ready, arrived), us from tile start:")
-    print("   " + " ".join("[%.1f %.1f %.1f %.1f]" % (us(8 + 4 * k), us(9 + 4 * k), us(10 + 4 * k), us(11 + 4 * k))
-                           for k in range(14) if r[8 + 4 * k] > 0))
-    print("   mma thread (tile landed, operands ready, issued + committed) per item:")
-    print("   " + " ".join("[%.1f %.1f %.1f]" % (us(72 + 3 * k), us(73 + 3 * k), us(74 + 3 * k)) for k in range(14)
-                           if r[72 + 3 * k] > 0))
-    print("   all handed +%.2f | Out ready +%.2f | end +%.2f" % (us(66), us(67), us(68)))
+    print("   prologue done +%.2f" % ((r[1] - r[0]) / 1e3))
+    for c in range(8):
+        if r[2 + 8 * c] == 0:
+            break
+        b = r[2 + 8 * c]
+        print("   chunk %d: top +%.2f | emit0 +%.2f | mma1 +%.2f emit1 +%.2f | mma2 +%.2f emit2 +%.2f" % (
+            c, (b - r[0]) / 1e3, (r[3 + 8 * c] - b) / 1e3, (r[4 + 8 * c] - b) / 1e3, (r[5 + 8 * c] - b) / 1e3,
+            (r[6 + 8 * c] - b) / 1e3, (r[7 + 8 * c] - b) / 1e3))
+    print("   workers done +%.2f | tmem_full +%.2f | end +%.2f" % ((r[66] - r[0]) / 1e3, (r[67] - r[0]) / 1e3,
+                                                                   (r[68] - r[0]) / 1e3))
+    print("   mma thread (B ready, A ready, issued) per k-block, us from tile start:")
+    print("   " + " ".join("[%.1f %.1f %.1f]" % ((r[72 + 3 * k] - r[0]) / 1e3, (r[73 + 3 * k] - r[0]) / 1e3,
+                                                   (r[74 + 3 * k] - r[0]) / 1e3) for k in range(16) if r[72 + 3 * k] > 0))
