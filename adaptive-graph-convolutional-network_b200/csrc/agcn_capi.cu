@@ -99,6 +99,16 @@ Saved carve_saved(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
   return s;
 }
 
+// dL_all of the per-graph recurrences is accumulated by several CTAs per graph (one per group of feature chunks), each
+// writing its own partial matrix: up to 8 parts as long as the scratch stays below 1 GB
+inline int64_t dl_stride(const agcn_plan* p) { return (p->LL + 63) & ~(int64_t)63; }
+inline int dl_parts(const agcn_sgcll_desc* d, const agcn_plan* p) {
+  if (d->K < 2) return 1;
+  int parts = std::min(8, (d->F + 31) / 32);
+  while (parts > 1 && (int64_t)parts * dl_stride(p) * 4 > ((int64_t)1 << 30)) --parts;
+  return std::max(1, parts);
+}
+
 struct Work {
   float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tcY, *tcM, *big, *ftY;
   size_t bytes;
@@ -122,7 +132,7 @@ Work carve_work(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
   }
   w.tn_part = c.take(tn);
   w.act_part = c.take(act_bwd_partial_floats(p->R, d->Fo));
-  w.dL = m.need_dL ? c.take((size_t)p->LL) : nullptr;
+  w.dL = m.need_dL ? c.take((size_t)dl_parts(d, p) * dl_stride(p)) : nullptr;
   w.dXW = m.full ? c.take((size_t)p->R * d->F) : nullptr;
   w.dalpha_part = c.take((size_t)p->B);
   w.dbeta_part = c.take((size_t)p->B);
@@ -242,8 +252,8 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
       AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_big_fork, 0));
       if ((rc = graph_chebyshev_fwd(ga, plan->big, AGCN_FUSE_MAX_N))) return rc;
       AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_side_join, 0));
-      if ((rc = fused_forward(plan, plan->ft_small_tiles, n_pre, d_X, Lf, ident, wk.ftY, d_bias, desc->activation, F, Fo,
-                              K, sv.T, d_Y, plan->big)))
+      if ((rc = pre_forward(plan, plan->ft_small_tiles, n_pre, d_X, sv.T, wk.ftY, d_bias, desc->activation, F, Fo, K, d_Y,
+                            plan->big)))
         return rc;
       AGCN_CUDA(cudaEventRecord(plan->ev_big_join, plan->big));
     }
@@ -317,6 +327,8 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   ga.T = sv.T; ga.Lall = m.shortcut ? nullptr : sv.Lall;
   ga.dist = sv.dist; ga.dis = sv.dis; ga.stats = sv.stats;
   ga.G = wk.G; ga.dLall_in = d_dLall_in; ga.dX = dXbuf; ga.dL = wk.dL;
+  ga.dl_parts = (m.need_dL && K >= 2) ? dl_parts(desc, plan) : 1;
+  ga.dl_stride = dl_stride(plan);
   ga.dLprev = has_prev ? d_dLprev : nullptr;
   ga.dXW = wk.dXW; ga.dalpha_part = wk.dalpha_part; ga.dbeta_part = m.reslap ? wk.dbeta_part : nullptr;
   ga.big_work = wk.big;
@@ -339,8 +351,8 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
     if (n_pre > 0) {
       AGCN_CUDA(cudaEventRecord(plan->ev_big_fork, st));
       AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_big_fork, 0));
-      if ((rc = fused_backward(plan, plan->ft_small_tiles, n_pre, d_dY, desc->activation == AGCN_ACT_RELU ? d_Y : nullptr, Lf, ident,
-                               sv.ftG, F, Fo, K, wk.G, d_dX, plan->big)))
+      if ((rc = pre_backward(plan, plan->ft_small_tiles, n_pre, d_dY, desc->activation == AGCN_ACT_RELU ? d_Y : nullptr,
+                             sv.ftG, F, Fo, K, wk.G, plan->big)))
         return rc;
       if ((rc = graph_recurrence_bwd(ga, false, plan->big, AGCN_FUSE_MAX_N))) return rc;
       AGCN_CUDA(cudaEventRecord(plan->ev_big_join, plan->big));

@@ -252,12 +252,14 @@ struct RecurArgs {
   const float* G;
   int64_t gslice;
   float* dX;
-  int need_dL;  // chunks must be 1
+  int need_dL;  // the `chunks` CTAs of a graph take the feature chunks ch, ch + chunks, ... and write their partial
+                // dL (+ dLall_in for ch == 0) to dL + ch * dl_stride; graph_laplacian_bwd adds the partials up
   const float* X;
   const float* T;
   int64_t tslice;
   const float* dLall_in;
   float* dL;
+  int64_t dl_stride;
 };
 
 __global__ void recur_bwd_kernel(RecurArgs p) {
@@ -275,13 +277,14 @@ __global__ void recur_bwd_kernel(RecurArgs p) {
   const int64_t loff = p.pp.lap_off[g];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   load_square(sL, pl, n, n4, p.L + loff);
-  if (p.need_dL) load_square(sdL, pl, n, n4, p.dLall_in ? p.dLall_in + loff : nullptr);
+  if (p.need_dL) load_square(sdL, pl, n, n4, (p.dLall_in && ch == 0) ? p.dLall_in + loff : nullptr);
   cp_async_wait_all();
   __syncthreads();
   if (p.add_identity) add_identity(sL, pl, n);
-  const int f_begin = p.need_dL ? 0 : ch * p.FC;
+  const int f_begin = ch * p.FC;
   const int f_end = p.need_dL ? p.F : min(p.F, f_begin + p.FC);
-  for (int f0 = f_begin; f0 < f_end; f0 += p.FC) {
+  const int f_step = p.need_dL ? p.chunks * p.FC : p.FC;
+  for (int f0 = f_begin; f0 < f_end; f0 += f_step) {
     const int fc = min(p.FC, p.F - f0);
     const int tc = (fc + 3) / 4, tiles = (n4 / 4) * tc;
     __syncthreads();
@@ -354,7 +357,7 @@ __global__ void recur_bwd_kernel(RecurArgs p) {
     __syncthreads();
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
       const int i = idx / n, j = idx - i * n;
-      p.dL[loff + idx] = sdL[i * pl + j];
+      p.dL[(int64_t)ch * p.dl_stride + loff + idx] = sdL[i * pl + j];
     }
   }
 }
@@ -513,7 +516,9 @@ struct LapBwdArgs {
   const float* dist;
   const float* dis;
   const float* stats;
-  const float* dL;
+  const float* dL;       // dl_parts partial sums, dl_stride elements apart (graph_recurrence_bwd)
+  int dl_parts;
+  int64_t dl_stride;
   float* dLprev;
   float* dXW;
   float* dalpha_part;
@@ -562,6 +567,11 @@ __global__ void lap_bwd_kernel(LapBwdArgs p) {
     return paper ? eye - (sdis[i] * sW[i * pl + j]) * sdis[j] : eye;
   };
   float acc_alpha = 0.f, acc_beta = 0.f;
+  auto dL_at = [&](int64_t e) -> float {   // fixed summation order: deterministic
+    float v = p.dL[e];
+    for (int c = 1; c < p.dl_parts; ++c) v += p.dL[(int64_t)c * p.dl_stride + e];
+    return v;
+  };
   if (reslap) {
     // L_all = leaky(s2 * Z): gradient w.r.t. v = s2 Z, and <gv, Z>
     float ip2 = 0.f;
@@ -570,7 +580,7 @@ __global__ void lap_bwd_kernel(LapBwdArgs p) {
       float z = leaky(Rval(i, j) * s1, alpha) + p.Lint[loff + idx];
       if (p.Lprev) z += p.Lprev[loff + idx] * beta;
       const float v = z * s2;
-      const float gd = p.dL[loff + idx];
+      const float gd = dL_at(loff + idx);
       acc_alpha -= gd * fmaxf(-v, 0.f);
       const float gv = gd * leaky_grad(v, alpha);
       ip2 += gv * z;
@@ -595,7 +605,7 @@ __global__ void lap_bwd_kernel(LapBwdArgs p) {
   } else {
     for (int idx = threadIdx.x; idx < n * n; idx += blockDim.x) {
       const int i = idx / n, j = idx - i * n;
-      sG[i * pl + j] = p.dL[loff + idx];
+      sG[i * pl + j] = dL_at(loff + idx);
     }
   }
   // res_L' = leaky(s1 R)
@@ -812,10 +822,12 @@ int graph_recurrence_bwd(const GraphArgs& a, bool need_dL, cudaStream_t st, int 
     if (!need_dL && bk.max_n > plan->cheb_small_max) continue;  // row-tiled below
     if (bk.limit <= above_n) continue;                          // owned by the fused tile kernel
     ChunkCfg c = chunk_cfg(bk.max_n, a.F, need_dL ? 3 : 2, need_dL ? 2 : 1, need_dL);
+    if (need_dL) c.chunks = std::max(1, std::min(a.dl_parts, (a.F + c.FC - 1) / c.FC));
     rc = set_smem(recur_bwd_kernel, c.smem);
     if (rc) return rc;
     RecurArgs k{plan_ptrs(plan), bk.start, c.chunks, c.FC, a.F, a.K, shortcut ? a.Lint : a.Lall, shortcut ? 1 : 0,
-                a.G, (int64_t)plan->R * a.F, a.dX, need_dL ? 1 : 0, a.X, a.T, (int64_t)plan->R * a.F, a.dLall_in, a.dL};
+                a.G, (int64_t)plan->R * a.F, a.dX, need_dL ? 1 : 0, a.X, a.T, (int64_t)plan->R * a.F, a.dLall_in, a.dL,
+                a.dl_stride};
     cudaStream_t s = (b == 0) ? st : plan->aux[(b - 1) % 3];
     {
       ProfScope prof("recur_bwd_kernel", s);
@@ -874,7 +886,8 @@ int graph_laplacian_bwd(const GraphArgs& a, cudaStream_t st) {
     rc = set_smem(lap_bwd_kernel, smem);
     if (rc) return rc;
     LapBwdArgs k{plan_ptrs(plan), bk.start, a.F, FCD, a.variant, a.lap_mode, a.metric_full, a.XW, a.Lint, a.Lprev,
-                 a.alpha, a.beta, a.dist, a.dis, a.stats, a.dL, a.dLprev, a.dXW, a.dalpha_part, a.dbeta_part};
+                 a.alpha, a.beta, a.dist, a.dis, a.stats, a.dL, a.dl_parts, a.dl_stride, a.dLprev, a.dXW, a.dalpha_part,
+                 a.dbeta_part};
     cudaStream_t s = (b == 0) ? st : plan->aux[(b - 1) % 3];
     const int threads = (bk.max_n <= 32) ? 128 : (bk.max_n <= 64 ? 256 : 512);
     {

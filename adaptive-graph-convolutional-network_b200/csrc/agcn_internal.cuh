@@ -233,7 +233,9 @@ struct GraphArgs {
   const float* G = nullptr;      // [K][R][F]  dY * W_k^T
   const float* dLall_in = nullptr;
   float* dX = nullptr;           // [R,F]
-  float* dL = nullptr;           // packed scratch: dL_all
+  float* dL = nullptr;           // packed scratch: dL_all, as dl_parts partial sums dl_stride elements apart (the
+  int dl_parts = 1;              //   recurrences of the graphs up to AGCN_SMALL_MAX nodes split the feature chunks over
+  int64_t dl_stride = 0;         //   dl_parts CTAs per graph; bigger graphs use part 0 only)
   float* dLprev = nullptr;       // packed out
   float* dXW = nullptr;          // [R,F] out (metric_full)
   float* dalpha_part = nullptr;  // [B]
@@ -307,6 +309,13 @@ int fused_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, 
 // G receives G_z for the rows of graphs with n > AGCN_FUSE_MAX_N only
 int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY, const float* Y, const float* L,
                    int add_identity, const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st);
+
+// ---------------------------------------------------------------- transform product of the 128-row ranges of graphs
+// above AGCN_FUSE_MAX_N (agcn_pre_tile.cu); same parameter operands as the fused tile kernels
+int pre_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, const float* T, const float* wsplit,
+                const float* bias, int act, int F, int Fo, int K, float* Y, cudaStream_t st);
+int pre_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY, const float* Y, const float* wsplit, int F,
+                 int Fo, int K, float* G, cudaStream_t st);
 
 // ---------------------------------------------------------------- live per-kernel timing (agcn_profile.cu)
 // RAII bracket around ONE kernel launch in a host wrapper; records only while agcn_profile_enable(1) is in effect and

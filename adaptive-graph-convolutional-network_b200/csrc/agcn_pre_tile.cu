@@ -1,0 +1,477 @@
+// Transform product of the graphs that do not fit a fused tile (agcn_fused_tile.cu): 128-row ranges ("pre tiles") of
+// graphs above AGCN_FUSE_MAX_N nodes -- the mid-size molecules of a Tox21 / ToxCast batch and every point cloud.  Their
+// Chebyshev recurrences run in the per-graph / row-tiled kernels (agcn_graph_small.cu, agcn_big_tc.cu); what is left
+// per 128-row range is a plain dense contraction on the tensor cores:
+//
+//   forward   Y = act(sum_s T_s W_s + b)        graphconv.py:238-247, :118-123   (T_0 = X, T_s saved by the recurrences)
+//   backward  G_z = dYpre W_z^T, z = 0..K-1     dYpre = dY * relu'(Y); input of the reverse recurrences
+//
+// One CTA per range.  Every hand-off ("item") is one 32-column chunk of one operand matrix: the 8 worker warps
+// (thread = tile row x column half) load their 16 values from global memory one item ahead, split them into hi / lo TF32
+// halves and write them once into a K-major SWIZZLE_128B operand slot; TMA brings the matching pre-split parameter
+// tile; one thread issues the 3xTF32 products into a TMEM accumulator.  Items are independent, so three slots keep
+// loads, splits and tensor-core work of consecutive items in flight together (0.4 .. 0.5 us per item against 0.9 us
+// + a dependent recurrence step in the fused tile kernel's hand-off; profiles/r02_b_tile_v2_timeline_ts_n64_staged.txt).
+#include <cuda.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "agcn_internal.cuh"
+
+namespace agcn {
+namespace pt {
+
+constexpr int TM = 128;            // rows per tile (UMMA M)
+constexpr int CH = 32;             // feature columns per chunk = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;          // tf32
+constexpr int A_BYTES = TM * CH * 4;   // 16 KB: one half (hi or lo) of a rows x chunk operand
+constexpr int WORKERS = 256;       // warps 2..9: two threads per tile row (column halves)
+constexpr int THREADS = 64 + WORKERS;
+constexpr int SLOTS = 3;
+constexpr uint32_t SPIN_LIMIT = 1u << 26;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (!done) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (!done && ++spins > SPIN_LIMIT) __trap();  // a protocol bug becomes an error, not a hang
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, SWIZZLE_128B, 8-row atoms of 1024 bytes
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 16 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float v[16]) {
+  uint32_t u[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];\n"
+      : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+        "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
+}
+__device__ __forceinline__ void sts128(uint32_t a, float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};\n" ::"r"(a), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ int ldsi32(uint32_t a) {
+  int v;
+  asm volatile("ld.shared.s32 %0, [%1];\n" : "=r"(v) : "r"(a) : "memory");
+  return v;
+}
+__device__ __forceinline__ void worker_sync() { asm volatile("bar.sync 1, 256;\n" ::: "memory"); }
+
+// My half (16 columns: 16-byte groups 4h .. 4h+3) of row `row` of a rows x chunk operand ([128][32] K-major,
+// SWIZZLE_128B), split into hi / lo TF32 halves.
+__device__ __forceinline__ void write_rows_operand(uint32_t a_hi, uint32_t a_lo, int row, int h, const float v[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g) {
+    float4 hi, lo;
+    hi.x = tf32_rn(v[4 * g]);     hi.y = tf32_rn(v[4 * g + 1]);
+    hi.z = tf32_rn(v[4 * g + 2]); hi.w = tf32_rn(v[4 * g + 3]);
+    lo.x = tf32_rn(v[4 * g] - hi.x);     lo.y = tf32_rn(v[4 * g + 1] - hi.y);
+    lo.z = tf32_rn(v[4 * g + 2] - hi.z); lo.w = tf32_rn(v[4 * g + 3] - hi.w);
+    const uint32_t off = (uint32_t)(row * 128 + (((4 * h + g) ^ (row & 7)) << 4));
+    sts128(a_hi + off, hi);
+    sts128(a_lo + off, lo);
+  }
+}
+
+struct SmemPlan {
+  int w_bytes;     // one half of a parameter tile: N x 128 bytes
+  int slot_bytes;  // rows operand (hi, lo) + parameter tile (hi, lo)
+  int off_bars;
+  int total;
+};
+__host__ __device__ inline SmemPlan smem_plan(int N) {
+  SmemPlan s;
+  s.w_bytes = N * 128;
+  s.slot_bytes = 2 * A_BYTES + 2 * s.w_bytes;
+  s.off_bars = SLOTS * s.slot_bytes;
+  s.total = s.off_bars + 256 + 1024;  // + alignment slack
+  return s;
+}
+
+struct PreArgs {
+  const int4* tile_graphs;     // 2 x int4 per entry: {g, row_start, nrows, -1}, {node_off, ...}
+  const int32_t* tile_gstart;  // [tiles + 1]
+  int tile0;                   // first tile of this launch
+  int Fin;                     // columns of the operand matrices: F forward, Fo backward
+  int Fout;                    // columns of the result: Fo forward, F backward
+  int K;
+  int N;                       // MMA N (Fout padded to 16)
+  int nchunks;                 // ceil(Fin / 32)
+  int tmem_cols;               // power of two >= N
+  const float* In;             // [R, Fin]   forward: X, backward: dY
+  const float* Mask;           // backward: Y (dYpre = dY * [Y > 0]) or NULL
+  const float* T;              // forward: saved T_1 .. T_{K-1}, [K-1][R][Fin]
+  long long t_slice;
+  const float* bias;           // forward
+  int act;
+  float* Out;                  // forward: Y [R, Fout]; backward: G [K][R][Fout]
+  long long out_slice;         // backward: elements between G_z
+  int forward;
+};
+
+__global__ void __launch_bounds__(THREADS, 1)
+pre_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, PreArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(base);
+  const SmemPlan sp = smem_plan(p.N);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + sp.off_bars);
+  uint64_t* full_bar = bars;            // [SLOTS] parameter tile landed (TMA)
+  uint64_t* ops_bar = bars + SLOTS;     // [SLOTS] operand rows written by the 8 worker warps
+  uint64_t* done_bar = bars + 2 * SLOTS;  // [SLOTS] the MMAs that read the slot retired
+  uint64_t* out_bar = bars + 3 * SLOTS;     // accumulator complete (forward: once; backward: once per z)
+  uint64_t* outfree_bar = bars + 3 * SLOTS + 1;  // backward: accumulator drained by the workers
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * SLOTS + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = p.tile0 + blockIdx.x;
+  const int K = p.K, N = p.N, nc = p.nchunks, Fin = p.Fin, Fout = p.Fout;
+  // forward: ONE accumulation over all (chunk, s) items; backward: K passes over the chunks, one G_z each
+  const int passes = p.forward ? 1 : K;
+  const int per_pass = p.forward ? nc * K : nc;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SLOTS; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&ops_bar[s], WORKERS / 32);
+      mbar_init(&done_bar[s], 1);
+    }
+    mbar_init(out_bar, 1);
+    mbar_init(outfree_bar, WORKERS / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    const uint32_t s = smem_u32(tmem_slot);
+    switch (p.tmem_cols) {
+      case 32: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;\n" ::"r"(s) : "memory"); break;
+      case 64: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;\n" ::"r"(s) : "memory"); break;
+      default: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n" ::"r"(s) : "memory"); break;
+    }
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // item t of a pass: forward (chunk, s) = (t / K, t % K); backward chunk t of pass z.  Parameter tile (chunk, slice).
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int t_all = 0;
+      for (int z = 0; z < passes; ++z)
+        for (int t = 0; t < per_pass; ++t, ++t_all) {
+          const int slot = t_all % SLOTS, u = t_all / SLOTS;
+          if (u > 0) mbar_wait(&done_bar[slot], (uint32_t)((u - 1) & 1));
+          const int cc = p.forward ? t / K : t, sl = p.forward ? t % K : z;
+          const uint32_t dst = sbase + slot * sp.slot_bytes + 2 * A_BYTES;
+          mbar_expect_tx(&full_bar[slot], 2 * sp.w_bytes);
+          tma_load_2d(dst, &tmBhi, &full_bar[slot], cc * CH, sl * N);
+          tma_load_2d(dst + sp.w_bytes, &tmBlo, &full_bar[slot], cc * CH, sl * N);
+        }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      // D = f32, A = B = tf32, both K-major
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      int t_all = 0;
+      for (int z = 0; z < passes; ++z) {
+        if (z > 0) {
+          mbar_wait(outfree_bar, (uint32_t)((z - 1) & 1));
+          tc_fence_after();
+        }
+        for (int t = 0; t < per_pass; ++t, ++t_all) {
+          const int slot = t_all % SLOTS, u = t_all / SLOTS;
+          mbar_wait(&full_bar[slot], (uint32_t)(u & 1));
+          mbar_wait(&ops_bar[slot], (uint32_t)(u & 1));
+          tc_fence_after();
+          const uint32_t sa = sbase + slot * sp.slot_bytes, sa_lo = sa + A_BYTES;
+          const uint32_t sw = sa + 2 * A_BYTES, sw_lo = sw + sp.w_bytes;
+#pragma unroll
+          for (int k = 0; k < CH / UMMA_K; ++k) {
+            const uint32_t koff = k * UMMA_K * 4;
+            const uint64_t a_hi = make_desc(sa + koff), a_lo = make_desc(sa_lo + koff);
+            const uint64_t b_hi = make_desc(sw + koff), b_lo = make_desc(sw_lo + koff);
+            umma_ss(tmem_base, a_lo, b_hi, idesc, (t | k) != 0);
+            umma_ss(tmem_base, a_hi, b_lo, idesc, 1);
+            umma_ss(tmem_base, a_hi, b_hi, idesc, 1);
+          }
+          umma_commit(&done_bar[slot]);
+        }
+        umma_commit(out_bar);
+      }
+    }
+  } else {
+    // ================= workers =================
+    const int q = warp & 3;             // TMEM lane quarter of this warp
+    const int h = (warp - 2) >> 2;      // column half
+    const int r = q * 32 + lane;        // my tile row
+    int grow = -1;
+    {
+      const int4 e0 = __ldg(p.tile_graphs + 2 * p.tile_gstart[tile]);       // {g, row_start, nrows, -1}
+      const int4 e1 = __ldg(p.tile_graphs + 2 * p.tile_gstart[tile] + 1);   // {node_off, ...}
+      if (r < e0.z) grow = e1.x + e0.y + r;
+    }
+    const bool vecIn = ((Fin & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.In) & 15) == 0) &&
+                       (!p.Mask || (reinterpret_cast<uintptr_t>(p.Mask) & 15) == 0) &&
+                       (!p.T || (((reinterpret_cast<uintptr_t>(p.T) & 15) == 0) && ((p.t_slice & 3) == 0)));
+    // my 16 columns of chunk cc of operand matrix sl (forward: T_sl; backward: dYpre)
+    auto load_item = [&](int cc, int sl, float v[16]) {
+      const int c0 = cc * CH + 16 * h;
+      const float* src = (p.forward && sl > 0) ? p.T + (long long)(sl - 1) * p.t_slice : p.In;
+      const float* msk = p.forward ? nullptr : p.Mask;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int col = c0 + 4 * g;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (grow >= 0 && col < Fin) {
+          const long long o = (long long)grow * Fin + col;
+          if (vecIn) {
+            x = __ldg(reinterpret_cast<const float4*>(src + o));
+            if (msk) {  // relu'(0) = 0 (TF's ReluGrad)
+              const float4 y = __ldg(reinterpret_cast<const float4*>(msk + o));
+              x.x = y.x > 0.f ? x.x : 0.f; x.y = y.y > 0.f ? x.y : 0.f;
+              x.z = y.z > 0.f ? x.z : 0.f; x.w = y.w > 0.f ? x.w : 0.f;
+            }
+          } else {
+            float t[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (col + e < Fin) {
+                t[e] = __ldg(src + o + e);
+                if (msk && !(__ldg(msk + o + e) > 0.f)) t[e] = 0.f;
+              }
+            x = make_float4(t[0], t[1], t[2], t[3]);
+          }
+        }
+        v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
+      }
+    };
+    auto coords = [&](int z, int t, int& cc, int& sl) {
+      cc = p.forward ? t / K : t;
+      sl = p.forward ? t % K : z;
+    };
+    // accumulator -> global rows (bias + activation in the forward direction)
+    auto drain_out = [&](float* dstm) {
+      const bool vecO = ((Fout & 3) == 0) && ((reinterpret_cast<uintptr_t>(dstm) & 15) == 0);
+      for (int c0 = 16 * h; c0 < N && c0 < Fout; c0 += 32) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        if (grow < 0) continue;
+        if (p.forward) {
+#pragma unroll
+          for (int u = 0; u < 16; ++u) {
+            float o = v[u] + ((p.bias && c0 + u < Fout) ? __ldg(p.bias + c0 + u) : 0.f);
+            if (p.act == AGCN_ACT_RELU) o = fmaxf(o, 0.f);
+            v[u] = o;
+          }
+        }
+        float* dst = dstm + (long long)grow * Fout + c0;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (c0 + 4 * g >= Fout) continue;
+          if (vecO && c0 + 4 * g + 3 < Fout) {
+            *reinterpret_cast<float4*>(dst + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              if (c0 + 4 * g + e < Fout) dst[4 * g + e] = v[4 * g + e];
+          }
+        }
+      }
+    };
+
+    int t_all = 0;
+    float nxt[16];
+    {
+      int cc, sl;
+      coords(0, 0, cc, sl);
+      load_item(cc, sl, nxt);
+    }
+    for (int z = 0; z < passes; ++z) {
+      for (int t = 0; t < per_pass; ++t, ++t_all) {
+        float v[16];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) v[e] = nxt[e];
+        {  // the next item's values travel while this one is split and handed over
+          int zn = z, tn = t + 1;
+          if (tn == per_pass) { tn = 0; ++zn; }
+          if (zn < passes) {
+            int cc, sl;
+            coords(zn, tn, cc, sl);
+            load_item(cc, sl, nxt);
+          }
+        }
+        const int slot = t_all % SLOTS, u = t_all / SLOTS;
+        if (u > 0) {
+          if (lane == 0) mbar_wait(&done_bar[slot], (uint32_t)((u - 1) & 1));
+          __syncwarp();
+        }
+        const uint32_t st = sbase + slot * sp.slot_bytes;
+        write_rows_operand(st, st + A_BYTES, r, h, v);
+        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&ops_bar[slot]);
+      }
+      if (lane == 0) mbar_wait(out_bar, (uint32_t)(z & 1));
+      __syncwarp();
+      tc_fence_after();
+      drain_out(p.forward ? p.Out : p.Out + (long long)z * p.out_slice);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(outfree_bar);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    switch (p.tmem_cols) {
+      case 32: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;\n" ::"r"(tmem_base) : "memory"); break;
+      case 64: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;\n" ::"r"(tmem_base) : "memory"); break;
+      default: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" ::"r"(tmem_base) : "memory"); break;
+    }
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// [rows, cols] fp32 row-major, box = 32 columns x box_rows, 128-byte swizzle
+static int make_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t cols, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return AGCN_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)CH, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+    return AGCN_ERR_CUDA;
+  }
+  return AGCN_OK;
+}
+
+
+static int pad16(int x) { return (x + 15) & ~15; }
+static int pad32(int x) { return (x + 31) & ~31; }
+
+static int launch(const agcn_plan* plan, int tile0, int ntiles, PreArgs& a, const float* wsplit, int Kp, const char* name,
+                  cudaStream_t st) {
+  const long long half = (long long)a.K * a.N * Kp;
+  CUtensorMap mhi, mlo;
+  int rc;
+  if ((rc = make_map(&mhi, wsplit, (uint64_t)a.K * a.N, (uint64_t)Kp, (uint32_t)a.N))) return rc;
+  if ((rc = make_map(&mlo, wsplit + half, (uint64_t)a.K * a.N, (uint64_t)Kp, (uint32_t)a.N))) return rc;
+  a.tile_graphs = reinterpret_cast<const int4*>(plan->d_ft_entries);
+  a.tile_gstart = plan->d_ft_gstart;
+  a.tile0 = tile0;
+  a.nchunks = Kp / CH;
+  a.tmem_cols = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : 128);
+  const SmemPlan sp = smem_plan(a.N);
+  static std::once_flag once;
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(pre_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  });
+  {
+    ProfScope prof(name, st);
+    pre_tile_kernel<<<ntiles, THREADS, sp.total, st>>>(mhi, mlo, a);
+  }
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+}  // namespace pt
+
+// Y = act(sum_s T_s W_s + b) over the 128-row ranges [tile0, tile0 + ntiles) of the plan's tile list; wsplit = the
+// pre-split W_s of fused_fwd_prep
+int pre_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, const float* T, const float* wsplit,
+                const float* bias, int act, int F, int Fo, int K, float* Y, cudaStream_t st) {
+  if (ntiles <= 0) return AGCN_OK;
+  pt::PreArgs a{};
+  a.Fin = F; a.Fout = Fo; a.K = K; a.N = pt::pad16(Fo);
+  a.In = X; a.Mask = nullptr; a.T = T; a.t_slice = (long long)plan->R * F;
+  a.bias = bias; a.act = act; a.Out = Y; a.out_slice = 0; a.forward = 1;
+  return pt::launch(plan, tile0, ntiles, a, wsplit, pt::pad32(F), "pt::pre_tile_kernel(fwd)", st);
+}
+
+// G_z = dYpre W_z^T (z = 0..K-1) over the same ranges; wsplit = the pre-split W_z^T of fused_bwd_prep
+int pre_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY, const float* Y, const float* wsplit, int F,
+                 int Fo, int K, float* G, cudaStream_t st) {
+  if (ntiles <= 0) return AGCN_OK;
+  pt::PreArgs a{};
+  a.Fin = Fo; a.Fout = F; a.K = K; a.N = pt::pad16(F);
+  a.In = dY; a.Mask = Y; a.T = nullptr; a.t_slice = 0;
+  a.bias = nullptr; a.act = AGCN_ACT_LINEAR; a.Out = G; a.out_slice = (long long)plan->R * F; a.forward = 0;
+  return pt::launch(plan, tile0, ntiles, a, wsplit, pt::pad32(Fo), "pt::pre_tile_kernel(bwd)", st);
+}
+
+}  // namespace agcn
