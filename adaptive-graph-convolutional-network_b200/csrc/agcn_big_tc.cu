@@ -546,14 +546,14 @@ static EncodeTiledFn encode_fn() {
 #define AGCN_BIG_TC_DEFAULT 1
 static bool big_paths_on() {
   static const bool on = [] {
-    const char* e = getenv("AGCN_BIG_TC");
+    const char* e = ab_env("AGCN_BIG_TC");
     return e ? atoi(e) != 0 : AGCN_BIG_TC_DEFAULT != 0;
   }();
   return on;
 }
 
 bool grouped_tc_supported(const GroupedArgs& g) {
-  static const bool off = getenv("AGCN_DISABLE_TCGEN05") != nullptr;
+  static const bool off = ab_env("AGCN_DISABLE_TCGEN05") != nullptr;
   if (off || !big_paths_on()) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (g.F < 16 || (g.F & 3)) return false;

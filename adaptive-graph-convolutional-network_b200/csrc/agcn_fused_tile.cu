@@ -961,7 +961,7 @@ static TileArgs tile_args(const agcn_plan* plan, const float* L, int add_identit
 void fused_debug_set(void* d_buf) { ft::g_dbg = reinterpret_cast<unsigned long long*>(d_buf); }
 
 bool fused_enabled() {
-  static const bool off = getenv("AGCN_DISABLE_FUSED") != nullptr || getenv("AGCN_DISABLE_TCGEN05") != nullptr;
+  static const bool off = ab_env("AGCN_DISABLE_FUSED") != nullptr || ab_env("AGCN_DISABLE_TCGEN05") != nullptr;
   return !off;
 }
 

@@ -52,6 +52,16 @@ struct Bucket {
   int limit;  // upper size limit of the bucket (every graph of the bucket has n <= limit)
 };
 
+// A/B tuning switches (AGCN_DISABLE_TCGEN05, AGCN_DISABLE_FUSED, AGCN_BIG_TC, AGCN_CHEB_SMALL_MAX) exist only in builds
+// made with -DAGCN_AB_SWITCHES (tools/gpu_check.sh); the shipped library has ONE code path per shape and reads no
+// environment variables.
+#ifdef AGCN_AB_SWITCHES
+#include <cstdlib>
+inline const char* ab_env(const char* name) { return getenv(name); }
+#else
+inline const char* ab_env(const char*) { return nullptr; }
+#endif
+
 void set_error(const std::string& msg);
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 extern std::atomic<uint64_t> g_launches;

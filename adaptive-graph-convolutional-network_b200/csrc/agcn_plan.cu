@@ -366,7 +366,7 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
     for (int i = pos; i < B && p->n[p->order[i]] > AGCN_FUSE_MAX_N; ++i) ++mid;
     if (mid >= AGCN_MID_TILED_MIN) p->cheb_small_max = AGCN_FUSE_MAX_N;
   }
-  if (const char* e = getenv("AGCN_CHEB_SMALL_MAX")) p->cheb_small_max = std::min(AGCN_SMALL_MAX, std::max(16, atoi(e)));
+  if (const char* e = ab_env("AGCN_CHEB_SMALL_MAX")) p->cheb_small_max = std::min(AGCN_SMALL_MAX, std::max(16, atoi(e)));
   for (int i = 0; i < B && p->n[p->order[i]] > p->cheb_small_max; ++i) {
     const int g = p->order[i];
     if (i <= p->large_count) p->big_tile_start.push_back((int32_t)p->tile_graph.size());

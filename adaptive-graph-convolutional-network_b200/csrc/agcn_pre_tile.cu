@@ -145,7 +145,8 @@ struct PreArgs {
   int K;
   int N;                       // MMA N (Fout padded to 16)
   int nchunks;                 // ceil(Fin / 32)
-  int tmem_cols;               // power of two >= N
+  int tmem_cols;               // allocation: acc_stride (forward) or 2 * acc_stride (backward: two accumulators)
+  int acc_stride;              // power of two >= N
   const float* In;             // [R, Fin]   forward: X, backward: dY
   const float* Mask;           // backward: Y (dYpre = dY * [Y > 0]) or NULL
   const float* T;              // forward: saved T_1 .. T_{K-1}, [K-1][R][Fin]
@@ -193,7 +194,8 @@ pre_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant
     switch (p.tmem_cols) {
       case 32: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;\n" ::"r"(s) : "memory"); break;
       case 64: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 64;\n" ::"r"(s) : "memory"); break;
-      default: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n" ::"r"(s) : "memory"); break;
+      case 128: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;\n" ::"r"(s) : "memory"); break;
+      default: asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" ::"r"(s) : "memory"); break;
     }
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
@@ -225,10 +227,11 @@ pre_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
       int t_all = 0;
       for (int z = 0; z < passes; ++z) {
-        if (z > 0) {
-          mbar_wait(outfree_bar, (uint32_t)((z - 1) & 1));
+        if (z > 1) {   // accumulator z & 1 was last used by pass z - 2: wait until the workers have drained it
+          mbar_wait(outfree_bar, (uint32_t)((z - 2) & 1));
           tc_fence_after();
         }
+        const uint32_t acc = tmem_base + (uint32_t)((z & 1) * p.acc_stride);
         for (int t = 0; t < per_pass; ++t, ++t_all) {
           const int slot = t_all % SLOTS, u = t_all / SLOTS;
           mbar_wait(&full_bar[slot], (uint32_t)(u & 1));
@@ -241,9 +244,9 @@ pre_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant
             const uint32_t koff = k * UMMA_K * 4;
             const uint64_t a_hi = make_desc(sa + koff), a_lo = make_desc(sa_lo + koff);
             const uint64_t b_hi = make_desc(sw + koff), b_lo = make_desc(sw_lo + koff);
-            umma_ss(tmem_base, a_lo, b_hi, idesc, (t | k) != 0);
-            umma_ss(tmem_base, a_hi, b_lo, idesc, 1);
-            umma_ss(tmem_base, a_hi, b_hi, idesc, 1);
+            umma_ss(acc, a_lo, b_hi, idesc, (t | k) != 0);
+            umma_ss(acc, a_hi, b_lo, idesc, 1);
+            umma_ss(acc, a_hi, b_hi, idesc, 1);
           }
           umma_commit(&done_bar[slot]);
         }
@@ -301,11 +304,11 @@ pre_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant
       sl = p.forward ? t % K : z;
     };
     // accumulator -> global rows (bias + activation in the forward direction)
-    auto drain_out = [&](float* dstm) {
+    auto drain_out = [&](float* dstm, uint32_t acc_col) {
       const bool vecO = ((Fout & 3) == 0) && ((reinterpret_cast<uintptr_t>(dstm) & 15) == 0);
       for (int c0 = 16 * h; c0 < N && c0 < Fout; c0 += 32) {
         float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc_col + (uint32_t)c0, v);
         if (grow < 0) continue;
         if (p.forward) {
 #pragma unroll
@@ -330,45 +333,57 @@ pre_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant
       }
     };
 
-    int t_all = 0;
-    float nxt[16];
-    {
+    // Items are independent: the values of item t + 3 are requested before item t is split and handed over (three
+    // register buffers, the loop unrolled by three so that they stay registers), which covers a cold HBM round trip
+    // (~1.5 us) at 0.4 .. 0.5 us of hand-off work per item.
+    const int total = passes * per_pass;
+    auto fetch = [&](int idx, float (&buf)[16]) {
+      if (idx >= total) return;
+      const int z = idx / per_pass, t = idx - z * per_pass;
       int cc, sl;
-      coords(0, 0, cc, sl);
-      load_item(cc, sl, nxt);
-    }
-    for (int z = 0; z < passes; ++z) {
-      for (int t = 0; t < per_pass; ++t, ++t_all) {
-        float v[16];
+      coords(z, t, cc, sl);
+      load_item(cc, sl, buf);
+    };
+    auto process = [&](int idx, float (&buf)[16]) {
+      if (idx >= total) return;
+      float v[16];
 #pragma unroll
-        for (int e = 0; e < 16; ++e) v[e] = nxt[e];
-        {  // the next item's values travel while this one is split and handed over
-          int zn = z, tn = t + 1;
-          if (tn == per_pass) { tn = 0; ++zn; }
-          if (zn < passes) {
-            int cc, sl;
-            coords(zn, tn, cc, sl);
-            load_item(cc, sl, nxt);
-          }
-        }
-        const int slot = t_all % SLOTS, u = t_all / SLOTS;
-        if (u > 0) {
-          if (lane == 0) mbar_wait(&done_bar[slot], (uint32_t)((u - 1) & 1));
-          __syncwarp();
-        }
-        const uint32_t st = sbase + slot * sp.slot_bytes;
-        write_rows_operand(st, st + A_BYTES, r, h, v);
-        asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
+      for (int e = 0; e < 16; ++e) v[e] = buf[e];
+      fetch(idx + 3, buf);
+      const int slot = idx % SLOTS, u = idx / SLOTS;
+      if (u > 0) {
+        if (lane == 0) mbar_wait(&done_bar[slot], (uint32_t)((u - 1) & 1));
         __syncwarp();
-        if (lane == 0) mbar_arrive(&ops_bar[slot]);
       }
-      if (lane == 0) mbar_wait(out_bar, (uint32_t)(z & 1));
+      const uint32_t st = sbase + slot * sp.slot_bytes;
+      write_rows_operand(st, st + A_BYTES, r, h, v);
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
       __syncwarp();
-      tc_fence_after();
-      drain_out(p.forward ? p.Out : p.Out + (long long)z * p.out_slice);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(outfree_bar);
+      if (lane == 0) mbar_arrive(&ops_bar[slot]);
+      const int z = idx / per_pass;
+      if (idx - z * per_pass == per_pass - 1) {
+        // last item of pass z handed over: drain pass z - 1 (its MMAs finished long ago; pass z's are still running
+        // on the other accumulator), and the last pass itself at the very end
+        for (int zd = (z > 0 ? z - 1 : z); zd <= z; ++zd) {
+          if (zd == z && z != passes - 1) break;
+          if (lane == 0) mbar_wait(out_bar, (uint32_t)(zd & 1));
+          __syncwarp();
+          tc_fence_after();
+          drain_out(p.forward ? p.Out : p.Out + (long long)zd * p.out_slice, (uint32_t)((zd & 1) * p.acc_stride));
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(outfree_bar);
+        }
+      }
+    };
+    float b0[16], b1[16], b2[16];
+    fetch(0, b0);
+    fetch(1, b1);
+    fetch(2, b2);
+    for (int idx = 0; idx < total; idx += 3) {
+      process(idx, b0);
+      process(idx + 1, b1);
+      process(idx + 2, b2);
     }
   }
   tc_fence_before();
@@ -377,7 +392,8 @@ pre_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant
     switch (p.tmem_cols) {
       case 32: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;\n" ::"r"(tmem_base) : "memory"); break;
       case 64: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 64;\n" ::"r"(tmem_base) : "memory"); break;
-      default: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" ::"r"(tmem_base) : "memory"); break;
+      case 128: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;\n" ::"r"(tmem_base) : "memory"); break;
+      default: asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem_base) : "memory"); break;
     }
   }
 }
@@ -435,7 +451,8 @@ static int launch(const agcn_plan* plan, int tile0, int ntiles, PreArgs& a, cons
   a.tile_gstart = plan->d_ft_gstart;
   a.tile0 = tile0;
   a.nchunks = Kp / CH;
-  a.tmem_cols = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : 128);
+  a.acc_stride = a.N <= 32 ? 32 : (a.N <= 64 ? 64 : 128);
+  a.tmem_cols = a.forward ? a.acc_stride : 2 * a.acc_stride;
   const SmemPlan sp = smem_plan(a.N);
   static std::once_flag once;
   std::call_once(once, [] {

@@ -634,7 +634,7 @@ static int tc_npad(int N) { return N <= 64 ? 64 : (N + 127) / 128 * 128; }
 static int tc_kpitch(int Kd) { return (Kd + 3) & ~3; }
 
 bool tc_gemm_supported(const GemmArgs& a) {
-  if (getenv("AGCN_DISABLE_TCGEN05")) return false;
+  if (ab_env("AGCN_DISABLE_TCGEN05")) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (a.M < 1 || a.Kd < 32) return false;
   if (a.S > 1 && a.Kd % 4 != 0) return false;  // stacked slices share one tensor map
@@ -745,7 +745,7 @@ int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
 namespace agcn {
 
 bool tc_gemm_tn_supported(const GemmTNArgs& a) {
-  if (getenv("AGCN_DISABLE_TCGEN05") || getenv("AGCN_DISABLE_TCGEN05_TN")) return false;
+  if (ab_env("AGCN_DISABLE_TCGEN05") || ab_env("AGCN_DISABLE_TCGEN05_TN")) return false;
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   if (a.M < 32 || a.Kd > 128 || a.Kd % 4 != 0 || a.N % 4 != 0) return false;
   if (a.lda0 % 4 != 0 || a.ldd % 4 != 0 || !al16(a.A0) || !al16(a.D)) return false;
