@@ -771,45 +771,46 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
     const TileRow me = tile_prologue(p.t, tile, r, h, wt, s_glist, s_grow, s_rowinfo, sL, &ng);
     const bool vecD = ((Fo & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.dYp) & 15) == 0) &&
                       ((reinterpret_cast<uintptr_t>(p.Y) & 15) == 0);
-    // mainloop: my half row of dYpre chunk c (L1-resident across the K passes) -> hi/lo operand rows; the row of
-    // the next k-block is in flight while this one is split and stored.
-    auto load_row = [&](int kb, float v[16]) {
+    // mainloop: my half row of dYpre chunk c (L1-resident across the K passes) -> hi/lo operand rows.  The rows of the
+    // next TWO k-blocks are in flight while this one is split and stored: dY and Y travel as RAW values and the
+    // relu' mask is applied only when the row is consumed -- masking at load time makes the compare wait for the
+    // load and turns the prefetch into a 1 - 2 us stall per k-block (ncu source view: every top stall of the
+    // round-1 kernel sat on those FSETPs).
+    auto load_raw = [&](int kb, float d[16], float m[16]) {
+      if (kb >= num_kb) return;
       const int c = kb % nc;
       if (vecD) {
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           const int col = c * CH + 16 * h + 4 * g;
-          float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = make_float4(1.f, 1.f, 1.f, 1.f);
           if (me.grow >= 0 && col < Fo) {
             x = __ldg(reinterpret_cast<const float4*>(p.dYp + (long long)me.grow * Fo + col));
-            if (p.Y) {  // relu'(0) = 0 (TF's ReluGrad)
-              const float4 y = __ldg(reinterpret_cast<const float4*>(p.Y + (long long)me.grow * Fo + col));
-              x.x = y.x > 0.f ? x.x : 0.f; x.y = y.y > 0.f ? x.y : 0.f;
-              x.z = y.z > 0.f ? x.z : 0.f; x.w = y.w > 0.f ? x.w : 0.f;
-            }
+            if (p.Y) y = __ldg(reinterpret_cast<const float4*>(p.Y + (long long)me.grow * Fo + col));
           }
-          v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
+          d[4 * g] = x.x; d[4 * g + 1] = x.y; d[4 * g + 2] = x.z; d[4 * g + 3] = x.w;
+          m[4 * g] = y.x; m[4 * g + 1] = y.y; m[4 * g + 2] = y.z; m[4 * g + 3] = y.w;
         }
       } else {
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
           const int col = c * CH + 16 * h + u;
-          float x = 0.f;
+          float x = 0.f, y = 1.f;
           if (me.grow >= 0 && col < Fo) {
             x = __ldg(p.dYp + (long long)me.grow * Fo + col);
-            if (p.Y && !(__ldg(p.Y + (long long)me.grow * Fo + col) > 0.f)) x = 0.f;
+            if (p.Y) y = __ldg(p.Y + (long long)me.grow * Fo + col);
           }
-          v[u] = x;
+          d[u] = x;
+          m[u] = y;
         }
       }
     };
-    float nxt[16];
-    load_row(0, nxt);
-    for (int kb = 0; kb < num_kb; ++kb) {
+    auto hand_over = [&](int kb, float d[16], float m[16]) {
+      if (kb >= num_kb) return;
       float v[16];
 #pragma unroll
-      for (int u = 0; u < 16; ++u) v[u] = nxt[u];
-      if (kb + 1 < num_kb) load_row(kb + 1, nxt);
+      for (int u = 0; u < 16; ++u) v[u] = (m[u] > 0.f) ? d[u] : 0.f;   // relu'(0) = 0 (TF's ReluGrad)
+      load_raw(kb + 2, d, m);
       const int stage = kb % sp.stages, phase = (kb / sp.stages) & 1;
       if (lane == 0) mbar_wait(&empty_bar[stage], phase ^ 1);
       __syncwarp();
@@ -818,6 +819,15 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
       asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&split_bar[stage]);
+    };
+    {
+      float d0[16], m0[16], d1[16], m1[16];
+      load_raw(0, d0, m0);
+      load_raw(1, d1, m1);
+      for (int kb = 0; kb < num_kb; kb += 2) {
+        hand_over(kb, d0, m0);
+        hand_over(kb + 1, d1, m1);
+      }
     }
     // ---- epilogue: reverse recurrence on the accumulators
     cp_async_wait_all();  // the L matrices of the tile (issued in the prologue)

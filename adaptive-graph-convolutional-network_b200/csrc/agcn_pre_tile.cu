@@ -267,36 +267,36 @@ pre_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant
     const bool vecIn = ((Fin & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.In) & 15) == 0) &&
                        (!p.Mask || (reinterpret_cast<uintptr_t>(p.Mask) & 15) == 0) &&
                        (!p.T || (((reinterpret_cast<uintptr_t>(p.T) & 15) == 0) && ((p.t_slice & 3) == 0)));
-    // my 16 columns of chunk cc of operand matrix sl (forward: T_sl; backward: dYpre)
-    auto load_item = [&](int cc, int sl, float v[16]) {
+    // my 16 columns of chunk cc of operand matrix sl (forward: T_sl; backward: dY with Y for the relu' mask), as RAW
+    // values: the mask is applied when the item is consumed -- a compare at load time would wait for the load and
+    // turn the prefetch into a stall (ncu source view of the first version: all top stalls on those FSETPs)
+    auto load_item = [&](int cc, int sl, float v[16], float m[16]) {
       const int c0 = cc * CH + 16 * h;
       const float* src = (p.forward && sl > 0) ? p.T + (long long)(sl - 1) * p.t_slice : p.In;
       const float* msk = p.forward ? nullptr : p.Mask;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int col = c0 + 4 * g;
-        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = make_float4(1.f, 1.f, 1.f, 1.f);
         if (grow >= 0 && col < Fin) {
           const long long o = (long long)grow * Fin + col;
           if (vecIn) {
             x = __ldg(reinterpret_cast<const float4*>(src + o));
-            if (msk) {  // relu'(0) = 0 (TF's ReluGrad)
-              const float4 y = __ldg(reinterpret_cast<const float4*>(msk + o));
-              x.x = y.x > 0.f ? x.x : 0.f; x.y = y.y > 0.f ? x.y : 0.f;
-              x.z = y.z > 0.f ? x.z : 0.f; x.w = y.w > 0.f ? x.w : 0.f;
-            }
+            if (msk) y = __ldg(reinterpret_cast<const float4*>(msk + o));
           } else {
-            float t[4] = {0.f, 0.f, 0.f, 0.f};
+            float t[4] = {0.f, 0.f, 0.f, 0.f}, ty[4] = {1.f, 1.f, 1.f, 1.f};
 #pragma unroll
             for (int e = 0; e < 4; ++e)
               if (col + e < Fin) {
                 t[e] = __ldg(src + o + e);
-                if (msk && !(__ldg(msk + o + e) > 0.f)) t[e] = 0.f;
+                if (msk) ty[e] = __ldg(msk + o + e);
               }
             x = make_float4(t[0], t[1], t[2], t[3]);
+            y = make_float4(ty[0], ty[1], ty[2], ty[3]);
           }
         }
         v[4 * g] = x.x; v[4 * g + 1] = x.y; v[4 * g + 2] = x.z; v[4 * g + 3] = x.w;
+        m[4 * g] = y.x; m[4 * g + 1] = y.y; m[4 * g + 2] = y.z; m[4 * g + 3] = y.w;
       }
     };
     auto coords = [&](int z, int t, int& cc, int& sl) {
@@ -333,23 +333,22 @@ pre_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant
       }
     };
 
-    // Items are independent: the values of item t + 3 are requested before item t is split and handed over (three
-    // register buffers, the loop unrolled by three so that they stay registers), which covers a cold HBM round trip
-    // (~1.5 us) at 0.4 .. 0.5 us of hand-off work per item.
+    // Items are independent: the values of item t + 2 are requested before item t is split and handed over (two pairs
+    // of register buffers, the loop unrolled by two so that they stay registers).
     const int total = passes * per_pass;
-    auto fetch = [&](int idx, float (&buf)[16]) {
+    auto fetch = [&](int idx, float (&buf)[16], float (&mk)[16]) {
       if (idx >= total) return;
       const int z = idx / per_pass, t = idx - z * per_pass;
       int cc, sl;
       coords(z, t, cc, sl);
-      load_item(cc, sl, buf);
+      load_item(cc, sl, buf, mk);
     };
-    auto process = [&](int idx, float (&buf)[16]) {
+    auto process = [&](int idx, float (&buf)[16], float (&mk)[16]) {
       if (idx >= total) return;
       float v[16];
 #pragma unroll
-      for (int e = 0; e < 16; ++e) v[e] = buf[e];
-      fetch(idx + 3, buf);
+      for (int e = 0; e < 16; ++e) v[e] = (mk[e] > 0.f) ? buf[e] : 0.f;   // relu'(0) = 0 (TF's ReluGrad); forward: mk = 1
+      fetch(idx + 2, buf, mk);
       const int slot = idx % SLOTS, u = idx / SLOTS;
       if (u > 0) {
         if (lane == 0) mbar_wait(&done_bar[slot], (uint32_t)((u - 1) & 1));
@@ -376,14 +375,12 @@ pre_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant
         }
       }
     };
-    float b0[16], b1[16], b2[16];
-    fetch(0, b0);
-    fetch(1, b1);
-    fetch(2, b2);
-    for (int idx = 0; idx < total; idx += 3) {
-      process(idx, b0);
-      process(idx + 1, b1);
-      process(idx + 2, b2);
+    float b0[16], m0[16], b1[16], m1[16];
+    fetch(0, b0, m0);
+    fetch(1, b1, m1);
+    for (int idx = 0; idx < total; idx += 2) {
+      process(idx, b0, m0);
+      process(idx + 1, b1, m1);
     }
   }
   tc_fence_before();
