@@ -43,6 +43,28 @@ __device__ __forceinline__ float tf32_rn(float x) {
   asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
+
+// Wait on an mbarrier phase (shared-space address).  A protocol bug becomes a trap instead of a hang, but only after
+// TEN SECONDS of wall time on the global timer: a spin COUNT is not a time (a box whose first nvidia-smi start or
+// clock ramp stalls the device for a few hundred milliseconds made a 2^24-spin limit fire in a correct kernel).
+__device__ __forceinline__ void mbar_wait_shared(uint32_t addr, uint32_t parity) {
+  uint32_t done = 0, spins = 0;
+  unsigned long long t0 = 0;
+  while (true) {
+    asm volatile(
+        "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity)
+        : "memory");
+    if (done) break;
+    if ((++spins & 0xFFFFu) == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;\n" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 10000000000ull) __trap();
+    }
+  }
+}
 #endif
 
 struct Bucket {
