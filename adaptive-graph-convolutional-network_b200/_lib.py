@@ -47,6 +47,7 @@ _SIGNATURES = {
     "agcn_fused_profile_read": (ctypes.c_int, [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_int)]),
     "agcn_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "agcn_profile_read": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
+    "agcn_profile_timeline": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_size_t, ctypes.POINTER(ctypes.c_size_t)]),
     "agcn_probe_fp32_fma": (ctypes.c_int, [_P, ctypes.c_int32, _P]),
     "agcn_pack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
     "agcn_unpack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
@@ -119,6 +120,17 @@ def launch_count():
 
 def profile_enable(on):
     check(lib().agcn_profile_enable(1 if on else 0))
+
+
+def profile_timeline():
+    """[(kernel name, start ms, end ms)] of the launches recorded since the last read, relative to the first one."""
+    buf = ctypes.create_string_buffer(1 << 18)
+    check(lib().agcn_profile_timeline(buf, len(buf), None))
+    out = []
+    for line in buf.value.decode().splitlines():
+        name, t0, t1 = line.split("\t")
+        out.append((name, float(t0), float(t1)))
+    return out
 
 
 def profile_read():

@@ -242,27 +242,24 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
   }
   ga.Lall = m.shortcut ? nullptr : sv.Lall;
   if (fuse_f) {
+    // Recurrences on the CUDA cores (agcn_cheb_tile.cu: small-graph tiles on this stream, mid-size graphs and the
+    // row-tiled products of the graphs above cheb_small_max on plan->big), then ONE tensor-core contraction over every
+    // packed row (agcn_pre_tile.cu): Y = act(sum_k T_k W_k + b)
     const float* Lf = m.shortcut ? d_Lint : sv.Lall;
-    const int ident = m.shortcut ? 1 : 0, n_pre = plan->ft_tiles - plan->ft_small_tiles;
-    if (n_pre > 0) {
-      // graphs above AGCN_FUSE_MAX_N keep their per-graph / row-tiled recurrences (chunk-parallel); their chain
-      // runs on its own stream beside the launch of the small-graph tiles and ends with its own tile launch,
-      // which reads the T_k it produced
+    const int ident = m.shortcut ? 1 : 0;
+    const bool other = cheb_tiles_has_mid(plan) || plan->large_tiles > 0;
+    if (other) {
       AGCN_CUDA(cudaEventRecord(plan->ev_big_fork, st));
       AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_big_fork, 0));
-      if ((rc = graph_chebyshev_fwd(ga, plan->big, AGCN_FUSE_MAX_N))) return rc;
-      AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_side_join, 0));
-      if ((rc = pre_forward(plan, plan->ft_small_tiles, n_pre, d_X, sv.T, wk.ftY, d_bias, desc->activation, F, Fo, K, d_Y,
-                            plan->big)))
-        return rc;
+    }
+    if ((rc = cheb_tiles_forward(plan, d_X, Lf, ident, F, K, sv.T, st, plan->big))) return rc;
+    if (plan->large_tiles > 0 && (rc = graph_chebyshev_fwd(ga, plan->big, AGCN_SMALL_MAX))) return rc;
+    if (other) {
       AGCN_CUDA(cudaEventRecord(plan->ev_big_join, plan->big));
+      AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_big_join, 0));
     }
     AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
-    if ((rc = fused_forward(plan, 0, plan->ft_small_tiles, d_X, Lf, ident, wk.ftY, d_bias, desc->activation, F, Fo, K,
-                            sv.T, d_Y, st)))
-      return rc;
-    if (n_pre > 0) AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_big_join, 0));
-    return AGCN_OK;
+    return pre_forward(plan, -1, 0, d_X, sv.T, wk.ftY, d_bias, desc->activation, F, Fo, K, d_Y, st);
   }
   if ((rc = graph_chebyshev_fwd(ga, st))) return rc;  // graphconv.py:221-236
   if (y_tc || g_tc || fuse_b) AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_side_join, 0));
@@ -344,22 +341,23 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   }
   AGCN_CUDA(cudaEventRecord(plan->ev_side_join, plan->side));
   if (fuse_b) {
-    // G_z = dYpre W_z^T and the reverse recurrence in one kernel; graphs above AGCN_FUSE_MAX_N get their G_z
-    // rows in wk.G and finish in the per-graph / row-tiled kernels
+    // G_z = dYpre W_z^T over every packed row on the tensor cores (relu' applied to the operand rows as they are
+    // loaded), then the reverse recurrences on the CUDA cores
     const float* Lf = m.shortcut ? d_Lint : sv.Lall;
-    const int ident = m.shortcut ? 1 : 0, n_pre = plan->ft_tiles - plan->ft_small_tiles;
-    if (n_pre > 0) {
+    const int ident = m.shortcut ? 1 : 0;
+    if ((rc = pre_backward(plan, -1, 0, d_dY, desc->activation == AGCN_ACT_RELU ? d_Y : nullptr, sv.ftG, F, Fo, K, wk.G, st)))
+      return rc;
+    const bool other = cheb_tiles_has_mid(plan) || plan->large_tiles > 0;
+    if (other) {
       AGCN_CUDA(cudaEventRecord(plan->ev_big_fork, st));
       AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_big_fork, 0));
-      if ((rc = pre_backward(plan, plan->ft_small_tiles, n_pre, d_dY, desc->activation == AGCN_ACT_RELU ? d_Y : nullptr,
-                             sv.ftG, F, Fo, K, wk.G, plan->big)))
-        return rc;
-      if ((rc = graph_recurrence_bwd(ga, false, plan->big, AGCN_FUSE_MAX_N))) return rc;
-      AGCN_CUDA(cudaEventRecord(plan->ev_big_join, plan->big));
     }
-    if ((rc = fused_backward(plan, 0, plan->ft_small_tiles, d_dY, desc->activation == AGCN_ACT_RELU ? d_Y : nullptr, Lf, ident,
-                             sv.ftG, F, Fo, K, wk.G, d_dX, st))) return rc;
-    if (n_pre > 0) AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_big_join, 0));
+    if ((rc = cheb_tiles_backward(plan, wk.G, Lf, ident, F, K, d_dX, st, plan->big))) return rc;
+    if (plan->large_tiles > 0 && (rc = graph_recurrence_bwd(ga, false, plan->big, AGCN_SMALL_MAX))) return rc;
+    if (other) {
+      AGCN_CUDA(cudaEventRecord(plan->ev_big_join, plan->big));
+      AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_big_join, 0));
+    }
   } else if (K >= 2) {
     if (need_G && (rc = graph_recurrence_bwd(ga, m.need_dL, st))) return rc;
   } else if (m.need_dL) {

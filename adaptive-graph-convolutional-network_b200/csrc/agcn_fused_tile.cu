@@ -264,6 +264,48 @@ __device__ __forceinline__ void lap_times_rows(uint32_t laddr, int lstride_bytes
   }
 }
 
+// ---- sparse rows.  The Laplacian of a molecule has ~3 non-zeros per row (reference_literal mode multiplies by
+// I + L_int, the normalised Laplacian of a graph of degree <= 4): a dense n x n product spends 80 .. 95 % of its shared
+// memory loads and FMAs on exact zeros.  Every worker keeps the non-zero pattern of its row (forward) / column
+// (backward) as a 64-bit mask (n <= AGCN_FUSE_MAX_N = 64) and walks the set bits; the values stay where they are.
+// Skipping a term whose coefficient is exactly 0 does not change an fp32 sum of finite values.
+__device__ __forceinline__ unsigned long long nonzero_mask(uint32_t laddr, int lstride_bytes, int n) {
+  unsigned long long m = 0;
+#pragma unroll 4
+  for (int j = 0; j < n; ++j)
+    if (lds32(laddr + (uint32_t)(j * lstride_bytes)) != 0.f) m |= 1ull << j;
+  return m;
+}
+// Warp-uniform choice between the dense loop (n x 21 instructions) and the masked loop (28 per non-zero); the warp runs
+// as long as its slowest lane either way.
+__device__ __forceinline__ bool prefer_masked(unsigned long long mask, int n) {
+  const unsigned dense_cost = __reduce_max_sync(0xffffffffu, (unsigned)(n * 3));
+  const unsigned masked_cost = __reduce_max_sync(0xffffffffu, (unsigned)(__popcll(mask) * 4));
+  return masked_cost < dense_cost;
+}
+// acc[:] += sum over the set bits j of L[laddr + j * lstride_bytes] * src[r0 + j][16h .. 16h+15], two terms per trip
+__device__ __forceinline__ void lap_times_rows_masked(uint32_t laddr, int lstride_bytes, uint32_t src, int r0,
+                                                      unsigned long long mask, int h, float acc[16]) {
+  const uint32_t tbase = src + (uint32_t)(r0 * CPITCH + h * 64);
+  while (mask) {
+    const int j0 = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
+    const bool two = mask != 0;
+    const int j1 = two ? __ffsll((long long)mask) - 1 : j0;
+    mask &= mask - 1;   // no-op when mask is already 0
+    const float a0 = lds32(laddr + (uint32_t)(j0 * lstride_bytes));
+    const float a1 = two ? lds32(laddr + (uint32_t)(j1 * lstride_bytes)) : 0.f;
+    float4 b0[4], b1[4];
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      b0[g] = lds128(tbase + (uint32_t)(j0 * CPITCH + 16 * g));
+      b1[g] = lds128(tbase + (uint32_t)(j1 * CPITCH + 16 * g));
+    }
+    fma_row(a0, b0, acc);
+    fma_row(a1, b1, acc);
+  }
+}
+
 // My half of one row of a 128x32 K-major SWIZZLE_128B operand tile, split into hi / lo TF32 halves.
 __device__ __forceinline__ void write_operand_half(uint32_t a_hi, uint32_t a_lo, int row, int h, const float v[16]) {
 #pragma unroll
@@ -566,12 +608,18 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
         emit(kb, v);
       }
     } else {
-    load_rows_async(xbuf[0], p.X, F, F, 0, s_grow, q, h, lane, vecX);
+      load_rows_async(xbuf[0], p.X, F, F, 0, s_grow, q, h, lane, vecX);
       cp_async_commit();
+      unsigned long long row_mask = 0;
+      bool masked = false;
       for (int c = 0; c < nc; ++c) {
         const int cur = c & 1;
         cp_async_wait_all();
         worker_sync();  // T_0 chunk c (and, first time, the L matrices) complete; chunk c-1 is finished everywhere
+        if (c == 0) {
+          row_mask = nonzero_mask(lrow, 4, me.n);
+          masked = prefer_masked(row_mask, me.n);
+        }
         if (wt == 0 && c < 8) FT_STAMP(2 + 8 * c);
         if (c + 1 < nc) {
           load_rows_async(xbuf[cur ^ 1], p.X, F, F, c + 1, s_grow, q, h, lane, vecX);
@@ -587,7 +635,10 @@ fused_fwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
           {
   #pragma unroll
             for (int u = 0; u < 16; ++u) t[u] = p.t.add_identity ? tm1[u] : 0.f;  // L_all = I + L_int (literal mode)
-            lap_times_rows(lrow, 4, src, me.r0, me.n, h, t);  // graphconv.py:231
+            if (masked)
+              lap_times_rows_masked(lrow, 4, src, me.r0, row_mask, h, t);
+            else
+              lap_times_rows(lrow, 4, src, me.r0, me.n, h, t);  // graphconv.py:231
             if (s >= 2) {
   #pragma unroll
               for (int u = 0; u < 16; ++u) t[u] = 2.f * t[u] - tm2[u];  // graphconv.py:234
@@ -828,6 +879,8 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
                       ((reinterpret_cast<uintptr_t>(p.G) & 15) == 0) && ((p.gslice & 3) == 0);
     const uint32_t lane_base = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(16 * h);
     const uint32_t lcol = sL + 4 * (me.lbase + me.i);  // column i of my graph's matrix: (L^T U)_i = sum_j L[j][i] U_j
+    const unsigned long long col_mask = me.pre ? 0ull : nonzero_mask(lcol, 4 * me.pitch, me.n);
+    const bool masked = prefer_masked(col_mask, me.n);
     const int nfc = (F + CH - 1) / CH;
     for (int fc = 0; fc < nfc; ++fc) {
       if (me.pre) {
@@ -853,7 +906,10 @@ fused_bwd_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constan
         float acc[16], g[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) acc[u] = p.t.add_identity ? u1[u] : 0.f;  // (I + L)^T U = U + L^T U
-        lap_times_rows(lcol, 4 * me.pitch, ub[cur], me.r0, me.n, h, acc);
+        if (masked)
+          lap_times_rows_masked(lcol, 4 * me.pitch, ub[cur], me.r0, col_mask, h, acc);
+        else
+          lap_times_rows(lcol, 4 * me.pitch, ub[cur], me.r0, me.n, h, acc);
         tmem_ld16(lane_base + (uint32_t)(j * p.acc_stride + fc * CH), g);
         const float cmul = (j + 1 >= 2) ? 2.f : 1.f;
 #pragma unroll
@@ -956,7 +1012,13 @@ static TileArgs tile_args(const agcn_plan* plan, const float* L, int add_identit
 // ------------------------------------------------------------------------------------------------
 // host API
 // ------------------------------------------------------------------------------------------------
-void fused_debug_set(void* d_buf) { ft::g_dbg = reinterpret_cast<unsigned long long*>(d_buf); }
+void rows_debug_set(void* d_buf);
+void cheb_debug_set(void* d_buf);
+void fused_debug_set(void* d_buf) {
+  ft::g_dbg = reinterpret_cast<unsigned long long*>(d_buf);
+  rows_debug_set(d_buf);   // the all-rows contraction (agcn_pre_tile.cu) stamps the same buffer
+  cheb_debug_set(d_buf);   // ... and the recurrence tiles (agcn_cheb_tile.cu), slots 100..
+}
 
 bool fused_enabled() {
   static const bool off = ab_env("AGCN_DISABLE_FUSED") != nullptr || ab_env("AGCN_DISABLE_TCGEN05") != nullptr;

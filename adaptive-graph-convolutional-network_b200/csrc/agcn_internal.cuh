@@ -349,6 +349,14 @@ int pre_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, co
 int pre_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY, const float* Y, const float* wsplit, int F,
                  int Fo, int K, float* G, cudaStream_t st);
 
+// ---------------------------------------------------------------- CUDA-core Chebyshev recurrences of the graphs up to
+// AGCN_SMALL_MAX nodes (agcn_cheb_tile.cu): small-graph tiles on st_small, mid-size graphs on st_mid
+bool cheb_tiles_has_mid(const agcn_plan* plan);
+int cheb_tiles_forward(const agcn_plan* plan, const float* X, const float* L, int add_identity, int F, int K, float* T,
+                       cudaStream_t st_small, cudaStream_t st_mid);
+int cheb_tiles_backward(const agcn_plan* plan, const float* G, const float* L, int add_identity, int F, int K, float* dX,
+                        cudaStream_t st_small, cudaStream_t st_mid);
+
 // ---------------------------------------------------------------- live per-kernel timing (agcn_profile.cu)
 // RAII bracket around ONE kernel launch in a host wrapper; records only while agcn_profile_enable(1) is in effect and
 // the stream is not capturing.

@@ -247,7 +247,13 @@ static cudaError_t acquire_res(PlanRes* out) {
   if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r.side, cudaStreamNonBlocking);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_side_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_side_join, cudaEventDisableTiming);
-  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&r.big, cudaStreamNonBlocking);
+  // the chain of the graphs above the tiles (a handful of CTAs that each need most of an SM's shared memory) gets the
+  // highest priority: its CTAs are placed before the hundreds of tile CTAs launched beside it, instead of behind them
+  if (e == cudaSuccess) {
+    int lo = 0, hi = 0;
+    if (cudaDeviceGetStreamPriorityRange(&lo, &hi) != cudaSuccess) { lo = hi = 0; (void)cudaGetLastError(); }
+    e = cudaStreamCreateWithPriority(&r.big, cudaStreamNonBlocking, hi);
+  }
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_big_fork, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_big_join, cudaEventDisableTiming);
   if (e == cudaSuccess) e = cudaEventCreateWithFlags(&r.ev_ready, cudaEventDisableTiming);

@@ -50,7 +50,7 @@ ProfScope::~ProfScope() {
 void prof_enable(int on) { g_prof_on.store(on ? 1 : 0); }
 
 // Drains the pending records.  only != NULL: sum of the records of that kernel name (the others are dropped).
-int prof_drain(const char* only, float* ms_sum, int* launches, std::string* table) {
+int prof_drain(const char* only, float* ms_sum, int* launches, std::string* table, std::string* timeline = nullptr) {
   std::vector<ProfRec> recs;
   {
     std::lock_guard<std::mutex> lock(g_prof_mu);
@@ -59,13 +59,21 @@ int prof_drain(const char* only, float* ms_sum, int* launches, std::string* tabl
   std::map<std::string, std::pair<int, double>> agg;
   float total = 0.f;
   int n = 0;
+  if (timeline) timeline->clear();
   for (ProfRec& r : recs) {
     float ms = 0.f;
     cudaError_t e = cudaEventSynchronize(r.e1);
     if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, r.e0, r.e1);
-    cudaEventDestroy(r.e0);
-    cudaEventDestroy(r.e1);
-    if (e != cudaSuccess) return cuda_fail(e, "profile read", __FILE__, __LINE__);
+    if (e == cudaSuccess && timeline) {   // start / end relative to the first record's start (events of any stream compare)
+      float t0 = 0.f;
+      e = cudaEventSynchronize(recs[0].e0);
+      if (e == cudaSuccess) e = cudaEventElapsedTime(&t0, recs[0].e0, r.e0);
+      *timeline += std::string(r.name) + "\t" + std::to_string(t0) + "\t" + std::to_string(t0 + ms) + "\n";
+    }
+    if (e != cudaSuccess) {
+      for (ProfRec& d : recs) { cudaEventDestroy(d.e0); cudaEventDestroy(d.e1); }
+      return cuda_fail(e, "profile read", __FILE__, __LINE__);
+    }
     auto& a = agg[r.name];
     a.first += 1;
     a.second += ms;
@@ -74,6 +82,7 @@ int prof_drain(const char* only, float* ms_sum, int* launches, std::string* tabl
       ++n;
     }
   }
+  for (ProfRec& d : recs) { cudaEventDestroy(d.e0); cudaEventDestroy(d.e1); }
   if (ms_sum) *ms_sum = total;
   if (launches) *launches = n;
   if (table) {
@@ -112,6 +121,19 @@ int agcn_probe_fp32_fma(float* d_sink, int32_t iters, void* stream) {
   AGCN_REQUIRE(d_sink && iters >= 1, "probe_fp32_fma: bad arguments");
   agcn::fma_probe_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(d_sink, iters);
   AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+int agcn_profile_timeline(char* buf, size_t cap, size_t* needed) {
+  std::string table, timeline;
+  int rc = agcn::prof_drain(nullptr, nullptr, nullptr, &table, &timeline);
+  if (rc) return rc;
+  if (needed) *needed = timeline.size() + 1;
+  if (buf && cap) {
+    const size_t n = timeline.size() < cap - 1 ? timeline.size() : cap - 1;
+    timeline.copy(buf, n);
+    buf[n] = 0;
+  }
   return AGCN_OK;
 }
 

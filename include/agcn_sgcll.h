@@ -115,6 +115,9 @@ int agcn_fused_profile_read(float* ms_sum, int* launches);
  * (NUL-terminated, truncated to cap); *needed receives the size the whole table takes. */
 int agcn_profile_enable(int enable);
 int agcn_profile_read(char* buf, size_t cap, size_t* needed);
+/* The same records as a timeline instead of sums: one line per launch, "name<TAB>start_ms<TAB>end_ms\n", times relative
+ * to the start of the first recorded launch (the streams of a step overlap: this shows what is on the critical path). */
+int agcn_profile_timeline(char* buf, size_t cap, size_t* needed);
 /* fp32-FMA peak probe for the roofline denominators (SURVEY.md section 8d asks for a measured fp32 peak next to the
  * recorded bf16 one): 148 x 8 CTAs of 256 threads, 8 independent FMA chains of `iters` trips per thread, i.e.
  * 148 * 8 * 256 * 8 * 2 * iters FLOP; d_sink needs 148 * 8 * 256 floats.  The caller times it with CUDA events. */
