@@ -160,17 +160,190 @@ int check_desc(const agcn_sgcll_desc* d, const agcn_plan* p) {
 
 }  // namespace
 
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Feature padding.  75 atom features (the first layer of every molecule network) are neither a multiple of 4 (no
+// 16-byte row accesses) nor of 32 (no TMA row tiles): the layer then ran on the scalar / generic kernels and cost twice
+// a hidden layer (profiles/r02p_timeline_c2.txt: 60 + 38 us against 22 + 24 us).  With the literal shortcut (no metric
+// block, M_L unused) the layer is LINEAR in the feature columns, so it runs on zero-padded copies instead: X -> [R, Fp],
+// weight -> [Fp K, Fo] (rows f K + k of the padded features are zero), Fp = F rounded up to 32.  T_k, dweight and dX of
+// the padded problem contain the unpadded ones as their leading columns / rows.
+// ------------------------------------------------------------------------------------------------
+int padded_features(const agcn_sgcll_desc* d, const agcn_plan* p) {
+  const int F = d->F;
+  if (F < 33 || F % 32 == 0) return F;
+  if (!literal_shortcut(d->variant, d->laplacian_mode)) return F;
+  if (d->flags & (AGCN_OUT_RES_L | AGCN_OUT_RES_W | AGCN_OUT_L_ALL)) return F;
+  const int Fp = (F + 31) & ~31;
+  if (!fused_fwd_supported(p, Fp, d->Fo, d->K)) return F;
+  return Fp;
+}
+
+struct PadSaved {
+  float *Xp, *Wp;
+  void* inner;
+  size_t bytes;
+};
+PadSaved carve_pad_saved(const agcn_sgcll_desc* d2, const agcn_plan* p, void* base) {
+  Carver c(base);
+  PadSaved s{};
+  s.Xp = c.take((size_t)p->R * d2->F);
+  s.Wp = c.take((size_t)d2->F * d2->K * d2->Fo);
+  s.inner = base ? reinterpret_cast<char*>(base) + c.off : nullptr;
+  s.bytes = c.off + carve_saved(d2, p, nullptr).bytes + 256;
+  return s;
+}
+struct PadWork {
+  float *dXp, *dWp, *dMp;
+  void* inner;
+  size_t inner_bytes, bytes;
+};
+PadWork carve_pad_work(const agcn_sgcll_desc* d2, const agcn_plan* p, void* base) {
+  Carver c(base);
+  PadWork w{};
+  w.dXp = c.take((size_t)p->R * d2->F);
+  w.dWp = c.take((size_t)d2->F * d2->K * d2->Fo);
+  w.dMp = c.take((size_t)d2->F * d2->F);
+  w.inner = base ? reinterpret_cast<char*>(base) + c.off : nullptr;
+  w.inner_bytes = carve_work(d2, p, nullptr).bytes + 256;
+  w.bytes = c.off + w.inner_bytes;
+  return w;
+}
+
+// dst[r, c] = c < Fs ? src[r, c] : 0   (rows x Fd)
+__global__ void pad_cols_kernel(const float* __restrict__ src, int Fs, float* __restrict__ dst, int Fd, long long rows) {
+  const long long total = rows * Fd;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / Fd;
+    const int c = (int)(e - r * Fd);
+    dst[e] = c < Fs ? src[r * Fs + c] : 0.f;
+  }
+}
+// dst[r, c] = src[r, c] for c < Fd   (rows x Fd out of rows x Fs)
+__global__ void unpad_cols_kernel(const float* __restrict__ src, int Fs, float* __restrict__ dst, int Fd, long long rows) {
+  const long long total = rows * Fd;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long r = e / Fd;
+    const int c = (int)(e - r * Fd);
+    dst[e] = src[r * Fs + c];
+  }
+}
+// dst[0 .. n_copy) = src, dst[n_copy .. n_total) = 0
+__global__ void copy_then_zero_kernel(const float* __restrict__ src, float* __restrict__ dst, long long n_copy, long long n_total) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n_total; e += (long long)gridDim.x * blockDim.x)
+    dst[e] = e < n_copy ? src[e] : 0.f;
+}
+inline unsigned grid_for(long long total) { return (unsigned)std::max<long long>(1, std::min<long long>((total + 255) / 256, 1184)); }
+
+int forward_impl(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* d_X, const float* d_Lint,
+                 const float* d_Lprev, const float* d_M_L, const float* d_weight, const float* d_bias,
+                 const float* d_alpha, const float* d_beta, float* d_Y, float* d_resL, float* d_resW, float* d_Lall,
+                 void* d_saved, void* d_work, size_t work_bytes, void* stream);
+int backward_impl(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* d_X, const float* d_Lint,
+                  const float* d_Lprev, const float* d_M_L, const float* d_weight, const float* d_alpha,
+                  const float* d_beta, const float* d_Y, const float* d_dY, const float* d_dLall_in, const void* d_saved,
+                  float* d_dX, float* d_dM_L, float* d_dweight, float* d_dbias, float* d_dalpha, float* d_dbeta,
+                  float* d_dLprev, void* d_work, size_t work_bytes, void* stream);
+
+}  // namespace
+
 extern "C" {
 
 int agcn_sgcll_workspace_bytes(const agcn_sgcll_desc* desc, const agcn_plan* plan, size_t* saved_bytes,
                                size_t* work_bytes) {
   AGCN_REQUIRE(desc && plan, "null desc or plan");
+  const int Fp = padded_features(desc, plan);
+  if (Fp != desc->F) {
+    agcn_sgcll_desc d2 = *desc;
+    d2.F = Fp;
+    if (saved_bytes) *saved_bytes = carve_pad_saved(&d2, plan, nullptr).bytes + 256;
+    if (work_bytes) *work_bytes = carve_pad_work(&d2, plan, nullptr).bytes + 256;
+    return AGCN_OK;
+  }
   if (saved_bytes) *saved_bytes = carve_saved(desc, plan, nullptr).bytes + 256;
   if (work_bytes) *work_bytes = carve_work(desc, plan, nullptr).bytes + 256;
   return AGCN_OK;
 }
 
 int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* d_X, const float* d_Lint,
+                       const float* d_Lprev, const float* d_M_L, const float* d_weight, const float* d_bias,
+                       const float* d_alpha, const float* d_beta, float* d_Y, float* d_resL, float* d_resW,
+                       float* d_Lall, void* d_saved, void* d_work, size_t work_bytes, void* stream) {
+  int rc = check_desc(desc, plan);
+  if (rc) return rc;
+  const int Fp = padded_features(desc, plan);
+  if (Fp == desc->F)
+    return forward_impl(desc, plan, d_X, d_Lint, d_Lprev, d_M_L, d_weight, d_bias, d_alpha, d_beta, d_Y, d_resL, d_resW,
+                        d_Lall, d_saved, d_work, work_bytes, stream);
+  AGCN_REQUIRE(d_X && d_weight && d_saved && d_work, "forward: null pointer");
+  agcn_sgcll_desc d2 = *desc;
+  d2.F = Fp;
+  PadSaved ps = carve_pad_saved(&d2, plan, d_saved);
+  PadWork pw = carve_pad_work(&d2, plan, d_work);
+  if (pw.bytes > work_bytes) {
+    set_error("forward: workspace too small");
+    return AGCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((rc = plan_use(plan, st))) return rc;
+  pad_cols_kernel<<<grid_for((long long)plan->R * Fp), 256, 0, st>>>(d_X, desc->F, ps.Xp, Fp, plan->R);
+  AGCN_LAUNCH_CHECK();
+  {
+    const long long n_copy = (long long)desc->F * desc->K * desc->Fo, n_total = (long long)Fp * desc->K * desc->Fo;
+    copy_then_zero_kernel<<<grid_for(n_total), 256, 0, st>>>(d_weight, ps.Wp, n_copy, n_total);
+    AGCN_LAUNCH_CHECK();
+  }
+  // M_L is not read in the literal shortcut (no similarity matrix is built): the impl only checks the pointer
+  return forward_impl(&d2, plan, ps.Xp, d_Lint, d_Lprev, d_M_L, ps.Wp, d_bias, d_alpha, d_beta, d_Y, d_resL, d_resW, d_Lall,
+                      ps.inner, pw.inner, pw.inner_bytes, stream);
+}
+
+int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* d_X, const float* d_Lint,
+                        const float* d_Lprev, const float* d_M_L, const float* d_weight, const float* d_alpha,
+                        const float* d_beta, const float* d_Y, const float* d_dY, const float* d_dLall_in,
+                        const void* d_saved, float* d_dX, float* d_dM_L, float* d_dweight, float* d_dbias,
+                        float* d_dalpha, float* d_dbeta, float* d_dLprev, void* d_work, size_t work_bytes,
+                        void* stream) {
+  int rc = check_desc(desc, plan);
+  if (rc) return rc;
+  const int Fp = padded_features(desc, plan);
+  if (Fp == desc->F)
+    return backward_impl(desc, plan, d_X, d_Lint, d_Lprev, d_M_L, d_weight, d_alpha, d_beta, d_Y, d_dY, d_dLall_in, d_saved,
+                         d_dX, d_dM_L, d_dweight, d_dbias, d_dalpha, d_dbeta, d_dLprev, d_work, work_bytes, stream);
+  AGCN_REQUIRE(d_saved && d_work && d_dM_L && d_dweight, "backward: null pointer");
+  agcn_sgcll_desc d2 = *desc;
+  d2.F = Fp;
+  PadSaved ps = carve_pad_saved(&d2, plan, const_cast<void*>(d_saved));
+  PadWork pw = carve_pad_work(&d2, plan, d_work);
+  if (pw.bytes > work_bytes) {
+    set_error("backward: workspace too small");
+    return AGCN_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  // the padded problem on the copies the forward pass saved; its gradients hold the real ones as leading rows / columns
+  rc = backward_impl(&d2, plan, ps.Xp, d_Lint, d_Lprev, d_M_L, ps.Wp, d_alpha, d_beta, d_Y, d_dY, d_dLall_in, ps.inner,
+                     d_dX ? pw.dXp : nullptr, pw.dMp, pw.dWp, d_dbias, d_dalpha, d_dbeta, d_dLprev, pw.inner, pw.inner_bytes,
+                     stream);
+  if (rc) return rc;
+  {
+    const long long n = (long long)desc->F * desc->K * desc->Fo;   // rows f K + k with f < F: a prefix of the padded dweight
+    copy_then_zero_kernel<<<grid_for(n), 256, 0, st>>>(pw.dWp, d_dweight, n, n);
+    AGCN_LAUNCH_CHECK();
+  }
+  if ((rc = zero_async(d_dM_L, (size_t)desc->F * desc->F, st))) return rc;   // tf.py_func has no gradient
+  if (d_dX) {
+    unpad_cols_kernel<<<grid_for((long long)plan->R * desc->F), 256, 0, st>>>(pw.dXp, Fp, d_dX, desc->F, plan->R);
+    AGCN_LAUNCH_CHECK();
+  }
+  return AGCN_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+int forward_impl(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* d_X, const float* d_Lint,
                        const float* d_Lprev, const float* d_M_L, const float* d_weight, const float* d_bias,
                        const float* d_alpha, const float* d_beta, float* d_Y, float* d_resL, float* d_resW,
                        float* d_Lall, void* d_saved, void* d_work, size_t work_bytes, void* stream) {
@@ -268,12 +441,11 @@ int agcn_sgcll_forward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const
   return AGCN_OK;
 }
 
-int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* d_X, const float* d_Lint,
-                        const float* d_Lprev, const float* d_M_L, const float* d_weight, const float* d_alpha,
-                        const float* d_beta, const float* d_Y, const float* d_dY, const float* d_dLall_in,
-                        const void* d_saved, float* d_dX, float* d_dM_L, float* d_dweight, float* d_dbias,
-                        float* d_dalpha, float* d_dbeta, float* d_dLprev, void* d_work, size_t work_bytes,
-                        void* stream) {
+int backward_impl(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float* d_X, const float* d_Lint,
+                  const float* d_Lprev, const float* d_M_L, const float* d_weight, const float* d_alpha,
+                  const float* d_beta, const float* d_Y, const float* d_dY, const float* d_dLall_in, const void* d_saved,
+                  float* d_dX, float* d_dM_L, float* d_dweight, float* d_dbias, float* d_dalpha, float* d_dbeta,
+                  float* d_dLprev, void* d_work, size_t work_bytes, void* stream) {
   int rc = check_desc(desc, plan);
   if (rc) return rc;
   AGCN_REQUIRE(d_X && d_Lint && d_M_L && d_weight && d_alpha && d_Y && d_dY && d_saved && d_work,
@@ -395,6 +567,10 @@ int agcn_sgcll_backward(const agcn_sgcll_desc* desc, const agcn_plan* plan, cons
   }
   return AGCN_OK;
 }
+
+}  // namespace
+
+extern "C" {
 
 /* Building block exported for tests and tuning: out[(f*S + s)*N + c] = sum_r A_s[r, f] * D[r, c].
  * use_tensor_cores = 0 forces the CUDA-core kernel.  scratch: agcn_gemm_tn_scratch_bytes() bytes. */

@@ -362,7 +362,7 @@ pre_tile_kernel(const __grid_constant__ CUtensorMap tmBhi, const __grid_constant
           drain_out(p.forward ? p.Out : p.Out + (long long)zd * p.out_slice, (uint32_t)((zd & 1) * p.acc_stride));
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(outfree_bar);
+          if (lane == 0 && zd + 2 < passes) mbar_arrive(outfree_bar);   // only pass zd + 2 waits for this accumulator
         }
       }
     };

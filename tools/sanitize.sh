@@ -1,18 +1,19 @@
 #!/bin/bash
-# compute-sanitizer over a subset of the GPU tests: memcheck, racecheck (shared-memory hazards of
-# the hand-rolled mbarrier / TMEM protocols), synccheck.  Summaries land in gpurun_out/sanitizer_*.log.
+# compute-sanitizer over a subset of the GPU tests: memcheck, synccheck, racecheck (shared-memory
+# hazards of the hand-rolled mbarrier / TMEM protocols).  Summaries land in gpurun_out/sanitizer_*.log.
 # Usage (on the GPU box, from the repo root):  bash tools/sanitize.sh
 mkdir -p gpurun_out
-SEL='test_sgc_ll_forward_backward or test_reslap_forward_backward or test_paper_full_metric_gradient or test_feature_shapes or test_big_graphs_all_modes or test_nonsymmetric or test_head_loss or test_first_layer_backward'
-SEL_SMALL='test_sgc_ll_forward_backward or test_paper_full_metric_gradient or test_nonsymmetric'
+rm -f gpurun_out/sanitizer_summary.log
+SEL='test_sgc_ll_forward_backward or test_reslap_forward_backward or test_feature_shapes or test_big_graphs_all_modes or test_head_loss or test_first_layer_backward'
+SEL_SMALL='test_sgc_ll_forward_backward or test_feature_shapes'
 for tool in memcheck synccheck; do
-  timeout 700 compute-sanitizer --tool $tool --error-exitcode 7 --print-limit 20 \
+  timeout 420 compute-sanitizer --tool $tool --error-exitcode 7 --print-limit 20 \
     python -m pytest tests/test_gpu_parity.py tests/test_gpu_block_layers.py -m gpu -q -x -k "$SEL or block or mlp or dropout" \
     > gpurun_out/sanitizer_$tool.log 2>&1
   echo "$tool rc=$?" >> gpurun_out/sanitizer_summary.log
   grep -E "ERROR SUMMARY|passed|failed|Error|RACECHECK SUMMARY" gpurun_out/sanitizer_$tool.log | tail -5 >> gpurun_out/sanitizer_summary.log
 done
-timeout 900 compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 7 --print-limit 20 \
+timeout 600 compute-sanitizer --tool racecheck --racecheck-report analysis --error-exitcode 7 --print-limit 20 \
   python -m pytest tests/test_gpu_parity.py -m gpu -q -x -k "$SEL_SMALL" > gpurun_out/sanitizer_racecheck.log 2>&1
 echo "racecheck rc=$?" >> gpurun_out/sanitizer_summary.log
 grep -E "ERROR SUMMARY|passed|failed|RACECHECK SUMMARY|hazard" gpurun_out/sanitizer_racecheck.log | tail -8 >> gpurun_out/sanitizer_summary.log
