@@ -227,12 +227,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(Cz) & 15) == 0);
     float loss_acc = 0.f;
     // bias has been added; accumulate / activation / loss epilogue of one element
-    auto finish = [&](float x, float old, int row, int col) -> float {
+    // y, w: this element's target and weight (fused loss epilogue only), fetched by the caller for a whole 32-column
+    // chunk at once: one load per element issued right where it is used made every one of a thread's 32 row visits
+    // wait for its own HBM round trip (the [B, 2 n_tasks] targets and weights are read exactly once: 63 us for the
+    // ToxCast logits, the longest kernel of the step)
+    auto finish = [&](float x, float old, float y, float w) -> float {
       if (p.accumulate) x += old;
       if (p.bce_y) {
         // weighted sigmoid cross-entropy with logits (multitask_classifier.py:41-44): loss and its gradient
-        const long long bo = (long long)row * p.bce_ld + col;
-        const float y = __ldg(p.bce_y + bo), w = __ldg(p.bce_w + bo);
         loss_acc += w * (fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x))));
         return w * (1.f / (1.f + expf(-x)) - y) * p.bce_scale;
       }
@@ -268,6 +270,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (cc + 2 < p.N) bv.z = p.bias[cc + 2];
         if (cc + 3 < p.N) bv.w = p.bias[cc + 3];
       }
+      // targets / weights of my 8 rows x 4 columns of this chunk, all 64 loads in flight together
+      float yv[8][4], wv[8][4];
+      if (p.bce_y) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int m = m0 + q * 32 + 4 * i + (lane >> 3);
+          const long long bo = (long long)m * p.bce_ld + cc;
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const bool ok = m < p.M && cc + e < p.N;
+            yv[i][e] = ok ? __ldg(p.bce_y + bo + e) : 0.f;
+            wv[i][e] = ok ? __ldg(p.bce_w + bo + e) : 0.f;
+          }
+        }
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int r = 4 * i + (lane >> 3);
@@ -280,14 +297,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (vec_ok && cc + 3 < p.N) {
             float4 old = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.accumulate) old = *reinterpret_cast<const float4*>(dst);
-            o.x = finish(o.x, old.x, m, cc); o.y = finish(o.y, old.y, m, cc + 1);
-            o.z = finish(o.z, old.z, m, cc + 2); o.w = finish(o.w, old.w, m, cc + 3);
+            o.x = finish(o.x, old.x, yv[i][0], wv[i][0]); o.y = finish(o.y, old.y, yv[i][1], wv[i][1]);
+            o.z = finish(o.z, old.z, yv[i][2], wv[i][2]); o.w = finish(o.w, old.w, yv[i][3], wv[i][3]);
             *reinterpret_cast<float4*>(dst) = o;
           } else {
             const float ov[4] = {o.x, o.y, o.z, o.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              if (cc + e < p.N) dst[e] = finish(ov[e], p.accumulate ? dst[e] : 0.f, m, cc + e);
+              if (cc + e < p.N) dst[e] = finish(ov[e], p.accumulate ? dst[e] : 0.f, yv[i][e], wv[i][e]);
             }
           }
         }
