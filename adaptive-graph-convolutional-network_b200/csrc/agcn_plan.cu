@@ -89,10 +89,11 @@ __global__ void pack_lap_kernel(const float* __restrict__ padded, float* __restr
 // Padded -> packed over the REAL rows only (the direction every training step takes): a persistent grid of at most
 // PACK_CTAS CTAs of 1024 threads walks the R packed rows, one warp per row, the row's graph found by binary search in
 // node_off.  When the padded array is a pinned host buffer read in place over PCIe, the kernel lives for the PCIe
-// transfer time (0.2 ms for a ToxCast batch) beside the previous training step, whose tile kernels need a whole SM
-// each (222 KB of shared memory, ~60 k registers): a pack CTA on EVERY SM keeps them from being scheduled anywhere
-// (measured: +0.15 ms per step), so the pack grid stays on a few SMs -- 24 x 32 warps keep ~80 KB in flight, enough to
-// saturate PCIe -- and leaves the other ~124 to the step (its 153 tiles need two waves on 148 SMs anyway).
+// transfer time beside the previous training step, whose kernels want every SM (three 74 KB recurrence CTAs or two
+// contraction CTAs per SM): a 1024-thread pack CTA takes half an SM's registers and thread slots away from them, so the
+// pack grid stays on a few SMs.  Measured on the pipelined ToxCast loop (round 2, bench.py e2e): 24 CTAs 0.926 ms per
+// step, 8 CTAs 0.895 ms, 4 CTAs 1.018 ms (then the PCIe reads themselves -- ~1.5 us each, 32 warps per CTA in flight --
+// no longer finish within one step).
 __device__ __forceinline__ int graph_of_row(const int32_t* __restrict__ node_off, int B, int r) {
   int lo = 0, hi = B;   // node_off[lo] <= r < node_off[hi]
   while (hi - lo > 1) {
@@ -102,7 +103,7 @@ __device__ __forceinline__ int graph_of_row(const int32_t* __restrict__ node_off
   return lo;
 }
 
-constexpr int PACK_CTAS = 24;
+constexpr int PACK_CTAS = 8;
 __global__ void __launch_bounds__(1024) pack_rows_kernel(const float* __restrict__ padded, float* __restrict__ packed,
                                                         const int32_t* __restrict__ n_nodes,
                                                         const int32_t* __restrict__ node_off,
