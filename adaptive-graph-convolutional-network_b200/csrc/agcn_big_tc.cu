@@ -66,7 +66,7 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
 
-// A: K-major, SWIZZLE_128B, 8-row atoms of 1024 bytes (same operand format as agcn_fused_tile.cu)
+// A: K-major, SWIZZLE_128B, 8-row atoms of 1024 bytes (same operand format as agcn_pre_tile.cu)
 __device__ __forceinline__ uint64_t make_desc_k(uint32_t saddr) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr & 0x3FFFF) >> 4);

@@ -110,7 +110,7 @@ inline int dl_parts(const agcn_sgcll_desc* d, const agcn_plan* p) {
 }
 
 struct Work {
-  float *XW, *dYp, *G, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tcY, *tcM, *big, *ftY;
+  float *XW, *dYp, *G, *V, *tn_part, *act_part, *dL, *dXW, *dalpha_part, *dbeta_part, *tcY, *tcM, *big, *ftY;
   size_t bytes;
 };
 
@@ -121,6 +121,7 @@ Work carve_work(const agcn_sgcll_desc* d, const agcn_plan* p, void* base) {
   w.XW = c.take((size_t)p->R * d->F);  // forward: X M_L (when the similarity is needed and not saved)
   w.dYp = c.take((size_t)p->R * d->Fo);
   w.G = c.take((size_t)d->K * p->R * d->F);
+  w.V = c.take((size_t)(d->K > 1 ? d->K - 1 : 0) * p->R * d->Fo);  // V_k = T_k(L^T) dYpre of the recurrence-first backward
   size_t tn = gemm_tn_partial_floats((int)p->R, d->F, d->Fo, d->K);
   if (m.full) tn = std::max(tn, gemm_tn_partial_floats((int)p->R, d->F, d->F, 1));
   {
@@ -374,7 +375,7 @@ int forward_impl(const agcn_sgcll_desc* desc, const agcn_plan* plan, const float
 
   // the parameter operands of the two big node-level GEMMs (this forward's Y and the backward's G) are
   // rearranged / split on the side stream while the per-graph kernels run
-  // Fused tile path: recurrence + transform in one tensor-core kernel (agcn_fused_tile.cu)
+  // Tile path: CUDA-core recurrences (agcn_cheb_tile.cu) + one tensor-core contraction over all rows (agcn_pre_tile.cu)
   const bool fuse_f = fused_fwd_supported(plan, F, Fo, K);
   const bool fuse_b = (desc->flags & AGCN_SAVE_FOR_BACKWARD) && !m.need_dL && fused_bwd_supported(plan, F, Fo, K);
   GemmArgs gy = y_gemm_args(desc, R, d_X, sv.T, d_weight, d_bias, d_Y);
@@ -468,12 +469,19 @@ int backward_impl(const agcn_sgcll_desc* desc, const agcn_plan* plan, const floa
   // d_dX == NULL: the caller does not need the gradient w.r.t. the node features (first layer)
   const bool fuse_b = (desc->flags & AGCN_SAVE_FOR_BACKWARD) && !m.need_dL && d_dX != nullptr &&
                       fused_bwd_supported(plan, F, Fo, K);
+  // Recurrence-first dX chain (batches whose graphs all take the recurrence tiles): V_k = T_k(L^T) dYpre on the CUDA cores,
+  // then dX = sum_k V_k W_k^T as ONE accumulator on the tensor cores -- the mirror image of the forward pass, same
+  // kernels (T_k(L)^T = T_k(L^T)).  Against G_z = dYpre W_z^T followed by the reverse recurrence it needs one TMEM
+  // accumulator instead of K (two contraction CTAs per SM: one wave for a batch of 155 row tiles) and reads / writes
+  // (K-1) [R, Fo] matrices instead of K [R, F] ones.  Row-tiled graphs (point clouds) keep the G_z form: their products
+  // are the expensive part and G_z keeps them F wide.
+  const bool vfirst = fuse_b && plan->large_tiles == 0;
   const bool need_G = !fuse_b && (d_dX != nullptr || (m.need_dL && K >= 2));
   // dYpre = dY * act'(Y) and per-CTA column sums; dbias = colsum(dYpre).  The parameter gradients depend on
   // dYpre only -> side stream, overlapping the dX chain.  The fused dX kernel applies act' itself, so in that case
   // (and when the main stream has no use for dYpre at all) the whole dYpre branch lives on the side stream.
   const float* dYp = (desc->activation == AGCN_ACT_RELU) ? wk.dYp : d_dY;
-  const bool act_on_side = fuse_b || (!need_G && !m.need_dL);
+  const bool act_on_side = !vfirst && (fuse_b || (!need_G && !m.need_dL));   // vfirst: the main chain starts from dYpre
   if (!act_on_side && (rc = act_bwd_partials(d_dY, d_Y, wk.dYp, wk.act_part, R, Fo, desc->activation, st))) return rc;
   AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
   AGCN_CUDA(cudaStreamWaitEvent(plan->side, plan->ev_side_fork, 0));
@@ -512,7 +520,21 @@ int backward_impl(const agcn_sgcll_desc* desc, const agcn_plan* plan, const floa
     if ((rc = node_gemm_tn(t, plan->side))) return rc;
   }
   AGCN_CUDA(cudaEventRecord(plan->ev_side_join, plan->side));
-  if (fuse_b) {
+  if (vfirst) {
+    const float* Lf = m.shortcut ? d_Lint : sv.Lall;
+    const int ident = m.shortcut ? 1 : 0;
+    const bool other = cheb_tiles_has_mid(plan);
+    if (other) {
+      AGCN_CUDA(cudaEventRecord(plan->ev_big_fork, st));
+      AGCN_CUDA(cudaStreamWaitEvent(plan->big, plan->ev_big_fork, 0));
+    }
+    if ((rc = cheb_tiles_forward(plan, dYp, Lf, ident, Fo, K, wk.V, st, plan->big, /*transL=*/1))) return rc;
+    if (other) {
+      AGCN_CUDA(cudaEventRecord(plan->ev_big_join, plan->big));
+      AGCN_CUDA(cudaStreamWaitEvent(st, plan->ev_big_join, 0));
+    }
+    if ((rc = pre_forward(plan, -1, 0, dYp, wk.V, sv.ftG, nullptr, AGCN_ACT_LINEAR, /*F=*/Fo, /*Fo=*/F, K, d_dX, st))) return rc;
+  } else if (fuse_b) {
     // G_z = dYpre W_z^T over every packed row on the tensor cores (relu' applied to the operand rows as they are
     // loaded), then the reverse recurrences on the CUDA cores
     const float* Lf = m.shortcut ? d_Lint : sv.Lall;

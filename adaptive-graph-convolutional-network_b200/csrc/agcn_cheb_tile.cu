@@ -4,7 +4,7 @@
 //   forward   T_0 = X, T_1 = L T_0, T_k = 2 L T_{k-1} - T_{k-2}            graphconv.py:221-236
 //   backward  U_{K-1} = G_{K-1}, U_j = G_j + c_{j+1} L^T U_{j+1} - U_{j+2},  dX = U_0   (reverse mode of the same lines)
 //
-// Why split (profiles/r02f_*): the fused tile kernels (agcn_fused_tile.cu) run ONE 320-thread CTA per SM (222 KB of shared
+// Why split (profiles/r02f_*): the fused tile kernels of round 1 ran ONE 320-thread CTA per SM (222 KB of shared
 // memory) through a serial chain of ~25 dependent phases per tile -- 26 us of worker chain against 6 us of tensor-core
 // work per tile, 5 % of the HBM roofline -- and nothing else can be resident beside them to hide the latencies.  Here a
 // CTA owns (tile, 32-column chunk): 256 threads (tile row x column half), ~74 KB of shared memory, three CTAs per SM, a
@@ -72,6 +72,7 @@ struct CtArgs {
   int lfloats;                 // floats of the shared-memory L region
   const float* L;              // packed Laplacians (Lint or L_all)
   int add_identity;
+  int transL;                  // forward kernel: multiply by L^T (the V_k = T_k(L^T) dYpre recurrences of the backward pass)
   int F, K;
   const float* X;              // forward  [R, F]
   float* T;                    //          [K-1][R][F]
@@ -321,7 +322,9 @@ __global__ void __launch_bounds__(TILE ? 256 : 320, TILE ? 3 : 1) cheb_tile_fwd_
   CT_STAMP(101);
   const bool vec = ((F & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.X) & 15) == 0) &&
                    ((reinterpret_cast<uintptr_t>(p.T) & 15) == 0) && ((p.tslice & 3) == 0);
-  const uint32_t lrow = sL + 4 * (me.lbase + me.i * me.pitch);
+  // my row of the graph's matrix, or (transL) my column: (L^T V)_i = sum_j L[j][i] V_j
+  const uint32_t lrow = p.transL ? sL + 4 * (me.lbase + me.i) : sL + 4 * (me.lbase + me.i * me.pitch);
+  const int lstep = p.transL ? 4 * me.pitch : 4;
   Mask<MW> mask;
   bool masked = false;
   const int c_beg = grp * p.cpc, c_end = min(p.chunks, c_beg + p.cpc);
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(TILE ? 256 : 320, TILE ? 3 : 1) cheb_tile_fwd_
     __syncthreads();  // (first chunk: the L matrices and) the T_0 chunk of every row have landed
     if (c == c_beg) {
       CT_STAMP(103);
-      mask = nonzero_mask<MW>(lrow, 4, me.n);
+      mask = nonzero_mask<MW>(lrow, lstep, me.n);
       masked = prefer_masked<MW>(mask, me.n);
       CT_STAMP(104);
     }
@@ -369,9 +372,9 @@ __global__ void __launch_bounds__(TILE ? 256 : 320, TILE ? 3 : 1) cheb_tile_fwd_
 #pragma unroll
       for (int u = 0; u < 16; ++u) t[u] = p.add_identity ? tm1[u] : 0.f;  // L_all = I + L_int (literal mode)
       if (masked)
-        lap_times_rows_masked<MW>(lrow, 4, src, me.r0, mask, h, t);
+        lap_times_rows_masked<MW>(lrow, lstep, src, me.r0, mask, h, t);
       else
-        lap_times_rows(lrow, 4, src, me.r0, me.n, h, t);                 // graphconv.py:231
+        lap_times_rows(lrow, lstep, src, me.r0, me.n, h, t);             // graphconv.py:231
       if (s >= 2) {
 #pragma unroll
         for (int u = 0; u < 16; ++u) t[u] = 2.f * t[u] - tm2[u];          // graphconv.py:234
@@ -547,9 +550,10 @@ bool cheb_tiles_has_mid(const agcn_plan* plan) { return ct::mid_bucket(plan) != 
 // T_1 .. T_{K-1} of every graph up to AGCN_SMALL_MAX nodes that is not row-tiled (small-graph tiles on st_small, the
 // mid-size graphs on st_mid)
 int cheb_tiles_forward(const agcn_plan* plan, const float* X, const float* L, int add_identity, int F, int K, float* T,
-                       cudaStream_t st_small, cudaStream_t st_mid) {
+                       cudaStream_t st_small, cudaStream_t st_mid, int transL) {
   if (K < 2) return AGCN_OK;
   ct::CtArgs a = ct::base_args(plan, L, add_identity, F, K);
+  a.transL = transL;
   a.X = X; a.T = T; a.tslice = (long long)plan->R * F;
   return ct::launch(plan, a, true, st_small, st_mid);
 }

@@ -16,10 +16,10 @@
 // Graphs above this size run their Chebyshev recurrences as row-tiled grouped GEMMs (one launch per step,
 // several CTAs per graph) instead of one CTA per (graph, feature chunk).
 #define AGCN_CHEB_SMALL_MAX 144
-// Fused tile kernels (agcn_fused_tile.cu): graphs up to this size are packed into 128-row tiles and run their
-// Chebyshev recurrences inside the tensor-core kernel; AGCN_FUSE_LCAP floats of shared memory hold the
-// per-graph matrices of one tile (row pitch n | 1; two 64-node graphs fit).  Larger graphs would make their
-// tile the critical path of the launch: their recurrences run chunk-parallel in the per-graph kernels instead.
+// Recurrence tiles (agcn_cheb_tile.cu): graphs up to this size are packed into 128-row tiles (whole graphs, first-fit
+// decreasing) and run their Chebyshev recurrences one CTA per (tile, feature chunks); AGCN_FUSE_LCAP floats of shared
+// memory hold the per-graph matrices of one tile (row pitch n | 1; two 64-node graphs fit).  Graphs between this size
+// and AGCN_SMALL_MAX take one CTA row range each (the same kernel, 160 rows).
 #define AGCN_FUSE_MAX_N 64
 #define AGCN_FUSE_LCAP 8320
 // Batches with at least this many graphs between AGCN_FUSE_MAX_N and AGCN_SMALL_MAX nodes send them through the
@@ -322,25 +322,17 @@ int grouped_tc(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStrea
 bool grouped_thin_supported(const GroupedArgs& g);
 int grouped_thin(int tiles, const GroupedArgs& g, cudaStream_t st);
 
-// ---------------------------------------------------------------- fused tile kernels (agcn_fused_tile.cu)
+// ---------------------------------------------------------------- tile path of a layer: parameter operands and shape
+// rules (agcn_layer_operands.cu); recurrences in agcn_cheb_tile.cu, contraction in agcn_pre_tile.cu
 void fused_profile_enable(int on);
 int fused_profile_read(float* ms_sum, int* launches);
 void prof_enable(int on);
-void fused_debug_set(void* d_buf);  // timeline buffer [tiles][128] uint64 of the NEXT fused forward launches, or NULL
+void fused_debug_set(void* d_buf);  // per-CTA timeline buffer [CTAs][128] uint64 of the NEXT contraction / recurrence launches, or NULL
 bool fused_fwd_supported(const agcn_plan* plan, int F, int Fo, int K);
 bool fused_bwd_supported(const agcn_plan* plan, int F, int Fo, int K);
 size_t fused_w_floats(int Nv, int Kv, int Z);  // floats of one pre-split parameter operand
 int fused_fwd_prep(const float* weight, int F, int Fo, int K, float* scratch, cudaStream_t st);
 int fused_bwd_prep(const float* weight, int F, int Fo, int K, float* scratch, cudaStream_t st);
-// T_1..T_{K-1} (saved) and Y = act(sum_k T_k W_k + b) for every tile of the plan; L = Lint (add_identity) or L_all
-// tile0 / ntiles: the tiles of this launch
-int fused_forward(const agcn_plan* plan, int tile0, int ntiles, const float* X, const float* L, int add_identity,
-                  const float* wsplit, const float* bias, int act, int F, int Fo, int K, float* T, float* Y,
-                  cudaStream_t st);
-// dX = U_0 of the reverse recurrence over G_z = dYpre W_z^T, dYpre = dY * [Y > 0] (Y == NULL: dYpre = dY);
-// G receives G_z for the rows of graphs with n > AGCN_FUSE_MAX_N only
-int fused_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY, const float* Y, const float* L,
-                   int add_identity, const float* wsplit, int F, int Fo, int K, float* G, float* dX, cudaStream_t st);
 
 // ---------------------------------------------------------------- transform product of the 128-row ranges of graphs
 // above AGCN_FUSE_MAX_N (agcn_pre_tile.cu); same parameter operands as the fused tile kernels
@@ -352,8 +344,9 @@ int pre_backward(const agcn_plan* plan, int tile0, int ntiles, const float* dY, 
 // ---------------------------------------------------------------- CUDA-core Chebyshev recurrences of the graphs up to
 // AGCN_SMALL_MAX nodes (agcn_cheb_tile.cu): small-graph tiles on st_small, mid-size graphs on st_mid
 bool cheb_tiles_has_mid(const agcn_plan* plan);
+// transL: the recurrences of L^T (backward pass: V_k = T_k(L^T) dYpre)
 int cheb_tiles_forward(const agcn_plan* plan, const float* X, const float* L, int add_identity, int F, int K, float* T,
-                       cudaStream_t st_small, cudaStream_t st_mid);
+                       cudaStream_t st_small, cudaStream_t st_mid, int transL = 0);
 int cheb_tiles_backward(const agcn_plan* plan, const float* G, const float* L, int add_identity, int F, int K, float* dX,
                         cudaStream_t st_small, cudaStream_t st_mid);
 

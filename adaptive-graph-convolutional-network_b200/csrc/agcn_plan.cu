@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(1024) pack_rows_kernel(const float* __restrict
 
 static unsigned pack_grid(int64_t R) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((R + 31) / 32, PACK_CTAS)); }
 
-// Fused tiles (agcn_fused_tile.cu): 128-row ranges of the graphs above AGCN_FUSE_MAX_N, then the small graphs
+// Tiles of the recurrence kernels (agcn_cheb_tile.cu): 128-row ranges of the graphs above AGCN_FUSE_MAX_N, then the small graphs
 // first-fit-decreasing into 128-row tiles under the shared-memory budget of their L matrices.  `order` lists the
 // graphs largest first.  gstart gets tiles + 1 entries.
 static void build_fused_tiles(const std::vector<int32_t>& n, const std::vector<int32_t>& order,

@@ -1,4 +1,4 @@
-// Transform product of the graphs that do not fit a fused tile (agcn_fused_tile.cu): 128-row ranges ("pre tiles") of
+// Transform product (the dense contraction of a layer) on the tensor cores.  GENERIC kernel first: 128-row ranges ("pre tiles") of
 // graphs above AGCN_FUSE_MAX_N nodes -- the mid-size molecules of a Tox21 / ToxCast batch and every point cloud.  Their
 // Chebyshev recurrences run in the per-graph / row-tiled kernels (agcn_graph_small.cu, agcn_big_tc.cu); what is left
 // per 128-row range is a plain dense contraction on the tensor cores:

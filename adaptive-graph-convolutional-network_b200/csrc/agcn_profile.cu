@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(float* __restrict__ sink
 }
 
 void fused_profile_enable(int on) { prof_enable(on); }
-int fused_profile_read(float* ms_sum, int* launches) { return prof_drain("ft::fused_fwd_kernel", ms_sum, launches, nullptr); }
+int fused_profile_read(float* ms_sum, int* launches) { return prof_drain("pt::rows_gemm_kernel(fwd)", ms_sum, launches, nullptr); }
 
 }  // namespace agcn
 

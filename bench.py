@@ -16,8 +16,9 @@ gradient all-reduce + Adam.  One "step" = one such pass over one batch.
            (graph_topology.py:84-98): every step builds its topology plan, the pack kernels read the pinned arrays
            in place (only the real rows cross PCIe) on a side stream while the previous step computes, the step
            runs eagerly, and its loss is read back to the host.  At every N.
-  roofline the dominant kernel (ft::fused_fwd_kernel, layer 3) timed live with CUDA events on its stream, against
-           MEASURED_PEAKS.json; `kernels` is the per-kernel table of one eager step
+  roofline the kernels of one layer forward (layer 3) timed live with CUDA events on their streams, each against its
+           own algorithmic bytes / flops and MEASURED_PEAKS.json; the top-level entry is the slowest of them;
+           `kernels` is the per-kernel table of one eager step
   configs  the other BASELINE.json shapes, each with its own graphs/s, e2e, kernel table and CPU baseline:
            C1 Tox21 (B = 256, 12 tasks), C3 ModelNet40 (B = 32 x 1024 points, 40 classes), C4 Sydney (ragged)
   cpu_baseline / --impl reference: the reference's algorithm as written (oracle port: per-graph Python loop with
@@ -608,8 +609,10 @@ def measure_peaks(dev):
 
 
 def layer3_roofline(r, peaks, tf32_peak):
-    """Dominant kernel of the step, timed alone: layer 3 (128 -> 128, K = 3) forward over this batch, L2 flushed
-    before every launch, CUDA events on the launching stream recorded by the library (agcn_profile_*)."""
+    """Kernels of one layer forward (layer 3: 128 -> 128, K = 3) over this batch, each timed alone with the L2 flushed
+    before the layer, CUDA events on the launching streams recorded by the library (agcn_profile_*).  Every kernel gets
+    ITS OWN algorithmic bytes / flops; `roofline` is the one that takes longest, `layer` the
+    SURVEY section 8d figure of the whole layer forward over the sum of its kernels."""
     import torch
     from agcn_b200 import _lib
     from agcn_b200.functional import sgc_ll_packed
@@ -631,37 +634,67 @@ def layer3_roofline(r, peaks, tf32_peak):
         _lib.profile_enable(False)
     n = r.n_nodes.astype(np.float64)
     R, LL = float(n.sum()), float((n * n).sum())
-    bytes_fwd = 4.0 * (R * F + LL + R * Fo) + 4.0 * (K * F * Fo + Fo)
+    small, mid = n[n <= 64], n[(n > 64) & (n <= 144)]
     if not table:
         return {"bound": "hbm", "kernel": None, "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": None,
                 "traffic": None, "note": "no profiled launch"}
-    name, (launches, ms) = max(table.items(), key=lambda kv: kv[1][1])
+    # algorithmic work of each kernel of the layer forward
+    work = {
+        # recurrences of the tiled graphs: read X and L once, write T_1 .. T_{K-1}
+        "ct::cheb_tile_fwd_kernel": {"bytes": 4.0 * (K * small.sum() * F + (small * small).sum()),
+                                     "flops": 2.0 * (K - 1) * (small * small).sum() * F},
+        "ct::cheb_tile_fwd_kernel(mid)": {"bytes": 4.0 * (K * mid.sum() * F + (mid * mid).sum()),
+                                          "flops": 2.0 * (K - 1) * (mid * mid).sum() * F},
+        # contraction over every packed row: read T_0 .. T_{K-1}, the weights once, write Y
+        "pt::rows_gemm_kernel(fwd)": {"bytes": 4.0 * (K * R * F + R * Fo + K * F * Fo + Fo), "flops": 2.0 * R * K * F * Fo},
+        "pt::pre_tile_kernel(fwd)": {"bytes": 4.0 * (K * R * F + R * Fo + K * F * Fo + Fo), "flops": 2.0 * R * K * F * Fo},
+        # one Chebyshev product L T over the graphs above 144 nodes (point clouds)
+        "bt::grouped_tc_kernel": {"bytes": 4.0 * (LL + 2 * R * F), "flops": 2.0 * LL * F},
+    }
+    rows = {}
+    for k, v in table.items():
+        per = v[1] / v[0]
+        row = {"launches": v[0], "ms_per_launch": per}
+        if k in work:
+            w = work[k]
+            row.update({"algorithmic_bytes_per_launch": w["bytes"], "achieved_gbs": w["bytes"] / (per * 1e-3) / 1e9,
+                        "hbm_frac": w["bytes"] / (per * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                        "algorithmic_flops_per_launch": w["flops"], "achieved_tflops": w["flops"] / (per * 1e-3) / 1e12,
+                        "tensor_frac": w["flops"] / (per * 1e-3) / 1e12 / tf32_peak})
+        rows[k] = row
+    name, (launches, ms) = max(table.items(), key=lambda kv: kv[1][1] / kv[1][0])
     per = ms / launches
-    rows = {k: {"launches": v[0], "ms_per_launch": v[1] / v[0]} for k, v in table.items()}
-    if name.startswith("bt::grouped_tc"):
-        # one launch = one product L T over every graph: tensor-bound (AI ~ n F / (n + 2 F) flop/B)
-        flops = 2.0 * LL * F
-        ach = flops / (per * 1e-3) / 1e12
-        return {"bound": "tensor", "kernel": name + ", layer 3 (one Chebyshev product L*T, F=128)", "achieved": ach,
-                "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": None,
-                "algorithmic_flops_per_launch": flops, "algorithmic_bytes_per_launch": 4.0 * (LL + 2 * R * F),
-                "ms_per_launch": per, "launches_timed": launches, "peak_source": "tf32 dense measured in this run",
-                "kernels_of_the_layer_forward": rows}
-    achieved = bytes_fwd / (per * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         t = json.load(open(tpath))
         traffic, traffic_src = t.get(name + "/" + r.cfg["key"]), t.get("source")
-    flops3 = 3.0 * 2.0 * R * K * F * Fo
-    return {"bound": "hbm", "kernel": name + ", layer 3 (F=128 -> Fo=128, K=3), whole-batch launch",
+    # the layer as a whole: SURVEY section 8d bytes / flops over the chain recurrences -> contraction
+    chain = sum(v["ms_per_launch"] for k, v in rows.items() if "(mid)" not in k)
+    layer_bytes = 4.0 * (R * F + LL + R * Fo) + 4.0 * (K * F * Fo + Fo)
+    layer_flops = 2.0 * (K - 1) * LL * F + 2.0 * R * K * F * Fo
+    layer_row = {"algorithmic_bytes": layer_bytes, "algorithmic_flops": layer_flops, "ms_chain": chain,
+                 "achieved_gbs": layer_bytes / (chain * 1e-3) / 1e9, "hbm_frac": layer_bytes / (chain * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                 "achieved_tflops": layer_flops / (chain * 1e-3) / 1e12,
+                 "tensor_frac": layer_flops / (chain * 1e-3) / 1e12 / tf32_peak,
+                 "note": "layer 3 forward (F=128 -> Fo=128, K=3): SURVEY section 8d work over the sum of its kernels "
+                         "(mid-size graphs run beside the tiles)"}
+    w = work.get(name)
+    if name.startswith("bt::grouped_tc") or (w and w["flops"] / max(w["bytes"], 1.0) > tf32_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)):
+        ach = w["flops"] / (per * 1e-3) / 1e12
+        return {"bound": "tensor", "kernel": name + ", layer 3 forward, whole-batch launch", "achieved": ach,
+                "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,
+                "traffic_source": traffic_src, "algorithmic_flops_per_launch": w["flops"],
+                "algorithmic_bytes_per_launch": w["bytes"], "ms_per_launch": per, "launches_timed": launches,
+                "peak_source": "tf32 dense measured in this run (cuBLAS); the kernel issues 3x these flops (3xTF32)",
+                "kernels_of_the_layer_forward": rows, "layer": layer_row}
+    bytes_k = w["bytes"] if w else layer_bytes
+    achieved = bytes_k / (per * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": name + ", layer 3 forward (F=128 -> Fo=128, K=3), whole-batch launch",
             "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
             "traffic": traffic, "traffic_source": traffic_src, "peak_source": peaks["source"],
-            "algorithmic_bytes_per_launch": bytes_fwd, "ms_per_launch": per, "launches_timed": launches,
-            "tensor": {"flops_3xtf32_per_launch": flops3, "achieved_tflops": flops3 / (per * 1e-3) / 1e12,
-                       "peak_tflops": tf32_peak, "frac": flops3 / (per * 1e-3) / 1e12 / tf32_peak,
-                       "peak_note": "tf32 dense measured in this run (cuBLAS)"},
-            "kernels_of_the_layer_forward": rows}
+            "algorithmic_bytes_per_launch": bytes_k, "ms_per_launch": per, "launches_timed": launches,
+            "kernels_of_the_layer_forward": rows, "layer": layer_row}
 
 
 def measure_workload(cfg, dev, rank, world, args, peaks, tf32_peak, full):

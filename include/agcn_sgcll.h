@@ -103,7 +103,7 @@ int agcn_fused_tiles_host(const int32_t* n_nodes_host, int32_t B, int32_t* gstar
                           int32_t* entries_out, int32_t entries_cap, int32_t* tiles_out, int32_t* n_entries_out);
 
 /* Measurement aid (no reference counterpart; bench.py's roofline): while enabled, every eager agcn_sgcll_forward on
- * the fused tile path brackets its main kernel launch with CUDA events on the launching stream;
+ * the tile path brackets the launch of its tensor-core contraction with CUDA events on the launching stream;
  * agcn_fused_profile_read waits for them and returns the summed duration (ms) and the number of launches since
  * the last read.  Must be off during CUDA graph capture. */
 int agcn_fused_profile(int enable);
