@@ -284,7 +284,9 @@ int agcn_head_loss_grad_ex(const agcn_plan* plan, const float* d_H, const float*
   // `pre` feeds a tanh that the sum over a molecule's atoms saturates: tanh'(a) = sech^2(a) has relative sensitivity
   // 2 |da|, so the absolute error of this [B, Fh] x [Fh, Fm] product (a few MFLOP) decides the accuracy of every
   // gradient behind it.  Plain fp32 FMAs (gemm_rows) keep it at fp32 rounding level; 3xTF32 is ~4x coarser.
-  const bool tc_pre = false, tc_dmol = tc_gemm_supported(g_dmol), tc_dhs = tc_gemm_supported(g_dhs);
+  // dhsum = dpre dense_W^T is [B, Fm] x [Fm, Fh] with Fh = 64: eight 128-row tiles of eight k-blocks each -- a latency chain
+  // of 30 us on 8 SMs on the tensor-core kernel, 12 us spread over every SM on the CUDA cores (33 MFLOP)
+  const bool tc_pre = false, tc_dmol = tc_gemm_supported(g_dmol), tc_dhs = tc_gemm_supported(g_dhs) && (int64_t)B * Fh * Fm > (1ll << 26);
   auto gemm_any = [&](const GemmArgs& g, const float* scratch, bool tc) { return tc ? tc_gemm(g, scratch, st) : gemm_rows(g, st); };
   AGCN_CUDA(cudaEventRecord(plan->ev_side_fork, st));
   AGCN_CUDA(cudaStreamWaitEvent(side, plan->ev_side_fork, 0));
