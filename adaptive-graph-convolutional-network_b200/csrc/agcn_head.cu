@@ -46,6 +46,21 @@ __global__ void segment_sum_kernel(const float* __restrict__ H, const int32_t* _
   }
 }
 
+// Labels as the reference feeds them (multitask_classifier.py:147-152,171-185: one label and one weight per sample and
+// task; the one-hot encoding happens inside the graph, :196-199 tf.one_hot(label, 2)) -> the [B, 2 T] targets / per-logit
+// weights the loss epilogue reads.  Plain loads of the inputs: pinned host arrays are read in place over PCIe (4 bytes of
+// label + weight per task instead of 16 bytes of expanded rows); a few persistent CTAs so that the kernel can live beside
+// the previous training step like the pack kernels.
+__global__ void __launch_bounds__(1024) expand_labels_kernel(const uint8_t* __restrict__ y, const float* __restrict__ w,
+                                                             long long n, float2* __restrict__ targets,
+                                                             float2* __restrict__ weights) {
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x) {
+    const float yv = y[e] ? 1.f : 0.f, wv = w[e];
+    targets[e] = make_float2(1.f - yv, yv);
+    weights[e] = make_float2(wv, wv);
+  }
+}
+
 // mol = tanh(a), a = pre + n_g b   (graphgather.py:77); `pre` is overwritten with tanh'(a) = sech^2(a) evaluated as
 // 4 e / (1 + e)^2, e = exp(-2 |a|): the sum over a molecule's atoms saturates the tanh, and 1 - mol^2 would then
 // cancel to a handful of significant bits (errors of 1e-4 .. 1e-3 relative in every gradient behind it)
@@ -212,6 +227,19 @@ HeadWork carve_head(const agcn_plan* plan, int Fh, int Fm, int Nt, void* base) {
 using namespace agcn;
 
 extern "C" {
+
+int agcn_expand_labels(const uint8_t* y, const float* w, int32_t B, int32_t n_tasks, float* d_targets, float* d_weights,
+                       void* stream) {
+  AGCN_REQUIRE(y && w && d_targets && d_weights && B >= 1 && n_tasks >= 1, "expand_labels: bad arguments");
+  AGCN_REQUIRE((reinterpret_cast<uintptr_t>(d_targets) & 7) == 0 && (reinterpret_cast<uintptr_t>(d_weights) & 7) == 0,
+               "expand_labels: outputs must be 8-byte aligned");
+  const long long n = (long long)B * n_tasks;
+  const unsigned grid = (unsigned)std::max<long long>(1, std::min<long long>((n + 1023) / 1024, 8));
+  expand_labels_kernel<<<grid, 1024, 0, (cudaStream_t)stream>>>(y, w, n, reinterpret_cast<float2*>(d_targets),
+                                                               reinterpret_cast<float2*>(d_weights));
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
 
 int agcn_head_workspace_bytes(const agcn_plan* plan, int32_t Fh, int32_t Fm, int32_t Nt, size_t* bytes) {
   AGCN_REQUIRE(plan && bytes && Fh >= 1 && Fm >= 1 && Nt >= 1, "head_workspace_bytes: bad arguments");

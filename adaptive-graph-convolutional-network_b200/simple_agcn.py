@@ -189,6 +189,29 @@ class SimpleAGCNStep(object):
         return loss
 
 
+def expand_labels(y, w, targets, weights, stream=None):
+    """Labels as the reference feeds them (multitask_classifier.py:147-152,171-185) -> the one-hot targets / per-logit
+    weights of the sigmoid heads (tf.one_hot(label, 2), :196-199), on the device in one kernel.
+    y: uint8 / bool [B, T], w: float32 [B, T]; CUDA tensors or PINNED host tensors (read in place over PCIe).
+    targets, weights: float32 CUDA [B, 2T], overwritten.  The caller keeps y / w unchanged until the stream gets there."""
+    B, T = y.shape
+    for t in (y, w):
+        if not t.is_cuda and not t.is_pinned():
+            raise ValueError("host label tensors must be pinned (tensor.pin_memory()) to be read by the device")
+    if y.dtype == torch.bool:
+        y = y.view(torch.uint8)
+    if y.dtype != torch.uint8 or w.dtype != torch.float32 or not y.is_contiguous() or not w.is_contiguous():
+        raise ValueError("expand_labels: y must be contiguous uint8 / bool, w contiguous float32")
+    if targets.shape != (B, 2 * T) or weights.shape != (B, 2 * T) or not targets.is_cuda or not weights.is_cuda:
+        raise ValueError("expand_labels: targets / weights must be CUDA [B, 2T]")
+    dev = targets.device
+    with torch.cuda.device(dev):
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        _lib.check(_lib.lib().agcn_expand_labels(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(w.data_ptr()), B, T,
+                                                 _ptr(targets), _ptr(weights), ctypes.c_void_p(st.cuda_stream)))
+    return targets, weights
+
+
 def synthetic_labels(B, n_tasks, seed, device, loss="sigmoid_ce"):
     """sigmoid_ce: Bernoulli(0.1) labels as one-hot float targets [B, 2T], weights [B, 2T] = 1.
     softmax_ce: uniform class labels as one-hot [B, T], per-sample weights [B] = 1."""

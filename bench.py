@@ -518,13 +518,12 @@ class Runner(object):
     def labels_to_device(self, dst):
         """Compact host labels -> the one-hot targets / per-logit weights the loss kernel reads (current stream)."""
         torch = self.torch
-        y = self.y_h.to(self.dev, non_blocking=True)
         if self.cfg["loss"] == "sigmoid_ce":
-            w = self.wc_h.to(self.dev, non_blocking=True)
-            yf = y.to(torch.float32)
-            torch.stack([1.0 - yf, yf], dim=-1, out=dst[0].view(self.B, -1, 2))        # tf.one_hot(label, 2)
-            dst[1].view(self.B, -1, 2).copy_(w.unsqueeze(-1).expand(-1, -1, 2))
+            # one kernel reads the pinned labels / weights in place and writes tf.one_hot(label, 2) + per-logit weights
+            from agcn_b200.simple_agcn import expand_labels
+            expand_labels(self.y_h, self.wc_h, dst[0], dst[1])
         else:
+            y = self.y_h.to(self.dev, non_blocking=True)
             dst[0].zero_()
             dst[0].scatter_(1, y.unsqueeze(1), 1.0)
             dst[1].copy_(self.wc_h, non_blocking=True)

@@ -236,6 +236,12 @@ int agcn_node_gemm(const float* d_A, int32_t lda, const float* d_B, int32_t ldb,
  * keyed by (seed, i).  Nothing is stored: the same call on dY with the same seed is the gradient.  d_Y may alias d_X. */
 int agcn_dropout(const float* d_X, float* d_Y, int64_t n, float p, uint64_t seed, void* stream);
 
+/* Labels as the reference feeds them (multitask_classifier.py:147-152,171-185: y[b, t] in {0, 1}, w[b, t]) -> the
+ * [B, 2 n_tasks] one-hot targets (tf.one_hot(label, 2), multitask_classifier.py:196-199) and per-logit weights that
+ * agcn_head_loss_grad reads.  y / w may be device pointers or PINNED host pointers (read in place over PCIe). */
+int agcn_expand_labels(const uint8_t* y, const float* w, int32_t B, int32_t n_tasks, float* d_targets, float* d_weights,
+                       void* stream);
+
 /* ---- the layers after the last SGC-LL layer, loss and gradient in one call:
  *   DenseMol (models/layers/dense_layer.py:33-50, linear) + GraphGatherMol (models/layers/graphgather.py:50-78:
  *   per-graph sum over the real atoms, tanh) + the n_tasks two-class heads (models/operators/model_operatos.py:

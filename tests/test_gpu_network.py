@@ -244,3 +244,28 @@ def test_plans_created_and_destroyed_back_to_back_behind_a_long_kernel():
     torch.cuda.synchronize()
     for packed, R in outs:
         assert torch.equal(packed, X[:R])
+
+
+@pytest.mark.gpu
+def test_expand_labels_from_pinned_host_matches_one_hot():
+    """agcn_expand_labels: tf.one_hot(label, 2) + per-logit weights (multitask_classifier.py:196-199) from the compact
+    labels the reference feeds, read in place from pinned host memory; bit-exact against the numpy construction."""
+    from agcn_b200.simple_agcn import expand_labels
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(5)
+    for B, T in ((7, 12), (1024, 617), (3, 1)):
+        y = rng.random((B, T)) < 0.3
+        w = rng.random((B, T)).astype(np.float32)
+        want_t = np.stack([1.0 - y, y], -1).astype(np.float32).reshape(B, 2 * T)
+        want_w = np.repeat(w, 2, axis=1)
+        tg = torch.full((B, 2 * T), -7.0, device=dev)
+        ww = torch.full((B, 2 * T), -7.0, device=dev)
+        expand_labels(torch.from_numpy(y).pin_memory(), torch.from_numpy(w).pin_memory(), tg, ww)
+        torch.cuda.synchronize()
+        assert np.array_equal(tg.cpu().numpy(), want_t) and np.array_equal(ww.cpu().numpy(), want_w)
+        tg.fill_(-7.0)
+        expand_labels(torch.from_numpy(y.astype(np.uint8)).to(dev), torch.from_numpy(w).to(dev), tg, ww)   # device inputs
+        torch.cuda.synchronize()
+        assert np.array_equal(tg.cpu().numpy(), want_t)
+    with pytest.raises(ValueError):
+        expand_labels(torch.zeros(2, 3, dtype=torch.uint8), torch.zeros(2, 3), tg, ww)   # pageable host memory
