@@ -403,6 +403,263 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// grouped_tcu_kernel: the same product for batches of EQUAL-SIZE graphs with n % 128 == 0 (ModelNet40-shape point clouds,
+// the N >= 128 sweep points), where every row of L is 16-byte aligned and L is one [B n, n] matrix for TMA.
+//
+// grouped_tc_kernel above loads its L tiles with register prefetch four k-blocks ahead -- and ends every k-block with
+// fence.proxy.async, which ptxas lowers to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: the MEMBAR waits for every load the thread
+// has in flight, so the prefetch never overlapped anything (1.05 us per k-block against 0.55 us of MMA work, 12 % of the
+// TF32 peak; profiles/r01_n_tc_timeline_3stage.txt).  Here, as in pt::rows_gemm_kernel:
+//   * raw fp32 L tiles arrive by TMA (128 rows x 32 columns SWIZZLE_128B; for L^T the 32 x 128 block of L, unswizzled,
+//     read column-wise -- the transposition costs nothing) from their own producer thread;
+//   * the workers split a staged tile into hi / lo TF32 halves and write them into an operand slot in TENSOR MEMORY
+//     (tcgen05.st): the MMAs take A from TMEM, shared memory serves only the node-matrix operand;
+//   * the node-matrix tile (MN-major, by TMA) is split in place as before; the proxy fence behind it is cheap now that
+//     no global load is outstanding in the fencing threads;
+//   * two CTAs per SM (256 TMEM columns, ~100 KB of shared memory each): 256 row tiles of a 32-cloud batch are one wave.
+// ------------------------------------------------------------------------------------------------
+constexpr int U_THREADS = 96 + 256;   // warp 0: node-matrix tiles, warp 1: MMA, warp 2: L tiles, warps 3..10 workers
+constexpr int U_NB = 2, U_NS = 2, U_NA = 2;
+constexpr int U_CTAS = 2, U_TMEM = 256;   // measured at C3 (32 x 1024 points, F = 128): 71 us per product; one CTA per SM with
+                                          // 4 / 4 / 3-deep rings and 512 TMEM columns: 93 us (256 tiles are then two waves)
+constexpr int U_SMEM = U_NB * 2 * B_BYTES + U_NS * A_BYTES + 256 + 1024;
+
+__device__ __forceinline__ void umma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const float v[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};\n" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])),
+      "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])),
+      "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])), "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])),
+      "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])), "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t a) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];\n" : "=f"(v) : "r"(a) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(U_THREADS, U_CTAS)
+grouped_tcu_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_constant__ CUtensorMap tmL, GroupedArgs p, int n) {
+  const int g = p.tile_graph[blockIdx.x], m0 = p.tile_row[blockIdx.x];
+  if (m0 & (TM - 1)) return;  // the plan lists 64-row tiles: every even one starts a 128-row tile of this kernel
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(base);
+  const uint32_t b_ring = sbase, s_ring = sbase + U_NB * 2 * B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + U_NB * 2 * B_BYTES + U_NS * A_BYTES);
+  uint64_t* b_full = bars;         // [NB] node-matrix tile landed (TMA)
+  uint64_t* b_split = bars + 4;    // [NB] ... and split in place by the 8 worker warps
+  uint64_t* b_empty = bars + 8;    // [NB] the MMAs that read it retired
+  uint64_t* s_full = bars + 12;    // [NS] raw L tile landed (TMA)
+  uint64_t* s_empty = bars + 16;   // [NS] the 8 worker warps have read it
+  uint64_t* a_full = bars + 20;    // [NA] operand slot in tensor memory written
+  uint64_t* a_empty = bars + 24;   // [NA] the MMAs that read the slot retired
+  uint64_t* out_bar = bars + 28;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = (long long)g * n;   // equal-size graphs: node_off[g] = g n, lap_off[g] = g n^2
+  const int F = p.F;
+  const int f0 = blockIdx.y * BN;
+  const int b_boxes = min(BN / 32, (F - f0 + 31) / 32);
+  const int nmma = 32 * b_boxes;
+  const int num_kb = n / BK;
+  constexpr int A_COL0 = 128;   // operand slots behind the accumulator: slot s = [hi 32 | lo 32] columns
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_split[s], 8);
+      mbar_init(&b_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 8);
+      mbar_init(&a_full[s], 8);
+      mbar_init(&a_empty[s], 1);
+    }
+    mbar_init(out_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(tmem_slot)), "n"(U_TMEM) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int slot = kb % U_NB, u = kb / U_NB;
+        if (u > 0) mbar_wait(&b_empty[slot], (uint32_t)((u - 1) & 1));
+        const uint32_t sb = b_ring + slot * 2 * B_BYTES;
+        mbar_expect_tx(&b_full[slot], b_boxes * 4096);
+        for (int b = 0; b < b_boxes; ++b)
+          tma_load_2d(sb + b * 4096, &tmIn, &b_full[slot], f0 + 32 * b, (int)(row0 + (long long)kb * BK));
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int slot = kb % U_NS, u = kb / U_NS;
+        if (u > 0) mbar_wait(&s_empty[slot], (uint32_t)((u - 1) & 1));
+        mbar_expect_tx(&s_full[slot], A_BYTES);
+        if (!p.transL)   // rows m0.. of L_g, columns of the k-block
+          tma_load_2d(s_ring + slot * A_BYTES, &tmL, &s_full[slot], kb * BK, (int)(row0 + m0));
+        else             // rows of the k-block of L_g, columns m0..: read column-wise by the workers
+          tma_load_2d(s_ring + slot * A_BYTES, &tmL, &s_full[slot], m0, (int)(row0 + (long long)kb * BK));
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = f32, A = tf32 from tensor memory, B = tf32 MN-major, N = nmma, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 16) | ((uint32_t)(nmma >> 3) << 17) |
+                             ((uint32_t)(TM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int aslot = kb % U_NA, bslot = kb % U_NB;
+        mbar_wait(&a_full[aslot], (uint32_t)((kb / U_NA) & 1));
+        mbar_wait(&b_split[bslot], (uint32_t)((kb / U_NB) & 1));
+        tc_fence_after();
+        const uint32_t ta_hi = tmem_base + (uint32_t)(A_COL0 + aslot * 2 * BK), ta_lo = ta_hi + BK;
+        const uint32_t sb = b_ring + bslot * 2 * B_BYTES, sb_lo = sb + B_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t b_hi = make_desc_mn(sb + k * 1024), b_lo = make_desc_mn(sb_lo + k * 1024);
+          umma_ts(tmem_base, ta_lo + k * UMMA_K, b_hi, idesc, (kb | k) != 0);
+          umma_ts(tmem_base, ta_hi + k * UMMA_K, b_lo, idesc, 1);
+          umma_ts(tmem_base, ta_hi + k * UMMA_K, b_hi, idesc, 1);
+        }
+        umma_commit(&b_empty[bslot]);
+        umma_commit(&a_empty[aslot]);
+      }
+      umma_commit(out_bar);
+    }
+  } else {
+    const int wi = warp - 3, q = warp & 3, h = wi >> 2, r = q * 32 + lane;
+    const int wt = wi * 32 + lane;
+    uint32_t soff[4];
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) soff[gq] = (uint32_t)(r * 128 + (((4 * h + gq) ^ (r & 7)) << 4));
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int sslot = kb % U_NS, aslot = kb % U_NA, bslot = kb % U_NB;
+      // ---- A: staged raw L tile -> hi / lo halves of my 16 contraction columns in my TMEM lane
+      if (lane == 0) {
+        mbar_wait(&s_full[sslot], (uint32_t)((kb / U_NS) & 1));
+        if (kb >= U_NA) mbar_wait(&a_empty[aslot], (uint32_t)((kb / U_NA - 1) & 1));
+      }
+      __syncwarp();
+      const uint32_t st = s_ring + sslot * A_BYTES;
+      float x[16];
+      if (!p.transL) {
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) {
+          const float4 v = lds128(st + soff[gq]);
+          x[4 * gq] = v.x; x[4 * gq + 1] = v.y; x[4 * gq + 2] = v.z; x[4 * gq + 3] = v.w;
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) x[u] = lds32(st + (uint32_t)((16 * h + u) * (TM * 4) + r * 4));   // L[k0 + 16h + u][m0 + r]
+      }
+      float hi[16], lo[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u) {
+        hi[u] = tf32_hi(x[u]);
+        lo[u] = tf32_lo(x[u], hi[u]);
+      }
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(A_COL0 + aslot * 2 * BK + 16 * h);
+      tmem_st16(ta, hi);
+      tmem_st16(ta + BK, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[sslot]);
+        mbar_arrive(&a_full[aslot]);
+      }
+      // ---- B: split the landed node-matrix tile in place
+      mbar_wait(&b_full[bslot], (uint32_t)((kb / U_NB) & 1));   // every lane: the TMA bytes are read right below
+      const uint32_t sb = b_ring + bslot * 2 * B_BYTES + 16 * wt;
+      float4 y[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        y[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (wt + 256 * t < b_boxes * 256) y[t] = lds128(sb + 16 * 256 * t);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        if (wt + 256 * t < b_boxes * 256) {
+          float4 bh, bl;
+          bh.x = tf32_hi(y[t].x); bh.y = tf32_hi(y[t].y); bh.z = tf32_hi(y[t].z); bh.w = tf32_hi(y[t].w);
+          bl.x = tf32_lo(y[t].x, bh.x); bl.y = tf32_lo(y[t].y, bh.y); bl.z = tf32_lo(y[t].z, bh.z); bl.w = tf32_lo(y[t].w, bh.w);
+          sts128(sb + 16 * 256 * t, bh);
+          sts128(sb + 16 * 256 * t + B_BYTES, bl);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");  // generic-proxy writes -> tensor-core reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_split[bslot]);
+    }
+    // ---- epilogue
+    if (lane == 0) mbar_wait(out_bar, 0);
+    __syncwarp();
+    tc_fence_after();
+    __syncwarp();
+    asm volatile("bar.sync 1, 256;\n" ::: "memory");   // every worker is past its last tile before the rings are reused
+    const uint32_t stg = sbase + (uint32_t)(wi * (32 * 36 * 4));
+    for (int c0 = 32 * h; c0 < nmma; c0 += 64) {
+      float v[32];
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        sts128(stg + 4 * (lane * 36 + 4 * u), make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+      __syncwarp();
+      const int c = f0 + c0 + 4 * (lane & 7);
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        const int rr = 4 * t + (lane >> 3);
+        const int i = m0 + q * 32 + rr;
+        if (c >= F) continue;  // F % 4 == 0: a float4 is inside or outside as a whole
+        const float4 a4 = lds128(stg + 4 * (rr * 36 + 4 * (lane & 7)));
+        const long long o = (row0 + i) * F + c;
+        float4 r4 = make_float4(p.cmul * a4.x, p.cmul * a4.y, p.cmul * a4.z, p.cmul * a4.w);
+        if (p.add_identity) {  // (L + I) In = L In + In
+          const float4 xx = *reinterpret_cast<const float4*>(p.In + o);
+          r4.x = fmaf(p.cmul, xx.x, r4.x); r4.y = fmaf(p.cmul, xx.y, r4.y);
+          r4.z = fmaf(p.cmul, xx.z, r4.z); r4.w = fmaf(p.cmul, xx.w, r4.w);
+        }
+        if (p.Add) {
+          const float4 xx = *reinterpret_cast<const float4*>(p.Add + o);
+          r4.x += xx.x; r4.y += xx.y; r4.z += xx.z; r4.w += xx.w;
+        }
+        if (p.Sub) {
+          const float4 xx = *reinterpret_cast<const float4*>(p.Sub + o);
+          r4.x -= xx.x; r4.y -= xx.y; r4.z -= xx.z; r4.w -= xx.w;
+        }
+        if (p.RowScale) {
+          const float sc = p.RowScale[row0 + i];
+          const float4 xx = *reinterpret_cast<const float4*>(p.ScaleIn + o);
+          r4.x = fmaf(sc, xx.x, r4.x); r4.y = fmaf(sc, xx.y, r4.y); r4.z = fmaf(sc, xx.z, r4.z); r4.w = fmaf(sc, xx.w, r4.w);
+        }
+        *reinterpret_cast<float4*>(p.Out + o) = r4;
+        if (p.Out2) *reinterpret_cast<float4*>(p.Out2 + o) = r4;
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(tmem_base), "n"(U_TMEM) : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------
 // F <= 8: stream L once.  One CTA per 64-row tile, 8 warps.
 // ------------------------------------------------------------------------------------------------
 template <int FP>
@@ -568,11 +825,38 @@ int grouped_tc(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStrea
     set_error("cuTensorMapEncodeTiled (grouped_tc) failed with code " + std::to_string((int)r));
     return AGCN_ERR_CUDA;
   }
+  dim3 grid(tiles, (g.F + BN - 1) / BN);
+  // equal-size graphs with 128-row tiles that all exist and 16-byte aligned rows of L: TMA-staged L tiles, A in TMEM
+  const int un = plan->uniform_n;
+  if (un > 0 && un % TM == 0 && (reinterpret_cast<uintptr_t>(g.L) & 15) == 0 && tiles == plan->large_tiles &&
+      (long long)plan->B * un < (1ll << 31)) {
+    CUtensorMap mapL;
+    cuuint64_t ld[2] = {(cuuint64_t)un, (cuuint64_t)plan->B * un};
+    cuuint64_t ls[1] = {(cuuint64_t)un * sizeof(float)};
+    cuuint32_t lbox[2] = {32, 128};
+    if (g.transL) { lbox[0] = 128; lbox[1] = 32; }
+    r = fn(&mapL, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(g.L), ld, ls, lbox, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           g.transL ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      set_error("cuTensorMapEncodeTiled (grouped_tcu, L) failed with code " + std::to_string((int)r));
+      return AGCN_ERR_CUDA;
+    }
+    static std::once_flag once_u;
+    std::call_once(once_u, [] {
+      cudaFuncSetAttribute(grouped_tcu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM);
+    });
+    {
+      ProfScope prof("bt::grouped_tcu_kernel", st);
+      grouped_tcu_kernel<<<grid, U_THREADS, U_SMEM, st>>>(map, mapL, g, un);
+    }
+    AGCN_LAUNCH_CHECK();
+    return AGCN_OK;
+  }
   static std::once_flag once;
   std::call_once(once, [] {
     cudaFuncSetAttribute(grouped_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_TOTAL);
   });
-  dim3 grid(tiles, (g.F + BN - 1) / BN);
   {
     ProfScope prof("bt::grouped_tc_kernel", st);
     grouped_tc_kernel<<<grid, THREADS, SMEM_TOTAL, st>>>(map, g);

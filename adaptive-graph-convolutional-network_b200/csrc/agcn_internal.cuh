@@ -113,6 +113,7 @@ extern std::atomic<uint64_t> g_launches;
 
 struct agcn_plan {
   int32_t B = 0, Nmax = 0, max_n = 0;
+  int32_t uniform_n = 0;   // n when every graph of the batch has the same size (then node_off[g] = g n, lap_off[g] = g n^2), else 0
   int32_t cheb_small_max = AGCN_CHEB_SMALL_MAX;  // overridable with the environment variable of the same name
   int64_t R = 0;   // total nodes
   int64_t LL = 0;  // total n^2

@@ -358,6 +358,9 @@ int agcn_plan_create(const int32_t* n_nodes_host, int32_t B, int32_t Nmax, void*
   }
   p->R = p->node_off[B];
   p->LL = p->lap_off[B];
+  p->uniform_n = p->max_n;
+  for (int g = 0; g < B; ++g)
+    if (p->n[g] != p->max_n) p->uniform_n = 0;
   // largest first: long-running graphs are scheduled first (LPT)
   p->order.resize(B);
   std::iota(p->order.begin(), p->order.end(), 0);

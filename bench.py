@@ -649,6 +649,7 @@ def layer3_roofline(r, peaks, tf32_peak):
         "pt::pre_tile_kernel(fwd)": {"bytes": 4.0 * (K * R * F + R * Fo + K * F * Fo + Fo), "flops": 2.0 * R * K * F * Fo},
         # one Chebyshev product L T over the graphs above 144 nodes (point clouds)
         "bt::grouped_tc_kernel": {"bytes": 4.0 * (LL + 2 * R * F), "flops": 2.0 * LL * F},
+        "bt::grouped_tcu_kernel": {"bytes": 4.0 * (LL + 2 * R * F), "flops": 2.0 * LL * F},
     }
     rows = {}
     for k, v in table.items():
@@ -679,7 +680,7 @@ def layer3_roofline(r, peaks, tf32_peak):
                  "note": "layer 3 forward (F=128 -> Fo=128, K=3): SURVEY section 8d work over the sum of its kernels "
                          "(mid-size graphs run beside the tiles)"}
     w = work.get(name)
-    if name.startswith("bt::grouped_tc") or (w and w["flops"] / max(w["bytes"], 1.0) > tf32_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)):
+    if w is not None and (name.startswith("bt::grouped_tc") or w["flops"] / max(w["bytes"], 1.0) > tf32_peak * 1e12 / (peaks["hbm_gbs"] * 1e9)):
         ach = w["flops"] / (per * 1e-3) / 1e12
         return {"bound": "tensor", "kernel": name + ", layer 3 forward, whole-batch launch", "achieved": ach,
                 "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak, "traffic": traffic,

@@ -264,6 +264,30 @@ def test_nonsymmetric_laplacian_transpose_paths(F, Fo, K):
     print(compare(cu, orc, skip=("res_L", "res_W", "L_all")))
 
 
+@pytest.mark.parametrize("sizes,F,Fo,K,laplacian,metric_grad", [
+    ([256, 256, 256], 64, 32, 3, "reference_literal", "reference"),
+    ([384, 384], 128, 128, 2, "reference_literal", "reference"),     # two 128-column... one column block, 3 row tiles
+    ([256, 256], 160, 16, 3, "reference_literal", "reference"),      # two column blocks (128 + 32)
+    ([256, 256], 32, 32, 3, "paper", "full"),                        # dense L_all, dL, the RowScale product
+    ([1024], 16, 16, 2, "reference_literal", "reference")])
+def test_equal_size_graphs_take_the_uniform_tensor_core_products(sizes, F, Fo, K, laplacian, metric_grad):
+    """Batches of equal-size graphs with n % 128 == 0 (ModelNet40-shape point clouds) run their L T / L^T U products in
+    bt::grouped_tcu_kernel (TMA-staged L tiles, A operand in tensor memory).  A non-symmetric intrinsic matrix tells L
+    from L^T (forward recurrence against the reverse one)."""
+    Nmax = max(sizes)
+    X, _, n = make_batch(sizes, F, Nmax, seed=F + K)
+    X *= 0.5
+    L = _dense_laplacians(sizes, Nmax, seed=K + 3)
+    rng = np.random.default_rng(19)
+    for g, k in enumerate(sizes):
+        L[g, :k, :k] += (rng.standard_normal((k, k)) * 0.01).astype(np.float32)
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=F + 2, dtype=torch.float64)
+    cY = _cot((len(sizes), Nmax, Fo), 17)
+    orc = oracle_run(X, L, n, p, K, "SGC_LL", laplacian, metric_grad, cot_Y=cY, compute_similarity=(laplacian == "paper"))
+    cu = cuda_run(X, L, n, p, K, "SGC_LL", laplacian, metric_grad, cot_Y=cY, want_res=False)
+    print(sizes, compare(cu, orc, skip=("res_L", "res_W", "L_all")))
+
+
 @pytest.mark.parametrize("variant,laplacian,metric_grad,with_prev", [
     ("SGC_LL", "paper", "reference", False),
     ("SGC_LL", "paper", "full", False),
