@@ -828,8 +828,12 @@ int grouped_tc(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStrea
   dim3 grid(tiles, (g.F + BN - 1) / BN);
   // equal-size graphs with 128-row tiles that all exist and 16-byte aligned rows of L: TMA-staged L tiles, A in TMEM
   const int un = plan->uniform_n;
+  // ... when there are more 128-row CTAs than SMs (two of them share an SM and hide each other's latencies; with at most
+  // one per SM the deeper rings of grouped_tc_kernel win: N = 4096, B = 4 measured 0.91 against 0.70 ms per layer)
+  int sms = 148, dev = 0;
+  if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   if (un > 0 && un % TM == 0 && (reinterpret_cast<uintptr_t>(g.L) & 15) == 0 && tiles == plan->large_tiles &&
-      (long long)plan->B * un < (1ll << 31)) {
+      (long long)plan->B * un < (1ll << 31) && ((long long)(tiles / 2) * grid.y > sms || g.force_uniform)) {
     CUtensorMap mapL;
     cuuint64_t ld[2] = {(cuuint64_t)un, (cuuint64_t)plan->B * un};
     cuuint64_t ls[1] = {(cuuint64_t)un * sizeof(float)};

@@ -214,6 +214,11 @@ extern "C" int agcn_debug_grouped_product(const agcn_plan* plan, const float* d_
   switch (impl) {
     case 1: return grouped_simt(tiles, g, st);
     case 2: return grouped_tc(plan, tiles, g, st);
+    case 4:   // the equal-size-graph kernel whatever the grid size (errors out when the batch is not eligible)
+      g.force_uniform = 1;
+      AGCN_REQUIRE(plan->uniform_n > 0 && plan->uniform_n % 128 == 0 && grouped_tc_supported(g),
+                   "debug_grouped_product: impl 4 needs equal-size graphs with n % 128 == 0");
+      return grouped_tc(plan, tiles, g, st);
     case 3: return grouped_thin(tiles, g, st);
     default: return grouped_launch(plan, tiles, g, st);
   }

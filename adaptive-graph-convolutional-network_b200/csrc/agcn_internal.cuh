@@ -313,6 +313,7 @@ struct GroupedArgs {
   const float* RowScale;  // optional: Out += RowScale[row] * ScaleIn[row, c]
   const float* ScaleIn;
   unsigned long long* dbg;  // tuning aid: timeline of the first CTA of grouped_tc_kernel (NULL in production)
+  int force_uniform;        // tests: take bt::grouped_tcu_kernel whenever the batch is eligible, whatever the grid size
 };
 int grouped_launch(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStream_t st);
 int grouped_simt(int tiles, const GroupedArgs& g, cudaStream_t st);

@@ -130,7 +130,8 @@ int agcn_fused_debug_set(void* d_buf);
 /* Tuning / debugging aid (no reference counterpart): Out = cmul * op(L_g) In over the rows of every graph with more
  * than AGCN_CHEB_SMALL_MAX nodes (the row-tiled path; other rows of Out are not written), op = L (+I) or L^T (+I);
  * impl 0 = the library's own choice, 1 = SIMT kernel, 2 = tcgen05 kernel (F % 4 == 0, F >= 16), 3 = streaming kernel
- * (F <= 8).  tools/dbg_grouped.py compares the implementations block by block. */
+ * (F <= 8), 4 = the equal-size-graph tcgen05 kernel (n % 128 == 0 for every graph of the batch) whatever the grid size.
+ * tools/dbg_grouped.py compares the implementations block by block. */
 int agcn_debug_grouped_product(const agcn_plan* plan, const float* d_L /*packed*/, const float* d_In /*[R,F]*/,
                                float* d_Out /*[R,F]*/, int32_t F, int32_t transL, int32_t add_identity, float cmul,
                                int32_t impl, void* stream);

@@ -269,11 +269,12 @@ def test_nonsymmetric_laplacian_transpose_paths(F, Fo, K):
     ([384, 384], 128, 128, 2, "reference_literal", "reference"),     # two 128-column... one column block, 3 row tiles
     ([256, 256], 160, 16, 3, "reference_literal", "reference"),      # two column blocks (128 + 32)
     ([256, 256], 32, 32, 3, "paper", "full"),                        # dense L_all, dL, the RowScale product
-    ([1024], 16, 16, 2, "reference_literal", "reference")])
-def test_equal_size_graphs_take_the_uniform_tensor_core_products(sizes, F, Fo, K, laplacian, metric_grad):
-    """Batches of equal-size graphs with n % 128 == 0 (ModelNet40-shape point clouds) run their L T / L^T U products in
-    bt::grouped_tcu_kernel (TMA-staged L tiles, A operand in tensor memory).  A non-symmetric intrinsic matrix tells L
-    from L^T (forward recurrence against the reverse one)."""
+    ([1024], 16, 16, 2, "reference_literal", "reference"),
+    ([1024] * 19, 32, 16, 2, "reference_literal", "reference")])     # 152 row tiles > 148 SMs: bt::grouped_tcu_kernel
+def test_equal_size_graphs_row_tiled_products(sizes, F, Fo, K, laplacian, metric_grad):
+    """Batches of equal-size graphs with n % 128 == 0 (ModelNet40-shape point clouds), whole layer forward + backward.
+    A non-symmetric intrinsic matrix tells L from L^T (forward recurrence against the reverse one).  (Grids above one
+    CTA per SM take bt::grouped_tcu_kernel: the 19-cloud case below and test_uniform_tensor_core_product.)"""
     Nmax = max(sizes)
     X, _, n = make_batch(sizes, F, Nmax, seed=F + K)
     X *= 0.5
@@ -428,3 +429,36 @@ def test_head_loss_and_gradients_match_oracle(Fh, Fm, Nt, kind):
     assert O.rel_err(Hc.grad.cpu(), Hr.grad) <= TOL
     for a, b, name in zip(pc, pr, ("dense_W", "dense_b", "head_W", "head_b")):
         assert O.rel_err(a.grad.cpu(), b.grad) <= TOL, name
+
+
+@pytest.mark.parametrize("sizes,F", [([256, 256, 256], 64), ([384, 384], 160), ([256], 16), ([1024, 1024], 128)])
+def test_uniform_tensor_core_product(sizes, F):
+    """bt::grouped_tcu_kernel (TMA-staged L tiles, A operand in tensor memory, equal-size graphs) forced through the
+    debug entry, every op(L) variant, against a float64 product on the device."""
+    import ctypes
+    import agcn_b200
+    from agcn_b200 import _lib
+    from agcn_b200.batch import _ptr, _stream_ptr
+    dev = torch.device("cuda:0")
+    gen = torch.Generator(device=dev).manual_seed(5)
+    batch = agcn_b200.GraphBatch(sizes, max(sizes), device=dev)
+    R = batch.total_nodes
+    L = torch.randn(batch.total_lap, device=dev, generator=gen) * 0.1
+    X = torch.randn(R, F, device=dev, generator=gen)
+    for transL in (0, 1):
+        for add_identity in (0, 1):
+            ref = torch.zeros(R, F, device=dev, dtype=torch.float64)
+            for g, n in enumerate(sizes):
+                Lg = batch.lap_view(L, g).double()
+                Lg = Lg.t() if transL else Lg
+                if add_identity:
+                    Lg = Lg + torch.eye(n, device=dev, dtype=torch.float64)
+                r0 = int(batch.node_off[g])
+                ref[r0:r0 + n] = 2.0 * (Lg @ X[r0:r0 + n].double())
+            out = torch.full((R, F), float("nan"), device=dev)
+            _lib.check(_lib.lib().agcn_debug_grouped_product(batch.handle, _ptr(L), _ptr(X), _ptr(out), F, transL,
+                                                             add_identity, 2.0, 4, _stream_ptr()))
+            torch.cuda.synchronize()
+            assert torch.isfinite(out).all()
+            err = float((out.double() - ref).abs().max() / ref.abs().max())
+            assert err <= 1e-5, (sizes, F, transL, add_identity, err)
