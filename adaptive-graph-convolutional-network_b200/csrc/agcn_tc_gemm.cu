@@ -97,19 +97,21 @@ struct Args {
   float* loss_part;  // [CTAs][4]
 };
 
-template <int BN>
+// ST = 0: as many stages as one CTA per SM affords; ST = 2: two stages, so that TWO CTAs share an SM (wide, short
+// contractions with fewer 128-column tiles than SMs: the multitask logits)
+template <int BN, int ST = 0>
 struct Smem {
   static constexpr int B_TILE_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;
-  static constexpr int STAGES = (BN <= 64) ? 4 : 3;
+  static constexpr int STAGES = ST > 0 ? ST : ((BN <= 64) ? 4 : 3);
   static constexpr int TOTAL = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-template <int BN>
-__global__ void __launch_bounds__(192, 1)
+template <int BN, int ST = 0>
+__global__ void __launch_bounds__(192, ST == 2 ? 2 : 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmBhi, const __grid_constant__ CUtensorMap tmBlo, Args p) {
-  using SM = Smem<BN>;
+  using SM = Smem<BN, ST>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = reinterpret_cast<uint64_t*>(base + SM::STAGES * SM::STAGE_BYTES);
@@ -649,8 +651,18 @@ bool tc_gemm_supported(const GemmArgs& a) {
   return true;
 }
 
+// The fused-loss logits product (M = batch, N = 2 n_tasks) has fewer 128-column tiles than SMs and a long epilogue per
+// tile: 64-column tiles, two stages, two CTAs per SM put twice as many CTAs to work at once
+// (ToxCast head, 1024 x 1234 x 256: 55 us with 80 CTAs of 128 columns).
+static bool tc_gemm_narrow2(const GemmArgs& a) {
+  const int Npad = tc_npad(a.N);
+  if (!a.bce_y || Npad <= 64) return false;
+  const int tiles128 = ((a.M + tc::BM - 1) / tc::BM) * a.Z * (Npad / 128);
+  return tiles128 < 148;
+}
+
 int tc_gemm_loss_parts(const GemmArgs& a) {
-  const int Npad = tc_npad(a.N), BN = Npad <= 64 ? 64 : 128;
+  const int Npad = tc_npad(a.N), BN = (Npad <= 64 || tc_gemm_narrow2(a)) ? 64 : 128;
   return 4 * ((a.M + tc::BM - 1) / tc::BM) * a.Z * (Npad / BN);
 }
 
@@ -690,7 +702,8 @@ int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
   } else {
     mA1 = mA0;
   }
-  const int BN = Npad <= 64 ? 64 : 128;
+  const bool narrow2 = tc_gemm_narrow2(a);
+  const int BN = (Npad <= 64 || narrow2) ? 64 : 128;
   if ((rc = make_map(&mBhi, Bhi, (uint64_t)slices * Npad, (uint64_t)a.Kd, (uint64_t)Kp, BN))) return rc;
   if ((rc = make_map(&mBlo, Blo, (uint64_t)slices * Npad, (uint64_t)a.Kd, (uint64_t)Kp, BN))) return rc;
   Args p;
@@ -698,7 +711,7 @@ int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
   p.kb_per_slice = (a.Kd + BK - 1) / BK;
   const int total_kb = a.S * p.kb_per_slice;
   // split-K for long contractions with few output tiles (plain outputs only): partial sums + one reduction
-  const int out_tiles = ((a.M + BM - 1) / BM) * a.Z * (Npad / (Npad <= 64 ? 64 : 128));
+  const int out_tiles = ((a.M + BM - 1) / BM) * a.Z * (Npad / BN);
   int ksplit = 1;
   if (a.split_k_partial && !a.bias && !a.scale && a.act == AGCN_ACT_LINEAR && !a.accumulate && !a.bce_y && a.ldc == a.N && a.Z == 1 &&
       total_kb >= 16 && out_tiles < 74)
@@ -719,7 +732,16 @@ int tc_gemm(const GemmArgs& a, const float* scratch, cudaStream_t st) {
   p.bce_ld = a.bce_ld > 0 ? a.bce_ld : a.ldc;
   dim3 grid((a.M + BM - 1) / BM, a.Z * ksplit, Npad / BN);
   static std::once_flag once64, once128;
-  if (BN == 64) {
+  if (narrow2) {
+    static std::once_flag once642;
+    std::call_once(once642, [] {
+      cudaFuncSetAttribute(tc_gemm_kernel<64, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64, 2>::TOTAL);
+    });
+    {
+      ProfScope prof("tc::tc_gemm_kernel", st);
+      tc_gemm_kernel<64, 2><<<grid, 192, Smem<64, 2>::TOTAL, st>>>(mA0, mA1, mBhi, mBlo, p);
+    }
+  } else if (BN == 64) {
     std::call_once(once64, [] {
       cudaFuncSetAttribute(tc_gemm_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<64>::TOTAL);
     });
