@@ -5,5 +5,5 @@ mkdir -p gpurun_out
 B="python bench.py --steps 2 --warmup 3 --skip-cpu --no-graph --no-paper --no-configs"
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/r02_launches_c2.csv $B > gpurun_out/r02_ncu_launches.log 2>&1
 timeout 500 ncu --set full --clock-control none --import-source on -k regex:"cheb_tile_fwd_kernel|rows_gemm_kernel|tc_gemm_tn_kernel" -s 30 -c 12 -f -o gpurun_out/r02_ncu_full_c2 $B > gpurun_out/r02_ncu_full_c2.log 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"grouped_tc_kernel|rows_gemm_kernel" -s 30 -c 4 -f -o gpurun_out/r02_ncu_full_c3 python bench.py --workload C3 --steps 2 --warmup 3 --skip-cpu --no-graph --no-paper --no-configs > gpurun_out/r02_ncu_full_c3.log 2>&1
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"grouped_tc|rows_gemm_kernel" -s 30 -c 6 -f -o gpurun_out/r02_ncu_full_c3 python bench.py --workload C3 --steps 2 --warmup 3 --skip-cpu --no-graph --no-paper --no-configs > gpurun_out/r02_ncu_full_c3.log 2>&1
 ls -la gpurun_out | grep r02_
