@@ -93,7 +93,7 @@ __global__ void pack_lap_kernel(const float* __restrict__ padded, float* __restr
 // contraction CTAs per SM): a 1024-thread pack CTA takes half an SM's registers and thread slots away from them, so the
 // pack grid stays on a few SMs.  Measured on the pipelined ToxCast loop (round 2, bench.py e2e): 24 CTAs 0.926 ms per
 // step, 8 CTAs 0.895 ms, 4 CTAs 1.018 ms (then the PCIe reads themselves -- ~1.5 us each, 32 warps per CTA in flight --
-// no longer finish within one step).
+// no longer finish within one step); 32 CTAs of 256 threads (a quarter of an SM each) 0.958 ms.
 __device__ __forceinline__ int graph_of_row(const int32_t* __restrict__ node_off, int B, int r) {
   int lo = 0, hi = B;   // node_off[lo] <= r < node_off[hi]
   while (hi - lo > 1) {
