@@ -660,6 +660,358 @@ grouped_tcu_kernel(const __grid_constant__ CUtensorMap tmIn, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// pair_tcu_kernel: 128 x 128 tiles of the n x n PAIR matrices of big equal-size graphs on the tensor cores (the learned
+// metric of graphconv.py:163-209 and its gradient; north_star item 1):
+//
+//   SIM   gram_ij = <xw_i, xw_j>  ->  dist_ij = sqrt(|xw_i|^2 + |xw_j|^2 - 2 gram_ij),  W_ij = exp(-dist_ij), W_ii = 0,
+//         row sums of W per 64-column block (the degree vector)                              graphconv.py:171-178,195
+//   DL    dL_ij = dLall_in_ij + sum_{s} c_s <U_s[i, :], T_{s-1}[j, :]>                        (reverse mode of :231-234)
+//
+// Both operands are K-major row panels of node matrices ([128 nodes x 32 features], raw fp32 by TMA): the i panel is
+// split into hi / lo TF32 halves into an operand slot in tensor memory, the j panel in place in shared memory (3xTF32).
+// SIM: the Gram expansion cancels for near-duplicate rows: an entry whose Gram error (~1e-6 of the norms)
+// would move W = exp(-dist) or the metric gradient by more than 1e-5 is recomputed from direct differences in fp32 --
+// the nearest neighbours of a point; far pairs (W ~ 0) never are.  The SIMT kernel this replaces (big_pair_kernel, 64 x 64 tiles of direct
+// differences / FMAs) took 290 us (SIM) and 410 us (DL) per layer at 32 x 1024 points, F = 128.
+// ------------------------------------------------------------------------------------------------
+struct PairTcArgs {
+  const int32_t* tile_graph;
+  const int32_t* tile_row;
+  int n, R, F, S, mode;          // mode 0 = SIM, 1 = DL; S = slices summed (SIM: 1)
+  const float* dL_in;            // DL, optional
+  float* out;                    // DL: dL
+  const float* XW;               // SIM: the node matrix itself (fix-up) ...
+  const float* mu;               //      [B][F] per-graph mean row: the Gram runs on CENTERED rows (distances do not change,
+                                 //      the norms shrink to the spread of the cloud, so the expansion cancels far less)
+  const float* norms;            //      |xw_i - mu|^2 per packed row
+  float* dist;                   //      optional
+  float* resW;                   //      optional
+  float* rowpart;                //      optional [R][ncb] row sums of W per 64-column block
+  int ncb;
+  int nofix;                     //      A/B builds only: skip the direct-difference fix-up (timing experiment)
+};
+
+__global__ void __launch_bounds__(U_THREADS, 2)
+pair_tcu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
+                const __grid_constant__ CUtensorMap tmB1, PairTcArgs p) {
+  const int g = p.tile_graph[blockIdx.x], m0 = p.tile_row[blockIdx.x];
+  if (m0 & (TM - 1)) return;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* base = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  const uint32_t sbase = smem_u32(base);
+  const uint32_t b_ring = sbase, s_ring = sbase + U_NB * 2 * B_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + U_NB * 2 * B_BYTES + U_NS * A_BYTES);
+  uint64_t* b_full = bars;
+  uint64_t* b_split = bars + 4;
+  uint64_t* b_empty = bars + 8;
+  uint64_t* s_full = bars + 12;
+  uint64_t* s_empty = bars + 16;
+  uint64_t* a_full = bars + 20;
+  uint64_t* a_empty = bars + 24;
+  uint64_t* out_bar = bars + 28;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 29);
+  const uint32_t s_mu = sbase + U_NB * 2 * B_BYTES + U_NS * A_BYTES + 256;   // F floats (SIM)
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = p.n, F = p.F, nc = F / BK;
+  const long long row0 = (long long)g * n;
+  const int j0 = blockIdx.y * TM;
+  const int num_kb = p.S * nc;
+  constexpr int A_COL0 = 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&b_full[s], 1);
+      mbar_init(&b_split[s], 8);
+      mbar_init(&b_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_empty[s], 8);
+      mbar_init(&a_full[s], 8);
+      mbar_init(&a_empty[s], 1);
+    }
+    mbar_init(out_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" ::"r"(smem_u32(tmem_slot)) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
+  }
+  for (int f = threadIdx.x; f < F; f += blockDim.x) sts32(s_mu + 4 * f, (!p.mode && p.mu) ? __ldg(p.mu + (long long)g * F + f) : 0.f);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {   // j panel: B_s = XW (SIM) | s == 0 ? X : T_s (DL)
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int slot = kb % U_NB, u = kb / U_NB;
+        if (u > 0) mbar_wait(&b_empty[slot], (uint32_t)((u - 1) & 1));
+        const int s = kb / nc, c = kb - s * nc;
+        mbar_expect_tx(&b_full[slot], A_BYTES);
+        if (s == 0)
+          tma_load_2d(b_ring + slot * 2 * B_BYTES, &tmB0, &b_full[slot], c * BK, (int)(row0 + j0));
+        else
+          tma_load_2d(b_ring + slot * 2 * B_BYTES, &tmB1, &b_full[slot], c * BK, (int)((long long)(s - 1) * p.R + row0 + j0));
+      }
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {   // i panel: A_s = XW (SIM) | U_{s+1} (DL: slice s + 1 of the G buffer)
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int slot = kb % U_NS, u = kb / U_NS;
+        if (u > 0) mbar_wait(&s_empty[slot], (uint32_t)((u - 1) & 1));
+        const int s = kb / nc, c = kb - s * nc;
+        const long long arow = (p.mode ? (long long)(s + 1) * p.R : 0) + row0 + m0;
+        mbar_expect_tx(&s_full[slot], A_BYTES);
+        tma_load_2d(s_ring + slot * A_BYTES, &tmA, &s_full[slot], c * BK, (int)arow);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // D = f32, A = tf32 from tensor memory, B = tf32 K-major, N = 128, M = 128
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TM >> 3) << 17) | ((uint32_t)(TM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; ++kb) {
+        const int aslot = kb % U_NA, bslot = kb % U_NB;
+        mbar_wait(&a_full[aslot], (uint32_t)((kb / U_NA) & 1));
+        mbar_wait(&b_split[bslot], (uint32_t)((kb / U_NB) & 1));
+        tc_fence_after();
+        const uint32_t ta_hi = tmem_base + (uint32_t)(A_COL0 + aslot * 2 * BK), ta_lo = ta_hi + BK;
+        const uint32_t sb = b_ring + bslot * 2 * B_BYTES, sb_lo = sb + B_BYTES;
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          const uint64_t b_hi = make_desc_k(sb + k * UMMA_K * 4), b_lo = make_desc_k(sb_lo + k * UMMA_K * 4);
+          umma_ts(tmem_base, ta_lo + k * UMMA_K, b_hi, idesc, (kb | k) != 0);
+          umma_ts(tmem_base, ta_hi + k * UMMA_K, b_lo, idesc, 1);
+          umma_ts(tmem_base, ta_hi + k * UMMA_K, b_hi, idesc, 1);
+        }
+        umma_commit(&b_empty[bslot]);
+        umma_commit(&a_empty[aslot]);
+      }
+      umma_commit(out_bar);
+    }
+  } else {
+    const int wi = warp - 3, q = warp & 3, h = wi >> 2, r = q * 32 + lane;
+    const int wt = wi * 32 + lane;
+    uint32_t soff[4];
+#pragma unroll
+    for (int gq = 0; gq < 4; ++gq) soff[gq] = (uint32_t)(r * 128 + (((4 * h + gq) ^ (r & 7)) << 4));
+    for (int kb = 0; kb < num_kb; ++kb) {
+      const int sslot = kb % U_NS, aslot = kb % U_NA, bslot = kb % U_NB;
+      const float coef = (p.mode && kb / nc + 1 >= 2) ? 2.f : 1.f;   // c_1 = 1, c_k = 2 (DL)
+      if (lane == 0) {
+        mbar_wait(&s_full[sslot], (uint32_t)((kb / U_NS) & 1));
+        if (kb >= U_NA) mbar_wait(&a_empty[aslot], (uint32_t)((kb / U_NA - 1) & 1));
+      }
+      __syncwarp();
+      const uint32_t st = s_ring + sslot * A_BYTES;
+      const int fc = (kb - (kb / nc) * nc) * BK;   // first feature column of this k-block
+      float hi[16], lo[16];
+#pragma unroll
+      for (int gq = 0; gq < 4; ++gq) {
+        const float4 v = lds128(st + soff[gq]);
+        const float4 m4 = lds128(s_mu + 4 * (fc + 16 * h + 4 * gq));   // zeros in DL mode
+        const float x[4] = {coef * (v.x - m4.x), coef * (v.y - m4.y), coef * (v.z - m4.z), coef * (v.w - m4.w)};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          hi[4 * gq + e] = tf32_hi(x[e]);
+          lo[4 * gq + e] = tf32_lo(x[e], hi[4 * gq + e]);
+        }
+      }
+      const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(A_COL0 + aslot * 2 * BK + 16 * h);
+      tmem_st16(ta, hi);
+      tmem_st16(ta + BK, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;\n" ::: "memory");
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&s_empty[sslot]);
+        mbar_arrive(&a_full[aslot]);
+      }
+      // j panel: split in place (the swizzled K-major layout is the same for the raw tile and both halves)
+      mbar_wait(&b_full[bslot], (uint32_t)((kb / U_NB) & 1));
+      const uint32_t sb = b_ring + bslot * 2 * B_BYTES + 16 * wt;
+      float4 y[4];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        y[t] = lds128(sb + 16 * 256 * t);
+        // 16-byte slot idx of the swizzled tile: row idx / 8, logical chunk (idx % 8) ^ (row % 8)
+        const int idx = wt + 256 * t, brow = idx >> 3, chunk = (idx & 7) ^ (brow & 7);
+        const float4 m4 = lds128(s_mu + 4 * (fc + 4 * chunk));
+        y[t].x -= m4.x; y[t].y -= m4.y; y[t].z -= m4.z; y[t].w -= m4.w;
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float4 bh, bl;
+        bh.x = tf32_hi(y[t].x); bh.y = tf32_hi(y[t].y); bh.z = tf32_hi(y[t].z); bh.w = tf32_hi(y[t].w);
+        bl.x = tf32_lo(y[t].x, bh.x); bl.y = tf32_lo(y[t].y, bh.y); bl.z = tf32_lo(y[t].z, bh.z); bl.w = tf32_lo(y[t].w, bh.w);
+        sts128(sb + 16 * 256 * t, bh);
+        sts128(sb + 16 * 256 * t + B_BYTES, bl);
+      }
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&b_split[bslot]);
+    }
+    // ---- epilogue: my row i = m0 + r, my 64 columns j0 + 64 h ..
+    if (lane == 0) mbar_wait(out_bar, 0);
+    __syncwarp();
+    tc_fence_after();
+    const int i = m0 + r;
+    if (p.mode) {
+      // every accumulator is complete: the rings are free.  Rows of 32 values go through a 32 x 36 block per warp so
+      // that dL_in is read and dL written as whole 128-byte row segments
+      const uint32_t stg = sbase + 1024 + (uint32_t)(wi * (32 * 36 * 4));
+      for (int cb = 0; cb < 2; ++cb) {
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 * h + 32 * cb), v);
+        const long long tile0 = (long long)g * n * n + (long long)(m0 + q * 32) * n + j0 + 64 * h + 32 * cb;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          sts128(stg + 4 * (lane * 36 + 4 * u), make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+        __syncwarp();
+        float4 a4[8];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const long long o = tile0 + (long long)(4 * t + (lane >> 3)) * n + 4 * (lane & 7);
+          a4[t] = p.dL_in ? __ldg(reinterpret_cast<const float4*>(p.dL_in + o)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int rr = 4 * t + (lane >> 3);
+          float4 o = lds128(stg + 4 * (rr * 36 + 4 * (lane & 7)));
+          o.x += a4[t].x; o.y += a4[t].y; o.z += a4[t].z; o.w += a4[t].w;
+          *reinterpret_cast<float4*>(p.out + tile0 + (long long)rr * n + 4 * (lane & 7)) = o;
+        }
+        __syncwarp();
+      }
+    } else {
+      // every accumulator is complete: the rings are free.  Norms of the j tile and a 32 x 36 transposition buffer per warp
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      const uint32_t s_nj = sbase;                                        // 128 floats
+      const uint32_t stg = sbase + 1024 + (uint32_t)(wi * (32 * 36 * 4));   // my warp's staging block
+      if (wt < TM) sts32(s_nj + 4 * wt, __ldg(p.norms + row0 + j0 + wt));
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
+      const float ni = __ldg(p.norms + row0 + i);
+      float rs[8];
+#pragma unroll
+      for (int t = 0; t < 8; ++t) rs[t] = 0.f;
+      for (int cb = 0; cb < 2; ++cb) {
+        // pass A (my row i, 32 columns): squared distances from the Gram into the staging block, and which of them the
+        // Gram cannot be trusted for
+        float v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 * h + 32 * cb), v);
+        const int jb = 64 * h + 32 * cb;
+        unsigned flagged = 0u;
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+          const float nj = lds32(s_nj + 4 * (jb + u));
+          const float d2 = fmaxf(ni + nj - 2.f * v[u], 0.f);
+          // The 3xTF32 Gram leaves ~1e-6 (|xw_i|^2 + |xw_j|^2) of absolute error in d2.  It matters where it moves
+          // W = exp(-d) (|dW| = W dd) or the metric gradient (~ W dd / d) by more than 1e-5: near-duplicates against the
+          // (centred) norms.  Far pairs (W ~ 0) never are.
+          const float dg = sqrtf(d2);
+          if (i != j0 + jb + u && __expf(-dg) * (ni + nj) > 20.f * fminf(dg, d2)) flagged |= 1u << u;
+          v[u] = d2;
+        }
+        if (p.nofix) flagged = 0u;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+          sts128(stg + 4 * (lane * 36 + 4 * u), make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]));
+        __syncwarp();
+        // fix-up: flagged entries are recomputed from direct differences, the warp working together on one entry at a
+        // time (lanes stride over the features), and patched in the staging block
+        unsigned cols = __reduce_or_sync(0xffffffffu, flagged);
+        while (cols) {
+          const int u = __ffs(cols) - 1;
+          cols &= cols - 1;
+          const float* xj = p.XW + (row0 + j0 + jb + u) * (long long)F;
+          unsigned todo = __ballot_sync(0xffffffffu, (flagged >> u) & 1u);
+          while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const float* xs = p.XW + (row0 + m0 + q * 32 + src) * (long long)F;
+            float acc = 0.f;
+            for (int f = lane; f < F; f += 32) {
+              const float df = __ldg(xs + f) - __ldg(xj + f);
+              acc = fmaf(df, df, acc);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) sts32(stg + 4 * (src * 36 + u), acc);
+          }
+        }
+        __syncwarp();
+        // pass B, in the layout of the stores: lane holds row 4 t + lane / 8, columns 4 (lane & 7) ..
+        const long long tile0 = (long long)g * n * n + (long long)(m0 + q * 32) * n + j0 + jb;
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          const int rr = 4 * t + (lane >> 3), c4 = 4 * (lane & 7);
+          const float4 q2 = lds128(stg + 4 * (rr * 36 + c4));
+          const int dj = (m0 + q * 32 + rr) - (j0 + jb + c4);   // the diagonal entry of this quad, if 0 <= dj < 4
+          float4 d, w;
+          d.x = dj == 0 ? 0.f : sqrtf(q2.x); w.x = dj == 0 ? 0.f : expf(-d.x);
+          d.y = dj == 1 ? 0.f : sqrtf(q2.y); w.y = dj == 1 ? 0.f : expf(-d.y);
+          d.z = dj == 2 ? 0.f : sqrtf(q2.z); w.z = dj == 2 ? 0.f : expf(-d.z);
+          d.w = dj == 3 ? 0.f : sqrtf(q2.w); w.w = dj == 3 ? 0.f : expf(-d.w);
+          rs[t] += (w.x + w.y) + (w.z + w.w);
+          const long long o = tile0 + (long long)rr * n + c4;
+          if (p.dist) *reinterpret_cast<float4*>(p.dist + o) = d;
+          if (p.resW) *reinterpret_cast<float4*>(p.resW + o) = w;
+        }
+        __syncwarp();
+      }
+      if (p.rowpart) {
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+          float r8 = rs[t];
+          r8 += __shfl_xor_sync(0xffffffffu, r8, 1);
+          r8 += __shfl_xor_sync(0xffffffffu, r8, 2);
+          r8 += __shfl_xor_sync(0xffffffffu, r8, 4);
+          if ((lane & 7) == 0) p.rowpart[(row0 + m0 + q * 32 + 4 * t + (lane >> 3)) * p.ncb + (j0 / 64 + h)] = r8;
+        }
+      }
+
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;\n" ::"r"(tmem_base) : "memory");
+}
+
+// mu[g][f] = mean over the n rows of graph g (equal-size graphs: rows g n ..): grid (B, F / 32), block (32, 8)
+__global__ void graph_mean_kernel(const float* __restrict__ X, int n, int F, float* __restrict__ mu) {
+  __shared__ float red[8][33];
+  const int g = blockIdx.x, f = blockIdx.y * 32 + threadIdx.x;
+  float s = 0.f;
+  if (f < F)
+    for (int r = threadIdx.y; r < n; r += 8) s += X[((long long)g * n + r) * F + f];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && f < F) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+    mu[(long long)g * F + f] = t / (float)n;
+  }
+}
+
+// |x_r - mu_g|^2 per packed row: one warp per row
+__global__ void row_norms_kernel(const float* __restrict__ X, const float* __restrict__ mu, int n, long long R, int F,
+                                 float* __restrict__ norms) {
+  const long long r = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const float* m = mu + (r / n) * F;
+  float s = 0.f;
+  for (int f = lane; f < F; f += 32) {
+    const float v = X[r * F + f] - m[f];
+    s = fmaf(v, v, s);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) norms[r] = s;
+}
+
+// ------------------------------------------------------------------------------------------------
 // F <= 8: stream L once.  One CTA per 64-row tile, 8 warps.
 // ------------------------------------------------------------------------------------------------
 template <int FP>
@@ -867,6 +1219,86 @@ int grouped_tc(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStrea
   }
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
+}
+
+// ---- pair matrices of big equal-size graphs on the tensor cores (see pair_tcu_kernel)
+bool pair_tc_supported(const agcn_plan* plan, int F) {
+  static const bool off = ab_env("AGCN_DISABLE_TCGEN05") != nullptr;
+  const int un = plan->uniform_n;
+  return !off && big_paths_on() && un > 0 && un % bt::TM == 0 && F % bt::BK == 0 && F >= bt::BK && F <= 256 && plan->big_tiles == plan->large_tiles &&
+         plan->big_tiles > 0 && (long long)plan->B * un * 8 < (1ll << 31);
+}
+
+static int pair_map(CUtensorMap* map, const float* ptr, uint64_t rows, int F) {
+  using namespace bt;
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return AGCN_ERR_CUDA;
+  }
+  cuuint64_t gdim[2] = {(cuuint64_t)F, rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)F * sizeof(float)};
+  cuuint32_t box[2] = {32, 128};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(ptr), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (pair_tc) failed with code " + std::to_string((int)r));
+    return AGCN_ERR_CUDA;
+  }
+  return AGCN_OK;
+}
+
+static int pair_launch(const agcn_plan* plan, const CUtensorMap& mA, const CUtensorMap& mB0, const CUtensorMap& mB1,
+                       bt::PairTcArgs& k, const char* name, cudaStream_t st) {
+  using namespace bt;
+  k.tile_graph = plan->d_tile_graph; k.tile_row = plan->d_tile_row;
+  k.n = plan->uniform_n; k.R = (int)plan->R;
+  static std::once_flag once;
+  constexpr int P_SMEM = U_SMEM + 1024;   // + the graph's mean row
+  std::call_once(once, [] { cudaFuncSetAttribute(pair_tcu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM + 1024); });
+  dim3 grid(plan->big_tiles, plan->uniform_n / TM);
+  {
+    ProfScope prof(name, st);
+    pair_tcu_kernel<<<grid, U_THREADS, P_SMEM, st>>>(mA, mB0, mB1, k);
+  }
+  AGCN_LAUNCH_CHECK();
+  return AGCN_OK;
+}
+
+// SIM: dist / resW / rowpart of every big graph from XW [R, F]; norms: scratch of R + 64 + B F floats
+int pair_tc_similarity(const agcn_plan* plan, const float* XW, int F, float* norms, float* dist, float* resW, float* rowpart,
+                       int ncb, cudaStream_t st) {
+  using namespace bt;
+  float* mu = norms + ((plan->R + 63) & ~(int64_t)63);   // scratch: norms [R] then mu [B][F]
+  graph_mean_kernel<<<dim3(plan->B, (F + 31) / 32), dim3(32, 8), 0, st>>>(XW, plan->uniform_n, F, mu);
+  AGCN_LAUNCH_CHECK();
+  row_norms_kernel<<<(unsigned)((plan->R * 32 + 255) / 256), 256, 0, st>>>(XW, mu, plan->uniform_n, plan->R, F, norms);
+  AGCN_LAUNCH_CHECK();
+  CUtensorMap m;
+  int rc;
+  if ((rc = pair_map(&m, XW, (uint64_t)plan->R, F))) return rc;
+  PairTcArgs k{};
+  k.F = F; k.S = 1; k.mode = 0;
+  k.nofix = ab_env("AGCN_PAIR_NOFIX") != nullptr;
+  k.XW = XW; k.mu = mu; k.norms = norms; k.dist = dist; k.resW = resW; k.rowpart = rowpart; k.ncb = ncb;
+  return pair_launch(plan, m, m, m, k, "bt::pair_tcu_kernel<SIM>", st);
+}
+
+// DL: dL = dL_in + sum_{k=1}^{K-1} c_k U_k T_{k-1}^T; U = [K][R][F] (slice k = U_k), X = T_0, T = T_1 .. T_{K-1}
+int pair_tc_dL(const agcn_plan* plan, const float* U, const float* X, const float* T, int F, int K, const float* dL_in,
+               float* dL, cudaStream_t st) {
+  using namespace bt;
+  CUtensorMap mA, mB0, mB1;
+  int rc;
+  if ((rc = pair_map(&mA, U, (uint64_t)K * plan->R, F))) return rc;
+  if ((rc = pair_map(&mB0, X, (uint64_t)plan->R, F))) return rc;
+  if ((rc = pair_map(&mB1, K > 2 ? T : X, (uint64_t)(K > 2 ? (K - 2) : 1) * plan->R, F))) return rc;
+  PairTcArgs k{};
+  k.F = F; k.S = K - 1; k.mode = 1;
+  k.dL_in = dL_in; k.out = dL;
+  return pair_launch(plan, mA, mB0, mB1, k, "bt::pair_tcu_kernel<DL>", st);
 }
 
 bool grouped_thin_supported(const GroupedArgs& g) {

@@ -465,13 +465,14 @@ size_t big_work_floats(const agcn_plan* plan, bool full) {
   size_t f = (size_t)plan->R * ncb + 64;            // rowpart
   f += (size_t)plan->big_tiles * 8 + 64;            // tilepart
   f += 2 * ((size_t)plan->B * 4 + 64);              // gstat, stats_tmp
+  f += (size_t)plan->R + 128 + (size_t)plan->B * 256;  // norms + per-graph mean rows (tensor-core pair kernel, F <= 256)
   if (full) f += 2 * (size_t)plan->R + (size_t)plan->LL + 192;  // dd, rs, C
   return f;
 }
 
 namespace {
 struct BigWork {
-  float *rowpart, *tilepart, *gstat, *stats_tmp, *dd, *rs, *C;
+  float *rowpart, *tilepart, *gstat, *stats_tmp, *norms, *dd, *rs, *C;
   int ncb;
 };
 BigWork carve_big(const agcn_plan* plan, float* base, bool full) {
@@ -483,6 +484,7 @@ BigWork carve_big(const agcn_plan* plan, float* base, bool full) {
   w.tilepart = base + off; off += r64((size_t)plan->big_tiles * 8);
   w.gstat = base + off; off += r64((size_t)plan->B * 4);
   w.stats_tmp = base + off; off += r64((size_t)plan->B * 4);
+  w.norms = base + off; off += r64((size_t)plan->R) + r64((size_t)plan->B * 256);
   if (full) {
     w.dd = base + off; off += r64((size_t)plan->R);
     w.rs = base + off; off += r64((size_t)plan->R);
@@ -501,15 +503,21 @@ int big_build_laplacian(const GraphArgs& a, bool need_W, float* big_work, cudaSt
   const BigPtrs pp = big_ptrs(plan);
   const int tiles = plan->big_tiles;
   if (need_W) {
-    PairArgs k{};
-    k.pp = pp; k.F = a.F; k.XW = a.XW; k.dist = a.dist; k.resW = a.resW;
-    k.rowpart = paper ? w.rowpart : nullptr; k.ncb = w.ncb;
-    dim3 grid(tiles, w.ncb);
-    {
-      ProfScope prof("big_pair_kernel<SIM>", st);
-      big_pair_kernel<PAIR_SIM><<<grid, 256, 0, st>>>(k);
+    if (pair_tc_supported(plan, a.F)) {
+      // equal-size clouds: Gram tiles on the tensor cores, direct-difference fix-up for near-duplicates (agcn_big_tc.cu)
+      int rc = pair_tc_similarity(plan, a.XW, a.F, w.norms, a.dist, a.resW, paper ? w.rowpart : nullptr, w.ncb, st);
+      if (rc) return rc;
+    } else {
+      PairArgs k{};
+      k.pp = pp; k.F = a.F; k.XW = a.XW; k.dist = a.dist; k.resW = a.resW;
+      k.rowpart = paper ? w.rowpart : nullptr; k.ncb = w.ncb;
+      dim3 grid(tiles, w.ncb);
+      {
+        ProfScope prof("big_pair_kernel<SIM>", st);
+        big_pair_kernel<PAIR_SIM><<<grid, 256, 0, st>>>(k);
+      }
+      AGCN_LAUNCH_CHECK();
     }
-    AGCN_LAUNCH_CHECK();
     if (paper) {
       big_dis_kernel<<<tiles, PT, 0, st>>>(pp, w.rowpart, w.ncb, a.dis);
       AGCN_LAUNCH_CHECK();
@@ -546,6 +554,8 @@ int big_build_laplacian(const GraphArgs& a, bool need_W, float* big_work, cudaSt
 int big_dL(const GraphArgs& a, const float* U, cudaStream_t st) {
   const agcn_plan* plan = a.plan;
   if (plan->large_count == 0) return AGCN_OK;
+  if (a.K >= 2 && pair_tc_supported(plan, a.F) && ((reinterpret_cast<uintptr_t>(a.dL) | reinterpret_cast<uintptr_t>(a.dLall_in)) & 15) == 0)
+    return pair_tc_dL(plan, U, a.X, a.T, a.F, a.K, a.dLall_in, a.dL, st);
   PairArgs k{};
   k.pp = big_ptrs(plan); k.F = a.F;
   k.S = a.K - 1; k.U = U; k.X = a.X; k.T = a.T; k.slice = (int64_t)plan->R * a.F;

@@ -320,6 +320,12 @@ int grouped_simt(int tiles, const GroupedArgs& g, cudaStream_t st);
 // tcgen05 3xTF32 implementation (F % 4 == 0, F >= 16, 16-byte aligned node matrices)
 bool grouped_tc_supported(const GroupedArgs& g);
 int grouped_tc(const agcn_plan* plan, int tiles, const GroupedArgs& g, cudaStream_t st);
+// pair matrices (similarity / dL) of big equal-size graphs on the tensor cores (agcn_big_tc.cu, pair_tcu_kernel)
+bool pair_tc_supported(const agcn_plan* plan, int F);
+int pair_tc_similarity(const agcn_plan* plan, const float* XW, int F, float* norms, float* dist, float* resW, float* rowpart,
+                       int ncb, cudaStream_t st);
+int pair_tc_dL(const agcn_plan* plan, const float* U, const float* X, const float* T, int F, int K, const float* dL_in,
+               float* dL, cudaStream_t st);
 // streaming implementation for F <= 8 (HBM-bound: the Laplacian is read once, coalesced)
 bool grouped_thin_supported(const GroupedArgs& g);
 int grouped_thin(int tiles, const GroupedArgs& g, cudaStream_t st);

@@ -462,3 +462,28 @@ def test_uniform_tensor_core_product(sizes, F):
             assert torch.isfinite(out).all()
             err = float((out.double() - ref).abs().max() / ref.abs().max())
             assert err <= 1e-5, (sizes, F, transL, add_identity, err)
+
+
+@pytest.mark.parametrize("metric_grad", ["reference", "full"])
+def test_equal_size_big_graphs_metric_block_with_near_duplicates(metric_grad):
+    """Paper semantics on equal-size big graphs: the pair matrices come from bt::pair_tcu_kernel (Gram tiles on the tensor
+    cores).  Exact duplicates, near-duplicates (0.04 .. 0.8 apart at norms of ~3, where the Gram expansion cancels: SURVEY Q7) and far
+    rows in one batch: similarity, Laplacian and every gradient within the layer's budget."""
+    sizes, F, Fo, K = [256, 256], 64, 32, 3
+    Nmax = max(sizes)
+    X, _, n = make_batch(sizes, F, Nmax, seed=23)
+    X *= 0.4
+    rng = np.random.default_rng(4)
+    for g in range(len(sizes)):
+        X[g, 9] = X[g, 5]                                                   # exact duplicates
+        X[g, 200] = X[g, 5]
+        # (closer pairs than ~5e-3 make 1 / dist amplify the fp32 error of ANY dL by > 1e3: not a layer-budget case)
+        for a, b, eps in ((11, 7, 1e-2), (40, 41, 3e-2), (100, 180, 1e-1), (33, 250, 5e-3)):
+            X[g, a] = X[g, b] + (rng.standard_normal(F) * eps).astype(np.float32)
+    L = _dense_laplacians(sizes, Nmax, seed=6)
+    p = O.make_params(F, Fo, K, "SGC_LL", seed=3, dtype=torch.float64)
+    cY = _cot((len(sizes), Nmax, Fo), 29)
+    orc = oracle_run(X, L, n, p, K, "SGC_LL", "paper", metric_grad, cot_Y=cY)
+    cu = cuda_run(X, L, n, p, K, "SGC_LL", "paper", metric_grad, cot_Y=cY)
+    errs = compare(cu, orc)
+    print(metric_grad, errs)
