@@ -213,6 +213,66 @@ struct SweepArgs {
   float* tilepart;  // [tiles][8]
 };
 
+// one element of a sweep: inputs by value, outputs through o* (written back by the caller when the pass stores them)
+struct SweepCtx {
+  float alpha, beta, s1, s2, k2;
+  bool paper, reslap, has_prev, clipped2;
+};
+
+template <int PASS>
+__device__ __forceinline__ void sweep_elem(const SweepCtx& c, bool diag, float dis_i, float dis_j, float dist, float lint,
+                                           float lprev, float gd, float (&part)[4], float& o_resl, float& o_lall,
+                                           float& o_dl, float& o_dlprev) {
+  const float eye = diag ? 1.f : 0.f;
+  float R = eye;
+  if (c.paper) {
+    const float w = diag ? 0.f : expf(-dist);
+    R = eye - (dis_i * w) * dis_j;  // I - D^-1/2 W D^-1/2
+  }
+  if (PASS == SW_NORM) {
+    part[0] += R * R;
+    if (c.reslap) {
+      const float lr = leaky(R, c.alpha);
+      float cc = lint;
+      if (c.has_prev) cc += lprev * c.beta;
+      part[1] += lr * lr;
+      part[2] += lr * cc;
+      part[3] += cc * cc;
+    }
+    return;
+  }
+  const float u = R * c.s1;
+  const float rl = leaky(u, c.alpha);    // graphconv.py:213
+  float z = rl + lint;                   // graphconv.py:216
+  if (c.has_prev) z += lprev * c.beta;   // graphconv_reslap.py:190
+  if (PASS == SW_FINAL) {
+    o_resl = rl;
+    o_lall = c.reslap ? leaky(z * c.s2, c.alpha) : z;  // graphconv_reslap.py:194-195
+  } else if (PASS == SW_B1) {
+    // L_all = leaky(s2 Z): gradient w.r.t. v = s2 Z and <gv, Z>
+    const float v = z * c.s2;
+    part[0] -= gd * fmaxf(-v, 0.f);  // d alpha
+    const float gv = gd * leaky_grad(v, c.alpha);
+    part[1] += gv * z;
+    o_dl = gv;
+  } else {  // SW_B2
+    float gz = gd;
+    if (c.reslap && c.clipped2) gz = c.s2 * gz - z * c.k2;
+    if (c.has_prev) {
+      part[1] += gz * lprev;  // d beta
+      o_dlprev = c.beta * gz;
+    }
+    part[0] -= gz * fmaxf(-u, 0.f);  // d alpha
+    const float gu = gz * leaky_grad(u, c.alpha);
+    part[2] += gu * R;
+    o_dl = gu;
+  }
+}
+
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ void stg4(float* p, const float4& v) { *reinterpret_cast<float4*>(p) = v; }
+
+// Which matrices a pass reads: a sweep is HBM-bound, so nothing is loaded that the pass does not use.
 template <int PASS>
 __global__ void __launch_bounds__(256) big_sweep_kernel(SweepArgs p) {
   __shared__ float red[8 * 4];
@@ -222,70 +282,73 @@ __global__ void __launch_bounds__(256) big_sweep_kernel(SweepArgs p) {
   const int64_t row0 = p.pp.node_off[g];
   const int64_t loff = p.pp.lap_off[g];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const float alpha = p.alpha[0];
-  const bool has_prev = p.reslap && p.Lprev != nullptr;
-  const float beta = has_prev ? p.beta[0] : 0.f;
-  float s1 = 1.f, s2 = 1.f, k2 = 0.f;
+  SweepCtx c;
+  c.alpha = p.alpha[0];
+  c.paper = p.paper != 0;
+  c.reslap = p.reslap != 0;
+  c.has_prev = c.reslap && p.Lprev != nullptr;
+  c.beta = c.has_prev ? p.beta[0] : 0.f;
+  c.s1 = 1.f; c.s2 = 1.f; c.k2 = 0.f;
   if (PASS != SW_NORM) {
-    s1 = p.stats[4 * g + 0];
-    s2 = p.stats[4 * g + 1];
+    c.s1 = p.stats[4 * g + 0];
+    c.s2 = p.stats[4 * g + 1];
   }
-  if (PASS == SW_B2) k2 = p.gstat[4 * g + 0];
-  const bool clipped2 = s2 < 1.f;
+  if (PASS == SW_B2) c.k2 = p.gstat[4 * g + 0];
+  c.clipped2 = c.s2 < 1.f;
+  const bool rd_dist = c.paper;
+  const bool rd_lint = PASS == SW_NORM ? c.reslap : (PASS == SW_B2 ? (c.reslap && c.clipped2) : true);
+  const bool rd_prev = c.has_prev;
+  const bool rd_dl = PASS == SW_B1 || PASS == SW_B2;
   float part[4] = {0.f, 0.f, 0.f, 0.f};
+  // rows of 4-float quads when the graph's rows are 16-byte aligned (every equal-size cloud); scalars otherwise
+  const bool vec = (n & 3) == 0 && (loff & 3) == 0 && (row0 & 3) == 0;
   for (int r = 0; r < 8; ++r) {
     const int i = m0 + wid * 8 + r;
     if (i >= n) break;
-    const float dis_i = p.paper ? p.dis[row0 + i] : 0.f;
+    const float dis_i = c.paper ? p.dis[row0 + i] : 0.f;
     const int64_t base = loff + (int64_t)i * n;
-#pragma unroll 4
-    for (int j = lane; j < n; j += 32) {
-      const int64_t idx = base + j;
-      const float eye = (i == j) ? 1.f : 0.f;
-      float R = eye;
-      if (p.paper) {
-        const float w = (i == j) ? 0.f : expf(-p.dist[idx]);
-        R = eye - (dis_i * w) * p.dis[row0 + j];  // I - D^-1/2 W D^-1/2
-      }
-      if (PASS == SW_NORM) {
-        part[0] += R * R;
-        if (p.reslap) {
-          const float lr = leaky(R, alpha);
-          float c = p.Lint[idx];
-          if (has_prev) c += p.Lprev[idx] * beta;
-          part[1] += lr * lr;
-          part[2] += lr * c;
-          part[3] += c * c;
-        }
-      } else {
-        const float u = R * s1;
-        const float rl = leaky(u, alpha);  // graphconv.py:213
-        float z = rl + p.Lint[idx];        // graphconv.py:216
-        if (has_prev) z += p.Lprev[idx] * beta;  // graphconv_reslap.py:190
+    if (vec) {
+#pragma unroll 2
+      for (int j = 4 * lane; j < n; j += 128) {
+        const int64_t idx = base + j;
+        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 dist = rd_dist ? ldg4(p.dist + idx) : z4;
+        const float4 lint = rd_lint ? ldg4(p.Lint + idx) : z4;
+        const float4 prev = rd_prev ? ldg4(p.Lprev + idx) : z4;
+        const float4 gd = rd_dl ? *reinterpret_cast<const float4*>(p.dL + idx) : z4;
+        const float4 dj = c.paper ? ldg4(p.dis + row0 + j) : z4;
+        float4 resl, lall, dl, dlp;
+        sweep_elem<PASS>(c, i == j, dis_i, dj.x, dist.x, lint.x, prev.x, gd.x, part, resl.x, lall.x, dl.x, dlp.x);
+        sweep_elem<PASS>(c, i == j + 1, dis_i, dj.y, dist.y, lint.y, prev.y, gd.y, part, resl.y, lall.y, dl.y, dlp.y);
+        sweep_elem<PASS>(c, i == j + 2, dis_i, dj.z, dist.z, lint.z, prev.z, gd.z, part, resl.z, lall.z, dl.z, dlp.z);
+        sweep_elem<PASS>(c, i == j + 3, dis_i, dj.w, dist.w, lint.w, prev.w, gd.w, part, resl.w, lall.w, dl.w, dlp.w);
         if (PASS == SW_FINAL) {
-          if (p.resL) p.resL[idx] = rl;
-          const float v = p.reslap ? leaky(z * s2, alpha) : z;  // graphconv_reslap.py:194-195
-          if (p.Lall) p.Lall[idx] = v;
-          if (p.Lall2) p.Lall2[idx] = v;
-        } else if (PASS == SW_B1) {
-          // L_all = leaky(s2 Z): gradient w.r.t. v = s2 Z and <gv, Z>
-          const float v = z * s2;
-          const float gd = p.dL[idx];
-          part[0] -= gd * fmaxf(-v, 0.f);  // d alpha
-          const float gv = gd * leaky_grad(v, alpha);
-          part[1] += gv * z;
-          p.dL[idx] = gv;
-        } else {  // SW_B2
-          float gz = p.dL[idx];
-          if (p.reslap && clipped2) gz = s2 * gz - z * k2;
-          if (has_prev) {
-            part[1] += gz * p.Lprev[idx];  // d beta
-            if (p.dLprev) p.dLprev[idx] = beta * gz;
-          }
-          part[0] -= gz * fmaxf(-u, 0.f);  // d alpha
-          const float gu = gz * leaky_grad(u, alpha);
-          part[2] += gu * R;
-          p.dL[idx] = gu;
+          if (p.resL) stg4(p.resL + idx, resl);
+          if (p.Lall) stg4(p.Lall + idx, lall);
+          if (p.Lall2) stg4(p.Lall2 + idx, lall);
+        } else if (PASS != SW_NORM) {
+          stg4(p.dL + idx, dl);
+          if (PASS == SW_B2 && c.has_prev && p.dLprev) stg4(p.dLprev + idx, dlp);
+        }
+      }
+    } else {
+#pragma unroll 4
+      for (int j = lane; j < n; j += 32) {
+        const int64_t idx = base + j;
+        const float dist = rd_dist ? p.dist[idx] : 0.f;
+        const float lint = rd_lint ? p.Lint[idx] : 0.f;
+        const float prev = rd_prev ? p.Lprev[idx] : 0.f;
+        const float gd = rd_dl ? p.dL[idx] : 0.f;
+        const float dj = c.paper ? p.dis[row0 + j] : 0.f;
+        float resl, lall, dl, dlp;
+        sweep_elem<PASS>(c, i == j, dis_i, dj, dist, lint, prev, gd, part, resl, lall, dl, dlp);
+        if (PASS == SW_FINAL) {
+          if (p.resL) p.resL[idx] = resl;
+          if (p.Lall) p.Lall[idx] = lall;
+          if (p.Lall2) p.Lall2[idx] = lall;
+        } else if (PASS != SW_NORM) {
+          p.dL[idx] = dl;
+          if (PASS == SW_B2 && c.has_prev && p.dLprev) p.dLprev[idx] = dlp;
         }
       }
     }
@@ -359,6 +422,13 @@ __global__ void big_stats_kernel(StatArgs p) {
 // ------------------------------------------------------------------------------------------------
 // metric block backward (paper semantics, metric_grad = full): sweeps that need element (i,j) and (j,i)
 // ------------------------------------------------------------------------------------------------
+// Everything here is symmetric in (i, j) up to the pair (gu_ij, gu_ji): W, dist and R are, and so are the summands
+//   e_ij = (dR_ij + dR_ji) W_ij                      -> d dis_m = -sum_j e_mj dis_j                       (TR_DD)
+//   C_ij = -W_ij (dW_ij + dW_ji) / dist_ij = C_ji                                                        (TR_C)
+// so one CTA takes a PAIR of 64 x 64 tiles (I, J), I <= J: it reads gu[I, J], gu[J, I] and dist[I, J] once, writes C[I, J]
+// and (transposed through shared memory) C[J, I], and leaves the sums over its columns for the rows of I and over its
+// rows for the rows of J as partials part[row][column block] -- each (row, block) is written by exactly one CTA, a
+// second kernel adds them in block order (deterministic, no atomics).
 enum { TR_DD = 0, TR_C = 1 };
 
 struct TransArgs {
@@ -371,26 +441,40 @@ struct TransArgs {
   float* dd;        // [R] gradient w.r.t. the degree d_m
   float* C;         // packed: C_ij = (d dist_ij + d dist_ji) / dist_ij
   float* rs;        // [R] rowsum(C)
+  float* part;      // [R][ncb]
+  int ncb;
 };
 
 template <int PASS>
 __global__ void __launch_bounds__(256) big_trans_kernel(TransArgs p) {
-  __shared__ float sA[PT][PT + 1];  // gu[i-tile, j-block]
-  __shared__ float sB[PT][PT + 1];  // gu[j-block, i-tile]
+  __shared__ float sA[PT][PT + 1];   // gu[I, J]
+  __shared__ float sB[PT][PT + 1];   // gu[J, I]; then C[J, I]
+  __shared__ float scol[8][PT];
   const int t = blockIdx.x;
   const int g = p.pp.tile_graph[t], m0 = p.pp.tile_row[t];
   const int n = p.pp.n_nodes[g];
+  const int j0 = blockIdx.y * PT;
+  if (j0 < m0 || j0 >= n) return;
+  const bool diag_tile = j0 == m0;
   const int64_t row0 = p.pp.node_off[g];
   const int64_t loff = p.pp.lap_off[g];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const float s1 = p.stats[4 * g + 0];
   const float k1 = p.gstat[4 * g + 1];
   const bool clipped1 = s1 < 1.f;
-  float acc[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) acc[r] = 0.f;
-  for (int j0 = 0; j0 < n; j0 += PT) {
-    __syncthreads();
+  if ((n & 3) == 0 && (loff & 3) == 0) {
+    for (int e = threadIdx.x; e < PT * PT / 4; e += 256) {
+      const int a = e / (PT / 4), b = 4 * (e % (PT / 4));
+      const int i = m0 + a, j = j0 + b;   // rows of n % 4 == 0 floats: a quad is inside or outside as a whole
+      const float4 va = (i < n && j < n) ? __ldg(reinterpret_cast<const float4*>(p.gu + loff + (int64_t)i * n + j))
+                                         : make_float4(0.f, 0.f, 0.f, 0.f);
+      sA[a][b] = va.x; sA[a][b + 1] = va.y; sA[a][b + 2] = va.z; sA[a][b + 3] = va.w;
+      const int jj = j0 + a, ii = m0 + b;
+      const float4 vb = (jj < n && ii < n) ? __ldg(reinterpret_cast<const float4*>(p.gu + loff + (int64_t)jj * n + ii))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+      sB[a][b] = vb.x; sB[a][b + 1] = vb.y; sB[a][b + 2] = vb.z; sB[a][b + 3] = vb.w;
+    }
+  } else {
     for (int e = threadIdx.x; e < PT * PT; e += 256) {
       const int a = e / PT, b = e % PT;
       const int i = m0 + a, j = j0 + b;
@@ -398,21 +482,38 @@ __global__ void __launch_bounds__(256) big_trans_kernel(TransArgs p) {
       const int jj = j0 + a, ii = m0 + b;
       sB[a][b] = (jj < n && ii < n) ? p.gu[loff + (int64_t)jj * n + ii] : 0.f;
     }
-    __syncthreads();
+  }
+  __syncthreads();
+  float colacc[2] = {0.f, 0.f};
+  float dis_j[2], dd_j[2];
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
-      const int a = wid * 8 + r, i = m0 + a;
-      if (i >= n) continue;
-      const float dis_i = p.dis[row0 + i];
+  for (int h = 0; h < 2; ++h) {
+    const int j = j0 + lane + 32 * h;
+    dis_j[h] = j < n ? p.dis[row0 + j] : 0.f;
+    dd_j[h] = (PASS == TR_C && j < n) ? p.dd[row0 + j] : 0.f;
+  }
+  float dst[8][2];
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const int b = lane + 32 * h, j = j0 + b;
-        if (j >= n || j == i) continue;
-        const int64_t idx = loff + (int64_t)i * n + j;
-        const float dst = p.dist[idx];
-        const float w = expf(-dst);
-        const float dis_j = p.dis[row0 + j];
-        const float R = -(dis_i * w) * dis_j;
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int i = m0 + wid * 8 + r, j = j0 + lane + 32 * h;
+      dst[r][h] = (i < n && j < n) ? __ldg(p.dist + loff + (int64_t)i * n + j) : 0.f;
+    }
+#pragma unroll
+  for (int r = 0; r < 8; ++r) {
+    const int a = wid * 8 + r, i = m0 + a;
+    const bool row_ok = i < n;
+    const float dis_i = row_ok ? p.dis[row0 + i] : 0.f;
+    const float dd_i = (PASS == TR_C && row_ok) ? p.dd[row0 + i] : 0.f;
+    float rowacc = 0.f;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int b = lane + 32 * h, j = j0 + b;
+      float val = 0.f;   // e_ij | C_ij
+      if (row_ok && j < n && j != i) {
+        const float w = expf(-dst[r][h]);
+        const float R = -(dis_i * w) * dis_j[h];
         float g_ij = sA[a][b], g_ji = sB[b][a];
         if (clipped1) {  // s1 = c |R|^-1: dR = s1 gu - R (s1^3 / c^2) <gu, R>
           g_ij = s1 * g_ij - R * k1;
@@ -420,37 +521,62 @@ __global__ void __launch_bounds__(256) big_trans_kernel(TransArgs p) {
         }
         if (PASS == TR_DD) {
           // d dis_m = -sum_j dR_mj W_mj dis_j - sum_j dR_jm W_jm dis_j
-          acc[r] += (g_ij + g_ji) * w * dis_j;
+          val = (g_ij + g_ji) * w;
+          rowacc += val * dis_j[h];
+          colacc[h] += val * dis_i;
         } else {
-          const float dd_i = p.dd[row0 + i], dd_j = p.dd[row0 + j];
-          const float dw_ij = -g_ij * dis_i * dis_j + dd_j;
-          const float dw_ji = -g_ji * dis_i * dis_j + dd_i;
+          const float dw_ij = -g_ij * dis_i * dis_j[h] + dd_j[h];
+          const float dw_ji = -g_ji * dis_i * dis_j[h] + dd_i;
           const float ddist = -w * (dw_ij + dw_ji);
-          const float c = (dst > 0.f) ? ddist / dst : 0.f;  // sub-gradient 0 at exact duplicates
-          p.C[idx] = c;
-          acc[r] += c;
+          val = (dst[r][h] > 0.f) ? ddist / dst[r][h] : 0.f;  // sub-gradient 0 at exact duplicates
+          rowacc += val;
+          colacc[h] += val;
         }
       }
       if (PASS == TR_C) {
-        const int b = i - j0;  // the diagonal element of this block, if any
-        if (b >= 0 && b < PT && (b & 31) == lane) p.C[loff + (int64_t)i * n + i] = 0.f;
+        if (row_ok && j < n) p.C[loff + (int64_t)i * n + j] = val;   // the diagonal gets its 0 here
+        sB[b][a] = val;   // same thread read this element: no hazard
       }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) rowacc += __shfl_xor_sync(0xffffffffu, rowacc, o);
+    if (lane == 0 && row_ok) p.part[(row0 + i) * p.ncb + blockIdx.y] = rowacc;
+  }
+  if (diag_tile) return;   // the row sums covered every pair of this tile
+  scol[wid][lane] = colacc[0];
+  scol[wid][lane + 32] = colacc[1];
+  __syncthreads();
+  if (threadIdx.x < PT) {
+    const int j = j0 + threadIdx.x;
+    float v = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v += scol[k][threadIdx.x];
+    if (j < n) p.part[(row0 + j) * p.ncb + m0 / PT] = v;
+  }
+  if (PASS == TR_C) {
+    for (int e = threadIdx.x; e < PT * PT; e += 256) {
+      const int b = e / PT, a = e % PT;   // row j0 + b of C, columns m0 + a
+      if (j0 + b < n && m0 + a < n) p.C[loff + (int64_t)(j0 + b) * n + m0 + a] = sB[b][a];
     }
   }
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    float v = acc[r];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    const int i = m0 + wid * 8 + r;
-    if (lane == 0 && i < n) {
-      if (PASS == TR_DD) {
-        const float dm = p.dis[row0 + i];
-        p.dd[row0 + i] = -0.5f * dm * dm * dm * (-v);  // dd_m = -1/2 dis_m^3 d dis_m  (0 when d_m == 0)
-      } else {
-        p.rs[row0 + i] = v;
-      }
-    }
+}
+
+// fold the column-block partials of a row (block order) into dd (TR_DD) or rowsum(C) (TR_C)
+template <int PASS>
+__global__ void big_trans_fold_kernel(TransArgs p) {
+  const int t = blockIdx.x;
+  const int g = p.pp.tile_graph[t], i = p.pp.tile_row[t] + threadIdx.x;
+  const int n = p.pp.n_nodes[g];
+  if (i >= n) return;
+  const int64_t row = p.pp.node_off[g] + i;
+  const int nb = (n + PT - 1) / PT;
+  float v = 0.f;
+  for (int b = 0; b < nb; ++b) v += p.part[row * p.ncb + b];
+  if (PASS == TR_DD) {
+    const float dm = p.dis[row];
+    p.dd[row] = -0.5f * dm * dm * dm * (-v);  // dd_m = -1/2 dis_m^3 d dis_m  (0 when d_m == 0)
+  } else {
+    p.rs[row] = v;
   }
 }
 
@@ -609,16 +735,21 @@ int big_laplacian_bwd(const GraphArgs& a, float* big_work, cudaStream_t st) {
   if (!full) return AGCN_OK;
   TransArgs t{};
   t.pp = pp; t.dist = a.dist; t.dis = a.dis; t.stats = a.stats; t.gstat = w.gstat; t.gu = a.dL;
-  t.dd = w.dd; t.C = w.C; t.rs = w.rs;
+  t.dd = w.dd; t.C = w.C; t.rs = w.rs; t.part = w.rowpart; t.ncb = w.ncb;   // rowpart: free in backward
+  const dim3 pairs(tiles, w.ncb);
   {
     ProfScope prof("big_trans_kernel", st);
-    big_trans_kernel<TR_DD><<<tiles, 256, 0, st>>>(t);
+    big_trans_kernel<TR_DD><<<pairs, 256, 0, st>>>(t);
   }
+  AGCN_LAUNCH_CHECK();
+  big_trans_fold_kernel<TR_DD><<<tiles, PT, 0, st>>>(t);
   AGCN_LAUNCH_CHECK();
   {
     ProfScope prof("big_trans_kernel", st);
-    big_trans_kernel<TR_C><<<tiles, 256, 0, st>>>(t);
+    big_trans_kernel<TR_C><<<pairs, 256, 0, st>>>(t);
   }
+  AGCN_LAUNCH_CHECK();
+  big_trans_fold_kernel<TR_C><<<tiles, PT, 0, st>>>(t);
   AGCN_LAUNCH_CHECK();
   // dXW_i = rowsum(C)_i xw_i - (C XW)_i
   return grouped_rows_gemm(plan, tiles, w.C, a.XW, -1.f, w.rs, a.XW, a.dXW, a.F, st);
