@@ -691,6 +691,7 @@ struct PairTcArgs {
   int nofix;                     //      A/B builds only: skip the direct-difference fix-up (timing experiment)
 };
 
+template <bool DL>
 __global__ void __launch_bounds__(U_THREADS, 2)
 pair_tcu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB0,
                 const __grid_constant__ CUtensorMap tmB1, PairTcArgs p) {
@@ -736,7 +737,7 @@ pair_tcu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;\n" ::"r"(smem_u32(tmem_slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::: "memory");
   }
-  for (int f = threadIdx.x; f < F; f += blockDim.x) sts32(s_mu + 4 * f, (!p.mode && p.mu) ? __ldg(p.mu + (long long)g * F + f) : 0.f);
+  for (int f = threadIdx.x; f < F; f += blockDim.x) sts32(s_mu + 4 * f, (!DL && p.mu) ? __ldg(p.mu + (long long)g * F + f) : 0.f);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -761,7 +762,7 @@ pair_tcu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         const int slot = kb % U_NS, u = kb / U_NS;
         if (u > 0) mbar_wait(&s_empty[slot], (uint32_t)((u - 1) & 1));
         const int s = kb / nc, c = kb - s * nc;
-        const long long arow = (p.mode ? (long long)(s + 1) * p.R : 0) + row0 + m0;
+        const long long arow = (DL ? (long long)(s + 1) * p.R : 0) + row0 + m0;
         mbar_expect_tx(&s_full[slot], A_BYTES);
         tma_load_2d(s_ring + slot * A_BYTES, &tmA, &s_full[slot], c * BK, (int)arow);
       }
@@ -795,22 +796,26 @@ pair_tcu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     uint32_t soff[4];
 #pragma unroll
     for (int gq = 0; gq < 4; ++gq) soff[gq] = (uint32_t)(r * 128 + (((4 * h + gq) ^ (r & 7)) << 4));
+    int fc = -BK;   // first feature column of the k-block
     for (int kb = 0; kb < num_kb; ++kb) {
       const int sslot = kb % U_NS, aslot = kb % U_NA, bslot = kb % U_NB;
-      const float coef = (p.mode && kb / nc + 1 >= 2) ? 2.f : 1.f;   // c_1 = 1, c_k = 2 (DL)
+      const float coef = (DL && kb >= nc) ? 2.f : 1.f;   // c_1 = 1, c_k = 2 (DL)
+      fc = fc + BK == F ? 0 : fc + BK;
       if (lane == 0) {
         mbar_wait(&s_full[sslot], (uint32_t)((kb / U_NS) & 1));
         if (kb >= U_NA) mbar_wait(&a_empty[aslot], (uint32_t)((kb / U_NA - 1) & 1));
       }
       __syncwarp();
       const uint32_t st = s_ring + sslot * A_BYTES;
-      const int fc = (kb - (kb / nc) * nc) * BK;   // first feature column of this k-block
       float hi[16], lo[16];
 #pragma unroll
       for (int gq = 0; gq < 4; ++gq) {
-        const float4 v = lds128(st + soff[gq]);
-        const float4 m4 = lds128(s_mu + 4 * (fc + 16 * h + 4 * gq));   // zeros in DL mode
-        const float x[4] = {coef * (v.x - m4.x), coef * (v.y - m4.y), coef * (v.z - m4.z), coef * (v.w - m4.w)};
+        float4 v = lds128(st + soff[gq]);
+        if (!DL) {
+          const float4 m4 = lds128(s_mu + 4 * (fc + 16 * h + 4 * gq));
+          v.x -= m4.x; v.y -= m4.y; v.z -= m4.z; v.w -= m4.w;
+        }
+        const float x[4] = {DL ? coef * v.x : v.x, DL ? coef * v.y : v.y, DL ? coef * v.z : v.z, DL ? coef * v.w : v.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           hi[4 * gq + e] = tf32_hi(x[e]);
@@ -834,10 +839,12 @@ pair_tcu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
         y[t] = lds128(sb + 16 * 256 * t);
-        // 16-byte slot idx of the swizzled tile: row idx / 8, logical chunk (idx % 8) ^ (row % 8)
-        const int idx = wt + 256 * t, brow = idx >> 3, chunk = (idx & 7) ^ (brow & 7);
-        const float4 m4 = lds128(s_mu + 4 * (fc + 4 * chunk));
-        y[t].x -= m4.x; y[t].y -= m4.y; y[t].z -= m4.z; y[t].w -= m4.w;
+        if (!DL) {
+          // 16-byte slot idx of the swizzled tile: row idx / 8, logical chunk (idx % 8) ^ (row % 8)
+          const int idx = wt + 256 * t, brow = idx >> 3, chunk = (idx & 7) ^ (brow & 7);
+          const float4 m4 = lds128(s_mu + 4 * (fc + 4 * chunk));
+          y[t].x -= m4.x; y[t].y -= m4.y; y[t].z -= m4.z; y[t].w -= m4.w;
+        }
       }
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
@@ -856,7 +863,7 @@ pair_tcu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     __syncwarp();
     tc_fence_after();
     const int i = m0 + r;
-    if (p.mode) {
+    if (DL) {
       // every accumulator is complete: the rings are free.  Rows of 32 values go through a 32 x 36 block per warp so
       // that dL_in is read and dL written as whole 128-byte row segments
       const uint32_t stg = sbase + 1024 + (uint32_t)(wi * (32 * 36 * 4));
@@ -908,8 +915,13 @@ pair_tcu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           // The 3xTF32 Gram leaves ~1e-6 (|xw_i|^2 + |xw_j|^2) of absolute error in d2.  It matters where it moves
           // W = exp(-d) (|dW| = W dd) or the metric gradient (~ W dd / d) by more than 1e-5: near-duplicates against the
           // (centred) norms.  Far pairs (W ~ 0) never are.
-          const float dg = sqrtf(d2);
-          if (i != j0 + jb + u && __expf(-dg) * (ni + nj) > 20.f * fminf(dg, d2)) flagged |= 1u << u;
+          // Test: exp(-d) (ni + nj) > 20 min(d, d^2).  exp(-d) <= 1 settles almost every entry without sqrt / exp.
+          const float sn = ni + nj;
+          const bool maybe = d2 >= 1.f ? sn * sn > 400.f * d2 : sn > 20.f * d2;
+          if (maybe && i != j0 + jb + u) {
+            const float dg = sqrtf(d2);
+            if (__expf(-dg) * sn > 20.f * fminf(dg, d2)) flagged |= 1u << u;
+          }
           v[u] = d2;
         }
         if (p.nofix) flagged = 0u;
@@ -947,11 +959,14 @@ pair_tcu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const int rr = 4 * t + (lane >> 3), c4 = 4 * (lane & 7);
           const float4 q2 = lds128(stg + 4 * (rr * 36 + c4));
           const int dj = (m0 + q * 32 + rr) - (j0 + jb + c4);   // the diagonal entry of this quad, if 0 <= dj < 4
+          // sqrt as x rsqrt(x) and exp through ex2.approx: ~2 ulp each, far inside the 1e-4 of the parity tests, and a
+          // third of the instructions of sqrtf / expf in a pass that is issue-bound
+          auto root = [](float x) { return x > 0.f ? x * rsqrtf(x) : 0.f; };
           float4 d, w;
-          d.x = dj == 0 ? 0.f : sqrtf(q2.x); w.x = dj == 0 ? 0.f : expf(-d.x);
-          d.y = dj == 1 ? 0.f : sqrtf(q2.y); w.y = dj == 1 ? 0.f : expf(-d.y);
-          d.z = dj == 2 ? 0.f : sqrtf(q2.z); w.z = dj == 2 ? 0.f : expf(-d.z);
-          d.w = dj == 3 ? 0.f : sqrtf(q2.w); w.w = dj == 3 ? 0.f : expf(-d.w);
+          d.x = dj == 0 ? 0.f : root(q2.x); w.x = dj == 0 ? 0.f : __expf(-d.x);
+          d.y = dj == 1 ? 0.f : root(q2.y); w.y = dj == 1 ? 0.f : __expf(-d.y);
+          d.z = dj == 2 ? 0.f : root(q2.z); w.z = dj == 2 ? 0.f : __expf(-d.z);
+          d.w = dj == 3 ? 0.f : root(q2.w); w.w = dj == 3 ? 0.f : __expf(-d.w);
           rs[t] += (w.x + w.y) + (w.z + w.w);
           const long long o = tile0 + (long long)rr * n + c4;
           if (p.dist) *reinterpret_cast<float4*>(p.dist + o) = d;
@@ -1257,11 +1272,17 @@ static int pair_launch(const agcn_plan* plan, const CUtensorMap& mA, const CUten
   k.n = plan->uniform_n; k.R = (int)plan->R;
   static std::once_flag once;
   constexpr int P_SMEM = U_SMEM + 1024;   // + the graph's mean row
-  std::call_once(once, [] { cudaFuncSetAttribute(pair_tcu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM + 1024); });
+  std::call_once(once, [] {
+    cudaFuncSetAttribute(pair_tcu_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM + 1024);
+    cudaFuncSetAttribute(pair_tcu_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, U_SMEM + 1024);
+  });
   dim3 grid(plan->big_tiles, plan->uniform_n / TM);
   {
     ProfScope prof(name, st);
-    pair_tcu_kernel<<<grid, U_THREADS, P_SMEM, st>>>(mA, mB0, mB1, k);
+    if (k.mode)
+      pair_tcu_kernel<true><<<grid, U_THREADS, P_SMEM, st>>>(mA, mB0, mB1, k);
+    else
+      pair_tcu_kernel<false><<<grid, U_THREADS, P_SMEM, st>>>(mA, mB0, mB1, k);
   }
   AGCN_LAUNCH_CHECK();
   return AGCN_OK;
