@@ -446,7 +446,7 @@ struct TransArgs {
 };
 
 template <int PASS>
-__global__ void __launch_bounds__(256) big_trans_kernel(TransArgs p) {
+__global__ void __launch_bounds__(256, PASS == TR_C ? 4 : 5) big_trans_kernel(TransArgs p) {
   __shared__ float sA[PT][PT + 1];   // gu[I, J]
   __shared__ float sB[PT][PT + 1];   // gu[J, I]; then C[J, I]
   __shared__ float scol[8][PT];
