@@ -355,7 +355,11 @@ grouped_tc_kernel(const __grid_constant__ CUtensorMap tmIn, GroupedArgs p) {
     if (wt == 0) BT_STAMP(521);
     const int q = warp & 3;      // TMEM lane quarter of this warp
     const int h = ww >> 2;       // 32-column group of this warp (NW / 4 groups)
-    const uint32_t stg = sbase + (uint32_t)(ww * (32 * 36 * 4));  // the operand stages are free now
+    // The operand stages are free now: the accumulator barrier fires after the last MMA, which waited for every warp's
+    // operand stores.  The named barrier says so in a form compute-sanitizer's racecheck understands (it does not follow
+    // mbarrier / tcgen05.commit ordering and reported the staging stores against the other warps' operand stores).
+    asm volatile("bar.sync 1, %0;\n" ::"n"(WORKERS) : "memory");
+    const uint32_t stg = sbase + (uint32_t)(ww * (32 * 36 * 4));
     for (int c0 = 32 * h; c0 < nmma; c0 += 32 * (NW / 4)) {
       float v[32];
       tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);
@@ -867,6 +871,9 @@ pair_tcu_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       // every accumulator is complete: the rings are free.  Rows of 32 values go through a 32 x 36 block per warp so
       // that dL_in is read and dL written as whole 128-byte row segments
       const uint32_t stg = sbase + 1024 + (uint32_t)(wi * (32 * 36 * 4));
+      // (the accumulator barrier already orders every warp's operand stores before this point -- the last MMA waited for
+      // all of them; the named barrier states it in a form compute-sanitizer's racecheck can see)
+      asm volatile("bar.sync 1, 256;\n" ::: "memory");
       for (int cb = 0; cb < 2; ++cb) {
         float v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(64 * h + 32 * cb), v);

@@ -4,8 +4,8 @@
 # Usage (on the GPU box, from the repo root):  bash tools/sanitize.sh
 mkdir -p gpurun_out
 rm -f gpurun_out/sanitizer_summary.log
-SEL='test_sgc_ll_forward_backward or test_reslap_forward_backward or test_feature_shapes or test_big_graphs_all_modes or test_head_loss or test_first_layer_backward'
-SEL_SMALL='test_sgc_ll_forward_backward or test_feature_shapes'
+SEL='test_sgc_ll_forward_backward or test_reslap_forward_backward or test_feature_shapes or test_big_graphs_all_modes or test_head_loss or test_first_layer_backward or test_equal_size_big_graphs_metric_block or test_uniform_tensor_core_product'
+SEL_SMALL='test_sgc_ll_forward_backward or test_feature_shapes or test_equal_size_big_graphs_metric_block'
 for tool in memcheck synccheck; do
   timeout 420 compute-sanitizer --tool $tool --error-exitcode 7 --print-limit 20 \
     python -m pytest tests/test_gpu_parity.py tests/test_gpu_block_layers.py -m gpu -q -x -k "$SEL or block or mlp or dropout" \
