@@ -86,14 +86,21 @@ __global__ void pack_lap_kernel(const float* __restrict__ padded, float* __restr
 }
 
 
-// Padded -> packed over the REAL rows only (the direction every training step takes): a persistent grid of at most
-// PACK_CTAS CTAs of 1024 threads walks the R packed rows, one warp per row, the row's graph found by binary search in
-// node_off.  When the padded array is a pinned host buffer read in place over PCIe, the kernel lives for the PCIe
-// transfer time beside the previous training step, whose kernels want every SM (three 74 KB recurrence CTAs or two
-// contraction CTAs per SM): a 1024-thread pack CTA takes half an SM's registers and thread slots away from them, so the
-// pack grid stays on a few SMs.  Measured on the pipelined ToxCast loop (round 2, bench.py e2e): 24 CTAs 0.926 ms per
-// step, 8 CTAs 0.895 ms, 4 CTAs 1.018 ms (then the PCIe reads themselves -- ~1.5 us each, 32 warps per CTA in flight --
-// no longer finish within one step); 32 CTAs of 256 threads (a quarter of an SM each) 0.958 ms.
+// Padded -> packed over the REAL rows only (the direction every training step takes).  When the padded array is a pinned
+// host buffer read in place over PCIe, the kernel lives for the PCIe transfer time beside the previous training step.
+// Three measurements of round 2 (tools/pack_time.py, tools/pack_sweep.sh, tools/e2e_host_split.py) shaped it:
+//  1. A zero-copy read crosses PCIe per L2 sector group: unaligned scalar row reads decay to 32-byte requests and the
+//     link's outstanding-read tags saturate at ~18 GB/s whatever the number of threads; whole aligned 128-byte lines
+//     (eight lanes x float4, elements outside the segment dropped) reach 40 GB/s.
+//  2. What the transfer costs the step running beside it does not depend on the SMs it occupies (8 x 1024 threads and
+//     148 x 32 threads cost the same) and a plain copy-engine cudaMemcpyAsync of the same bytes costs it too: bulk
+//     GPU-initiated PCIe reads delay the front end's fetches of the step's ~80 eager launch commands from host memory
+//     (ToxCast: 0.69 ms per step alone, 0.81-0.85 ms with 8 MB arriving beside it; a feeder thread that gathers on the
+//     host and sends one contiguous copy was slower still, 0.90 ms).
+//  3. So the pack runs on TWO 1024-thread CTAs whatever the batch: ~130 KB of reads in flight is 28-47 GB/s, and the
+//     gaps it leaves let the command fetches through.  Pipelined loop, ms per step with 2 / 4 / 8 / 14-16 CTAs:
+//     ToxCast 0.81 / 0.81 / 0.85 / -, ragged clouds (C4, 42 MB) 1.62 / 1.64 / - / 2.00, ModelNet40-shape (C3, 134 MB)
+//     2.86 / - / 2.94 / 3.22; one CTA is too slow (C4: 3.1 ms, transfer-bound).
 __device__ __forceinline__ int graph_of_row(const int32_t* __restrict__ node_off, int B, int r) {
   int lo = 0, hi = B;   // node_off[lo] <= r < node_off[hi]
   while (hi - lo > 1) {
@@ -103,7 +110,85 @@ __device__ __forceinline__ int graph_of_row(const int32_t* __restrict__ node_off
   return lo;
 }
 
-constexpr int PACK_CTAS = 8;
+// The source is read in whole, aligned 128-byte lines (eight lanes x float4 per line): a zero-copy read over PCIe is
+// issued per L2 sector group, and 32-byte requests (what unaligned scalar row reads decay to) saturate the link's
+// outstanding-read tags at ~18 GB/s, whatever the number of threads.  Elements of a line outside the segment are dropped;
+// the destination (device memory) takes scalar stores.
+//   LAP = false: one segment per graph, its n real rows of X are contiguous in both layouts (n F floats); a warp per graph,
+//                its four lane groups striding over the lines, PACK_U lines per group in flight;
+//   LAP = true : one segment per row of L (n floats at stride Nmax); a warp takes four rows at a time, a lane group each.
+constexpr int PACK_U = 4;
+template <bool LAP>
+__global__ void __launch_bounds__(1024) pack_lines_kernel(const float* __restrict__ padded, float* __restrict__ packed,
+                                                         const int32_t* __restrict__ n_nodes,
+                                                         const int32_t* __restrict__ node_off,
+                                                         const int64_t* __restrict__ lap_off, int B, int Nmax, int F, int R,
+                                                         int64_t total) {
+  const int lane = threadIdx.x & 31, q = lane >> 3, l8 = lane & 7;
+  const int warps = (gridDim.x * blockDim.x) >> 5;
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // line `l` of a segment that starts at float s0 (first line starts at a0 = s0 rounded down to 32 floats)
+  auto load_line = [&](int64_t a0, int l, bool on) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int64_t idx = a0 + 32 * (int64_t)l + 4 * l8;
+    if (on) {
+      if (idx + 4 <= total) {
+        v = __ldg(reinterpret_cast<const float4*>(padded + idx));
+      } else {   // the last, partial float4 of the array
+        if (idx < total) v.x = __ldg(padded + idx);
+        if (idx + 1 < total) v.y = __ldg(padded + idx + 1);
+        if (idx + 2 < total) v.z = __ldg(padded + idx + 2);
+      }
+    }
+    return v;
+  };
+  auto store_line = [&](int64_t a0, int l, int64_t s0, int64_t len, int64_t d0, const float4& v, bool on) {
+    if (!on) return;
+    const int64_t o = a0 + 32 * (int64_t)l + 4 * l8 - s0;   // offset of v.x in the segment
+    float* dst = packed + d0 + o;
+    if (o >= 0 && o < len) dst[0] = v.x;
+    if (o + 1 >= 0 && o + 1 < len) dst[1] = v.y;
+    if (o + 2 >= 0 && o + 2 < len) dst[2] = v.z;
+    if (o + 3 >= 0 && o + 3 < len) dst[3] = v.w;
+  };
+  if (!LAP) {
+    for (int g = w; g < B; g += warps) {
+      const int64_t s0 = (int64_t)g * Nmax * F, len = (int64_t)n_nodes[g] * F, d0 = (int64_t)node_off[g] * F;
+      const int64_t a0 = s0 & ~(int64_t)31;
+      const int nl = (int)((s0 - a0 + len + 31) >> 5);
+      for (int l = q; l < nl; l += 4 * PACK_U) {
+        float4 v[PACK_U];
+#pragma unroll
+        for (int u = 0; u < PACK_U; ++u) v[u] = load_line(a0, l + 4 * u, l + 4 * u < nl);
+#pragma unroll
+        for (int u = 0; u < PACK_U; ++u) store_line(a0, l + 4 * u, s0, len, d0, v[u], l + 4 * u < nl);
+      }
+    }
+  } else {
+    for (int r0 = 4 * w; r0 < R; r0 += 4 * warps) {
+      const int r = r0 + q;
+      int64_t s0 = 0, len = 0, d0 = 0;
+      if (r < R) {
+        const int g = graph_of_row(node_off, B, r);
+        const int i = r - node_off[g], n = n_nodes[g];
+        s0 = ((int64_t)g * Nmax + i) * Nmax;
+        d0 = lap_off[g] + (int64_t)i * n;
+        len = n;
+      }
+      const int64_t a0 = s0 & ~(int64_t)31;
+      const int nl = len ? (int)((s0 - a0 + len + 31) >> 5) : 0;
+      for (int l = 0; __any_sync(0xffffffffu, l < nl); l += PACK_U) {
+        float4 v[PACK_U];
+#pragma unroll
+        for (int u = 0; u < PACK_U; ++u) v[u] = load_line(a0, l + u, l + u < nl);
+#pragma unroll
+        for (int u = 0; u < PACK_U; ++u) store_line(a0, l + u, s0, len, d0, v[u], l + u < nl);
+      }
+    }
+  }
+}
+
+// fallback for a source that is not 16-byte aligned: one row per warp, scalar loads
 __global__ void __launch_bounds__(1024) pack_rows_kernel(const float* __restrict__ padded, float* __restrict__ packed,
                                                         const int32_t* __restrict__ n_nodes,
                                                         const int32_t* __restrict__ node_off,
@@ -127,16 +212,36 @@ __global__ void __launch_bounds__(1024) pack_rows_kernel(const float* __restrict
       dst = packed + (int64_t)r * F;
       len = F;
     }
-    if (((len & 3) == 0) && (((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(dst)) & 15) == 0)) {
-      for (int c = lane; c < (len >> 2); c += 32)
-        reinterpret_cast<float4*>(dst)[c] = __ldg(reinterpret_cast<const float4*>(src) + c);
-    } else {
-      for (int c = lane; c < len; c += 32) dst[c] = __ldg(src + c);
-    }
+    for (int c = lane; c < len; c += 32) dst[c] = __ldg(src + c);
   }
 }
 
-static unsigned pack_grid(int64_t R) { return (unsigned)std::max<int64_t>(1, std::min<int64_t>((R + 31) / 32, PACK_CTAS)); }
+// grid of the pack kernels (finding 3 above; A/B builds: AGCN_PACK_CTAS / AGCN_PACK_THREADS override)
+constexpr int PACK_CTAS = 2, PACK_THREADS = 1024;
+static void pack_shape(int64_t warp_items, unsigned* ctas, unsigned* threads) {
+  static const int c = ab_env("AGCN_PACK_CTAS") ? atoi(ab_env("AGCN_PACK_CTAS")) : PACK_CTAS;
+  static const int t = ab_env("AGCN_PACK_THREADS") ? atoi(ab_env("AGCN_PACK_THREADS")) : PACK_THREADS;
+  *threads = (unsigned)t;
+  *ctas = (unsigned)std::max<int64_t>(1, std::min<int64_t>((std::max<int64_t>(1, warp_items) * 32 + t - 1) / t, c));
+}
+
+static void launch_pack(const agcn_plan* plan, const float* padded, float* packed, int F, int lap, cudaStream_t st) {
+  unsigned ctas, threads;
+  if ((reinterpret_cast<uintptr_t>(padded) & 15) != 0) {
+    pack_shape(plan->R, &ctas, &threads);
+    pack_rows_kernel<<<ctas, threads, 0, st>>>(padded, packed, plan->d_n, plan->d_node_off, plan->d_lap_off, plan->B,
+                                              plan->Nmax, F, (int)plan->R, lap);
+  } else if (lap) {
+    pack_shape((plan->R + 3) / 4, &ctas, &threads);
+    pack_lines_kernel<true><<<ctas, threads, 0, st>>>(padded, packed, plan->d_n, plan->d_node_off, plan->d_lap_off, plan->B,
+                                                     plan->Nmax, F, (int)plan->R,
+                                                     (int64_t)plan->B * plan->Nmax * plan->Nmax);
+  } else {
+    pack_shape(plan->B, &ctas, &threads);
+    pack_lines_kernel<false><<<ctas, threads, 0, st>>>(padded, packed, plan->d_n, plan->d_node_off, plan->d_lap_off, plan->B,
+                                                      plan->Nmax, F, (int)plan->R, (int64_t)plan->B * plan->Nmax * F);
+  }
+}
 
 // Tiles of the recurrence kernels (agcn_cheb_tile.cu): 128-row ranges of the graphs above AGCN_FUSE_MAX_N, then the small graphs
 // first-fit-decreasing into 128-row tiles under the shared-memory budget of their L matrices.  `order` lists the
@@ -527,9 +632,7 @@ static int pack_nodes_impl(const agcn_plan* plan, const float* padded, float* pa
   AGCN_REQUIRE(plan && padded && packed && F >= 1, "null pointer or F < 1");
   if (int rc = plan_use(plan, (cudaStream_t)stream)) return rc;
   if (!to_padded) {
-    pack_rows_kernel<<<pack_grid(plan->R), 1024, 0, (cudaStream_t)stream>>>(padded, packed, plan->d_n, plan->d_node_off,
-                                                                           plan->d_lap_off, plan->B, plan->Nmax, F,
-                                                                           (int)plan->R, 0);
+    launch_pack(plan, padded, packed, F, 0, (cudaStream_t)stream);
     AGCN_LAUNCH_CHECK();
     return AGCN_OK;
   }
@@ -552,9 +655,7 @@ static int pack_lap_impl(const agcn_plan* plan, const float* padded, float* pack
   AGCN_REQUIRE(plan && padded && packed, "null pointer");
   if (int rc = plan_use(plan, (cudaStream_t)stream)) return rc;
   if (!to_padded) {
-    pack_rows_kernel<<<pack_grid(plan->R), 1024, 0, (cudaStream_t)stream>>>(padded, packed, plan->d_n, plan->d_node_off,
-                                                                           plan->d_lap_off, plan->B, plan->Nmax, 0,
-                                                                           (int)plan->R, 1);
+    launch_pack(plan, padded, packed, 0, 1, (cudaStream_t)stream);
     AGCN_LAUNCH_CHECK();
     return AGCN_OK;
   }

@@ -126,6 +126,13 @@ def test_pack_reads_pinned_host_buffers_in_place():
         off += n
     with pytest.raises(ValueError):
         batch.pack_nodes(torch.from_numpy(X))
+    # a source that is not 16-byte aligned takes the scalar-row kernel
+    bufX, bufL = torch.empty(X.size + 1).pin_memory(), torch.empty(L.size + 3).pin_memory()
+    Xo, Lo = bufX[1:].view(B, N, F), bufL[3:].view(B, N, N)
+    Xo.copy_(torch.from_numpy(X))
+    Lo.copy_(torch.from_numpy(L))
+    assert Xo.data_ptr() % 16 != 0 and Lo.data_ptr() % 16 != 0
+    assert torch.equal(batch.pack_nodes(Xo), Xb) and torch.equal(batch.pack_lap(Lo), Lb)
 
 
 def test_point_cloud_graph_construction_matches_reference_goldens():
