@@ -52,6 +52,10 @@ _SIGNATURES = {
     "agcn_pack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
     "agcn_unpack_nodes": (ctypes.c_int, [_P, _P, _P, ctypes.c_int32, _P]),
     "agcn_pack_lap": (ctypes.c_int, [_P, _P, _P, _P]),
+    "agcn_capture_begin": (ctypes.c_int, [_P]),
+    "agcn_capture_end_launch": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32)]),
+    "agcn_capture_abort": (ctypes.c_int, [_P]),
+    "agcn_step_graph_destroy": (ctypes.c_int, [_P]),
     "agcn_unpack_lap": (ctypes.c_int, [_P, _P, _P, _P]),
     "agcn_debug_grouped_product": (ctypes.c_int, [_P, _P, _P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                   ctypes.c_float, ctypes.c_int32, _P]),

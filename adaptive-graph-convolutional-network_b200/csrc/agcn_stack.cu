@@ -198,4 +198,77 @@ int agcn_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v
   return AGCN_OK;
 }
 
+// ---- one graph launch per step (include/agcn_sgcll.h)
+// A few executable graphs are kept, most recently used first: batches of a data set alternate between a handful of node
+// topologies (which size buckets are populated, whether a graph above 144 nodes is present), and an in-place update only
+// works against an executable graph of the same topology.
+struct agcn_step_graph {
+  static constexpr int KEEP = 4;
+  cudaGraphExec_t exec[KEEP] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+int agcn_capture_begin(void* stream) {
+  AGCN_CUDA(cudaStreamBeginCapture((cudaStream_t)stream, cudaStreamCaptureModeThreadLocal));
+  return AGCN_OK;
+}
+
+int agcn_capture_end_launch(void* stream, agcn_step_graph** graph, int32_t* how) {
+  AGCN_REQUIRE(graph, "null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaGraph_t g = nullptr;
+  AGCN_CUDA(cudaStreamEndCapture(st, &g));
+  if (!*graph) *graph = new agcn_step_graph();
+  agcn_step_graph* sg = *graph;
+  constexpr int KEEP = agcn_step_graph::KEEP;
+  int hit = -1, why = 0;
+  for (int i = 0; i < KEEP && hit < 0; ++i) {
+    if (!sg->exec[i]) continue;
+    cudaGraphExecUpdateResultInfo info;
+    if (cudaGraphExecUpdate(sg->exec[i], g, &info) == cudaSuccess) {
+      hit = i;
+    } else {
+      (void)cudaGetLastError();   // another node topology is not an error
+      if (!why) why = (int)info.result;   // cudaGraphExecUpdateResult of the most recent executable graph
+    }
+  }
+  cudaGraphExec_t use = nullptr;
+  if (hit >= 0) {
+    use = sg->exec[hit];
+    for (int i = hit; i > 0; --i) sg->exec[i] = sg->exec[i - 1];
+  } else {
+    const cudaError_t e = cudaGraphInstantiate(&use, g, 0);
+    if (e != cudaSuccess) {
+      cudaGraphDestroy(g);
+      AGCN_CUDA(e);
+    }
+    if (sg->exec[KEEP - 1]) {   // evicted (rare): wait for its last launch before releasing it
+      AGCN_CUDA(cudaStreamSynchronize(st));
+      cudaGraphExecDestroy(sg->exec[KEEP - 1]);
+    }
+    for (int i = KEEP - 1; i > 0; --i) sg->exec[i] = sg->exec[i - 1];
+  }
+  sg->exec[0] = use;
+  cudaGraphDestroy(g);
+  if (how) *how = hit >= 0 ? 1 : -why;
+  AGCN_CUDA(cudaGraphLaunch(use, st));
+  return AGCN_OK;
+}
+
+int agcn_capture_abort(void* stream) {
+  cudaGraph_t g = nullptr;
+  (void)cudaStreamEndCapture((cudaStream_t)stream, &g);
+  if (g) cudaGraphDestroy(g);
+  (void)cudaGetLastError();
+  return AGCN_OK;
+}
+
+int agcn_step_graph_destroy(agcn_step_graph* graph) {
+  if (!graph) return AGCN_OK;
+  (void)cudaDeviceSynchronize();   // a launch may still be in flight
+  for (cudaGraphExec_t e : graph->exec)
+    if (e) cudaGraphExecDestroy(e);
+  delete graph;
+  return AGCN_OK;
+}
+
 }  // extern "C"

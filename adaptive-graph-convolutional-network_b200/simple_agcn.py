@@ -102,12 +102,21 @@ class SimpleAGCNStep(object):
         _lib.check(_lib.lib().agcn_stack_create(descs, len(self.layers), self.Fm, self.Nt, _lib.LOSS[loss], offs_c,
                                                 ctypes.byref(self._stack)))
         self._arena = None
+        self._step_graph = ctypes.c_void_p()
+        self._graph_stream = None
+        self._graph_miss_streak = 0
+        self._graph_disabled = False
+        self.step_graph_refusals = []   # cudaGraphExecUpdateResult codes of the steps that had to instantiate
+        self.step_graph_updates = 0     # steps whose executable graph was updated in place (not instantiated anew)
         self._loss = torch.zeros(1, device=self.device, dtype=torch.float32)
         self._pending = []
         self._notify = _lib.NOTIFY_FN(self._on_stage)     # keep the ctypes thunk alive
 
     def __del__(self):
         try:
+            if self._step_graph:
+                _lib.lib().agcn_step_graph_destroy(self._step_graph)
+                self._step_graph = ctypes.c_void_p()
             if self._stack:
                 _lib.lib().agcn_stack_destroy(self._stack)
                 self._stack = ctypes.c_void_p()
@@ -135,12 +144,15 @@ class SimpleAGCNStep(object):
             self.grads.all_reduce()
 
     # ---- engines --------------------------------------------------------------------------------------------
-    def _loss_grad_stack(self, X, Lint, batch, targets, weights):
+    def _ensure_arena(self, batch):
         nbytes = ctypes.c_size_t()
-        lib = _lib.lib()
-        _lib.check(lib.agcn_stack_workspace_bytes(self._stack, batch.handle, ctypes.byref(nbytes)))
+        _lib.check(_lib.lib().agcn_stack_workspace_bytes(self._stack, batch.handle, ctypes.byref(nbytes)))
         if self._arena is None or self._arena.numel() < nbytes.value:
             self._arena = torch.empty(int(nbytes.value * 1.25) + 4096, dtype=torch.uint8, device=self.device)
+
+    def _loss_grad_stack(self, X, Lint, batch, targets, weights):
+        lib = _lib.lib()
+        self._ensure_arena(batch)
         notify = ctypes.cast(self._notify, ctypes.c_void_p) if self.overlap_allreduce else None
         with torch.cuda.device(self.device):
             _lib.check(lib.agcn_stack_loss_grad(
@@ -186,6 +198,54 @@ class SimpleAGCNStep(object):
         loss = self.loss_and_grads(X, Lint, batch, targets, weights)
         self._all_reduce()
         self.apply_adam()
+        return loss
+
+
+    def step_graphed(self, X, Lint, batch, targets, weights):
+        """step() as ONE graph launch: the library calls of the step are captured (nothing runs, the host pays what the
+        launches cost), the executable graph of the previous step is updated in place with the new batch's kernel
+        parameters and launched (agcn_capture_begin / agcn_capture_end_launch).  For batches arriving over PCIe beside the
+        step: eager launch commands are fetched from host memory one by one and bulk transfers delay every fetch.
+        Single process only (the NCCL all-reduce of the multi-GPU step is launched by torch): falls back to step()."""
+        if self.world_size > 1 or self.engine != "stack" or self._graph_disabled:
+            return self.step(X, Lint, batch, targets, weights)
+        cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream == 0:            # the legacy default stream cannot be captured: borrow a stream of our own
+            if self._graph_stream is None:
+                self._graph_stream = torch.cuda.Stream(device=self.device)
+            gs = self._graph_stream
+            gs.wait_stream(cur)
+            with torch.cuda.stream(gs):
+                loss = self.step_graphed(X, Lint, batch, targets, weights)
+            cur.wait_stream(gs)
+            return loss
+        lib = _lib.lib()
+        self._ensure_arena(batch)           # no allocation inside the capture
+        st = _stream_ptr(self.device)
+        keep, self.overlap_allreduce = self.overlap_allreduce, False      # no host callbacks inside the capture
+        try:
+            with torch.cuda.device(self.device):
+                _lib.check(lib.agcn_capture_begin(st))
+                try:
+                    loss = self.loss_and_grads(X, Lint, batch, targets, weights)
+                    self.apply_adam()
+                except BaseException:
+                    lib.agcn_capture_abort(st)
+                    raise
+                how = ctypes.c_int32(0)
+                _lib.check(lib.agcn_capture_end_launch(st, ctypes.byref(self._step_graph), ctypes.byref(how)))
+        finally:
+            self.overlap_allreduce = keep
+        if how.value == 1:
+            self.step_graph_updates += 1
+            self._graph_miss_streak = 0
+        else:
+            self.step_graph_refusals.append(int(-how.value))
+            self._graph_miss_streak += 1
+            if self._graph_miss_streak >= 4:
+                # instantiating a graph costs several eager steps: a stream of batches that never matches a kept
+                # executable graph goes back to eager launches for good
+                self._graph_disabled = True
         return loss
 
 

@@ -303,6 +303,25 @@ int agcn_stack_loss_grad(const agcn_stack* stack, const agcn_plan* plan, const f
 int agcn_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v, int32_t* d_step, int64_t n, float lr,
                    float beta1, float beta2, float eps, void* stream);
 
+/* One graph launch per training step for batches whose topology changes every step.
+ * Eager launches of the ~80 kernels of a step are what bulk host->device traffic hurts: the next batch arriving over
+ * PCIe delays the front end's fetch of every launch command (0.70 -> 0.82 ms per ToxCast step), while a graph launch of
+ * the same step is not affected at all (tools/replay_vs_pcie.py).  A captured graph cannot simply be replayed for a new
+ * batch (grid sizes, tile tables and buffers differ), so the step is RE-CAPTURED for every batch -- capture submits no
+ * work, it costs the host what the launches cost -- and an executable graph kept from the previous step is updated in
+ * place with the new kernel parameters (cudaGraphExecUpdate: same nodes, new arguments and grids) and launched once.
+ * When the node topology itself differs (another set of size buckets) the executable graph is instantiated anew.
+ *   agcn_capture_begin(stream);  ... the library calls of the step on `stream` ...;  agcn_capture_end_launch(stream, &g, &how);
+ * *how: 1 = updated in place, 0 = instantiated (first use), -r = instantiated after the update of the most recent
+ * executable graph was refused with cudaGraphExecUpdateResult r (2 = topology changed, 4 = function changed, ...).  The plan of the batch must have been created (and its upload ordered
+ * before `stream`) outside the capture. */
+typedef struct agcn_step_graph agcn_step_graph;
+int agcn_capture_begin(void* stream);
+int agcn_capture_end_launch(void* stream, agcn_step_graph** graph /* in/out, *graph == NULL the first time */,
+                            int32_t* how);
+int agcn_capture_abort(void* stream);   /* after a failed call inside the capture: end it and drop what was recorded */
+int agcn_step_graph_destroy(agcn_step_graph* graph);
+
 /* Host-buffer convenience entry (the end-to-end path): padded HOST arrays in the reference's wire
  * layout in, padded HOST output out; host<->device copies are issued on `stream` inside the call.
  * Page-locked inputs (cudaMallocHost / cudaHostRegister / torch pin_memory) are read in place by the pack kernels

@@ -217,6 +217,46 @@ def test_step_decreases_loss_and_is_reproducible():
     assert traj[0] == traj[1]
 
 
+def test_graphed_step_follows_the_eager_step_bit_for_bit_over_changing_batches():
+    """step_graphed (the step captured anew for every batch, the executable graph of the previous step updated in place
+    and launched once) against step() (eager launches) over batches of different composition and size, some repeated:
+    same losses and same parameters bit for bit; batches of the same bucket structure update the graph in place, and
+    a batch with another node topology (point-cloud sizes: other kernels) falls back to a fresh instantiation."""
+    import agcn_b200
+    from agcn_b200.simple_agcn import SimpleAGCNStep, synthetic_labels
+    dev = torch.device("cuda:0")
+    B = 96
+    rng = np.random.default_rng(8)
+    batches = []
+    for seed, nmax in ((1, 132), (2, 132), (3, 40), (4, 132)):
+        X, L, n = O.synthetic_molecule_batch(B, 132, seed=seed)
+        if nmax < 132:                                  # a batch of small molecules only: other size buckets
+            n = np.minimum(n, nmax).astype(np.int32)
+        b = agcn_b200.GraphBatch(n, 132, device=dev)
+        batches.append((b, b.pack_nodes(torch.from_numpy(X).to(dev)), b.pack_lap(torch.from_numpy(L).to(dev))))
+    big_n = np.asarray([200, 150] + [12] * (B - 2), np.int32)     # two graphs above 144 nodes: row-tiled kernels join in
+    Xb = (rng.standard_normal((B, 200, 75)) * 0.3).astype(np.float32)
+    Lb = (rng.standard_normal((B, 200, 200)) * 0.02).astype(np.float32)
+    bb = agcn_b200.GraphBatch(big_n, 200, device=dev)
+    batches.append((bb, bb.pack_nodes(torch.from_numpy(Xb).to(dev)), bb.pack_lap(torch.from_numpy(Lb).to(dev))))
+    tg, w = synthetic_labels(B, 12, 3, dev)
+    order = [0, 1, 0, 2, 3, 4, 1, 4, 0]
+    runs = []
+    for graphed in (False, True):
+        model = SimpleAGCNStep(75, (64, 128, 128, 64), 256, 12, 3, B, device=dev, seed=5)
+        losses = []
+        for k in order:
+            b, Xd, Ld = batches[k]
+            fn = model.step_graphed if graphed else model.step
+            losses.append(float(fn(Xd, Ld, b, tg, w)))
+        torch.cuda.synchronize()
+        runs.append((losses, model.flat_params.flat.detach().clone(), model.step_graph_updates))
+    assert np.isfinite(runs[0][0]).all()
+    assert runs[0][0] == runs[1][0]
+    assert torch.equal(runs[0][1], runs[1][1])
+    assert runs[0][2] == 0 and runs[1][2] >= 3          # at least the repeated molecule batches were updated in place
+
+
 def test_plans_created_and_destroyed_back_to_back_behind_a_long_kernel():
     """A plan per batch with the host far ahead of the device: plans are destroyed while their table upload is still
     queued, so their pinned staging buffers go back to the pool in flight.  Re-acquiring them must neither reuse a
