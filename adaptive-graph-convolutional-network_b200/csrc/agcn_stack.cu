@@ -205,6 +205,14 @@ int agcn_adam_step(float* d_params, const float* d_grads, float* d_m, float* d_v
 struct agcn_step_graph {
   static constexpr int KEEP = 4;
   cudaGraphExec_t exec[KEEP] = {nullptr, nullptr, nullptr, nullptr};
+  // The captured graph whose parameters an executable graph was updated with stays alive until the launch that used them
+  // has finished: objects a library attached to the capture (NCCL's plan of a captured collective) live as long as
+  // that graph.  Ring of the last captures with an event behind their launch.
+  static constexpr int RING = 3;
+  cudaGraph_t src[RING] = {nullptr, nullptr, nullptr};
+  cudaEvent_t done[RING] = {nullptr, nullptr, nullptr};
+  int head = 0;
+  long long instantiated = 0;
 };
 
 int agcn_capture_begin(void* stream) {
@@ -241,6 +249,7 @@ int agcn_capture_end_launch(void* stream, agcn_step_graph** graph, int32_t* how)
       cudaGraphDestroy(g);
       AGCN_CUDA(e);
     }
+    sg->instantiated++;
     if (sg->exec[KEEP - 1]) {   // evicted (rare): wait for its last launch before releasing it
       AGCN_CUDA(cudaStreamSynchronize(st));
       cudaGraphExecDestroy(sg->exec[KEEP - 1]);
@@ -248,9 +257,18 @@ int agcn_capture_end_launch(void* stream, agcn_step_graph** graph, int32_t* how)
     for (int i = KEEP - 1; i > 0; --i) sg->exec[i] = sg->exec[i - 1];
   }
   sg->exec[0] = use;
-  cudaGraphDestroy(g);
   if (how) *how = hit >= 0 ? 1 : -why;
   AGCN_CUDA(cudaGraphLaunch(use, st));
+  // retire the oldest capture of the ring (its launch was two steps ago), park this one behind its launch
+  const int slot = sg->head;
+  sg->head = (sg->head + 1) % agcn_step_graph::RING;
+  if (sg->src[slot]) {
+    AGCN_CUDA(cudaEventSynchronize(sg->done[slot]));
+    cudaGraphDestroy(sg->src[slot]);
+  }
+  if (!sg->done[slot]) AGCN_CUDA(cudaEventCreateWithFlags(&sg->done[slot], cudaEventDisableTiming));
+  sg->src[slot] = g;
+  AGCN_CUDA(cudaEventRecord(sg->done[slot], st));
   return AGCN_OK;
 }
 
@@ -267,6 +285,10 @@ int agcn_step_graph_destroy(agcn_step_graph* graph) {
   (void)cudaDeviceSynchronize();   // a launch may still be in flight
   for (cudaGraphExec_t e : graph->exec)
     if (e) cudaGraphExecDestroy(e);
+  for (int i = 0; i < agcn_step_graph::RING; ++i) {
+    if (graph->src[i]) cudaGraphDestroy(graph->src[i]);
+    if (graph->done[i]) cudaEventDestroy(graph->done[i]);
+  }
   delete graph;
   return AGCN_OK;
 }

@@ -104,6 +104,9 @@ class SimpleAGCNStep(object):
         self._arena = None
         self._step_graph = ctypes.c_void_p()
         self._graph_stream = None
+        # opt-in: capture the NCCL all-reduce of the multi-GPU step too (launched by torch.distributed on its own stream,
+        # which the events of ProcessGroupNCCL fork from and join back into the capturing stream)
+        self.graph_collectives = False
         self._graph_miss_streak = 0
         self._graph_disabled = False
         self.step_graph_refusals = []   # cudaGraphExecUpdateResult codes of the steps that had to instantiate
@@ -206,8 +209,9 @@ class SimpleAGCNStep(object):
         launches cost), the executable graph of the previous step is updated in place with the new batch's kernel
         parameters and launched (agcn_capture_begin / agcn_capture_end_launch).  For batches arriving over PCIe beside the
         step: eager launch commands are fetched from host memory one by one and bulk transfers delay every fetch.
-        Single process only (the NCCL all-reduce of the multi-GPU step is launched by torch): falls back to step()."""
-        if self.world_size > 1 or self.engine != "stack" or self._graph_disabled:
+        With more than one process the step stays eager unless graph_collectives is set (the NCCL all-reduce is launched
+        by torch.distributed; captured with it: tools/e2e_multi.py)."""
+        if self.engine != "stack" or self._graph_disabled or (self.world_size > 1 and not self.graph_collectives):
             return self.step(X, Lint, batch, targets, weights)
         cur = torch.cuda.current_stream(self.device)
         if cur.cuda_stream == 0:            # the legacy default stream cannot be captured: borrow a stream of our own
@@ -228,6 +232,7 @@ class SimpleAGCNStep(object):
                 _lib.check(lib.agcn_capture_begin(st))
                 try:
                     loss = self.loss_and_grads(X, Lint, batch, targets, weights)
+                    self._all_reduce()          # (graph_collectives: torch's NCCL all-reduce joins the capture)
                     self.apply_adam()
                 except BaseException:
                     lib.agcn_capture_abort(st)
