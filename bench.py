@@ -794,7 +794,8 @@ def measure_workload(cfg, dev, rank, world, args, peaks, tf32_peak, full):
                               "kernels reading the host arrays in place over PCIe (only the real rows move) on a side "
                               "stream under the previous step, one agcn_stack_loss_grad call + all-reduce + Adam "
                               "(eager launches), loss read back"}
-    if world == 1:
+    if world == 1 or os.environ.get("AGCN_BENCH_GRAPH_COLLECTIVES"):
+        r.model.graph_collectives = world > 1     # opt-in: the NCCL all-reduce joins the capture (tools/e2e_multi.py)
         # the same loop with the step as ONE graph launch: re-captured for every batch (a new plan, new buffers and grid
         # sizes every step), the executable graph of the previous step updated in place (SimpleAGCNStep.step_graphed);
         # the next batch is staged by a feeder thread.  Bulk PCIe traffic delays eager launch commands, not a graph launch.
