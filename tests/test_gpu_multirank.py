@@ -1,7 +1,7 @@
 """Data-parallel parity on real GPUs: with the graphs of one batch sharded over 2 ranks, the
 NCCL all-reduced flat gradient must equal the 1-rank gradient of the union batch, the bucketed all-reduce issued
 while backward is still running must equal the single all-reduce bit for bit, and the replicas must stay identical
-after the Adam step; the graph-launched step with the all-reduce captured follows the eager step bit for bit.  Skipped on boxes with fewer than 2 GPUs (the gloo twin of this test runs on the CPU)."""
+after the Adam step.  Skipped on boxes with fewer than 2 GPUs (the gloo twin of this test runs on the CPU)."""
 import os
 import socket
 import sys
@@ -59,21 +59,6 @@ def _worker(rank, world, port, out_dir):
     loss_r, g_plain, p_plain = run(mine, world, False, per)
     _, g_over, p_over = run(mine, world, True, per)
     res = {"bucketed_equals_single": bool(torch.equal(g_plain, g_over) and torch.equal(p_plain, p_over))}
-    # three steps as graph launches with the NCCL all-reduce captured too (graph_collectives) against three eager steps
-    def steps(graphed):
-        batch = agcn_b200.GraphBatch(n[mine], 132, device=dev)
-        Xd = batch.pack_nodes(torch.from_numpy(X[mine]).to(dev))
-        Ld = batch.pack_lap(torch.from_numpy(L[mine]).to(dev))
-        model = SimpleAGCNStep(75, (64, 128, 128, 64), 256, 20, 3, per, device=dev, world_size=world, seed=3,
-                               overlap_allreduce=False)
-        model.graph_collectives = True
-        fn = model.step_graphed if graphed else model.step
-        losses = [float(fn(Xd, Ld, batch, tg[mine].to(dev), w[mine].to(dev))) for _ in range(3)]
-        torch.cuda.synchronize()
-        return losses, model.flat_params.flat.detach().clone(), model.step_graph_updates
-    l_e, p_e, _ = steps(False)
-    l_g, p_g, upd = steps(True)
-    res["graphed_equals_eager"] = bool(l_e == l_g and torch.equal(p_e, p_g) and upd == 2)
     # replicas identical
     other = [torch.empty_like(p_plain) for _ in range(world)]
     dist.all_gather(other, p_plain)
@@ -102,6 +87,5 @@ def test_two_rank_allreduced_gradient_equals_union_batch(tmp_path):
     res1 = torch.load(os.path.join(str(tmp_path), "res1.pt"))
     assert res["bucketed_equals_single"] and res1["bucketed_equals_single"]
     assert res["replicas_identical"] and res1["replicas_identical"]
-    assert res["graphed_equals_eager"] and res1["graphed_equals_eager"]
     assert abs(res["loss_sum_ranks"] - res["loss_union"]) <= 1e-5 * abs(res["loss_union"])
     assert res["grad_rel_err"] <= 1e-5, res
