@@ -214,6 +214,9 @@ class SimpleAGCNStep(object):
         if self.engine != "stack" or self._graph_disabled or (self.world_size > 1 and not self.graph_collectives):
             return self.step(X, Lint, batch, targets, weights)
         cur = torch.cuda.current_stream(self.device)
+        if cur.cuda_stream == 0 and self.world_size > 1:
+            # (capturing the all-reduce on a borrowed stream hung under mp.spawn in the 2-rank test: unexplained, refused)
+            raise RuntimeError("step_graphed with graph_collectives must be called on a non-default CUDA stream")
         if cur.cuda_stream == 0:            # the legacy default stream cannot be captured: borrow a stream of our own
             if self._graph_stream is None:
                 self._graph_stream = torch.cuda.Stream(device=self.device)
