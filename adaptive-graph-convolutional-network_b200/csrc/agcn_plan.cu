@@ -93,7 +93,8 @@ __global__ void pack_lap_kernel(const float* __restrict__ padded, float* __restr
 //     link's outstanding-read tags saturate at ~18 GB/s whatever the number of threads; whole aligned 128-byte lines
 //     (eight lanes x float4, elements outside the segment dropped) reach 40 GB/s.
 //  2. What the transfer costs the step running beside it does not depend on the SMs it occupies (8 x 1024 threads and
-//     148 x 32 threads cost the same) and a plain copy-engine cudaMemcpyAsync of the same bytes costs it too: bulk
+//     148 x 32 threads cost the same) and a plain copy-engine cudaMemcpyAsync of the same bytes costs it too, while a graph
+//     launch of the step is immune (tools/replay_vs_pcie.py).  The reading that fits (inferred from the timings): bulk
 //     GPU-initiated PCIe reads delay the front end's fetches of the step's ~80 eager launch commands from host memory
 //     (ToxCast: 0.69 ms per step alone, 0.81-0.85 ms with 8 MB arriving beside it; a feeder thread that gathers on the
 //     host and sends one contiguous copy was slower still, 0.90 ms).
